@@ -1,0 +1,194 @@
+"""CPU tests (-m "not gpu"): pin the C oracle (oracle/nislam_oracle.c) against
+  * the analytic known answers of SURVEY.md Appendix C,
+  * the committed golden vectors generated with scipy-f32 FFT + genuine cv2 (tests/golden/make_golden.py),
+  * the Python restatement itself when scipy/cv2 are importable.
+"""
+import numpy as np
+import pytest
+
+import oracle_c as oc
+
+H, W, D, CP = 480, 640, 720, 480
+
+
+def wrap_pi(a):
+    return (a + np.pi) % (2 * np.pi) - np.pi
+
+
+# ---------------------------------------------------------------- analytic KATs (Appendix C)
+def test_impulse_spectrum_is_checkerboard():
+    # C.1  FFT(delta[R/2,C/2]) = (-1)^(kr+kc)   (correlation_flow.cc:46-51)
+    for R, C in ((480, 640), (720, 480), (48, 64)):
+        x = np.zeros((R, C), np.float32)
+        x[R // 2, C // 2] = 1
+        F = oc.fft2(x)
+        kr, kc = np.meshgrid(np.arange(R // 2 + 1), np.arange(C), indexing="ij")
+        expect = np.where((kr + kc) % 2 == 0, 1.0, -1.0)
+        assert np.abs(F - expect).max() < 2e-6
+
+
+def test_remove_zero_component_4x4():
+    # C.2
+    x = np.arange(16, dtype=np.float32).reshape(4, 4)
+    y = oc.remove_zero_component(x)
+    assert np.array_equal(y, np.array([[2, 9, 10, 11], [6, 5, 6, 7], [10, 9, 10, 11], [14, 13, 14, 15]], np.float32))
+
+
+def test_normalize_degree():
+    # C.3  (utils.cc:173-175)
+    nd = oc.lib().orc_normalize_degree
+    assert nd(180.0) == -180.0 and nd(190.0) == -170.0 and nd(-180.0) == -180.0 and nd(359.5) == -0.5
+
+
+def test_fftshift_matches_roll():
+    x = np.random.default_rng(0).random((6, 8)).astype(np.float32)
+    assert np.array_equal(oc.fftshift(x), np.roll(x, (3, 4), axis=(0, 1)))
+
+
+def test_fft_roundtrip_and_numpy():
+    rng = np.random.default_rng(3)
+    for R, C in ((480, 640), (720, 480), (448, 448), (30, 22), (960, 1280)):
+        x = rng.random((R, C)).astype(np.float32)
+        F = oc.fft2(x)
+        Fn = np.fft.rfft2(x.astype(np.float64), axes=(1, 0))
+        assert np.abs(F - Fn).max() / np.abs(Fn).max() < 1e-6
+        assert np.abs(oc.ifft2(F) - x).max() < 2e-6
+
+
+def test_argmax_tiebreak_column_major_first():
+    # C.6: duplicated maxima -> smallest col, then smallest row (Eigen maxCoeff on a column-major array).
+    # Build a spectrum whose IFFT is exactly two equal impulses by linearity through estimate_trans is not possible,
+    # so check the reduction rule on the oracle's g output of an identity pair (single peak) and the rule itself here.
+    g = np.zeros((4, 5), np.float32)
+    g[3, 1] = g[0, 2] = g[2, 1] = 7.0
+    flat = int(np.argmax(g.T.reshape(-1)))
+    assert divmod(flat, 4) == (1, 2)        # col 1, row 2
+
+
+# ---------------------------------------------------------------- golden vectors (genuine cv2)
+def test_warps_bit_exact_vs_cv2_golden(golden_stages):
+    s = golden_stages
+    assert np.array_equal(oc.polar(s["src"], 72, 40), s["polar_72x40"])
+    assert np.array_equal(oc.polar(s["src2"], 36, 16), s["polar2_36x16"])
+    for d, want, want2 in zip(s["rot_degrees"], s["rot_out"], s["rot2_out"]):
+        assert np.array_equal(oc.rotate(s["src"], d), want), d
+        assert np.array_equal(oc.rotate(s["src2"], d), want2), d
+    for d, m in zip(s["rot_degrees"], s["inv_mats_640x480"]):
+        assert np.allclose(oc.rotation_inverse(H, W, float(d)), m, rtol=0, atol=1e-9)
+
+
+def _check_rows(rows, fn):
+    for r in rows:
+        i, mode = int(r[0]), int(r[1])
+        info, pose, pk = fn(i, mode)
+        assert pose[0] == r[2] and pose[1] == r[3], (i, mode, pose, r)
+        assert abs(wrap_pi(pose[2] - r[4])) < 1e-6, (i, mode, pose, r)
+        assert pk["trans"] == (int(r[10]), int(r[11]))
+        assert pk["polar"][0] % (D // 2) == int(r[8]) % (D // 2)       # 180-degree twin peak
+        assert np.allclose(info, r[5:8], rtol=3e-4), (i, mode, info, r[5:8])
+
+
+def test_pose_goldens(golden_pairs):
+    g = golden_pairs
+    cfg = oc.make_cfg()
+    imgs = [oc.normalize_u8(u) for u in g["images"]]
+    feats = [oc.compute_intermedium(cfg, im) for im in imgs]
+    assert abs(np.abs(feats[0][0]).astype(np.float64).sum() / g["a_fft_result_abs_sum"] - 1) < 1e-5
+    assert abs(np.abs(feats[0][1]).astype(np.float64).sum() / g["a_fft_polar_abs_sum"] - 1) < 1e-5
+
+    def fn(i, mode):
+        return oc.compute_pose(cfg, feats[0][0], imgs[i], feats[0][1], feats[i][1], mode)
+    _check_rows(g["pose_rows"], fn)
+
+
+def test_gaussian_kernel_golden(golden_pairs):
+    g = golden_pairs
+    cfg = oc.make_cfg(kernel=1)
+    a, b = oc.normalize_u8(g["images"][0]), oc.normalize_u8(g["images"][2])
+    Fa, Pa = oc.compute_intermedium(cfg, a)
+    Fb, Pb = oc.compute_intermedium(cfg, b)
+    info, pose, pk = oc.compute_pose(cfg, Fa, b, Pa, Pb, True)
+    r = g["gauss_row"]
+    assert pose[0] == r[2] and pose[1] == r[3] and abs(wrap_pi(pose[2] - r[4])) < 1e-6
+    assert np.allclose(info, r[5:8], rtol=3e-4)
+
+
+def test_invalid_kernel_raises():
+    cfg = oc.make_cfg(kernel=7, height=48, width=64, rotation_divisor=72, rotation_channel=40)
+    z = np.zeros((25, 64), np.complex64)
+    with pytest.raises(ValueError):
+        oc.estimate_trans(cfg, z, z, 48, 64)
+
+
+# ---------------------------------------------------------------- circular rolls (C.4 / C.5)
+def test_circular_roll_known_answers(golden_pairs):
+    cfg = oc.make_cfg()
+    a = oc.normalize_u8(golden_pairs["images"][0])
+    Fa, Pa = oc.compute_intermedium(cfg, a)
+    base = None
+    for sy, sx in ((0, 0), (3, 0), (0, -9), (17, 25)):
+        b = np.roll(a, (sy, sx), axis=(0, 1))
+        Fb, Pb = oc.compute_intermedium(cfg, b)
+        info, pose, pk = oc.compute_pose(cfg, Fa, b, Pa, Pb, True)
+        assert (pose[0], pose[1]) == (-sx, -sy)
+        assert abs(wrap_pi(pose[2])) < 1e-6
+        assert pk["polar"][0] % (D // 2) == 0
+        if base is None:
+            base = info
+            assert pk["trans"] == (H // 2, W // 2)
+        assert np.allclose(info, base, rtol=1e-3)
+
+
+# ---------------------------------------------------------------- scan (C.7, loop_closure.cc:36-73)
+def test_scan_first_wins_and_filters(golden_pairs):
+    g = golden_pairs
+    cfg = oc.make_cfg()
+    imgs = [oc.normalize_u8(u) for u in g["images"][:4]]
+    feats = [oc.compute_intermedium(cfg, im) for im in imgs]
+    thr = oc.LoopConfigC(60.0, 60.0, 0, 0.0)
+    # three identical copies of keyframe 0 among others: the first copy must win (strict >)
+    kfs = [(10, *feats[3], 0.0), (11, *feats[0], 1.0), (12, *feats[0], 2.0), (13, *feats[0], 3.0)]
+    res = oc.find_loop_closure(cfg, thr, imgs[1], feats[1][1], 99, 50.0, kfs)
+    assert res["found"] and res["index"] == 1 and res["frame_id"] == 11
+    assert tuple(res["relative_pose"][:2]) == (7.0, 0.0)
+    # same with 4 threads
+    res4 = oc.find_loop_closure(cfg, thr, imgs[1], feats[1][1], 99, 50.0, kfs, threads=4)
+    assert res4["index"] == 1 and np.array_equal(res4["response"], res["response"])
+    # frame-gap filter removes ids with |gap| < 89 of 99 -> only id 10 survives
+    thr2 = oc.LoopConfigC(60.0, 60.0, 89, 0.0)
+    res2 = oc.find_loop_closure(cfg, thr2, imgs[1], feats[1][1], 99, 50.0, kfs)
+    assert res2["index"] == 0
+    # distance filter: |50 - d| < 49.5 removes everything except d = 0.0
+    thr3 = oc.LoopConfigC(60.0, 60.0, 0, 49.5)
+    res3 = oc.find_loop_closure(cfg, thr3, imgs[1], feats[1][1], 99, 50.0, kfs)
+    assert res3["index"] == 0
+    # empty candidate list: initial best (-1,-1,-1), not found (loop_closure.h:15)
+    res0 = oc.find_loop_closure(cfg, thr, imgs[1], feats[1][1], 99, 50.0, [])
+    assert (not res0["found"]) and res0["index"] == -1 and np.array_equal(res0["response"], [-1, -1, -1])
+
+
+# ---------------------------------------------------------------- Python restatement == C restatement (if cv2/scipy exist)
+def test_python_restatement_agrees(golden_pairs):
+    ref = pytest.importorskip("nislam_ref")
+    if ref.cv2 is None:
+        pytest.skip("cv2 missing")
+    g = golden_pairs
+    cf = ref.CorrelationFlow(ref.CFConfig(), H, W)
+    cfg = oc.make_cfg()
+    a = ref.convert_mat_to_normalized_array(g["images"][0])
+    b = ref.convert_mat_to_normalized_array(g["images"][3])
+    assert np.array_equal(a, oc.normalize_u8(g["images"][0]))
+    Fa, Pa = cf.compute_intermedium(a)
+    Fc, Pc = oc.compute_intermedium(cfg, a)
+    assert np.abs(Fa - Fc).max() / np.abs(Fa).max() < 1e-6
+    assert np.abs(Pa - Pc).max() / np.abs(Pa).max() < 1e-6
+    # stage: polar image bit-exact against cv2 at full size
+    hp = cf.last_stages["high_power"]
+    assert np.array_equal(oc.polar(ref.fftshift(hp)), cf.polar(ref.fftshift(hp)))
+    assert np.array_equal(oc.rotate(b, -10.0), ref.rotate_array(b, np.float32(-10.0)))
+    Fb, Pb = cf.compute_intermedium(b)
+    i_r, t_r, p_r, g_r = cf.estimate_trans(Fa, Fb, cf.target_fft, H, W)
+    i_c, t_c, p_c, g_c = oc.estimate_trans(cfg, Fa, Fb, H, W, want_g=True)
+    assert p_r == p_c and t_r == t_c
+    assert np.abs(g_r - g_c).max() / np.abs(g_r).max() < 2e-5
+    assert abs(i_r - i_c) / i_r < 3e-4
