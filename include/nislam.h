@@ -1,0 +1,141 @@
+/*
+ * nislam.h -- C ABI of the B200-native NI-SLAM tracking / loop-closure hot path (libnislam.so).
+ *
+ * The reference (sair-lab/ni-slam) has no FFI or plugin interface for this path: it sits behind two plain C++
+ * classes.  Each entry point below names the reference interface it replaces (file:line under the reference
+ * tree); ni_slam_b200/host/correlation_flow.hpp re-exposes the reference's class signatures on top of them and
+ * INTEGRATION.md shows the binding a maintainer adds to MapBuilder.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int status (NIS_OK = 0); no exceptions cross the ABI.
+ *   - "reference layout" = Eigen column-major: a real R x C array is C lines of R floats; a half spectrum
+ *     ArrayXXcf((R/2+1), C) is C lines of (R/2+1) interleaved (re,im) float pairs.
+ *   - u8 images are cv::Mat-like row-major H x W.
+ *   - one context per device; calls on one context are serialised on its CUDA stream; a context is not re-entrant
+ *     (the reference's CorrelationFlow is not re-entrant either: FFTW planner calls, correlation_flow.cc:56-61).
+ *   - there is no CPU fallback: every compute entry point fails with NIS_ERR_CUDA when no device is usable.
+ */
+#ifndef NISLAM_H_
+#define NISLAM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  NIS_OK = 0,
+  NIS_ERR_INVALID_ARGUMENT = 1, /* NULL pointers, odd sizes ... */
+  NIS_ERR_INVALID_KERNEL = 2,   /* cfg.kernel not in {0,1}: std::invalid_argument("Received invalid kernel type"), correlation_flow.cc:168 */
+  NIS_ERR_UNSUPPORTED_SIZE = 3, /* transform length without an instantiated kernel (see csrc/nis_sizes.h) */
+  NIS_ERR_CUDA = 4,             /* CUDA runtime error; text in nis_last_error() */
+  NIS_ERR_OUT_OF_MEMORY = 5
+};
+
+typedef struct nis_ctx nis_ctx;     /* = CorrelationFlow + LoopClosure state on one GPU */
+typedef struct nis_frame nis_frame; /* device-resident Frame payload: image + fft_result + fft_polar (include/frame.h:34-36) */
+
+/* CFConfig (include/read_configs.h:15-25) minus width/height, which the ctor overwrites with the camera size
+ * (correlation_flow.cc:40-41). */
+typedef struct {
+  float lambda;
+  int kernel; /* 0 polynomial, 1 gaussian */
+  float sigma;
+  float offset;
+  int power;
+  int rotation_divisor;
+  int rotation_channel;
+} nis_cf_config;
+
+/* LoopClosureConfig (include/read_configs.h:38-44) minus to_find_loop (a caller decision, map_builder.cc:63). */
+typedef struct {
+  double position_response_thr;
+  double angle_response_thr;
+  int frame_gap_thr;
+  double distance_thr;
+} nis_loop_config;
+
+/* LoopClosureResult (include/loop_closure.h:8-25) with the FramePtr replaced by slot / frame id, plus the raw peaks. */
+typedef struct {
+  int32_t found;
+  int32_t slot;       /* DB slot of the winner, -1 if no candidate was evaluated */
+  int32_t frame_id;   /* its frame id */
+  int32_t hyp;        /* 0: "-deg" hypothesis kept, 1: "-deg+180" (correlation_flow.cc:121-131) */
+  double relative_pose[3];
+  double response[3]; /* (-1,-1,-1) when nothing was evaluated (loop_closure.h:15) */
+  int32_t peak[4];    /* polar row, polar col, translation row, translation col */
+  int32_t evaluated;  /* candidates that passed the gap / distance filters */
+} nis_loop_result;
+
+/* ---- lifecycle: CorrelationFlow::CorrelationFlow(CFConfig&, double& h, double& w), include/correlation_flow.h:11 ---- */
+int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int device, nis_ctx** out);
+int nis_destroy(nis_ctx* ctx);
+const char* nis_last_error(const nis_ctx* ctx); /* never NULL */
+const char* nis_strerror(int status);
+/* the CUDA stream all of this context's kernels are launched on (cudaStream_t), for event timing by the caller */
+void* nis_stream(nis_ctx* ctx);
+int nis_synchronize(nis_ctx* ctx);
+/* number of this library's kernels launched on the context so far */
+long long nis_kernel_launches(const nis_ctx* ctx);
+/* work-batch size (pairs / candidates in flight per kernel launch); 0 = library default */
+int nis_set_batch(nis_ctx* ctx, int batch);
+
+/* ---- features: MapBuilder::ComputeFFTResult = ConvertMatToNormalizedArray + CorrelationFlow::ComputeIntermedium
+ *      (src/map_builder.cc:72-75, src/utils.cc:110-118, include/correlation_flow.h:12) ---- */
+int nis_features_u8(nis_ctx* ctx, const uint8_t* image_rowmajor, nis_frame** out);   /* cv::Mat u8 H x W */
+int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out);    /* ArrayXXf H x W, reference layout */
+/* Frame::GetFFTResult (src/frame.cc:53-57): copy both spectra out in reference layout; either pointer may be NULL */
+int nis_frame_export(nis_ctx* ctx, const nis_frame* f, float* fft_result, float* fft_polar);
+/* build a frame from reference-layout arrays the caller already holds (image, fft_result, fft_polar) */
+int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, nis_frame** out);
+int nis_frame_free(nis_ctx* ctx, nis_frame* f);
+
+/* ---- solve: CorrelationFlow::ComputePose(last_fft_result, image, last_fft_polar, fft_polar, pose, not_large_rotation)
+ *      include/correlation_flow.h:13, src/correlation_flow.cc:97-143; returns info in info[3], pose = (dx_px, dy_px, theta_rad).
+ *      peak_rc (may be NULL) = polar row, polar col, translation row, translation col of the integer arg-max. ---- */
+int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, int not_large_rotation, double pose[3],
+                     double info[3], int32_t peak_rc[4]);
+
+/* ---- batched tracking of a stream with "every frame is a keyframe" (SURVEY 8d): solve i pairs frame i (last) with
+ *      frame i+1 (current), i.e. per frame ComputeIntermedium + ComputePose(..., true) exactly as
+ *      MapBuilder::AddNewInput does (src/map_builder.cc:30-70).  frames: n u8 images, host (nis_track_stream) or
+ *      device (nis_track_stream_dev) memory.  poses/infos: host, (n-1) x 3 doubles. ---- */
+int nis_track_stream(nis_ctx* ctx, const uint8_t* frames_host, int n, double* poses, double* infos);
+int nis_track_stream_dev(nis_ctx* ctx, const uint8_t* frames_dev, int n, double* poses, double* infos);
+
+/* ---- keyframe database = Map::AddFrame for the arrays the scan reads (include/frame.h:35-36, src/map.cc) ---- */
+int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distance, int* slot);
+/* bulk insert: n u8 images (host or device), features computed on the GPU straight into the DB */
+int nis_db_add_images(nis_ctx* ctx, const uint8_t* images_host, int n, const int* frame_ids, const double* acc_distances);
+int nis_db_add_images_dev(nis_ctx* ctx, const uint8_t* images_dev, int n, const int* frame_ids, const double* acc_distances);
+int nis_db_size(const nis_ctx* ctx);
+int nis_db_clear(nis_ctx* ctx);
+
+/* ---- scan: LoopClosure::FindLoopClosure(image, current_frame, frames), src/loop_closure.cc:36-73.
+ *      candidate_slots == NULL scans all slots in insertion order (the all-frames overload, loop_closure.cc:10-15);
+ *      otherwise the given order is the iteration order (ties: first wins, strict '>').
+ *      all_responses (may be NULL): n_candidates x 3 doubles, rows of skipped candidates are (-1,-1,-1). ---- */
+int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance,
+                  const nis_loop_config* cfg, const int32_t* candidate_slots, int n_candidates, nis_loop_result* out,
+                  double* all_responses);
+
+/* Multi-GPU: every rank scans its own shard with nis_loop_scan, the ranks all-gather their nis_loop_result records
+ * (NCCL), and each rank calls this to pick the winner with the reference's rule.  `order[i]` is the position of rank
+ * i's winner in the global iteration order (ties: smallest wins); pass NULL to use the rank index. */
+int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n_ranks, const nis_loop_config* cfg,
+                    nis_loop_result* out, int* winner_rank);
+
+/* ---- stage-level entry points used by the parity tests (host buffers, natural row-major numpy layout:
+ *      real (R, C), spectrum (R/2+1, C) complex64).  which: 0 = image size H x W, 1 = polar size D x Cp. ---- */
+int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_out);
+int nis_debug_ifft2(nis_ctx* ctx, int which, const float* spec_in, float* real_out);
+int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out);         /* fftshift(RemoveZero(power)) -> warpPolar */
+int nis_debug_rotate(nis_ctx* ctx, const float* image_in, float degree, float* image_out);
+int nis_debug_estimate_trans(nis_ctx* ctx, int which, const float* last_spec, const float* cur_spec, int32_t peak_rc[2],
+                             float* info, float* g_out /* may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NISLAM_H_ */

@@ -1,0 +1,10 @@
+"""ni_slam_b200 -- B200-native (sm_100a) implementation of NI-SLAM's tracking / loop-closure hot path.
+
+Only what the path needs: csrc/ (CUDA kernels + C ABI), host/ (C++ shim with the reference's class signatures),
+api.py (the same surface for Python) and build.py (in-tree nvcc build).  There is no CPU fallback.
+"""
+from .api import (CFConfig, CorrelationFlow, Frame, LoopClosure, LoopClosureConfig, LoopClosureResult, LoopResultC, NisError,
+                  LIB_PATH, SYMBOLS, load_library)
+
+__all__ = ["CFConfig", "CorrelationFlow", "Frame", "LoopClosure", "LoopClosureConfig", "LoopClosureResult", "LoopResultC",
+           "NisError", "LIB_PATH", "SYMBOLS", "load_library"]

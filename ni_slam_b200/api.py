@@ -1,0 +1,378 @@
+"""Host-side mirror of the reference's CorrelationFlow / LoopClosure call surface over the C ABI (include/nislam.h).
+
+The reference's host code is C++ (ni_slam_b200/host/correlation_flow.hpp is the drop-in shim for MapBuilder); this
+module is the same surface for Python callers, tests and bench.py.  Everything computes on the GPU through
+libnislam.so -- there is no CPU fallback: importing works anywhere, but creating a CorrelationFlow without the
+built library or without a CUDA device raises.
+
+Array conventions at this level are natural numpy: images (H, W); spectra (R/2+1, C) complex64 -- i.e. the same
+(row, col) indexing as the reference's Eigen arrays.  The C ABI itself speaks the reference's column-major layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnislam.so")
+
+NIS_OK, NIS_ERR_INVALID_ARGUMENT, NIS_ERR_INVALID_KERNEL, NIS_ERR_UNSUPPORTED_SIZE, NIS_ERR_CUDA, NIS_ERR_OOM = range(6)
+
+SYMBOLS = [
+    "nis_create", "nis_destroy", "nis_last_error", "nis_strerror", "nis_stream", "nis_synchronize", "nis_kernel_launches",
+    "nis_set_batch", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
+    "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
+    "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_debug_fft2",
+    "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans",
+]
+
+
+class NisError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("libnislam status %d: %s" % (status, msg))
+        self.status = status
+
+
+class _CfConfigC(C.Structure):
+    _fields_ = [("lam", C.c_float), ("kernel", C.c_int), ("sigma", C.c_float), ("offset", C.c_float), ("power", C.c_int),
+                ("rotation_divisor", C.c_int), ("rotation_channel", C.c_int)]
+
+
+class _LoopConfigC(C.Structure):
+    _fields_ = [("position_response_thr", C.c_double), ("angle_response_thr", C.c_double), ("frame_gap_thr", C.c_int),
+                ("distance_thr", C.c_double)]
+
+
+class LoopResultC(C.Structure):
+    _fields_ = [("found", C.c_int32), ("slot", C.c_int32), ("frame_id", C.c_int32), ("hyp", C.c_int32),
+                ("relative_pose", C.c_double * 3), ("response", C.c_double * 3), ("peak", C.c_int32 * 4),
+                ("evaluated", C.c_int32)]
+
+
+@dataclass
+class CFConfig:
+    """include/read_configs.h:15-25 (width/height are overridden by the ctor, correlation_flow.cc:40-41)."""
+    width: int = 640
+    height: int = 480
+    lam: float = 0.1
+    kernel: int = 0
+    sigma: float = 0.2
+    offset: float = 0.1
+    power: int = 3
+    rotation_divisor: int = 720
+    rotation_channel: int = 480
+
+
+@dataclass
+class LoopClosureConfig:
+    """include/read_configs.h:38-44."""
+    to_find_loop: bool = True
+    position_response_thr: float = 60.0
+    angle_response_thr: float = 60.0
+    frame_gap_thr: int = 0
+    distance_thr: float = 0.0
+
+
+@dataclass
+class LoopClosureResult:
+    """include/loop_closure.h:8-25 (FramePtr -> slot / frame id)."""
+    found: bool
+    response: np.ndarray
+    loop_slot: int
+    loop_frame_id: int
+    relative_pose: np.ndarray
+    hyp: int
+    peak: tuple
+    evaluated: int
+    raw: LoopResultC = None
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libnislam.so; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libnislam.so is not built (%s); run `python -m ni_slam_b200.build` -- this package has no CPU "
+                           "fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f64p = C.c_void_p, C.c_int, C.POINTER(C.c_double)
+    lib.nis_create.argtypes = [C.POINTER(_CfConfigC), i32, i32, i32, C.POINTER(vp)]
+    lib.nis_destroy.argtypes = [vp]
+    lib.nis_last_error.argtypes = [vp]; lib.nis_last_error.restype = C.c_char_p
+    lib.nis_strerror.argtypes = [i32]; lib.nis_strerror.restype = C.c_char_p
+    lib.nis_stream.argtypes = [vp]; lib.nis_stream.restype = vp
+    lib.nis_synchronize.argtypes = [vp]
+    lib.nis_kernel_launches.argtypes = [vp]; lib.nis_kernel_launches.restype = C.c_longlong
+    lib.nis_set_batch.argtypes = [vp, i32]
+    lib.nis_features_u8.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.nis_features_f32.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.nis_frame_export.argtypes = [vp, vp, vp, vp]
+    lib.nis_frame_import.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
+    lib.nis_frame_free.argtypes = [vp, vp]
+    lib.nis_compute_pose.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.nis_track_stream.argtypes = [vp, vp, i32, vp, vp]
+    lib.nis_track_stream_dev.argtypes = [vp, vp, i32, vp, vp]
+    lib.nis_db_add.argtypes = [vp, vp, i32, C.c_double, C.POINTER(i32)]
+    lib.nis_db_add_images.argtypes = [vp, vp, i32, vp, vp]
+    lib.nis_db_add_images_dev.argtypes = [vp, vp, i32, vp, vp]
+    lib.nis_db_size.argtypes = [vp]
+    lib.nis_db_clear.argtypes = [vp]
+    lib.nis_loop_scan.argtypes = [vp, vp, i32, C.c_double, C.POINTER(_LoopConfigC), vp, i32, C.POINTER(LoopResultC), vp]
+    lib.nis_loop_reduce.argtypes = [vp, vp, i32, C.POINTER(_LoopConfigC), C.POINTER(LoopResultC), C.POINTER(i32)]
+    lib.nis_debug_fft2.argtypes = [vp, i32, vp, vp]
+    lib.nis_debug_ifft2.argtypes = [vp, i32, vp, vp]
+    lib.nis_debug_polar.argtypes = [vp, vp, vp]
+    lib.nis_debug_rotate.argtypes = [vp, vp, C.c_float, vp]
+    lib.nis_debug_estimate_trans.argtypes = [vp, i32, vp, vp, vp, C.POINTER(C.c_float), vp]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Frame:
+    """Device-resident Frame payload (include/frame.h:34-36): image + fft_result + fft_polar."""
+
+    def __init__(self, cf, handle):
+        self._cf, self._h = cf, handle
+
+    def GetFFTResult(self):
+        """Frame::GetFFTResult (src/frame.cc:53-57) -> (fft_result (H/2+1, W), fft_polar (D/2+1, Cp)) complex64."""
+        cf = self._cf
+        F = np.empty((cf.W, cf.H // 2 + 1), np.complex64)      # reference layout: W lines of H/2+1
+        P = np.empty((cf.Cp, cf.D // 2 + 1), np.complex64)
+        cf._check(cf._lib.nis_frame_export(cf._ctx, self._h, _p(F), _p(P)))
+        return np.ascontiguousarray(F.T), np.ascontiguousarray(P.T)
+
+    def free(self):
+        if self._h is not None and self._cf._ctx is not None:
+            self._cf._lib.nis_frame_free(self._cf._ctx, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CorrelationFlow:
+    """include/correlation_flow.h:8-31.  ctor mirrors CorrelationFlow(CFConfig&, double& image_height, double& image_width)."""
+
+    def __init__(self, cf_config: CFConfig, image_height, image_width, device: int = 0):
+        self._lib = load_library()
+        self._ctx = None
+        self.cfg = cf_config
+        self.H, self.W = int(image_height), int(image_width)        # correlation_flow.cc:40-41
+        self.D, self.Cp = cf_config.rotation_divisor, cf_config.rotation_channel
+        c = _CfConfigC(cf_config.lam, cf_config.kernel, cf_config.sigma, cf_config.offset, cf_config.power, self.D, self.Cp)
+        ctx = C.c_void_p()
+        st = self._lib.nis_create(C.byref(c), self.H, self.W, int(device), C.byref(ctx))
+        if st != NIS_OK:
+            raise NisError(st, self._lib.nis_strerror(st).decode())
+        self._ctx = ctx
+
+    # ---- plumbing
+    def _check(self, st):
+        if st == NIS_OK:
+            return
+        msg = self._lib.nis_last_error(self._ctx).decode() or self._lib.nis_strerror(st).decode()
+        if st == NIS_ERR_INVALID_KERNEL:
+            raise ValueError("Received invalid kernel type")        # std::invalid_argument, correlation_flow.cc:168
+        raise NisError(st, msg)
+
+    def close(self):
+        if self._ctx is not None:
+            self._lib.nis_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.nis_stream(self._ctx) or 0)
+
+    def synchronize(self):
+        self._check(self._lib.nis_synchronize(self._ctx))
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.nis_kernel_launches(self._ctx))
+
+    def set_batch(self, b: int):
+        self._check(self._lib.nis_set_batch(self._ctx, int(b)))
+
+    # ---- reference surface
+    def ComputeIntermedium(self, image) -> Frame:
+        """MapBuilder::ComputeFFTResult (map_builder.cc:72-75): u8 (H, W) image (normalised on the GPU like
+        ConvertMatToNormalizedArray) or f32 (H, W) array -> Frame holding fft_result and fft_polar."""
+        image = np.asarray(image)
+        if image.shape != (self.H, self.W):
+            raise ValueError("image must be (%d, %d)" % (self.H, self.W))
+        h = C.c_void_p()
+        if image.dtype == np.uint8:
+            img = np.ascontiguousarray(image)
+            self._check(self._lib.nis_features_u8(self._ctx, _p(img), C.byref(h)))
+        else:
+            img = np.ascontiguousarray(image.astype(np.float32).T)          # reference layout (column-major)
+            self._check(self._lib.nis_features_f32(self._ctx, _p(img), C.byref(h)))
+        return Frame(self, h)
+
+    def ImportFrame(self, image_f32, fft_result, fft_polar) -> Frame:
+        img = np.ascontiguousarray(np.asarray(image_f32, np.float32).T)
+        F = np.ascontiguousarray(np.asarray(fft_result, np.complex64).T)
+        P = np.ascontiguousarray(np.asarray(fft_polar, np.complex64).T)
+        h = C.c_void_p()
+        self._check(self._lib.nis_frame_import(self._ctx, _p(img), _p(F), _p(P), C.byref(h)))
+        return Frame(self, h)
+
+    def ComputePose(self, last: Frame, cur: Frame, not_large_rotation: bool, return_peaks: bool = False):
+        """CorrelationFlow::ComputePose (correlation_flow.cc:97-143): returns (info[3], pose[3]) like the reference
+        returns `info` and fills `pose`; the current frame carries image and fft_polar."""
+        pose = np.zeros(3, np.float64)
+        info = np.zeros(3, np.float64)
+        peak = np.zeros(4, np.int32)
+        self._check(self._lib.nis_compute_pose(self._ctx, last._h, cur._h, int(bool(not_large_rotation)), _p(pose), _p(info), _p(peak)))
+        if return_peaks:
+            return info, pose, dict(polar=(int(peak[0]), int(peak[1])), trans=(int(peak[2]), int(peak[3])))
+        return info, pose
+
+    # ---- batched stream tracking (every frame a keyframe)
+    def TrackStream(self, frames_u8):
+        """frames (n, H, W) u8 in host memory -> (poses (n-1, 3), infos (n-1, 3))."""
+        frames = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+        n = frames.shape[0]
+        poses = np.zeros((max(n - 1, 0), 3), np.float64)
+        infos = np.zeros((max(n - 1, 0), 3), np.float64)
+        self._check(self._lib.nis_track_stream(self._ctx, _p(frames), n, _p(poses), _p(infos)))
+        return poses, infos
+
+    def TrackStreamPtr(self, ptr: int, n: int, on_device: bool):
+        """Same, frames given by raw pointer (pinned host or device memory, e.g. torch tensor .data_ptr())."""
+        poses = np.zeros((max(n - 1, 0), 3), np.float64)
+        infos = np.zeros((max(n - 1, 0), 3), np.float64)
+        fn = self._lib.nis_track_stream_dev if on_device else self._lib.nis_track_stream
+        self._check(fn(self._ctx, C.c_void_p(ptr), n, _p(poses), _p(infos)))
+        return poses, infos
+
+    # ---- stage-level entry points (parity tests)
+    def debug_fft2(self, x, which=0):
+        R, Cc = (self.H, self.W) if which == 0 else (self.D, self.Cp)
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.shape == (R, Cc)
+        out = np.empty((R // 2 + 1, Cc), np.complex64)
+        self._check(self._lib.nis_debug_fft2(self._ctx, which, _p(x), _p(out)))
+        return out
+
+    def debug_ifft2(self, xf, which=0):
+        R, Cc = (self.H, self.W) if which == 0 else (self.D, self.Cp)
+        xf = np.ascontiguousarray(xf, np.complex64)
+        assert xf.shape == (R // 2 + 1, Cc)
+        out = np.empty((R, Cc), np.float32)
+        self._check(self._lib.nis_debug_ifft2(self._ctx, which, _p(xf), _p(out)))
+        return out
+
+    def debug_polar(self, power):
+        power = np.ascontiguousarray(power, np.float32)
+        assert power.shape == (self.H, self.W)
+        out = np.empty((self.D, self.Cp), np.float32)
+        self._check(self._lib.nis_debug_polar(self._ctx, _p(power), _p(out)))
+        return out
+
+    def debug_rotate(self, img, degree):
+        img = np.ascontiguousarray(img, np.float32)
+        assert img.shape == (self.H, self.W)
+        out = np.empty((self.H, self.W), np.float32)
+        self._check(self._lib.nis_debug_rotate(self._ctx, _p(img), float(np.float32(degree)), _p(out)))
+        return out
+
+    def debug_estimate_trans(self, last_spec, cur_spec, which=0, want_g=False):
+        R, Cc = (self.H, self.W) if which == 0 else (self.D, self.Cp)
+        a = np.ascontiguousarray(last_spec, np.complex64)
+        b = np.ascontiguousarray(cur_spec, np.complex64)
+        assert a.shape == b.shape == (R // 2 + 1, Cc)
+        peak = np.zeros(2, np.int32)
+        info = C.c_float()
+        g = np.empty((R, Cc), np.float32) if want_g else None
+        self._check(self._lib.nis_debug_estimate_trans(self._ctx, which, _p(a), _p(b), _p(peak), C.byref(info), _p(g)))
+        trans = (-(int(peak[0]) - R // 2), -(int(peak[1]) - Cc // 2))
+        return float(info.value), trans, (int(peak[0]), int(peak[1])), g
+
+
+class LoopClosure:
+    """include/loop_closure.h:27-38 with the Map's frame store folded in (the keyframe DB lives on the GPU)."""
+
+    def __init__(self, loop_closure_config: LoopClosureConfig, correlation_flow: CorrelationFlow):
+        self._loop_thr = loop_closure_config
+        self._cf = correlation_flow
+
+    def _cfg_c(self):
+        t = self._loop_thr
+        return _LoopConfigC(t.position_response_thr, t.angle_response_thr, t.frame_gap_thr, t.distance_thr)
+
+    def AddFrame(self, frame: Frame, frame_id: int, acc_distance: float = 0.0) -> int:
+        """Map::AddFrame + Map::SetFrameDistance for the arrays the scan reads."""
+        slot = C.c_int()
+        self._cf._check(self._cf._lib.nis_db_add(self._cf._ctx, frame._h, int(frame_id), float(acc_distance), C.byref(slot)))
+        return slot.value
+
+    def AddImages(self, images_u8, frame_ids=None, acc_distances=None, ptr=None, n=None, on_device=False):
+        """Bulk insert; features are computed on the GPU straight into the DB."""
+        cf = self._cf
+        if ptr is None:
+            imgs = np.ascontiguousarray(images_u8, dtype=np.uint8)
+            n, ptr = imgs.shape[0], imgs.ctypes.data
+        ids = np.ascontiguousarray(frame_ids, np.int32) if frame_ids is not None else None
+        ds = np.ascontiguousarray(acc_distances, np.float64) if acc_distances is not None else None
+        fn = cf._lib.nis_db_add_images_dev if on_device else cf._lib.nis_db_add_images
+        cf._check(fn(cf._ctx, C.c_void_p(ptr), int(n), _p(ids), _p(ds)))
+
+    def size(self) -> int:
+        return int(self._cf._lib.nis_db_size(self._cf._ctx))
+
+    def clear(self):
+        self._cf._check(self._cf._lib.nis_db_clear(self._cf._ctx))
+
+    def FindLoopClosure(self, current_frame: Frame, current_frame_id: int = 0, current_distance: float = 0.0,
+                        candidate_slots=None, return_all: bool = False):
+        """LoopClosure::FindLoopClosure(image, current_frame[, frames]) (loop_closure.cc:10-15, :36-73)."""
+        cf = self._cf
+        cand = np.ascontiguousarray(candidate_slots, np.int32) if candidate_slots is not None else None
+        n = int(cand.shape[0]) if cand is not None else 0
+        n_in = n if cand is not None else self.size()
+        allr = np.zeros((n_in, 3), np.float64) if return_all else None
+        out = LoopResultC()
+        cfg = self._cfg_c()
+        cf._check(cf._lib.nis_loop_scan(cf._ctx, current_frame._h, int(current_frame_id), float(current_distance), C.byref(cfg),
+                                        _p(cand), n, C.byref(out), _p(allr)))
+        res = _result_from_c(out)
+        return (res, allr) if return_all else res
+
+    def Reduce(self, per_rank, order=None):
+        """Multi-GPU: pick the winner among per-rank results with the reference's rule (strict '>', first wins)."""
+        cf = self._cf
+        arr = (LoopResultC * len(per_rank))(*[r.raw if isinstance(r, LoopClosureResult) else r for r in per_rank])
+        o = np.ascontiguousarray(order, np.int64) if order is not None else None
+        out = LoopResultC()
+        win = C.c_int()
+        cfg = self._cfg_c()
+        cf._check(cf._lib.nis_loop_reduce(arr, _p(o), len(per_rank), C.byref(cfg), C.byref(out), C.byref(win)))
+        return _result_from_c(out), win.value
+
+
+def _result_from_c(out: LoopResultC) -> LoopClosureResult:
+    return LoopClosureResult(found=bool(out.found), response=np.array(out.response[:]), loop_slot=out.slot,
+                             loop_frame_id=out.frame_id, relative_pose=np.array(out.relative_pose[:]), hyp=out.hyp,
+                             peak=tuple(out.peak[:]), evaluated=out.evaluated, raw=out)

@@ -1,0 +1,873 @@
+// nis_api.cu -- context, keyframe database and the C ABI (include/nislam.h) over the sm_100a kernels.
+// Host-side mirror of CorrelationFlow (src/correlation_flow.cc) and LoopClosure (src/loop_closure.cc): the host
+// only builds constant tables, sizes batches and enqueues kernels; all per-pixel arithmetic runs on the GPU and
+// there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nislam.h"
+#include "nis_internal.h"
+
+using namespace nis;
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// -------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return (int)e;
+    bytes = n;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct nis_frame {
+  uint8_t* img_u8 = nullptr;   // exactly one of img_u8 / img_f32 is set (row-major H x W)
+  float* img_f32 = nullptr;
+  cpx* F = nullptr;            // fft_result  [H/2+1][W]
+  cpx* P = nullptr;            // fft_polar   [D/2+1][Cp]
+  void* block = nullptr;       // single allocation backing all of the above
+};
+
+struct SizeClass {             // one 2-D transform size: R rows (halved) x C cols
+  int R, C;
+  size_t spec, real;           // elements
+  Twiddles colf, coli, row;
+};
+
+struct nis_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  nis_cf_config cfg{};
+  int H = 0, W = 0, D = 0, Cp = 0;
+  SizeClass sz[2];             // 0: H x W, 1: D x Cp
+  size_t maxspec = 0, maxreal = 0;
+  std::string err;
+  long long launches = 0;
+  int batch = 16;
+  // constant tables
+  DevBuf tw, lut, cs, rho, mats, theta;
+  // workspace (capacity in pairs)
+  int cap = 0;
+  DevBuf t1, rk, kxz, kzz, rot, xs, maxzz, maxxz, stats_p, stats_t, sel, xxz, xxx, recs, best, cand;
+  int recs_cap = 0, cand_cap = 0;
+  // stream slabs
+  DevBuf sF, sP, sImg;
+  // keyframe DB
+  std::vector<void*> chunks;
+  int chunk_slots = 128;
+  std::vector<cpx*> slot_ptr;          // host copy of the device pointer table
+  std::vector<int> slot_frame_id;
+  std::vector<double> slot_dist;
+  DevBuf d_slot_ptr;
+  int d_slot_cap = 0;
+  // pinned staging
+  void* pin = nullptr; size_t pin_bytes = 0;
+};
+
+static int fail(nis_ctx* c, int status, const char* what, int cuda_err = 0) {
+  if (c) {
+    char buf[512];
+    if (cuda_err > 0) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString((cudaError_t)cuda_err));
+    else snprintf(buf, sizeof buf, "%s", what);
+    c->err = buf;
+  }
+  return status;
+}
+
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return fail(ctx, NIS_ERR_CUDA, #call, (int)e_);    \
+  } while (0)
+// kernel launch through a launcher returning cudaError_t-as-int (or -1 for an unsupported size)
+#define LAUNCH(call)                                                                      \
+  do {                                                                                    \
+    int e_ = (call);                                                                      \
+    if (e_ == -1) return fail(ctx, NIS_ERR_UNSUPPORTED_SIZE, "unsupported transform size: " #call); \
+    if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, #call, e_);                                \
+    ctx->launches++;                                                                      \
+  } while (0)
+#define RESERVE(buf, n)                                                                   \
+  do {                                                                                    \
+    int e_ = (buf).reserve(n);                                                            \
+    if (e_) return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc " #buf, e_);               \
+  } while (0)
+#define TRY(call)                \
+  do {                           \
+    int s_ = (call);             \
+    if (s_ != NIS_OK) return s_; \
+  } while (0)
+
+template <class T> static Src<T> src_slab(const T* base, long long stride, int shift = 0) {
+  return Src<T>{base, stride, nullptr, 0, nullptr, shift};
+}
+template <class T> static Src<T> src_null() { return Src<T>{nullptr, 0, nullptr, 0, nullptr, 0}; }
+
+// -------------------------------------------------------------------------------------------------------------
+// constant tables
+// -------------------------------------------------------------------------------------------------------------
+static void host_twiddles(const int r[3], std::vector<cpx>& out, size_t& off1, size_t& off2) {
+  const int R0 = r[0], R1 = r[1], R2 = r[2], N = R0 * R1 * R2;
+  off1 = out.size();
+  out.resize(off1 + (size_t)std::max(R1 - 1, 1) * R0, make_float2(1.f, 0.f));
+  for (int q = 1; q < R1; ++q)
+    for (int k = 0; k < R0; ++k) {
+      const double a = -2.0 * M_PI * (double)q * k / (double)(R0 * R1);
+      out[off1 + (size_t)(q - 1) * R0 + k] = make_float2((float)cos(a), (float)sin(a));
+    }
+  off2 = out.size();
+  out.resize(off2 + (size_t)std::max(R2 - 1, 1) * R0 * R1, make_float2(1.f, 0.f));
+  for (int q = 1; q < R2; ++q)
+    for (int k = 0; k < R0 * R1; ++k) {
+      const double a = -2.0 * M_PI * (double)q * k / (double)N;
+      out[off2 + (size_t)(q - 1) * R0 * R1 + k] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+// utils.cc:173-175
+static double normalize_degree(double a) { return a - 360.0 * floor((a + 180.0) / 360.0); }
+
+// cv::getRotationMatrix2D(Point2f(W/2., H/2.), degree, 1) followed by warpAffine's inversion (utils.cc:157-159)
+static void rotation_inverse(int H, int W, double degree, double* M) {
+  const float cxf = (float)(W / 2.), cyf = (float)(H / 2.);
+  const double a = degree * (M_PI / 180.0);
+  const double alpha = cos(a), beta = sin(a);
+  M[0] = alpha; M[1] = beta; M[2] = (1 - alpha) * cxf - beta * cyf;
+  M[3] = -beta; M[4] = alpha; M[5] = beta * cxf + (1 - alpha) * cyf;
+  double Dt = M[0] * M[4] - M[1] * M[3];
+  Dt = Dt != 0 ? 1. / Dt : 0;
+  const double A11 = M[4] * Dt, A22 = M[0] * Dt;
+  M[0] = A11; M[1] *= -Dt; M[3] *= -Dt; M[4] = A22;
+  const double b1 = -M[0] * M[2] - M[1] * M[5];
+  const double b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1; M[5] = b2;
+}
+
+static int build_tables(nis_ctx* ctx) {
+  const int H = ctx->H, W = ctx->W, D = ctx->D, Cp = ctx->Cp;
+  // twiddles
+  std::vector<cpx> tw;
+  size_t o[12];
+  int r[3];
+  for (int s = 0; s < 2; ++s) {
+    SizeClass& z = ctx->sz[s];
+    plan_radices_col(z.R, false, r); host_twiddles(r, tw, o[6 * s + 0], o[6 * s + 1]);
+    plan_radices_col(z.R, true, r);  host_twiddles(r, tw, o[6 * s + 2], o[6 * s + 3]);
+    plan_radices_row(z.C, r);        host_twiddles(r, tw, o[6 * s + 4], o[6 * s + 5]);
+  }
+  RESERVE(ctx->tw, tw.size() * sizeof(cpx));
+  CU(cudaMemcpy(ctx->tw.p, tw.data(), tw.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+  const cpx* base = ctx->tw.as<cpx>();
+  for (int s = 0; s < 2; ++s) {
+    SizeClass& z = ctx->sz[s];
+    z.colf = Twiddles{base + o[6 * s + 0], base + o[6 * s + 1]};
+    z.coli = Twiddles{base + o[6 * s + 2], base + o[6 * s + 3]};
+    z.row = Twiddles{base + o[6 * s + 4], base + o[6 * s + 5]};
+  }
+  // u8 -> f32/255 (utils.cc:117: matrix.array()/255.0)
+  float lut[256];
+  for (int u = 0; u < 256; ++u) lut[u] = (float)((double)(float)u / 255.0);
+  RESERVE(ctx->lut, sizeof lut);
+  CU(cudaMemcpy(ctx->lut.p, lut, sizeof lut, cudaMemcpyHostToDevice));
+  // warpPolar angle / radius tables (correlation_flow.cc:228-236 -> cv::warpPolar)
+  std::vector<double> cs(2 * (size_t)D);
+  const double Kangle = 2.0 * M_PI / D;
+  for (int phi = 0; phi < D; ++phi) { cs[2 * phi] = cos(Kangle * phi); cs[2 * phi + 1] = sin(Kangle * phi); }
+  std::vector<float> rho(Cp);
+  const double maxRadius = (double)std::min(H / 2, W / 2), Kmag = maxRadius / Cp;
+  for (int q = 0; q < Cp; ++q) rho[q] = (float)(q * Kmag);
+  RESERVE(ctx->cs, cs.size() * sizeof(double));
+  RESERVE(ctx->rho, rho.size() * sizeof(float));
+  CU(cudaMemcpy(ctx->cs.p, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->rho.p, rho.data(), rho.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // per polar-peak-row angle tables (correlation_flow.cc:105-136): every float/double step of the reference, once
+  std::vector<double> mats(3 * (size_t)D * 6), theta(3 * (size_t)D);
+  for (int row = 0; row < D; ++row) {
+    const int rots0 = -(row - D / 2);                                   // :176
+    float degree = (float)((double)rots0 * (2.0 / D) * 180);            // :105
+    degree = (float)normalize_degree((double)degree);                   // :106
+    // tracking (:108-109)
+    float dt = fabsf(degree) > 90 ? degree - 180 : degree;
+    rotation_inverse(H, W, (double)(-dt), &mats[(0 * (size_t)D + row) * 6]);
+    float fin = dt > 180 ? dt - 360 : dt;                               // :134
+    theta[0 * (size_t)D + row] = (double)(float)((double)(fin / 180) * M_PI);
+    // loop, "-deg" (:116) and "-deg+180" (:117)
+    rotation_inverse(H, W, (double)(-degree), &mats[(1 * (size_t)D + row) * 6]);
+    rotation_inverse(H, W, (double)(-degree + 180), &mats[(2 * (size_t)D + row) * 6]);
+    float d0 = degree; d0 = d0 > 180 ? d0 - 360 : d0;
+    float d1 = degree + 180; d1 = d1 > 180 ? d1 - 360 : d1;             // :130, :134
+    theta[1 * (size_t)D + row] = (double)(float)((double)(d0 / 180) * M_PI);
+    theta[2 * (size_t)D + row] = (double)(float)((double)(d1 / 180) * M_PI);
+  }
+  // one extra matrix slot (index 3*D) for nis_debug_rotate
+  mats.resize(mats.size() + 6, 0.0);
+  RESERVE(ctx->mats, mats.size() * sizeof(double));
+  RESERVE(ctx->theta, theta.size() * sizeof(double));
+  CU(cudaMemcpy(ctx->mats.p, mats.data(), mats.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->theta.p, theta.data(), theta.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return NIS_OK;
+}
+
+static int ensure_workspace(nis_ctx* ctx, int pairs) {
+  if (pairs <= ctx->cap) return NIS_OK;
+  const size_t E = 2 * (size_t)pairs;
+  RESERVE(ctx->t1, E * ctx->maxspec * sizeof(cpx));
+  RESERVE(ctx->rk, E * ctx->maxreal * sizeof(float));
+  RESERVE(ctx->kxz, E * ctx->maxspec * sizeof(cpx));
+  RESERVE(ctx->kzz, (size_t)pairs * ctx->maxspec * sizeof(cpx));
+  RESERVE(ctx->rot, E * ctx->maxreal * sizeof(float));
+  RESERVE(ctx->xs, E * ctx->sz[0].spec * sizeof(cpx));
+  RESERVE(ctx->maxzz, (size_t)pairs * sizeof(unsigned));
+  RESERVE(ctx->maxxz, E * sizeof(unsigned));
+  RESERVE(ctx->stats_p, (size_t)pairs * sizeof(PeakStats));
+  RESERVE(ctx->stats_t, E * sizeof(PeakStats));
+  RESERVE(ctx->sel, E * sizeof(int));
+  RESERVE(ctx->xxz, (size_t)pairs * sizeof(float));
+  RESERVE(ctx->xxx, E * sizeof(float));
+  RESERVE(ctx->best, sizeof(PoseRecord));
+  ctx->cap = pairs;
+  return NIS_OK;
+}
+
+static int ensure_recs(nis_ctx* ctx, int n) {
+  if (n <= ctx->recs_cap) return NIS_OK;
+  RESERVE(ctx->recs, (size_t)n * sizeof(PoseRecord));
+  ctx->recs_cap = n;
+  return NIS_OK;
+}
+
+static int ensure_pinned(nis_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pin_bytes) return NIS_OK;
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  ctx->pin = nullptr; ctx->pin_bytes = 0;
+  CU(cudaMallocHost(&ctx->pin, bytes));
+  ctx->pin_bytes = bytes;
+  return NIS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// batched stages
+// -------------------------------------------------------------------------------------------------------------
+// 2-D r2c: real [B][R][C] (f32 slab or u8 source) -> spectrum
+static int fft2_batch(nis_ctx* ctx, int s, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> out) {
+  const SizeClass& z = ctx->sz[s];
+  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)z.spec};
+  if (is_u8) LAUNCH(launch_col_fwd_u8(z.R, z.colf, ProRealU8{u8, z.C, ctx->lut.as<float>()}, t1, z.C, B, ctx->stream));
+  else LAUNCH(launch_col_fwd_f32(z.R, z.colf, ProRealF32{f32, z.C}, t1, z.C, B, ctx->stream));
+  LAUNCH(launch_row_fwd(z.C, z.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, z.R / 2 + 1, B, ctx->stream));
+  return NIS_OK;
+}
+
+// ComputeIntermedium (correlation_flow.cc:89-95) for B images
+static int features_batch(nis_ctx* ctx, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> F, Dst<cpx> P) {
+  TRY(ensure_workspace(ctx, B));
+  const SizeClass& zt = ctx->sz[0];
+  const SizeClass& zp = ctx->sz[1];
+  TRY(fft2_batch(ctx, 0, f32, u8, is_u8, B, F));                                              // fft_result = FFT(image)
+  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)zt.spec};
+  Dst<float> power{ctx->rk.as<float>(), (long long)zt.real};
+  Dst<float> pol{ctx->rot.as<float>(), (long long)zp.real};
+  LAUNCH(launch_row_inv_abs(zt.C, zt.row, ProAbs{src_slab<cpx>(F.base, F.stride)}, EpiSpecStore{t1}, zt.R / 2 + 1, B, ctx->stream));
+  LAUNCH(launch_col_inv_store(zt.R, zt.coli, src_slab<cpx>(t1.base, t1.stride), EpiStore{power, zt.C, (float)zt.real}, zt.C, B,
+                              ctx->stream));                                                   // power = IFFT(|F|)
+  LAUNCH(launch_polar(src_slab<float>(power.base, power.stride), pol, ctx->H, ctx->W, ctx->D, ctx->Cp, ctx->cs.as<double>(),
+                      ctx->rho.as<float>(), B, ctx->stream));                                  // polar(fftshift(RemoveZero(power)))
+  TRY(fft2_batch(ctx, 1, src_slab<float>(pol.base, pol.stride), src_null<uint8_t>(), false, B, P));   // fft_polar
+  return NIS_OK;
+}
+
+// kernel(x, z) (polynomial / gaussian, correlation_flow.cc:181-226) for E entries, unnormalised spectrum + max
+static int kernel_batch(nis_ctx* ctx, int s, Src<cpx> X, Src<cpx> Z, int E, const float* xx, const float* zz, int zz_shift,
+                        unsigned* maxbuf, Dst<cpx> out) {
+  const SizeClass& z = ctx->sz[s];
+  const nis_cf_config& c = ctx->cfg;
+  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)z.spec};
+  Dst<float> rk{ctx->rk.as<float>(), (long long)z.real};
+  CU(cudaMemsetAsync(maxbuf, 0, sizeof(unsigned) * E, ctx->stream));
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{X, Z}, EpiSpecStore{t1}, z.R / 2 + 1, E, ctx->stream));
+  EpiKernel ek{rk, z.C, (float)z.real, c.kernel, c.offset, c.power, -1.f / (c.sigma * c.sigma), xx, zz, zz_shift, maxbuf};
+  LAUNCH(launch_col_inv_kernel(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ek, z.C, E, ctx->stream));
+  TRY(fft2_batch(ctx, s, src_slab<float>(rk.base, rk.stride), src_null<uint8_t>(), false, E, out));
+  return NIS_OK;
+}
+
+// EstimateTrans (correlation_flow.cc:145-179) for E entries; entry e uses keyframe spectrum Z.at(e) and Kzz number e>>zshift
+static int estimate_trans_batch(nis_ctx* ctx, int s, Src<cpx> Zzz, int nzz, Src<cpx> Z, Src<cpx> X, int E, int zshift,
+                                PeakStats* stats, float* g_debug) {
+  const SizeClass& z = ctx->sz[s];
+  if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return fail(ctx, NIS_ERR_INVALID_KERNEL, "Received invalid kernel type");
+  const float* xxz = nullptr; const float* xxx = nullptr;
+  if (ctx->cfg.kernel == 1) {
+    LAUNCH(launch_spec_sqsum(Zzz, (int)z.spec, (float)(unsigned)z.real, ctx->xxz.as<float>(), nzz, ctx->stream));
+    LAUNCH(launch_spec_sqsum(X, (int)z.spec, (float)(unsigned)z.real, ctx->xxx.as<float>(), E, ctx->stream));
+    xxz = ctx->xxz.as<float>(); xxx = ctx->xxx.as<float>();
+  }
+  Dst<cpx> kzz{ctx->kzz.as<cpx>(), (long long)z.spec}, kxz{ctx->kxz.as<cpx>(), (long long)z.spec};
+  TRY(kernel_batch(ctx, s, Zzz, Zzz, nzz, xxz, xxz, 0, ctx->maxzz.as<unsigned>(), kzz));            // Kzz
+  TRY(kernel_batch(ctx, s, X, Z, E, xxx, xxz, zshift, ctx->maxxz.as<unsigned>(), kxz));             // Kxz
+  CU(cudaMemsetAsync(stats, 0, sizeof(PeakStats) * E, ctx->stream));
+  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)z.spec};
+  ProFilter pf{src_slab<cpx>(kzz.base, kzz.stride, zshift), src_slab<cpx>(kxz.base, kxz.stride), ctx->maxzz.as<unsigned>(),
+               ctx->maxxz.as<unsigned>(), zshift, ctx->cfg.lambda};
+  LAUNCH(launch_row_inv_filter(z.C, z.row, pf, EpiSpecStore{t1}, z.R / 2 + 1, E, ctx->stream));
+  EpiPeak ep{stats, z.R, (float)z.real, g_debug, (long long)z.real, z.C};
+  LAUNCH(launch_col_inv_peak(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ep, z.C, E, ctx->stream));
+  return NIS_OK;
+}
+
+// ComputePose (correlation_flow.cc:97-138) for B pairs -> device records
+static int compute_pose_batch(nis_ctx* ctx, bool loop_mode, Src<cpx> Fz, Src<cpx> Pz, Src<cpx> Px, Src<float> img_f32,
+                              Src<uint8_t> img_u8, bool is_u8, int B, int index0, PoseRecord* recs) {
+  TRY(ensure_workspace(ctx, B));
+  PeakStats* sp = ctx->stats_p.as<PeakStats>();
+  PeakStats* st = ctx->stats_t.as<PeakStats>();
+  TRY(estimate_trans_batch(ctx, 1, Pz, B, Pz, Px, B, 0, sp, nullptr));                              // rotation
+  LAUNCH(launch_polar_select(sp, ctx->D, loop_mode ? 1 : 0, ctx->sel.as<int>(), B, ctx->stream));
+  const int shift = loop_mode ? 1 : 0, E = B << shift;
+  Dst<float> rot{ctx->rot.as<float>(), (long long)ctx->sz[0].real};
+  Src<float> i32 = img_f32; i32.shift = shift;
+  Src<uint8_t> i8 = img_u8; i8.shift = shift;
+  if (is_u8) i32 = src_null<float>(); else i8 = src_null<uint8_t>();
+  LAUNCH(launch_rotate(i32, i8, ctx->lut.as<float>(), rot, ctx->H, ctx->W, ctx->mats.as<double>(), ctx->sel.as<int>(), E,
+                       ctx->stream));                                                                // RotateArray(image, -deg[+180])
+  Dst<cpx> xs{ctx->xs.as<cpx>(), (long long)ctx->sz[0].spec};
+  TRY(fft2_batch(ctx, 0, src_slab<float>(rot.base, rot.stride), src_null<uint8_t>(), false, E, xs));
+  Src<cpx> Fze = Fz; Fze.shift = shift;
+  TRY(estimate_trans_batch(ctx, 0, Fz, B, Fze, src_slab<cpx>(xs.base, xs.stride), E, shift, st, nullptr));   // translation
+  AngleTables tabs{ctx->mats.as<double>(), ctx->theta.as<double>()};
+  LAUNCH(launch_pose_finalize(sp, st, tabs, ctx->H, ctx->W, ctx->D, ctx->Cp, loop_mode ? 1 : 0, index0, recs, B, ctx->stream));
+  return NIS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// layout conversion at the boundary (reference column-major <-> internal row-major); boundary utilities only
+// -------------------------------------------------------------------------------------------------------------
+template <class T> static void transpose_to(const T* in, int rows_in, int cols_in, T* out) {   // in[rows_in][cols_in] -> out[cols_in][rows_in]
+  for (int r = 0; r < rows_in; ++r)
+    for (int c = 0; c < cols_in; ++c) out[(size_t)c * rows_in + r] = in[(size_t)r * cols_in + c];
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* nis_strerror(int status) {
+  switch (status) {
+    case NIS_OK: return "ok";
+    case NIS_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case NIS_ERR_INVALID_KERNEL: return "Received invalid kernel type";
+    case NIS_ERR_UNSUPPORTED_SIZE: return "unsupported transform size";
+    case NIS_ERR_CUDA: return "CUDA error";
+    case NIS_ERR_OUT_OF_MEMORY: return "out of device memory";
+  }
+  return "unknown status";
+}
+
+const char* nis_last_error(const nis_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int device, nis_ctx** out) {
+  if (!cfg || !out) return NIS_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  const int H = image_height, W = image_width, D = cfg->rotation_divisor, Cp = cfg->rotation_channel;
+  if (H <= 0 || W <= 0 || D <= 0 || Cp <= 0 || (H & 1) || (D & 1) || (W % 32) || (Cp % 32)) return NIS_ERR_INVALID_ARGUMENT;
+  if (!col_size_supported(H) || !col_size_supported(D) || !row_size_supported(W) || !row_size_supported(Cp))
+    return NIS_ERR_UNSUPPORTED_SIZE;
+  // the kernel id is only checked when EstimateTrans runs, like the reference (correlation_flow.cc:157-169)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NIS_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return NIS_ERR_CUDA;
+  nis_ctx* ctx = new nis_ctx();
+  ctx->device = device; ctx->cfg = *cfg;
+  ctx->H = H; ctx->W = W; ctx->D = D; ctx->Cp = Cp;
+  ctx->sz[0].R = H; ctx->sz[0].C = W; ctx->sz[1].R = D; ctx->sz[1].C = Cp;
+  for (int s = 0; s < 2; ++s) {
+    ctx->sz[s].spec = (size_t)(ctx->sz[s].R / 2 + 1) * ctx->sz[s].C;
+    ctx->sz[s].real = (size_t)ctx->sz[s].R * ctx->sz[s].C;
+  }
+  ctx->maxspec = std::max(ctx->sz[0].spec, ctx->sz[1].spec);
+  ctx->maxreal = std::max(ctx->sz[0].real, ctx->sz[1].real);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NIS_ERR_CUDA; }
+  const char* eb = getenv("NIS_BATCH");
+  if (eb && atoi(eb) > 0) ctx->batch = atoi(eb);
+  int st = build_tables(ctx);
+  if (st != NIS_OK) { nis_destroy(ctx); return st; }
+  *out = ctx;
+  return NIS_OK;
+}
+
+int nis_destroy(nis_ctx* ctx) {
+  if (!ctx) return NIS_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->t1, &ctx->rk, &ctx->kxz, &ctx->kzz,
+                    &ctx->rot, &ctx->xs, &ctx->maxzz, &ctx->maxxz, &ctx->stats_p, &ctx->stats_t, &ctx->sel, &ctx->xxz, &ctx->xxx,
+                    &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF, &ctx->sP, &ctx->sImg, &ctx->d_slot_ptr};
+  for (DevBuf* b : bufs) b->release();
+  for (void* c : ctx->chunks) cudaFree(c);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NIS_OK;
+}
+
+void* nis_stream(nis_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int nis_synchronize(nis_ctx* ctx) {
+  if (!ctx) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return NIS_OK;
+}
+long long nis_kernel_launches(const nis_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int nis_set_batch(nis_ctx* ctx, int batch) {
+  if (!ctx || batch < 0) return NIS_ERR_INVALID_ARGUMENT;
+  ctx->batch = batch > 0 ? batch : 16;
+  return NIS_OK;
+}
+
+// ---- frames -------------------------------------------------------------------------------------------------
+static int frame_alloc(nis_ctx* ctx, bool u8, nis_frame** out) {
+  nis_frame* f = new nis_frame();
+  const size_t bF = ctx->sz[0].spec * sizeof(cpx), bP = ctx->sz[1].spec * sizeof(cpx);
+  const size_t bI = ctx->sz[0].real * (u8 ? 1 : sizeof(float));
+  cudaError_t e = cudaMalloc(&f->block, bF + bP + bI);
+  if (e != cudaSuccess) { delete f; return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc frame", (int)e); }
+  char* p = (char*)f->block;
+  f->F = (cpx*)p; f->P = (cpx*)(p + bF);
+  if (u8) f->img_u8 = (uint8_t*)(p + bF + bP); else f->img_f32 = (float*)(p + bF + bP);
+  *out = f;
+  return NIS_OK;
+}
+
+int nis_frame_free(nis_ctx* ctx, nis_frame* f) {
+  if (!f) return NIS_OK;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (f->block) cudaFree(f->block);
+  delete f;
+  return NIS_OK;
+}
+
+int nis_features_u8(nis_ctx* ctx, const uint8_t* image, nis_frame** out) {
+  if (!ctx || !image || !out) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  nis_frame* f = nullptr;
+  TRY(frame_alloc(ctx, true, &f));
+  cudaError_t e = cudaMemcpyAsync(f->img_u8, image, ctx->sz[0].real, cudaMemcpyHostToDevice, ctx->stream);
+  int st = e == cudaSuccess ? features_batch(ctx, src_null<float>(), src_slab<uint8_t>(f->img_u8, 0), true, 1,
+                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
+                            : fail(ctx, NIS_ERR_CUDA, "cudaMemcpyAsync image", (int)e);
+  if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
+  if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
+  *out = f;
+  return NIS_OK;
+}
+
+int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out) {
+  if (!ctx || !image_colmajor || !out) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  nis_frame* f = nullptr;
+  TRY(frame_alloc(ctx, false, &f));
+  std::vector<float> rm(ctx->sz[0].real);
+  transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());      // [W][H] lines -> [H][W]
+  cudaError_t e = cudaMemcpy(f->img_f32, rm.data(), rm.size() * sizeof(float), cudaMemcpyHostToDevice);
+  int st = e == cudaSuccess ? features_batch(ctx, src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1,
+                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
+                            : fail(ctx, NIS_ERR_CUDA, "cudaMemcpy image", (int)e);
+  if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
+  if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
+  *out = f;
+  return NIS_OK;
+}
+
+int nis_frame_export(nis_ctx* ctx, const nis_frame* f, float* fft_result, float* fft_polar) {
+  if (!ctx || !f) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < 2; ++s) {
+    float* dst = s == 0 ? fft_result : fft_polar;
+    if (!dst) continue;
+    const SizeClass& z = ctx->sz[s];
+    std::vector<cpx> rm(z.spec);
+    CU(cudaMemcpy(rm.data(), s == 0 ? f->F : f->P, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
+    transpose_to(rm.data(), z.R / 2 + 1, z.C, (cpx*)dst);       // [half][C] -> C lines of half
+  }
+  return NIS_OK;
+}
+
+int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, nis_frame** out) {
+  if (!ctx || !image_colmajor || !fft_result || !fft_polar || !out) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  nis_frame* f = nullptr;
+  TRY(frame_alloc(ctx, false, &f));
+  std::vector<float> rm(ctx->sz[0].real);
+  transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());
+  cudaError_t e = cudaMemcpy(f->img_f32, rm.data(), rm.size() * sizeof(float), cudaMemcpyHostToDevice);
+  for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+    const SizeClass& z = ctx->sz[s];
+    std::vector<cpx> t(z.spec);
+    transpose_to((const cpx*)(s == 0 ? fft_result : fft_polar), z.C, z.R / 2 + 1, t.data());
+    e = cudaMemcpy(s == 0 ? f->F : f->P, t.data(), z.spec * sizeof(cpx), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { nis_frame_free(ctx, f); return fail(ctx, NIS_ERR_CUDA, "frame import copy", (int)e); }
+  *out = f;
+  return NIS_OK;
+}
+
+// ---- ComputePose ----------------------------------------------------------------------------------------------
+static void record_out(const PoseRecord& r, double pose[3], double info[3], int32_t peak[4]) {
+  for (int i = 0; i < 3; ++i) { if (pose) pose[i] = r.pose[i]; if (info) info[i] = r.info[i]; }
+  if (peak) for (int i = 0; i < 4; ++i) peak[i] = r.peak[i];
+}
+
+int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, int not_large_rotation, double pose[3],
+                     double info[3], int32_t peak_rc[4]) {
+  if (!ctx || !last || !cur || !pose || !info) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_recs(ctx, 1));
+  const bool u8 = cur->img_u8 != nullptr;
+  TRY(compute_pose_batch(ctx, !not_large_rotation, src_slab<cpx>(last->F, 0), src_slab<cpx>(last->P, 0), src_slab<cpx>(cur->P, 0),
+                         src_slab<float>(cur->img_f32, 0), src_slab<uint8_t>(cur->img_u8, 0), u8, 1, 0, ctx->recs.as<PoseRecord>()));
+  PoseRecord r;
+  CU(cudaMemcpyAsync(&r, ctx->recs.p, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  record_out(r, pose, info, peak_rc);
+  return NIS_OK;
+}
+
+// ---- stream tracking --------------------------------------------------------------------------------------------
+static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, int n, double* poses, double* infos) {
+  if (!ctx || !frames || n < 1 || (n > 1 && (!poses || !infos))) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec;
+  RESERVE(ctx->sF, (size_t)n * spt * sizeof(cpx));
+  RESERVE(ctx->sP, (size_t)n * spp * sizeof(cpx));
+  const uint8_t* d_frames = frames;
+  if (on_host) {
+    RESERVE(ctx->sImg, (size_t)n * npx);
+    CU(cudaMemcpyAsync(ctx->sImg.p, frames, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
+    d_frames = ctx->sImg.as<uint8_t>();
+  }
+  TRY(ensure_recs(ctx, std::max(n - 1, 1)));
+  const int B = ctx->batch;
+  cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
+  for (int t0 = 0; t0 < n; t0 += B) {
+    const int nb = std::min(B, n - t0);
+    TRY(features_batch(ctx, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
+                       Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp}));
+  }
+  for (int p0 = 0; p0 < n - 1; p0 += B) {
+    const int nb = std::min(B, n - 1 - p0);
+    TRY(compute_pose_batch(ctx, false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt), src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp),
+                           src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp), src_null<float>(),
+                           src_slab<uint8_t>(d_frames + (size_t)(p0 + 1) * npx, (long long)npx), true, nb, p0,
+                           ctx->recs.as<PoseRecord>() + p0));
+  }
+  if (n > 1) {
+    TRY(ensure_pinned(ctx, (size_t)(n - 1) * sizeof(PoseRecord)));
+    CU(cudaMemcpyAsync(ctx->pin, ctx->recs.p, (size_t)(n - 1) * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  const PoseRecord* r = (const PoseRecord*)ctx->pin;
+  for (int i = 0; i < n - 1; ++i) record_out(r[i], poses + 3 * i, infos + 3 * i, nullptr);
+  return NIS_OK;
+}
+int nis_track_stream(nis_ctx* ctx, const uint8_t* frames_host, int n, double* poses, double* infos) {
+  return track_stream_impl(ctx, frames_host, true, n, poses, infos);
+}
+int nis_track_stream_dev(nis_ctx* ctx, const uint8_t* frames_dev, int n, double* poses, double* infos) {
+  return track_stream_impl(ctx, frames_dev, false, n, poses, infos);
+}
+
+// ---- keyframe DB ------------------------------------------------------------------------------------------------
+static int db_reserve_slots(nis_ctx* ctx, int n_new, int* first) {
+  const size_t rec = ctx->sz[0].spec + ctx->sz[1].spec;
+  const int old = (int)ctx->slot_ptr.size();
+  *first = old;
+  for (int i = 0; i < n_new; ++i) {
+    const int slot = old + i;
+    const int ch = slot / ctx->chunk_slots, within = slot % ctx->chunk_slots;
+    if (ch >= (int)ctx->chunks.size()) {
+      void* p = nullptr;
+      cudaError_t e = cudaMalloc(&p, (size_t)ctx->chunk_slots * rec * sizeof(cpx));
+      if (e != cudaSuccess) return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc DB chunk", (int)e);
+      ctx->chunks.push_back(p);
+    }
+    ctx->slot_ptr.push_back((cpx*)ctx->chunks[ch] + (size_t)within * rec);
+  }
+  const int total = old + n_new;
+  if (total > ctx->d_slot_cap) {
+    int cap = std::max(4096, ctx->d_slot_cap);
+    while (cap < total) cap *= 2;
+    CU(cudaStreamSynchronize(ctx->stream));
+    RESERVE(ctx->d_slot_ptr, (size_t)cap * sizeof(cpx*));
+    ctx->d_slot_cap = cap;
+    CU(cudaMemcpy(ctx->d_slot_ptr.p, ctx->slot_ptr.data(), (size_t)total * sizeof(cpx*), cudaMemcpyHostToDevice));
+  } else {
+    CU(cudaMemcpy(ctx->d_slot_ptr.as<cpx*>() + old, ctx->slot_ptr.data() + old, (size_t)n_new * sizeof(cpx*), cudaMemcpyHostToDevice));
+  }
+  return NIS_OK;
+}
+
+int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distance, int* slot) {
+  if (!ctx || !f) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  int s0 = 0;
+  TRY(db_reserve_slots(ctx, 1, &s0));
+  cpx* dst = ctx->slot_ptr[s0];
+  CU(cudaMemcpyAsync(dst, f->F, ctx->sz[0].spec * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dst + ctx->sz[0].spec, f->P, ctx->sz[1].spec * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->slot_frame_id.push_back(frame_id);
+  ctx->slot_dist.push_back(acc_distance);
+  if (slot) *slot = s0;
+  return NIS_OK;
+}
+
+static int db_add_images_impl(nis_ctx* ctx, const uint8_t* images, bool on_host, int n, const int* ids, const double* dists) {
+  if (!ctx || (!images && n > 0) || n < 0) return NIS_ERR_INVALID_ARGUMENT;
+  if (n == 0) return NIS_OK;
+  CU(cudaSetDevice(ctx->device));
+  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, rec = ctx->sz[0].spec + ctx->sz[1].spec;
+  int s0 = 0;
+  TRY(db_reserve_slots(ctx, n, &s0));
+  const int B = ctx->batch;
+  if (on_host) RESERVE(ctx->sImg, (size_t)B * npx);
+  for (int i0 = 0; i0 < n;) {
+    const int slot = s0 + i0;
+    const int room = ctx->chunk_slots - slot % ctx->chunk_slots;       // stay inside one chunk (contiguous records)
+    const int nb = std::min(std::min(B, n - i0), room);
+    const uint8_t* src = images + (size_t)i0 * npx;
+    if (on_host) {
+      CU(cudaMemcpyAsync(ctx->sImg.p, src, (size_t)nb * npx, cudaMemcpyHostToDevice, ctx->stream));
+      src = ctx->sImg.as<uint8_t>();
+    }
+    cpx* base = ctx->slot_ptr[slot];
+    TRY(features_batch(ctx, src_null<float>(), src_slab<uint8_t>(src, (long long)npx), true, nb, Dst<cpx>{base, (long long)rec},
+                       Dst<cpx>{base + spt, (long long)rec}));
+    if (on_host) CU(cudaStreamSynchronize(ctx->stream));                // staging buffer reuse
+    i0 += nb;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    ctx->slot_frame_id.push_back(ids ? ids[i] : s0 + i);
+    ctx->slot_dist.push_back(dists ? dists[i] : 0.0);
+  }
+  return NIS_OK;
+}
+int nis_db_add_images(nis_ctx* ctx, const uint8_t* images_host, int n, const int* frame_ids, const double* acc_distances) {
+  return db_add_images_impl(ctx, images_host, true, n, frame_ids, acc_distances);
+}
+int nis_db_add_images_dev(nis_ctx* ctx, const uint8_t* images_dev, int n, const int* frame_ids, const double* acc_distances) {
+  return db_add_images_impl(ctx, images_dev, false, n, frame_ids, acc_distances);
+}
+int nis_db_size(const nis_ctx* ctx) { return ctx ? (int)ctx->slot_frame_id.size() : 0; }
+int nis_db_clear(nis_ctx* ctx) {
+  if (!ctx) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (void* c : ctx->chunks) cudaFree(c);
+  ctx->chunks.clear(); ctx->slot_ptr.clear(); ctx->slot_frame_id.clear(); ctx->slot_dist.clear();
+  return NIS_OK;
+}
+
+// ---- loop-closure scan (loop_closure.cc:36-73) --------------------------------------------------------------------
+int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance, const nis_loop_config* cfg,
+                  const int32_t* candidate_slots, int n_candidates, nis_loop_result* out, double* all_responses) {
+  if (!ctx || !query || !cfg || !out || n_candidates < 0) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  const int ndb = nis_db_size(ctx);
+  const int n_in = candidate_slots ? n_candidates : ndb;
+  std::vector<int> cand; cand.reserve(n_in);
+  std::vector<int> pos; pos.reserve(n_in);            // position in the caller's candidate list
+  for (int i = 0; i < n_in; ++i) {
+    const int slot = candidate_slots ? candidate_slots[i] : i;
+    if (slot < 0 || slot >= ndb) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "candidate slot out of range");
+    if (cfg->frame_gap_thr > 0 && abs(query_frame_id - ctx->slot_frame_id[slot]) < cfg->frame_gap_thr) continue;      // :43-46
+    if (cfg->distance_thr > 0 && fabs(query_acc_distance - ctx->slot_dist[slot]) < cfg->distance_thr) continue;        // :47-53
+    cand.push_back(slot); pos.push_back(i);
+  }
+  const int n = (int)cand.size();
+  memset(out, 0, sizeof *out);
+  out->slot = -1; out->frame_id = -1; out->evaluated = n;
+  out->response[0] = out->response[1] = out->response[2] = -1.0;                                                       // loop_closure.h:15
+  for (int i = 0; i < 4; ++i) out->peak[i] = -1;
+  if (all_responses) for (int i = 0; i < 3 * n_in; ++i) all_responses[i] = -1.0;
+  if (n == 0) return NIS_OK;
+  if (n > ctx->cand_cap) { RESERVE(ctx->cand, (size_t)n * sizeof(int)); ctx->cand_cap = n; }
+  CU(cudaMemcpyAsync(ctx->cand.p, cand.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(ensure_recs(ctx, n));
+  const bool u8 = query->img_u8 != nullptr;
+  const int B = ctx->batch;
+  const cpx* const* ptrs = ctx->d_slot_ptr.as<const cpx*>();
+  for (int b0 = 0; b0 < n; b0 += B) {
+    const int nb = std::min(B, n - b0);
+    const int* idx = ctx->cand.as<int>() + b0;
+    Src<cpx> Fz{nullptr, 0, ptrs, 0, idx, 0};
+    Src<cpx> Pz{nullptr, 0, ptrs, (long long)ctx->sz[0].spec, idx, 0};
+    TRY(compute_pose_batch(ctx, true, Fz, Pz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
+                           src_slab<uint8_t>(query->img_u8, 0), u8, nb, b0, ctx->recs.as<PoseRecord>() + b0));
+  }
+  LAUNCH(launch_scan_reduce(ctx->recs.as<PoseRecord>(), n, ctx->best.as<PoseRecord>(), ctx->stream));
+  PoseRecord best;
+  CU(cudaMemcpyAsync(&best, ctx->best.p, sizeof best, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<PoseRecord> all;
+  if (all_responses) {
+    all.resize(n);
+    CU(cudaMemcpyAsync(all.data(), ctx->recs.p, (size_t)n * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (all_responses)
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) all_responses[3 * pos[i] + k] = all[i].info[k];
+  if (best.index >= 0) {
+    out->slot = cand[best.index];
+    out->frame_id = ctx->slot_frame_id[out->slot];
+    out->hyp = best.hyp;
+    for (int k = 0; k < 3; ++k) { out->relative_pose[k] = best.pose[k]; out->response[k] = best.info[k]; }
+    for (int k = 0; k < 4; ++k) out->peak[k] = best.peak[k];
+  }
+  out->found = (out->response[0] > cfg->position_response_thr) && (out->response[2] > cfg->angle_response_thr);        // :68-71
+  return NIS_OK;
+}
+
+int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n_ranks, const nis_loop_config* cfg,
+                    nis_loop_result* out, int* winner_rank) {
+  if (!per_rank || !cfg || !out || n_ranks <= 0) return NIS_ERR_INVALID_ARGUMENT;
+  int best = -1;
+  double bs = -3.0;
+  int evaluated = 0;
+  for (int r = 0; r < n_ranks; ++r) {
+    evaluated += per_rank[r].evaluated;
+    if (per_rank[r].slot < 0) continue;
+    const double s = per_rank[r].response[0] + per_rank[r].response[1] + per_rank[r].response[2];
+    const bool earlier = best >= 0 && s == bs && (order ? order[r] < order[best] : r < best);
+    if (s > bs || earlier) { bs = s; best = r; }
+  }
+  if (best >= 0) *out = per_rank[best];
+  else {
+    memset(out, 0, sizeof *out);
+    out->slot = -1; out->frame_id = -1;
+    out->response[0] = out->response[1] = out->response[2] = -1.0;
+    for (int i = 0; i < 4; ++i) out->peak[i] = -1;
+  }
+  out->evaluated = evaluated;
+  out->found = (out->response[0] > cfg->position_response_thr) && (out->response[2] > cfg->angle_response_thr);
+  if (winner_rank) *winner_rank = best;
+  return NIS_OK;
+}
+
+// ---- stage-level debug entry points (tests) ---------------------------------------------------------------------
+int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_out) {
+  if (!ctx || !real_in || !spec_out || which < 0 || which > 1) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_workspace(ctx, 1));
+  const SizeClass& z = ctx->sz[which];
+  CU(cudaMemcpy(ctx->rk.p, real_in, z.real * sizeof(float), cudaMemcpyHostToDevice));
+  TRY(fft2_batch(ctx, which, src_slab<float>(ctx->rk.as<float>(), 0), src_null<uint8_t>(), false, 1, Dst<cpx>{ctx->kxz.as<cpx>(), 0}));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(spec_out, ctx->kxz.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
+  return NIS_OK;
+}
+
+int nis_debug_ifft2(nis_ctx* ctx, int which, const float* spec_in, float* real_out) {
+  if (!ctx || !spec_in || !real_out || which < 0 || which > 1) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_workspace(ctx, 1));
+  const SizeClass& z = ctx->sz[which];
+  CU(cudaMemcpy(ctx->kxz.p, spec_in, z.spec * sizeof(cpx), cudaMemcpyHostToDevice));
+  Dst<cpx> t1{ctx->t1.as<cpx>(), 0};
+  // the inverse row pass has no plain-load instantiation: multiply by conj(1) through ProMulConj instead
+  {
+    std::vector<cpx> ones(z.spec, make_float2(1.f, 0.f));
+    CU(cudaMemcpy(ctx->kzz.p, ones.data(), z.spec * sizeof(cpx), cudaMemcpyHostToDevice));
+  }
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(ctx->kxz.as<cpx>(), 0), src_slab<cpx>(ctx->kzz.as<cpx>(), 0)},
+                                EpiSpecStore{t1}, z.R / 2 + 1, 1, ctx->stream));
+  LAUNCH(launch_col_inv_store(z.R, z.coli, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{ctx->rk.as<float>(), 0}, z.C, (float)z.real},
+                              z.C, 1, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(real_out, ctx->rk.p, z.real * sizeof(float), cudaMemcpyDeviceToHost));
+  return NIS_OK;
+}
+
+int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
+  if (!ctx || !power_in || !polar_out) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_workspace(ctx, 1));
+  CU(cudaMemcpy(ctx->rk.p, power_in, ctx->sz[0].real * sizeof(float), cudaMemcpyHostToDevice));
+  LAUNCH(launch_polar(src_slab<float>(ctx->rk.as<float>(), 0), Dst<float>{ctx->rot.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
+                      ctx->cs.as<double>(), ctx->rho.as<float>(), 1, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(polar_out, ctx->rot.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
+  return NIS_OK;
+}
+
+int nis_debug_rotate(nis_ctx* ctx, const float* image_in, float degree, float* image_out) {
+  if (!ctx || !image_in || !image_out) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_workspace(ctx, 1));
+  double M[6];
+  rotation_inverse(ctx->H, ctx->W, (double)degree, M);
+  const int slot = 3 * ctx->D;
+  CU(cudaMemcpy(ctx->mats.as<double>() + 6 * (size_t)slot, M, sizeof M, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->sel.p, &slot, sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->rk.p, image_in, ctx->sz[0].real * sizeof(float), cudaMemcpyHostToDevice));
+  LAUNCH(launch_rotate(src_slab<float>(ctx->rk.as<float>(), 0), src_null<uint8_t>(), ctx->lut.as<float>(), Dst<float>{ctx->rot.as<float>(), 0},
+                       ctx->H, ctx->W, ctx->mats.as<double>(), ctx->sel.as<int>(), 1, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(image_out, ctx->rot.p, ctx->sz[0].real * sizeof(float), cudaMemcpyDeviceToHost));
+  return NIS_OK;
+}
+
+int nis_debug_estimate_trans(nis_ctx* ctx, int which, const float* last_spec, const float* cur_spec, int32_t peak_rc[2], float* info,
+                             float* g_out) {
+  if (!ctx || !last_spec || !cur_spec || !peak_rc || !info || which < 0 || which > 1) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_workspace(ctx, 1));
+  const SizeClass& z = ctx->sz[which];
+  // inputs parked in xs (Z) and the second half of rot (X); g in the first half of rot... keep it simple: two dedicated temporaries
+  DevBuf dz, dx, dg;
+  RESERVE(dz, z.spec * sizeof(cpx)); RESERVE(dx, z.spec * sizeof(cpx));
+  if (g_out) RESERVE(dg, z.real * sizeof(float));
+  int st = NIS_OK;
+  if (cudaMemcpy(dz.p, last_spec, z.spec * sizeof(cpx), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dx.p, cur_spec, z.spec * sizeof(cpx), cudaMemcpyHostToDevice) != cudaSuccess)
+    st = fail(ctx, NIS_ERR_CUDA, "debug copy", (int)cudaGetLastError());
+  PeakStats ps;
+  if (st == NIS_OK) st = estimate_trans_batch(ctx, which, src_slab<cpx>(dz.as<cpx>(), 0), 1, src_slab<cpx>(dz.as<cpx>(), 0),
+                                              src_slab<cpx>(dx.as<cpx>(), 0), 1, 0, ctx->stats_t.as<PeakStats>(), g_out ? dg.as<float>() : nullptr);
+  if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug sync", (int)cudaGetLastError());
+  if (st == NIS_OK && cudaMemcpy(&ps, ctx->stats_t.p, sizeof ps, cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug copy back");
+  if (st == NIS_OK && g_out && cudaMemcpy(g_out, dg.p, z.real * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug g copy");
+  dz.release(); dx.release(); dg.release();
+  if (st != NIS_OK) return st;
+  const uint32_t idx = 0xffffffffu - (uint32_t)(ps.key & 0xffffffffull);
+  const int col = (int)(idx / (uint32_t)z.R), row = (int)(idx % (uint32_t)z.R);
+  const float peak = ord2f((uint32_t)(ps.key >> 32));
+  const double n = (double)z.real;
+  const float m = ((float)ps.sum - peak) / (float)(n - 1.0);
+  double var = (ps.sumsq - 2.0 * (double)m * ps.sum + n * (double)m * (double)m) / n;
+  var = var > 0 ? var : 0;
+  *info = (float)((double)(peak - m) / ((double)sqrtf((float)var) + 1e-7));
+  peak_rc[0] = row; peak_rc[1] = col;
+  return NIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// nis_fft.cuh -- shared-memory mixed-radix FFT building blocks for the KCC hot path (sm_100a).
+//
+// Replaces the reference's FFTW3f calls (src/correlation_flow.cc:53-77: fftwf_plan_dft_r2c_2d / c2r_2d,
+// planned and destroyed per call) with two batched kernel families:
+//   * column pass  (transform along image rows r, the halved dimension): one CTA owns a tile of 32 adjacent real
+//     columns = 16 complex lines (two real columns ride as re/im of one complex line), lanes <-> lines, so every
+//     shared-memory access is conflict-free and every global access is a 128..256 B contiguous segment.
+//   * row pass     (transform along image columns c, contiguous): lanes <-> butterfly index, first radix 16,
+//     one pad slot per 16 complex keeps the Stockham exchanges conflict-free.
+// Both families do stage 0 straight from global memory and the last stage straight to global memory; only two
+// exchanges go through shared memory.  Element-wise work of the KCC (spectrum products, |F|, the kernel function,
+// the H*Kxz filter, arg-max / sum / sum-of-squares) rides in the prologue / epilogue functors of these passes.
+//
+// The bodies are written as barrier-free "phases" so the same code runs on the host under tests/cpp (thread-by-
+// thread emulation of a CTA) -- there is no GPU in the build container.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NIS_HD __host__ __device__ __forceinline__
+#define NIS_HDC __host__ __device__ constexpr
+#else
+#define NIS_HD inline
+#define NIS_HDC constexpr
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#endif
+
+namespace nis {
+
+typedef float2 cpx;
+
+NIS_HD cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
+NIS_HD cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
+NIS_HD cpx cmul(cpx a, cpx b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+NIS_HD cpx cmulc(cpx a, cpx b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+NIS_HD cpx cscale(cpx a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by -i (forward) / +i (inverse)
+template <bool INV> NIS_HD cpx mul_mi(cpx a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+// twiddle as stored (forward, exp(-i..)) or conjugated (inverse)
+template <bool INV> NIS_HD cpx tw(cpx w) { return INV ? make_float2(w.x, -w.y) : w; }
+
+// ---------------------------------------------------------------------------------------------------------
+// in-register DFTs.  dft<R,INV>(v): v[k] <- sum_n v[n] exp(-/+ 2 pi i n k / R)
+// ---------------------------------------------------------------------------------------------------------
+template <int R, bool INV> struct Dft;
+
+template <bool INV> struct Dft<1, INV> { static NIS_HD void run(cpx*) {} };
+
+template <bool INV> struct Dft<2, INV> {
+  static NIS_HD void run(cpx* v) {
+    cpx a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  }
+};
+
+template <bool INV> struct Dft<3, INV> {
+  static NIS_HD void run(cpx* v) {
+    const float s3 = 0.86602540378443864676f;
+    cpx a = v[0], s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+    cpx m = make_float2(a.x - 0.5f * s.x, a.y - 0.5f * s.y);
+    cpx t = cscale(mul_mi<INV>(d), s3);
+    v[0] = cadd(a, s); v[1] = cadd(m, t); v[2] = csub(m, t);
+  }
+};
+
+template <bool INV> struct Dft<4, INV> {
+  static NIS_HD void run(cpx* v) {
+    cpx s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]), s2 = cadd(v[1], v[3]), s3 = mul_mi<INV>(csub(v[1], v[3]));
+    v[0] = cadd(s0, s2); v[2] = csub(s0, s2); v[1] = cadd(s1, s3); v[3] = csub(s1, s3);
+  }
+};
+
+template <bool INV> struct Dft<5, INV> {
+  static NIS_HD void run(cpx* v) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    cpx a = v[0];
+    cpx p1 = cadd(v[1], v[4]), m1 = csub(v[1], v[4]), p2 = cadd(v[2], v[3]), m2 = csub(v[2], v[3]);
+    cpx t1 = make_float2(a.x + c1 * p1.x + c2 * p2.x, a.y + c1 * p1.y + c2 * p2.y);
+    cpx t2 = make_float2(a.x + c2 * p1.x + c1 * p2.x, a.y + c2 * p1.y + c1 * p2.y);
+    cpx u = mul_mi<INV>(make_float2(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y));
+    cpx w = mul_mi<INV>(make_float2(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y));
+    v[0] = make_float2(a.x + p1.x + p2.x, a.y + p1.y + p2.y);
+    v[1] = cadd(t1, u); v[4] = csub(t1, u); v[2] = cadd(t2, w); v[3] = csub(t2, w);
+  }
+};
+
+// radix 8 = 2 x 4 with W8 twiddles
+template <bool INV> struct Dft<8, INV> {
+  static NIS_HD void run(cpx* v) {
+    const float h = 0.70710678118654752440f;
+    cpx e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4, INV>::run(e); Dft<4, INV>::run(o);
+    // w8^1 = (1 -/+ i)/sqrt2, w8^2 = -/+ i, w8^3 = (-1 -/+ i)/sqrt2
+    cpx o1 = INV ? make_float2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y)) : make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+    cpx o2 = mul_mi<INV>(o[2]);
+    cpx o3 = INV ? make_float2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y)) : make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+  }
+};
+
+// radix 16 = 2 x 8 with W16 twiddles
+template <bool INV> struct Dft<16, INV> {
+  static NIS_HD void run(cpx* v) {
+    const float h = 0.70710678118654752440f, c = 0.92387953251128675613f, s = 0.38268343236508977173f;
+    cpx e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Dft<8, INV>::run(e); Dft<8, INV>::run(o);
+    // forward twiddles w16^k = (wr, wi): k=1:(c,-s) 2:(h,-h) 3:(s,-c) 4:(0,-1) 5:(-s,-c) 6:(-h,-h) 7:(-c,-s)
+    const float wr[8] = {1.f, c, h, s, 0.f, -s, -h, -c};
+    const float wi[8] = {0.f, -s, -h, -c, -1.f, -c, -h, -s};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      cpx w = make_float2(wr[k], INV ? -wi[k] : wi[k]);
+      cpx t = (k == 0) ? o[0] : cmul(o[k], w);
+      v[k] = cadd(e[k], t); v[k + 8] = csub(e[k], t);
+    }
+  }
+};
+
+// radix 9 = 3 x 3 with W9 twiddles
+template <bool INV> struct Dft<9, INV> {
+  static NIS_HD void run(cpx* v) {
+    const float c1 = 0.76604444311897803520f, s1 = 0.64278760968653932632f;   // cos/sin(2pi/9)
+    const float c2 = 0.17364817766693034885f, s2 = 0.98480775301220805937f;   // cos/sin(4pi/9)
+    const float c4 = -0.93969262078590838405f, s4 = 0.34202014332566873304f;  // cos/sin(8pi/9)
+    cpx y[3][3];
+#pragma unroll
+    for (int n2 = 0; n2 < 3; ++n2) {
+      cpx t[3] = {v[n2], v[3 + n2], v[6 + n2]};
+      Dft<3, INV>::run(t);
+      y[n2][0] = t[0]; y[n2][1] = t[1]; y[n2][2] = t[2];
+    }
+    y[1][1] = cmul(y[1][1], make_float2(c1, INV ? s1 : -s1));
+    y[1][2] = cmul(y[1][2], make_float2(c2, INV ? s2 : -s2));
+    y[2][1] = cmul(y[2][1], make_float2(c2, INV ? s2 : -s2));
+    y[2][2] = cmul(y[2][2], make_float2(c4, INV ? s4 : -s4));
+#pragma unroll
+    for (int k1 = 0; k1 < 3; ++k1) {
+      cpx t[3] = {y[0][k1], y[1][k1], y[2][k1]};
+      Dft<3, INV>::run(t);
+      v[k1] = t[0]; v[k1 + 3] = t[1]; v[k1 + 6] = t[2];
+    }
+  }
+};
+
+// Good-Thomas prime-factor DFT for coprime N1*N2 (no twiddles, only index maps resolved at compile time)
+NIS_HDC int cx_modinv(int a, int m) {
+  for (int x = 1; x < m; ++x)
+    if ((a * x) % m == 1) return x;
+  return 1;
+}
+template <int N1, int N2, bool INV> struct DftPfa {
+  static NIS_HD void run(cpx* v) {
+    constexpr int N = N1 * N2;
+    constexpr int A = N2 * cx_modinv(N2 % N1, N1), B = N1 * cx_modinv(N1 % N2, N2);
+    cpx t[N];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) {
+#pragma unroll
+      for (int n1 = 0; n1 < N1; ++n1) t[n2 * N1 + n1] = v[(N2 * n1 + N1 * n2) % N];
+      Dft<N1, INV>::run(t + n2 * N1);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) {
+      cpx u[N2];
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) u[n2] = t[n2 * N1 + k1];
+      Dft<N2, INV>::run(u);
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) v[(k1 * A + k2 * B) % N] = u[k2];
+    }
+  }
+};
+template <bool INV> struct Dft<6, INV> { static NIS_HD void run(cpx* v) { DftPfa<2, 3, INV>::run(v); } };
+template <bool INV> struct Dft<10, INV> { static NIS_HD void run(cpx* v) { DftPfa<2, 5, INV>::run(v); } };
+template <bool INV> struct Dft<12, INV> { static NIS_HD void run(cpx* v) { DftPfa<4, 3, INV>::run(v); } };
+template <bool INV> struct Dft<15, INV> { static NIS_HD void run(cpx* v) { DftPfa<3, 5, INV>::run(v); } };
+
+// ---------------------------------------------------------------------------------------------------------
+// twiddle tables (built on the host in double, stored f32): for a 3-stage plan (R0,R1,R2), N = R0*R1*R2
+//   tw1[(r-1)*R0 + k]       = exp(-2 pi i r k / (R0*R1)),  r in [1,R1), k in [0,R0)
+//   tw2[(r-1)*R0*R1 + k]    = exp(-2 pi i r k / N),        r in [1,R2), k in [0,R0*R1)
+// ---------------------------------------------------------------------------------------------------------
+struct Twiddles {
+  const cpx* tw1;
+  const cpx* tw2;
+};
+
+#if defined(__CUDA_ARCH__)
+#define NIS_LDG(p) __ldg(p)
+#else
+#define NIS_LDG(p) (*(p))
+#endif
+
+// =========================================================================================================
+// COLUMN PASS: lanes <-> 16 complex lines (32 real columns).  smem: cpx[N][16].  T threads, G = T/16 groups.
+// =========================================================================================================
+constexpr int kColLanes = 16;
+
+template <int N, int R0, int R1, int R2, int T> struct ColGeom {
+  static_assert(R0 * R1 * R2 == N, "bad factorisation");
+  static_assert(T % kColLanes == 0, "T must be a multiple of 16");
+  static constexpr int G = T / kColLanes;
+  static constexpr int M0 = N / R0, M1 = N / R1, M2 = N / R2;   // butterflies per line per stage
+  static constexpr int NS1 = R0, NS2 = R0 * R1;
+  static constexpr int ROUNDS1 = (M1 + G - 1) / G;
+  static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)N * kColLanes;
+};
+
+template <int R1, int ROUNDS> struct CarryRegs { cpx v[ROUNDS][R1]; };
+
+// ---- shared middle stage (in place: read all -> barrier -> write all), both directions
+template <int N, int R0, int R1, int R2, int T, bool INV>
+NIS_HD void col_stage1_read(int tid, const cpx* smem, const Twiddles& twd, CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1>& st) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+#pragma unroll
+  for (int it = 0; it < Gm::ROUNDS1; ++it) {
+    const int j = gi + it * Gm::G;
+    if (j < Gm::M1) {
+      const int k = j % Gm::NS1;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        cpx x = smem[(j + r * Gm::M1) * kColLanes + l];
+        if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + k])));
+        st.v[it][r] = x;
+      }
+      Dft<R1, INV>::run(st.v[it]);
+    }
+  }
+}
+template <int N, int R0, int R1, int R2, int T, bool INV>
+NIS_HD void col_stage1_write(int tid, cpx* smem, const CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1>& st) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+#pragma unroll
+  for (int it = 0; it < Gm::ROUNDS1; ++it) {
+    const int j = gi + it * Gm::G;
+    if (j < Gm::M1) {
+      const int k = j % Gm::NS1, j0 = (j / Gm::NS1) * Gm::NS1 * R1 + k;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) smem[(j0 + r * Gm::NS1) * kColLanes + l] = st.v[it][r];
+    }
+  }
+}
+
+// ---- forward r2c column pass ------------------------------------------------------------------------------
+// Pro::load(row, l) -> cpx (re = real column c0+2l, im = real column c0+2l+1 at image row `row`)
+// phase 0: stage 0 from global
+template <int N, int R0, int R1, int R2, int T, class Pro>
+NIS_HD void col_fwd_phase0(int tid, cpx* smem, const Pro& pro) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+  for (int j = gi; j < Gm::M0; j += Gm::G) {
+    cpx v[R0];
+#pragma unroll
+    for (int r = 0; r < R0; ++r) v[r] = pro.load(j + r * Gm::M0, l);
+    Dft<R0, false>::run(v);
+#pragma unroll
+    for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = v[r];
+  }
+}
+
+// separation of the two real lines packed in Z:  A[k] = (Z[k]+conj Z[N-k])/2,  B[k] = (Z[k]-conj Z[N-k])/(2i)
+NIS_HD float4 r2c_split(cpx zk, cpx zn) {
+  return make_float4(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y), 0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+}
+
+// phase 2: stage 2, butterflies j and NS2-j handled by one thread so Z[k] and Z[N-k] meet in registers.
+// out: spectrum rows k in [0,N/2], row pitch `pitch` complex; this CTA's columns start at c0 (even).
+template <int N, int R0, int R1, int R2, int T>
+NIS_HD void col_fwd_phase2(int tid, const cpx* smem, const Twiddles& twd, cpx* out, int pitch, int c0) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  constexpr int NS2 = Gm::NS2;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+  float4* out4 = reinterpret_cast<float4*>(out);   // (A.x,A.y,B.x,B.y) = two adjacent complex columns
+  for (int p = gi; 2 * p <= NS2; p += Gm::G) {
+    const bool single = (p == 0) || (2 * p == NS2);
+    cpx v[R2], u[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      cpx x = smem[(p + r * NS2) * kColLanes + l];
+      if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + p]));
+      v[r] = x;
+    }
+    Dft<R2, false>::run(v);
+    if (!single) {
+      const int q = NS2 - p;
+#pragma unroll
+      for (int r = 0; r < R2; ++r) {
+        cpx x = smem[(q + r * NS2) * kColLanes + l];
+        if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + q]));
+        u[r] = x;
+      }
+      Dft<R2, false>::run(u);
+    }
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      const int k = p + r * NS2;
+      cpx zk, zn;
+      int kk;
+      if (single) {
+        if (2 * k > N) continue;
+        kk = k;
+        zk = v[r];
+        zn = (p == 0) ? v[(R2 - r) % R2] : v[R2 - 1 - r];
+      } else if (2 * k <= N) {
+        kk = k; zk = v[r]; zn = u[R2 - 1 - r];
+      } else {
+        kk = N - k; zk = u[R2 - 1 - r]; zn = v[r];
+      }
+      out4[((size_t)kk * pitch + c0) / 2 + l] = r2c_split(zk, zn);
+    }
+  }
+}
+
+// ---- inverse c2r column pass ------------------------------------------------------------------------------
+// in: half spectrum rows k in [0,N/2] (pitch complex), this CTA's columns start at c0.
+// phase 0: stage 0 (inverse) with butterflies j and M0-j paired so one (A,B) load feeds Z[k] and Z[N-k].
+template <int N, int R0, int R1, int R2, int T>
+NIS_HD void col_inv_phase0(int tid, cpx* smem, const cpx* in, int pitch, int c0) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  constexpr int M0 = Gm::M0;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  for (int p = gi; 2 * p <= M0; p += Gm::G) {
+    const bool single = (p == 0) || (2 * p == M0);
+    cpx v[R0], u[R0];
+#pragma unroll
+    for (int r = 0; r < R0; ++r) {
+      const int k = p + r * M0;
+      const bool lo = (2 * k <= N);
+      const int kk = lo ? k : N - k;
+      float4 ab = NIS_LDG(&in4[((size_t)kk * pitch + c0) / 2 + l]);
+      if (kk == 0 || 2 * kk == N) { ab.y = 0.f; ab.w = 0.f; }     // c2r ignores these imaginary parts
+      const cpx zlo = make_float2(ab.x - ab.w, ab.y + ab.z);       // A + iB        = Z[kk]
+      const cpx zhi = make_float2(ab.x + ab.w, ab.z - ab.y);       // conjA + i conjB = Z[N-kk]
+      v[r] = lo ? zlo : zhi;
+      if (!single) u[R0 - 1 - r] = lo ? zhi : zlo;
+    }
+    Dft<R0, true>::run(v);
+#pragma unroll
+    for (int r = 0; r < R0; ++r) smem[(p * R0 + r) * kColLanes + l] = v[r];
+    if (!single) {
+      const int q = M0 - p;
+      Dft<R0, true>::run(u);
+#pragma unroll
+      for (int r = 0; r < R0; ++r) smem[(q * R0 + r) * kColLanes + l] = u[r];
+    }
+  }
+}
+
+// phase 2: stage 2 (inverse) -> epilogue.  Epi::put(row, l, re, im): re -> real column c0+2l, im -> c0+2l+1 (unnormalised).
+template <int N, int R0, int R1, int R2, int T, class Epi>
+NIS_HD void col_inv_phase2(int tid, const cpx* smem, const Twiddles& twd, Epi& epi) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  constexpr int NS2 = Gm::NS2;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+  for (int j = gi; j < NS2; j += Gm::G) {
+    cpx v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      cpx x = smem[(j + r * NS2) * kColLanes + l];
+      if (r > 0) x = cmul(x, tw<true>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
+      v[r] = x;
+    }
+    Dft<R2, true>::run(v);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) epi.put(j + r * NS2, l, v[r].x, v[r].y);
+  }
+}
+
+// =========================================================================================================
+// ROW PASS: contiguous complex lines of length N = 16*R1*R2, L lines per CTA, lanes <-> butterfly index.
+// smem: cpx[L][N + N/16] (one pad slot per 16).
+// =========================================================================================================
+template <int N, int R1, int R2, int L, int T> struct RowGeom {
+  static_assert(16 * R1 * R2 == N, "bad factorisation");
+  static constexpr int R0 = 16;
+  static constexpr int M0 = N / 16, M1 = N / R1, M2 = N / R2;
+  static constexpr int NS1 = 16, NS2 = 16 * R1;
+  static constexpr int PITCH = N + N / 16;
+  static constexpr int ROUNDS1 = (L * M1 + T - 1) / T;
+  static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)L * PITCH;
+  static NIS_HD int pad(int i) { return i + (i >> 4); }
+};
+
+// Pro::load(line, c) -> cpx for local line index `line` in [0,L) (caller guards valid lines); c in [0,N)
+template <int N, int R1, int R2, int L, int T, bool INV, class Pro>
+NIS_HD void row_phase0(int tid, cpx* smem, const Pro& pro, int nlines) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+  for (int w = tid; w < L * Gm::M0; w += T) {
+    const int ln = w / Gm::M0, j = w % Gm::M0;
+    if (ln >= nlines) break;
+    cpx v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = pro.load(ln, j + r * Gm::M0);
+    Dft<16, INV>::run(v);
+    cpx* s = smem + ln * Gm::PITCH + j * 17;     // pad(16 j + r) = 17 j + r
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s[r] = v[r];
+  }
+}
+
+template <int N, int R1, int R2, int L, int T, bool INV>
+NIS_HD void row_stage1_read(int tid, const cpx* smem, const Twiddles& twd, int nlines, CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1>& st) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+#pragma unroll
+  for (int it = 0; it < Gm::ROUNDS1; ++it) {
+    const int w = tid + it * T;
+    const int ln = w / Gm::M1, j = w % Gm::M1;
+    if (w < L * Gm::M1 && ln < nlines) {
+      const int k = j & 15;
+      const cpx* s = smem + ln * Gm::PITCH;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        cpx x = s[Gm::pad(j + r * Gm::M1)];
+        if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw1[(r - 1) * 16 + k])));
+        st.v[it][r] = x;
+      }
+      Dft<R1, INV>::run(st.v[it]);
+    }
+  }
+}
+template <int N, int R1, int R2, int L, int T, bool INV>
+NIS_HD void row_stage1_write(int tid, cpx* smem, int nlines, const CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1>& st) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+#pragma unroll
+  for (int it = 0; it < Gm::ROUNDS1; ++it) {
+    const int w = tid + it * T;
+    const int ln = w / Gm::M1, j = w % Gm::M1;
+    if (w < L * Gm::M1 && ln < nlines) {
+      const int k = j & 15, j0 = (j >> 4) * 16 * R1 + k;
+      cpx* s = smem + ln * Gm::PITCH;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) s[Gm::pad(j0 + r * 16)] = st.v[it][r];
+    }
+  }
+}
+
+// Epi::put(line, c, value)
+template <int N, int R1, int R2, int L, int T, bool INV, class Epi>
+NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines, Epi& epi) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+  constexpr int NS2 = Gm::NS2;
+  for (int w = tid; w < L * NS2; w += T) {
+    const int ln = w / NS2, j = w % NS2;
+    if (ln >= nlines) break;
+    const cpx* s = smem + ln * Gm::PITCH;
+    cpx v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      cpx x = s[Gm::pad(j + r * NS2)];
+      if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
+      v[r] = x;
+    }
+    Dft<R2, INV>::run(v);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) epi.put(ln, j + r * NS2, v[r]);
+  }
+}
+
+}  // namespace nis

@@ -1,0 +1,58 @@
+// nis_internal.h -- launcher declarations shared by the .cu translation units (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nis_ops.cuh"
+
+namespace nis {
+
+// per-candidate / per-pair result written by pose_finalize (device and host POD)
+struct PoseRecord {
+  double pose[3];      // (dx_px, dy_px, theta_rad)          correlation_flow.cc:136-138
+  double info[3];      // (info_trans, info_trans, info_rot)
+  int32_t peak[4];     // polar row, polar col, trans row, trans col
+  int32_t hyp;         // loop mode: 0 = "-deg" hypothesis kept, 1 = "-deg+180"
+  int32_t index;       // candidate index in the scan order (or pair index)
+};
+
+// host-built per-polar-row tables (see build_tables in nis_api.cu); all indexed by the polar peak row in [0,D)
+struct AngleTables {
+  const double* rot_mats;   // [3][D][6]  inverse affine matrices: 0 tracking(-deg folded), 1 loop "-deg", 2 loop "-deg+180"
+  const double* theta;      // [3][D]     final theta (float-rounded) per variant
+};
+
+bool col_size_supported(int N);
+bool row_size_supported(int N);
+void plan_radices_col(int N, bool inverse, int r[3]);
+void plan_radices_row(int N, int r[3]);
+
+// ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
+int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
+int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
+int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, int B, cudaStream_t s);
+int launch_col_inv_kernel(int N, Twiddles tw, Src<cpx> in, EpiKernel epi, int W, int B, cudaStream_t s);
+int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s);
+int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+int launch_row_inv_abs(int N, Twiddles tw, ProAbs pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+int launch_row_inv_filter(int N, Twiddles tw, ProFilter pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+
+// ---- warps and bookkeeping kernels -----------------------------------------------------------------------
+// polar: power [B][H][W] (IFFT(|F|), unshifted) -> polar image [B][D][Cp]; RemoveZeroComponent + fftshift fused in the taps
+int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
+                 int B, cudaStream_t s);
+// rotate: out[e] = warpAffine(image[e], rot_mats[sel[e]]) with BORDER_WRAP.  Exactly one of img_f32 / img_u8 is used.
+int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
+                  const int* sel, int E, cudaStream_t s);
+// gaussian kernel helper: out[b] = (float)(sum over half spectrum |x^2|) / n
+int launch_spec_sqsum(Src<cpx> x, int count, float n, float* out, int B, cudaStream_t s);
+// after the polar stage: per pair, pick the rotation-matrix slot(s) for the translation stage
+int launch_polar_select(const PeakStats* polar, int D, int loop_mode, int* sel, int B, cudaStream_t s);
+// per pair: info (GetInfo), hypothesis choice, pose
+int launch_pose_finalize(const PeakStats* polar, const PeakStats* trans, AngleTables tabs, int H, int W, int D, int Cp,
+                         int loop_mode, int index0, PoseRecord* out, int B, cudaStream_t s);
+// scan: best record by response.sum(), strict '>', first in iteration order wins (loop_closure.cc:61)
+int launch_scan_reduce(const PoseRecord* recs, int n, PoseRecord* best, cudaStream_t s);
+
+}  // namespace nis

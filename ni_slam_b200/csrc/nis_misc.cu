@@ -1,0 +1,243 @@
+// nis_misc.cu -- the two OpenCV-exact resampling kernels and the per-pair bookkeeping kernels (sm_100a).
+//   polar_kernel   : RemoveZeroComponent + fftshift + cv::warpPolar   (correlation_flow.cc:79-87, :94, :228-236)
+//   rotate_kernel  : RotateArray = getRotationMatrix2D + warpAffine   (utils.cc:154-161)
+//   polar_select / pose_finalize / scan_reduce : ComputePose control flow and the FindLoopClosure arg-max
+//   (correlation_flow.cc:97-138, loop_closure.cc:61-71) kept on the device so a batch never syncs with the host.
+// All interpolation arithmetic is written with explicit round-to-nearest intrinsics (no FMA contraction) so the
+// fixed-point coordinates and the 4-tap sums equal OpenCV's scalar code bit for bit.
+#include "nis_device.cuh"
+#include "nis_internal.h"
+
+namespace nis {
+
+__device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
+
+// OpenCV BilinearTab_f weights: {(1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy fx}, all exact in f32
+__device__ __forceinline__ float bilinear4(float v0, float v1, float v2, float v3, int fx, int fy) {
+  const float x = (float)fx * (1.f / 32.f), y = (float)fy * (1.f / 32.f);
+  const float x0 = 1.f - x, y0 = 1.f - y;
+  float acc = __fmul_rn(v0, y0 * x0);
+  acc = __fadd_rn(acc, __fmul_rn(v1, y0 * x));
+  acc = __fadd_rn(acc, __fmul_rn(v2, y * x0));
+  acc = __fadd_rn(acc, __fmul_rn(v3, y * x));
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// polar warp.  Source = fftshift(RemoveZeroComponent(power)) evaluated on the fly from `power`.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float shifted_tap(const float* __restrict__ p, int y, int x, int H, int W) {
+  if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) return 0.f;   // BORDER_CONSTANT(0) (WARP_FILL_OUTLIERS)
+  int r = y - H / 2; r += (r < 0) ? H : 0;                                     // circ_shift.h:238-244
+  int c = x - W / 2; c += (c < 0) ? W : 0;
+  if (c == 0) return __fadd_rn(__ldg(p + (size_t)r * W + 1), __ldg(p + (size_t)r * W + W - 1)) * 0.5f;   // col rule (incl. (0,0))
+  if (r == 0) return __fadd_rn(__ldg(p + (size_t)W + c), __ldg(p + (size_t)(H - 1) * W + c)) * 0.5f;      // row rule
+  return __ldg(p + (size_t)r * W + c);
+}
+
+__global__ void __launch_bounds__(256) polar_kernel(Src<float> power, Dst<float> out, int H, int W, int D, int Cp,
+                                                    const double* __restrict__ cs, const float* __restrict__ rho_tab) {
+  const int b = blockIdx.z, phi = blockIdx.y;
+  const int rho = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rho >= Cp) return;
+  const float* p = power.at(b);
+  const double cp = cs[2 * phi], sp = cs[2 * phi + 1];
+  const double rf = (double)rho_tab[rho];
+  const float cx = (float)W / 2, cy = (float)H / 2;
+  const float mx = (float)__dadd_rn(__dmul_rn(rf, cp), (double)cx);
+  const float my = (float)__dadd_rn(__dmul_rn(rf, sp), (double)cy);
+  const int sx = __float2int_rn(mx * 32.f), sy = __float2int_rn(my * 32.f);   // cvRound: half to even
+  const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+  const float v0 = shifted_tap(p, iy, ix, H, W), v1 = shifted_tap(p, iy, ix + 1, H, W);
+  const float v2 = shifted_tap(p, iy + 1, ix, H, W), v3 = shifted_tap(p, iy + 1, ix + 1, H, W);
+  out.at(b)[(size_t)phi * Cp + rho] = bilinear4(v0, v1, v2, v3, sx & 31, sy & 31);
+}
+
+int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
+                 int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  const int T = Cp >= 256 ? 256 : 128;
+  polar_kernel<<<dim3((Cp + T - 1) / T, D, B), T, 0, s>>>(power, out, H, W, D, Cp, cs_table, rho_table);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// rotation (warpAffine, INTER_LINEAR, BORDER_WRAP, AB_BITS = 10, INTER_BITS = 5)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wrap_idx(int p, int len) {
+  if ((unsigned)p < (unsigned)len) return p;
+  if (p < 0) p -= ((p - len + 1) / len) * len;
+  if (p >= len) p %= len;
+  return p;
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(256) rotate_kernel(Src<float> img_f32, Src<uint8_t> img_u8, const float* __restrict__ lut,
+                                                     Dst<float> out, int H, int W, const double* __restrict__ mats,
+                                                     const int* __restrict__ sel) {
+  const int e = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const double* M = mats + 6 * (size_t)sel[e];
+  const int X0 = __double2int_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]) * 1024.0) + 16;
+  const int Y0 = __double2int_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]) * 1024.0) + 16;
+  const int adelta = __double2int_rn(__dmul_rn(M[0], (double)x) * 1024.0);
+  const int bdelta = __double2int_rn(__dmul_rn(M[3], (double)x) * 1024.0);
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int ix = sat_short(X >> 5), iy = sat_short(Y >> 5);
+  const int x0 = wrap_idx(ix, W), x1 = wrap_idx(ix + 1, W), y0 = wrap_idx(iy, H), y1 = wrap_idx(iy + 1, H);
+  float v0, v1, v2, v3;
+  if (U8) {
+    const uint8_t* p = img_u8.at(e);
+    v0 = __ldg(&lut[p[(size_t)y0 * W + x0]]); v1 = __ldg(&lut[p[(size_t)y0 * W + x1]]);
+    v2 = __ldg(&lut[p[(size_t)y1 * W + x0]]); v3 = __ldg(&lut[p[(size_t)y1 * W + x1]]);
+  } else {
+    const float* p = img_f32.at(e);
+    v0 = __ldg(p + (size_t)y0 * W + x0); v1 = __ldg(p + (size_t)y0 * W + x1);
+    v2 = __ldg(p + (size_t)y1 * W + x0); v3 = __ldg(p + (size_t)y1 * W + x1);
+  }
+  out.at(e)[(size_t)y * W + x] = bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
+}
+
+int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
+                  const int* sel, int E, cudaStream_t s) {
+  if (E <= 0) return 0;
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, E);
+  if (img_u8.base || img_u8.ptrs) rotate_kernel<true><<<grid, 256, 0, s>>>(img_f32, img_u8, lut, out, H, W, mats, sel);
+  else rotate_kernel<false><<<grid, 256, 0, s>>>(img_f32, img_u8, lut, out, H, W, mats, sel);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gaussian kernel helper: xf.square().abs().sum()/N over the stored half spectrum (correlation_flow.cc:184-185)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spec_sqsum_kernel(Src<cpx> x, int count, float n, float* out) {
+  const int b = blockIdx.x;
+  const cpx* p = x.at(b);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const cpx v = __ldg(p + i);
+    acc += (double)hypotf(v.x * v.x - v.y * v.y, 2.f * v.x * v.y);
+  }
+  __shared__ double red[8];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out[b] = (float)t / n;
+  }
+}
+int launch_spec_sqsum(Src<cpx> x, int count, float n, float* out, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  spec_sqsum_kernel<<<B, 256, 0, s>>>(x, count, n, out);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ComputePose bookkeeping
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void key_to_rc(unsigned long long key, int R, int& row, int& col, float& val) {
+  const uint32_t idx = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
+  col = (int)(idx / (uint32_t)R);
+  row = (int)(idx % (uint32_t)R);
+  val = ord2f((uint32_t)(key >> 32));
+}
+
+// GetInfo (correlation_flow.cc:238-243) from sum / sum of squares:  mean((g-m)^2) = (S2 - 2 m S1 + n m^2)/n
+__device__ __forceinline__ float get_info(const PeakStats& st, float peak, double n) {
+  const float m = ((float)st.sum - peak) / (float)(n - 1.0);
+  const double md = (double)m;
+  double var = (st.sumsq - 2.0 * md * st.sum + n * md * md) / n;
+  var = var > 0.0 ? var : 0.0;
+  const float sd = sqrtf((float)var);
+  return (float)((double)(peak - m) / ((double)sd + 1e-7));
+}
+
+__global__ void polar_select_kernel(const PeakStats* __restrict__ polar, int D, int loop_mode, int* __restrict__ sel, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int row, col; float v;
+  key_to_rc(polar[b].key, D, row, col, v);
+  if (loop_mode) { sel[2 * b] = D + row; sel[2 * b + 1] = 2 * D + row; }
+  else sel[b] = row;
+}
+int launch_polar_select(const PeakStats* polar, int D, int loop_mode, int* sel, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  polar_select_kernel<<<(B + 127) / 128, 128, 0, s>>>(polar, D, loop_mode, sel, B);
+  return (int)cudaGetLastError();
+}
+
+__global__ void pose_finalize_kernel(const PeakStats* __restrict__ polar, const PeakStats* __restrict__ trans, AngleTables tabs,
+                                     int H, int W, int D, int Cp, int loop_mode, int index0, PoseRecord* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int prow, pcol; float pval;
+  key_to_rc(polar[b].key, D, prow, pcol, pval);
+  const float info_rot = get_info(polar[b], pval, (double)D * Cp);
+  int trow, tcol, hyp = 0, variant = 0; float tval, info_trans;
+  if (!loop_mode) {
+    key_to_rc(trans[b].key, H, trow, tcol, tval);
+    info_trans = get_info(trans[b], tval, (double)H * W);
+  } else {
+    int r0, c0, r1, c1; float v0, v1;
+    key_to_rc(trans[2 * b].key, H, r0, c0, v0);
+    key_to_rc(trans[2 * b + 1].key, H, r1, c1, v1);
+    const float i0 = get_info(trans[2 * b], v0, (double)H * W), i1 = get_info(trans[2 * b + 1], v1, (double)H * W);
+    if (i0 > i1) { info_trans = i0; trow = r0; tcol = c0; hyp = 0; variant = 1; }     // correlation_flow.cc:121
+    else { info_trans = i1; trow = r1; tcol = c1; hyp = 1; variant = 2; }
+  }
+  PoseRecord r;
+  r.pose[0] = (double)(-(tcol - W / 2));      // pose[0] = trans[1] = -(col - width/2)
+  r.pose[1] = (double)(-(trow - H / 2));      // pose[1] = trans[0] = -(row - height/2)
+  r.pose[2] = tabs.theta[(size_t)variant * D + prow];
+  r.info[0] = (double)info_trans; r.info[1] = (double)info_trans; r.info[2] = (double)info_rot;
+  r.peak[0] = prow; r.peak[1] = pcol; r.peak[2] = trow; r.peak[3] = tcol;
+  r.hyp = hyp; r.index = index0 + b;
+  out[b] = r;
+}
+int launch_pose_finalize(const PeakStats* polar, const PeakStats* trans, AngleTables tabs, int H, int W, int D, int Cp,
+                         int loop_mode, int index0, PoseRecord* out, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  pose_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(polar, trans, tabs, H, W, D, Cp, loop_mode, index0, out, B);
+  return (int)cudaGetLastError();
+}
+
+// best = first record with the strictly largest response.sum(); initial best = (-1,-1,-1) (loop_closure.h:15)
+__global__ void __launch_bounds__(256) scan_reduce_kernel(const PoseRecord* __restrict__ recs, int n, PoseRecord* __restrict__ best) {
+  __shared__ double ssum[256];
+  __shared__ int sidx[256];
+  double bs = -3.0; int bi = -1;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const double s = recs[i].info[0] + recs[i].info[1] + recs[i].info[2];
+    if (s > bs) { bs = s; bi = i; }          // per-thread indices ascend, so '>' keeps the first
+  }
+  ssum[threadIdx.x] = bs; sidx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double s2 = ssum[threadIdx.x + o]; const int i2 = sidx[threadIdx.x + o];
+      const double s1 = ssum[threadIdx.x]; const int i1 = sidx[threadIdx.x];
+      const bool take = (i2 >= 0) && (i1 < 0 || s2 > s1 || (s2 == s1 && i2 < i1));
+      if (take) { ssum[threadIdx.x] = s2; sidx[threadIdx.x] = i2; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (sidx[0] >= 0) *best = recs[sidx[0]];
+    else {
+      PoseRecord r;
+      r.pose[0] = r.pose[1] = r.pose[2] = 0.0;
+      r.info[0] = r.info[1] = r.info[2] = -1.0;
+      r.peak[0] = r.peak[1] = r.peak[2] = r.peak[3] = -1; r.hyp = 0; r.index = -1;
+      *best = r;
+    }
+  }
+}
+int launch_scan_reduce(const PoseRecord* recs, int n, PoseRecord* best, cudaStream_t s) {
+  scan_reduce_kernel<<<1, 256, 0, s>>>(recs, n, best);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace nis

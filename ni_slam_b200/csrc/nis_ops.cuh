@@ -1,0 +1,245 @@
+// nis_ops.cuh -- prologue / epilogue functors fused into the FFT passes (the element-wise arithmetic of
+// src/correlation_flow.cc:89-95, :145-243) plus the batch operand descriptors.
+#pragma once
+#include <math.h>
+#include "nis_fft.cuh"
+
+namespace nis {
+
+// Batch operand: element b lives at base + b*stride, or (DB keyframes) at ptrs[idx[b]] + offset.
+// `shift`: batch entry e reads element e >> shift (two rotation hypotheses of one pair share their operands).
+template <class Tp> struct Src {
+  const Tp* base;
+  long long stride;
+  const Tp* const* ptrs;
+  long long offset;
+  const int* idx;
+  int shift;
+  NIS_HD const Tp* at(int b) const {
+    const int e = b >> shift;
+    const int i = idx ? idx[e] : e;
+    return ptrs ? ptrs[i] + offset : base + (long long)i * stride;
+  }
+};
+template <class Tp> struct Dst {
+  Tp* base;
+  long long stride;
+  NIS_HD Tp* at(int b) const { return base + (long long)b * stride; }
+};
+
+// order-preserving map float -> uint32 (for atomicMax based arg-max)
+NIS_HD uint32_t f2ord(float f) {
+#if defined(__CUDA_ARCH__)
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+NIS_HD float ord2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+// key = (ordered value << 32) | (0xffffffff - column_major_index): max key = largest value, then the FIRST
+// element in column-major order (Eigen maxCoeff on a column-major array, correlation_flow.cc:175).
+NIS_HD unsigned long long peak_key(float v, int row, int col, int R) {
+  return ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(col * R + row));
+}
+
+struct PeakStats {            // per batch element, zero-initialised before the pass
+  unsigned long long key;
+  double sum, sumsq;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// column-pass prologues: load(row, l) -> (col c0+2l, col c0+2l+1) of a row-major real image
+// ---------------------------------------------------------------------------------------------------------
+struct ProRealF32 {
+  Src<float> src; int W;
+  struct Bound {
+    const float* img; int W, c0;
+    NIS_HD cpx load(int row, int l) const { return NIS_LDG(reinterpret_cast<const float2*>(img + (size_t)row * W + c0) + l); }
+  };
+  NIS_HD Bound bind(int b, int c0) const { return Bound{src.at(b), W, c0}; }
+};
+
+// u8 image -> f32/255 through a 256-entry table (utils.cc:110-118: (float)((double)u/255.0))
+struct ProRealU8 {
+  Src<uint8_t> src; int W; const float* lut;
+  struct Bound {
+    const uint8_t* img; int W, c0; const float* lut;
+    NIS_HD cpx load(int row, int l) const {
+      const uint8_t* p = img + (size_t)row * W + c0 + 2 * l;
+      return make_float2(NIS_LDG(&lut[p[0]]), NIS_LDG(&lut[p[1]]));
+    }
+  };
+  NIS_HD Bound bind(int b, int c0) const { return Bound{src.at(b), W, c0, lut}; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// column-pass (c2r) epilogues: put(row, l, re, im), values unnormalised (divide by n = R*C like IFFT :76)
+// ---------------------------------------------------------------------------------------------------------
+struct EpiStore {
+  Dst<float> dst; int W; float n;
+  struct Bound {
+    float* img; int W, c0; float n;
+    NIS_HD void put(int row, int l, float re, float im) {
+      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = make_float2(re / n, im / n);
+    }
+    template <class Sync> NIS_HD void finish(int, Sync&) {}
+  };
+  NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, n}; }
+};
+
+NIS_HD float powi_double(float x, int p) {
+  // Eigen 3.3 ArrayBase::pow(int) -> std::pow(float,int) -> double pow, rounded to float (correlation_flow.cc:213,223)
+  double b = (double)x, r = 1.0;
+  int e = p < 0 ? -p : p;
+  for (int i = 0; i < e; ++i) r *= b;
+  if (p < 0) r = 1.0 / r;
+  return (float)r;
+}
+
+// polynomial kernel (:208-226): k = (xz/n + offset)^power, unnormalised; max|k| reduced into maxbuf[b]
+// gaussian kernel   (:181-206): k = exp(-1/sigma^2 * (xx + zz - 2 xz/n)/n)
+struct EpiKernel {
+  Dst<float> dst; int W; float n;
+  int kernel; float offset; int power; float gcoef;   // gcoef = -1/(sigma*sigma)
+  const float* xx; const float* zz; int zz_shift;     // gaussian: half-spectrum sums / n; zz indexed by b >> zz_shift
+  unsigned int* maxbuf;                               // per batch, float bits of max|k| (>= 0 so uint order = float order)
+  struct Bound {
+    float* img; int W, c0; float n; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
+    NIS_HD float kfun(float v) const {
+      const float xz = v / n;
+      if (kernel == 0) return powi_double(xz + offset, power);
+      return expf(gcoef * ((xxzz - 2.f * xz) / n));
+    }
+    NIS_HD void put(int row, int l, float re, float im) {
+      const float a = kfun(re), b = kfun(im);
+      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = make_float2(a, b);
+      mx = fmaxf(mx, fmaxf(fabsf(a), fabsf(b)));
+    }
+    template <class Sync> NIS_HD void finish(int tid, Sync& sync) { sync.block_max_to(maxp, mx, tid); }
+  };
+  NIS_HD Bound bind(int b, int c0) const {
+    const float s = (kernel == 1) ? (xx[b] + zz[b >> zz_shift]) : 0.f;
+    return Bound{dst.at(b), W, c0, n, kernel, offset, power, gcoef, s, maxbuf + b, 0.f};
+  }
+};
+
+// final response (:173-178, :238-243): arg-max (column-major first), sum and sum of squares of g = v/n; g never stored
+struct EpiPeak {
+  PeakStats* stats; int R; float n;
+  float* g_out; long long g_stride; int W;            // optional debug store (nullptr in production)
+  struct Bound {
+    PeakStats* st; int R, c0; float n; float* g; int W;
+    unsigned long long key; float s, q;
+    NIS_HD void one(int row, int col, float v) {
+      const float x = v / n;
+      const unsigned long long k = peak_key(x, row, col, R);
+      key = k > key ? k : key;
+      s += x; q += x * x;
+      if (g) g[(size_t)row * W + col] = x;
+    }
+    NIS_HD void put(int row, int l, float re, float im) {
+      one(row, c0 + 2 * l, re);
+      one(row, c0 + 2 * l + 1, im);
+    }
+    template <class Sync> NIS_HD void finish(int tid, Sync& sync) { sync.block_peak_to(st, key, (double)s, (double)q, tid); }
+  };
+  NIS_HD Bound bind(int b, int c0) const {
+    return Bound{stats + b, R, c0, n, g_out ? g_out + (long long)b * g_stride : nullptr, W, 0ull, 0.f, 0.f};
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// row-pass prologues: load(ln, c) for local line ln of this CTA; global line g = line0+ln -> (b, k1)
+// ---------------------------------------------------------------------------------------------------------
+struct LineMap {
+  int line0, nrows, W;     // nrows = R/2+1 spectrum rows per batch element
+  NIS_HD void map(int ln, int& b, size_t& off, int& k1) const {
+    const int g = line0 + ln;
+    b = g / nrows; k1 = g - b * nrows;
+    off = (size_t)k1 * W;
+  }
+};
+
+struct ProSpec {      // plain spectrum load
+  Src<cpx> x;
+  struct Bound {
+    Src<cpx> x; LineMap m;
+    NIS_HD cpx load(int ln, int c) const { int b, k1; size_t off; m.map(ln, b, off, k1); return NIS_LDG(x.at(b) + off + c); }
+  };
+  NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
+};
+
+struct ProAbs {       // |F| (correlation_flow.cc:92: fft_result.abs())
+  Src<cpx> x;
+  struct Bound {
+    Src<cpx> x; LineMap m;
+    NIS_HD cpx load(int ln, int c) const {
+      int b, k1; size_t off; m.map(ln, b, off, k1);
+      const cpx v = NIS_LDG(x.at(b) + off + c);
+      return make_float2(hypotf(v.x, v.y), 0.f);
+    }
+  };
+  NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
+};
+
+struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:220-221)
+  Src<cpx> x, z;
+  struct Bound {
+    Src<cpx> x, z; LineMap m;
+    NIS_HD cpx load(int ln, int c) const {
+      int b, k1; size_t off; m.map(ln, b, off, k1);
+      return cmulc(NIS_LDG(x.at(b) + off + c), NIS_LDG(z.at(b) + off + c));
+    }
+  };
+  NIS_HD Bound bind(const LineMap& m) const { return Bound{x, z, m}; }
+};
+
+NIS_HD float bits2f(unsigned int u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// G = T / (Kzz + lambda) * Kxz  (:171-172) with T = FFT(delta[R/2,C/2]) = (-1)^(k1+c) and the deferred
+// max-normalisation of both kernels (FFT is linear: FFT(k/max) = FFT(k)/max).
+// max_zz is indexed by b >> zz_shift and kzz carries the same shift (two rotation hypotheses share one keyframe Kzz).
+struct ProFilter {
+  Src<cpx> kzz, kxz; const unsigned int* max_zz; const unsigned int* max_xz; int zz_shift; float lambda;
+  struct Bound {
+    Src<cpx> kzz, kxz; const unsigned int* max_zz; const unsigned int* max_xz; int zz_shift; float lambda; LineMap m;
+    NIS_HD cpx load(int ln, int c) const {
+      int b, k1; size_t off; m.map(ln, b, off, k1);
+      const int bz = b >> zz_shift;
+      const float izz = 1.0f / bits2f(max_zz[bz]), ixz = 1.0f / bits2f(max_xz[b]);
+      const cpx z = NIS_LDG(kzz.at(b) + off + c), x = NIS_LDG(kxz.at(b) + off + c);
+      const float dr = z.x * izz + lambda, di = z.y * izz;
+      const float t = ((k1 + c) & 1) ? -1.f : 1.f;
+      const float den = dr * dr + di * di;
+      const cpx h = make_float2(t * dr / den, -t * di / den);
+      return cmul(h, make_float2(x.x * ixz, x.y * ixz));
+    }
+  };
+  NIS_HD Bound bind(const LineMap& m) const { return Bound{kzz, kxz, max_zz, max_xz, zz_shift, lambda, m}; }
+};
+
+// row-pass epilogue: store the spectrum line
+struct EpiSpecStore {
+  Dst<cpx> dst;
+  struct Bound {
+    Dst<cpx> dst; LineMap m;
+    NIS_HD void put(int ln, int c, cpx v) { int b, k1; size_t off; m.map(ln, b, off, k1); dst.at(b)[off + c] = v; }
+  };
+  NIS_HD Bound bind(const LineMap& m) const { return Bound{dst, m}; }
+};
+
+}  // namespace nis

@@ -1,0 +1,65 @@
+// nis_row.cu -- row-pass kernels (complex transform along contiguous image columns), sm_100a.
+// One CTA = L consecutive spectrum lines out of the flattened (batch x (R/2+1)) line space.
+#include "nis_device.cuh"
+#include "nis_internal.h"
+#include "nis_sizes.h"
+
+namespace nis {
+
+template <int N, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
+__global__ void __launch_bounds__(T) row_kernel(Pro pro, Epi epi, Twiddles twd, int nrows, int total_lines) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cpx* smem = reinterpret_cast<cpx*>(smem_raw);
+  const int tid = threadIdx.x, line0 = blockIdx.x * L;
+  const int nl = min(L, total_lines - line0);
+  const LineMap m{line0, nrows, N};
+  const auto bp = pro.bind(m);
+  auto be = epi.bind(m);
+  row_phase0<N, R1, R2, L, T, INV>(tid, smem, bp, nl);
+  __syncthreads();
+  CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1> st;
+  row_stage1_read<N, R1, R2, L, T, INV>(tid, smem, twd, nl, st);
+  __syncthreads();
+  row_stage1_write<N, R1, R2, L, T, INV>(tid, smem, nl, st);
+  __syncthreads();
+  row_phase2<N, R1, R2, L, T, INV>(tid, smem, twd, nl, be);
+}
+
+template <int N, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
+static int run_row(Twiddles tw, Pro pro, Epi epi, int nrows, int B, cudaStream_t s) {
+  auto k = row_kernel<N, R1, R2, L, T, INV, Pro, Epi>;
+  const size_t smem = RowGeom<N, R1, R2, L, T>::kSmemBytes;
+  static int attr = set_smem(k, smem);
+  if (attr) return attr;
+  const int total = nrows * B;
+  k<<<(total + L - 1) / L, T, smem, s>>>(pro, epi, tw, nrows, total);
+  return (int)cudaGetLastError();
+}
+
+bool row_size_supported(int N) {
+#define X(n, r1, r2, l, t) if (N == n) return true;
+  NIS_ROW_PLANS(X)
+#undef X
+  return false;
+}
+void plan_radices_row(int N, int r[3]) {
+#define X(n, r1, r2, l, t) if (N == n) { r[0] = 16; r[1] = r1; r[2] = r2; return; }
+  NIS_ROW_PLANS(X)
+#undef X
+  r[0] = r[1] = r[2] = 0;
+}
+
+#define ROW_DISPATCH(INV)                \
+  if (B <= 0) return 0;                  \
+  switch (N) {                           \
+    NIS_ROW_PLANS(ROW_CASE_##INV)        \
+    default: return -1;                  \
+  }
+#define ROW_CASE_false(n, r1, r2, l, t) case n: return run_row<n, r1, r2, l, t, false>(tw, pro, epi, nrows, B, s);
+#define ROW_CASE_true(n, r1, r2, l, t) case n: return run_row<n, r1, r2, l, t, true>(tw, pro, epi, nrows, B, s);
+int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
+int launch_row_inv_abs(int N, Twiddles tw, ProAbs pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
+int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
+int launch_row_inv_filter(int N, Twiddles tw, ProFilter pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
+
+}  // namespace nis

@@ -1,0 +1,162 @@
+// Host emulation of the CUDA FFT passes: each CTA is replayed thread by thread, phase by phase (a phase is the
+// code between two __syncthreads()).  Lets tests/test_emulation.py validate the kernels' index logic against
+// numpy without a GPU.  Build: g++ -O2 -shared -fPIC -I ni_slam_b200/csrc tests/cpp/emu_fft.cc
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "nis_ops.cuh"
+#include "nis_sizes.h"
+
+using namespace nis;
+
+struct HostSync {
+  void block_max_to(unsigned int* p, float mx, int) {
+    union { float f; unsigned int u; } c; c.f = mx;
+    if (c.u > *p) *p = c.u;
+  }
+  void block_peak_to(PeakStats* st, unsigned long long key, double s, double q, int) {
+    if (key > st->key) st->key = key;
+    st->sum += s; st->sumsq += q;
+  }
+};
+
+static void make_tw(int R0, int R1, int R2, std::vector<cpx>& t1, std::vector<cpx>& t2) {
+  const int N = R0 * R1 * R2;
+  t1.assign((size_t)(R1 > 1 ? (R1 - 1) : 1) * R0, cpx{1, 0});
+  t2.assign((size_t)(R2 > 1 ? (R2 - 1) : 1) * R0 * R1, cpx{1, 0});
+  for (int r = 1; r < R1; ++r)
+    for (int k = 0; k < R0; ++k) {
+      double a = -2.0 * M_PI * r * k / (double)(R0 * R1);
+      t1[(size_t)(r - 1) * R0 + k] = cpx{(float)cos(a), (float)sin(a)};
+    }
+  for (int r = 1; r < R2; ++r)
+    for (int k = 0; k < R0 * R1; ++k) {
+      double a = -2.0 * M_PI * r * k / (double)N;
+      t2[(size_t)(r - 1) * R0 * R1 + k] = cpx{(float)cos(a), (float)sin(a)};
+    }
+}
+
+// ---- column forward: real [B][N][W] -> half-transformed spectrum [B][N/2+1][W]
+template <int N, int R0, int R1, int R2, int T>
+static void emu_col_fwd(const float* x, int B, int W, cpx* out) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  std::vector<cpx> t1, t2; make_tw(R0, R1, R2, t1, t2);
+  Twiddles twd{t1.data(), t2.data()};
+  std::vector<cpx> smem((size_t)N * kColLanes);
+  std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
+  ProRealF32 pro{Src<float>{x, (long long)N * W, nullptr, 0, nullptr, 0}, W};
+  for (int b = 0; b < B; ++b)
+    for (int c0 = 0; c0 < W; c0 += 32) {
+      auto bp = pro.bind(b, c0);
+      for (int t = 0; t < T; ++t) col_fwd_phase0<N, R0, R1, R2, T>(t, smem.data(), bp);
+      for (int t = 0; t < T; ++t) col_stage1_read<N, R0, R1, R2, T, false>(t, smem.data(), twd, st[t]);
+      for (int t = 0; t < T; ++t) col_stage1_write<N, R0, R1, R2, T, false>(t, smem.data(), st[t]);
+      for (int t = 0; t < T; ++t) col_fwd_phase2<N, R0, R1, R2, T>(t, smem.data(), twd, out + (size_t)b * (N / 2 + 1) * W, W, c0);
+    }
+}
+
+// ---- column inverse: spectrum [B][N/2+1][W] -> real [B][N][W] / n
+template <int N, int R0, int R1, int R2, int T, class Epi>
+static void emu_col_inv(const cpx* in, int B, int W, Epi& epi) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  std::vector<cpx> t1, t2; make_tw(R0, R1, R2, t1, t2);
+  Twiddles twd{t1.data(), t2.data()};
+  std::vector<cpx> smem((size_t)N * kColLanes);
+  std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
+  HostSync sync;
+  for (int b = 0; b < B; ++b)
+    for (int c0 = 0; c0 < W; c0 += 32) {
+      std::vector<typename Epi::Bound> eb(T, epi.bind(b, c0));
+      for (int t = 0; t < T; ++t) col_inv_phase0<N, R0, R1, R2, T>(t, smem.data(), in + (size_t)b * (N / 2 + 1) * W, W, c0);
+      for (int t = 0; t < T; ++t) col_stage1_read<N, R0, R1, R2, T, true>(t, smem.data(), twd, st[t]);
+      for (int t = 0; t < T; ++t) col_stage1_write<N, R0, R1, R2, T, true>(t, smem.data(), st[t]);
+      for (int t = 0; t < T; ++t) col_inv_phase2<N, R0, R1, R2, T>(t, smem.data(), twd, eb[t]);
+      for (int t = 0; t < T; ++t) eb[t].finish(t, sync);
+    }
+}
+
+// ---- row pass: [nlines][N] complex, forward or inverse, plain load/store
+template <int N, int R1, int R2, int L, int T, bool INV>
+static void emu_row(const cpx* in, int total_lines, cpx* out) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+  std::vector<cpx> t1, t2; make_tw(16, R1, R2, t1, t2);
+  Twiddles twd{t1.data(), t2.data()};
+  std::vector<cpx> smem((size_t)L * Gm::PITCH);
+  std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
+  ProSpec pro{Src<cpx>{in, (long long)total_lines * N, nullptr, 0, nullptr, 0}};
+  EpiSpecStore epi{Dst<cpx>{out, (long long)total_lines * N}};
+  for (int line0 = 0; line0 < total_lines; line0 += L) {
+    const int nl = total_lines - line0 < L ? total_lines - line0 : L;
+    LineMap m{line0, total_lines, N};
+    auto bp = pro.bind(m);
+    auto be = epi.bind(m);
+    for (int t = 0; t < T; ++t) row_phase0<N, R1, R2, L, T, INV>(t, smem.data(), bp, nl);
+    for (int t = 0; t < T; ++t) row_stage1_read<N, R1, R2, L, T, INV>(t, smem.data(), twd, nl, st[t]);
+    for (int t = 0; t < T; ++t) row_stage1_write<N, R1, R2, L, T, INV>(t, smem.data(), nl, st[t]);
+    for (int t = 0; t < T; ++t) row_phase2<N, R1, R2, L, T, INV>(t, smem.data(), twd, nl, be);
+  }
+}
+
+extern "C" {
+
+// returns 0 ok, -1 unsupported size
+int emu_col_fwd_f32(const float* x, int B, int N, int W, float* out) {
+#define X(n, f0, f1, f2, i0, i1, i2, t) \
+  if (N == n) { emu_col_fwd<n, f0, f1, f2, t>(x, B, W, (cpx*)out); return 0; }
+  NIS_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
+int emu_col_inv_store(const float* in, int B, int N, int W, float* out) {
+  EpiStore epi{Dst<float>{out, (long long)N * W}, W, (float)((long long)N * W)};
+#define X(n, f0, f1, f2, i0, i1, i2, t) \
+  if (N == n) { emu_col_inv<n, i0, i1, i2, t>((const cpx*)in, B, W, epi); return 0; }
+  NIS_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
+// c2r column pass with the peak epilogue; stats: B x {key(u64), sum, sumsq}
+int emu_col_inv_peak(const float* in, int B, int N, int W, void* stats, float* g_out) {
+  memset(stats, 0, sizeof(PeakStats) * B);
+  EpiPeak epi{(PeakStats*)stats, N, (float)((long long)N * W), g_out, (long long)N * W, W};
+#define X(n, f0, f1, f2, i0, i1, i2, t) \
+  if (N == n) { emu_col_inv<n, i0, i1, i2, t>((const cpx*)in, B, W, epi); return 0; }
+  NIS_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
+int emu_col_inv_kernel(const float* in, int B, int N, int W, float* out, unsigned int* maxbuf, float offset, int power) {
+  memset(maxbuf, 0, sizeof(unsigned int) * B);
+  EpiKernel epi{Dst<float>{out, (long long)N * W}, W, (float)((long long)N * W), 0, offset, power, 0.f, nullptr, nullptr, 0, maxbuf};
+#define X(n, f0, f1, f2, i0, i1, i2, t) \
+  if (N == n) { emu_col_inv<n, i0, i1, i2, t>((const cpx*)in, B, W, epi); return 0; }
+  NIS_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
+int emu_row(const float* in, int total_lines, int N, int inverse, float* out) {
+#define X(n, r1, r2, l, t)                                                              \
+  if (N == n) {                                                                         \
+    if (inverse) emu_row<n, r1, r2, l, t, true>((const cpx*)in, total_lines, (cpx*)out); \
+    else emu_row<n, r1, r2, l, t, false>((const cpx*)in, total_lines, (cpx*)out);        \
+    return 0;                                                                           \
+  }
+  NIS_ROW_PLANS(X)
+#undef X
+  return -1;
+}
+
+// in-register DFT check: v (R complex) -> DFT
+int emu_dft(float* v, int R, int inverse) {
+#define D(r) if (R == r) { if (inverse) Dft<r, true>::run((cpx*)v); else Dft<r, false>::run((cpx*)v); return 0; }
+  D(1) D(2) D(3) D(4) D(5) D(6) D(8) D(9) D(10) D(12) D(15) D(16)
+#undef D
+  return -1;
+}
+}

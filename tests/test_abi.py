@@ -1,0 +1,126 @@
+"""CPU tests: the C-ABI library builds, loads and exports every symbol include/nislam.h declares; the emulated CUDA
+FFT passes (tests/cpp/emu_fft.cc replays each CTA thread by thread on the host) agree with numpy."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ni_slam_b200 import build, api
+    lib_path = build.build()
+    lib = C.CDLL(lib_path)
+    hdr = open(os.path.join(ROOT, "include", "nislam.h")).read()
+    declared = sorted(set(re.findall(r"\b(nis_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(api.SYMBOLS) == declared
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ni_slam_b200 as nis
+    with pytest.raises(nis.NisError):
+        nis.CorrelationFlow(nis.CFConfig(), 480, 640)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ni_slam_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.lower(), os.path.join(dp, f)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(ROOT, "tests", "cpp", "_build", "libemu.so")
+    src = os.path.join(ROOT, "tests", "cpp", "emu_fft.cc")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    deps = [src] + [os.path.join(ROOT, "ni_slam_b200", "csrc", f) for f in ("nis_fft.cuh", "nis_ops.cuh", "nis_sizes.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", os.path.join(ROOT, "ni_slam_b200", "csrc"),
+                               src, "-o", so])
+    return C.CDLL(so)
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_emulated_register_dfts(emu):
+    rng = np.random.default_rng(0)
+    for R in (1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16):
+        for inv in (0, 1):
+            v = (rng.standard_normal(R) + 1j * rng.standard_normal(R)).astype(np.complex64)
+            w = v.copy()
+            assert emu.emu_dft(P(w), R, inv) == 0
+            ref = np.fft.ifft(v) * R if inv else np.fft.fft(v)
+            assert np.abs(w - ref).max() / np.abs(ref).max() < 1e-6, (R, inv)
+
+
+@pytest.mark.parametrize("N", [640, 480, 1280, 128, 64])
+def test_emulated_row_pass(emu, N):
+    rng = np.random.default_rng(N)
+    nl = 11          # not a multiple of the CTA's line count: exercises the ragged last CTA
+    x = (rng.standard_normal((nl, N)) + 1j * rng.standard_normal((nl, N))).astype(np.complex64)
+    for inv in (0, 1):
+        out = np.zeros_like(x)
+        assert emu.emu_row(P(x), nl, N, inv, P(out)) == 0
+        ref = np.fft.ifft(x.astype(np.complex128), axis=1) * N if inv else np.fft.fft(x.astype(np.complex128), axis=1)
+        assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-6
+
+
+@pytest.mark.parametrize("N,W", [(480, 64), (720, 32), (960, 32), (96, 64), (80, 32)])
+def test_emulated_column_pass(emu, N, W):
+    rng = np.random.default_rng(N)
+    B = 2
+    x = rng.standard_normal((B, N, W)).astype(np.float32)
+    out = np.zeros((B, N // 2 + 1, W), np.complex64)
+    assert emu.emu_col_fwd_f32(P(x), B, N, W, P(out)) == 0
+    ref = np.fft.rfft(x.astype(np.float64), axis=1)
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-6
+    back = np.zeros((B, N, W), np.float32)
+    assert emu.emu_col_inv_store(P(out), B, N, W, P(back)) == 0
+    assert np.abs(back * W - x).max() < 1e-5
+    # peak epilogue: arg-max (column-major first), sum, sum of squares
+    stats = np.zeros((B, 3), np.uint64)
+    g = np.zeros((B, N, W), np.float32)
+    assert emu.emu_col_inv_peak(P(out), B, N, W, P(stats), P(g)) == 0
+    for b in range(B):
+        key = int(stats[b, 0])
+        col, row = divmod(0xFFFFFFFF - (key & 0xFFFFFFFF), N)
+        assert (col, row) == divmod(int(np.argmax(g[b].T.reshape(-1))), N)
+        s, q = stats[b, 1:].view(np.float64)
+        assert abs(q / np.square(g[b].astype(np.float64)).sum() - 1) < 1e-5
+    # kernel epilogue: (x/n + offset)^3 and max|k|
+    kk = np.zeros((B, N, W), np.float32)
+    mx = np.zeros(B, np.uint32)
+    assert emu.emu_col_inv_kernel(P(out), B, N, W, P(kk), P(mx), C.c_float(0.1), 3) == 0
+    want = ((back.astype(np.float32) + np.float32(0.1)).astype(np.float64) ** 3).astype(np.float32)
+    assert np.abs(kk - want).max() < 1e-5 * np.abs(want).max()
+    assert np.allclose(mx.view(np.float32), np.abs(kk).reshape(B, -1).max(axis=1))
+
+
+def test_argmax_tiebreak_rule_in_kernel_key(emu):
+    # duplicated maxima -> smallest col, then smallest row.  Feed a spectrum whose inverse is exactly
+    # constant (only the DC bin set) so every element ties: the winner must be (row 0, col 0).
+    N, W = 96, 64
+    spec = np.zeros((1, N // 2 + 1, W), np.complex64)
+    spec[0, 0, 0] = N          # after the (omitted) row pass this is "DC per column": every column gets the same constant
+    spec[0, 0, :] = N
+    stats = np.zeros((1, 3), np.uint64)
+    g = np.zeros((1, N, W), np.float32)
+    assert emu.emu_col_inv_peak(P(spec), 1, N, W, P(stats), P(g)) == 0
+    assert np.all(g == g[0, 0, 0])
+    key = int(stats[0, 0])
+    assert divmod(0xFFFFFFFF - (key & 0xFFFFFFFF), N) == (0, 0)

@@ -1,0 +1,281 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ni_slam_b200.api -> libnislam.so), against
+the CPU oracle (oracle/nislam_oracle.c) on the same seeded inputs and against the committed golden vectors.
+
+Parity bar: translation-stage (row, col) bit-exact; polar row equal mod D/2 (the polar peak has an
+exact 180-degree twin); dx, dy exact; theta equal mod 2 pi to 1e-6; info within 3e-4 relative (two f32
+FFT chains agree to ~6e-5 on info; measured between the scipy and the C restatement); scan winner identical.
+"""
+import numpy as np
+import pytest
+
+import oracle_c as oc
+
+pytestmark = pytest.mark.gpu
+
+H, W, D, CP = 480, 640, 720, 480
+INFO_RTOL = 3e-4
+
+
+def wrap_pi(a):
+    return (a + np.pi) % (2 * np.pi) - np.pi
+
+
+@pytest.fixture(scope="module")
+def cf():
+    import ni_slam_b200 as nis
+    c = nis.CorrelationFlow(nis.CFConfig(), H, W)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return oc.make_cfg()
+
+
+@pytest.fixture(scope="module")
+def imgs(golden_pairs):
+    return golden_pairs["images"]
+
+
+# ------------------------------------------------------------------ stages
+def test_fft2_and_ifft2_match_oracle(cf):
+    rng = np.random.default_rng(0)
+    for which, (R, C) in enumerate(((H, W), (D, CP))):
+        x = rng.random((R, C)).astype(np.float32)
+        F = cf.debug_fft2(x, which)
+        Fo = oc.fft2(x)
+        assert np.abs(F - Fo).max() / np.abs(Fo).max() < 1e-6
+        xb = cf.debug_ifft2(F, which)
+        assert np.abs(xb - x).max() < 2e-6
+        assert np.abs(xb - oc.ifft2(Fo)).max() < 2e-6
+
+
+def test_impulse_spectrum_known_answer(cf):
+    x = np.zeros((H, W), np.float32)
+    x[H // 2, W // 2] = 1
+    F = cf.debug_fft2(x, 0)
+    kr, kc = np.meshgrid(np.arange(H // 2 + 1), np.arange(W), indexing="ij")
+    assert np.abs(F - np.where((kr + kc) % 2 == 0, 1.0, -1.0)).max() < 2e-6
+
+
+def test_polar_warp_bit_exact(cf):
+    rng = np.random.default_rng(1)
+    power = rng.random((H, W)).astype(np.float32)
+    want = oc.polar(oc.fftshift(oc.remove_zero_component(power)), D, CP)
+    got = cf.debug_polar(power)
+    assert np.array_equal(got, want)
+
+
+def test_rotate_bit_exact(cf, golden_stages):
+    rng = np.random.default_rng(2)
+    img = rng.random((H, W)).astype(np.float32)
+    for d in golden_stages["rot_degrees"]:
+        assert np.array_equal(cf.debug_rotate(img, d), oc.rotate(img, d)), d
+
+
+def test_estimate_trans_stage(cf, cfg, imgs):
+    a, b = oc.normalize_u8(imgs[0]), oc.normalize_u8(imgs[1])
+    Fa, Pa = oc.compute_intermedium(cfg, a)
+    Fb, Pb = oc.compute_intermedium(cfg, b)
+    for which, (za, zb, R, C) in enumerate(((Fa, Fb, H, W), (Pa, Pb, D, CP))):
+        io, to, po, go = oc.estimate_trans(cfg, za, zb, R, C, want_g=True)
+        ig, tg, pg, gg = cf.debug_estimate_trans(za, zb, which, want_g=True)
+        if which == 0:
+            assert pg == po and tg == to
+        else:
+            assert pg[0] % (D // 2) == po[0] % (D // 2)
+        assert abs(ig - io) / io < INFO_RTOL
+        assert np.sqrt(np.mean((gg - go) ** 2)) / go.std() < 2e-2
+
+
+# ------------------------------------------------------------------ features
+def test_features_match_oracle(cf, cfg, imgs):
+    for i in (0, 3):
+        fr = cf.ComputeIntermedium(imgs[i])                          # u8 path (ConvertMatToNormalizedArray on the GPU)
+        F, P = fr.GetFFTResult()
+        Fo, Po = oc.compute_intermedium(cfg, oc.normalize_u8(imgs[i]))
+        assert np.abs(F - Fo).max() / np.abs(Fo).max() < 1e-6
+        assert np.abs(P - Po).max() / np.abs(Po).max() < 2e-6
+        fr2 = cf.ComputeIntermedium(oc.normalize_u8(imgs[i]))        # f32 path
+        F2, P2 = fr2.GetFFTResult()
+        assert np.array_equal(F, F2) and np.array_equal(P, P2)
+
+
+def test_feature_checksums_golden(cf, golden_pairs, imgs):
+    F, P = cf.ComputeIntermedium(imgs[0]).GetFFTResult()
+    assert abs(np.abs(F).astype(np.float64).sum() / golden_pairs["a_fft_result_abs_sum"] - 1) < 1e-5
+    assert abs(np.abs(P).astype(np.float64).sum() / golden_pairs["a_fft_polar_abs_sum"] - 1) < 1e-5
+
+
+# ------------------------------------------------------------------ ComputePose
+def _check(info, pose, pk, r):
+    assert pose[0] == r[2] and pose[1] == r[3], (pose, r)
+    assert abs(wrap_pi(pose[2] - r[4])) < 1e-6, (pose, r)
+    assert pk["trans"] == (int(r[10]), int(r[11]))
+    assert pk["polar"][0] % (D // 2) == int(r[8]) % (D // 2)
+    assert np.allclose(info, r[5:8], rtol=INFO_RTOL), (info, r[5:8])
+
+
+def test_compute_pose_golden(cf, golden_pairs, imgs):
+    frames = [cf.ComputeIntermedium(u) for u in imgs]
+    for r in golden_pairs["pose_rows"]:
+        i, mode = int(r[0]), int(r[1])
+        info, pose, pk = cf.ComputePose(frames[0], frames[i], bool(mode), return_peaks=True)
+        _check(info, pose, pk, r)
+
+
+def test_compute_pose_matches_oracle_on_random_pairs(cf, cfg, golden_pairs, imgs):
+    # random circular rolls + the golden crops as "last" frames: exercises other keyframes than image 0
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        ia, ib = rng.choice(len(imgs) - 1, 2, replace=False)
+        a, b = oc.normalize_u8(imgs[ia]), oc.normalize_u8(imgs[ib])
+        Fa, Pa = oc.compute_intermedium(cfg, a)
+        Fb, Pb = oc.compute_intermedium(cfg, b)
+        fa, fb = cf.ComputeIntermedium(imgs[ia]), cf.ComputeIntermedium(imgs[ib])
+        for mode in (True, False):
+            io, po, pko = oc.compute_pose(cfg, Fa, b, Pa, Pb, mode)
+            ig, pg, pkg = cf.ComputePose(fa, fb, mode, return_peaks=True)
+            if pkg["polar"][0] % (D // 2) != pko["polar"][0] % (D // 2):
+                continue          # uncorrelated pair: polar peak is noise, nothing to compare
+            same_twin = pkg["polar"][0] == pko["polar"][0]
+            if same_twin or not mode:
+                assert pkg["trans"] == pko["trans"], (ia, ib, mode)
+                assert (pg[0], pg[1]) == (po[0], po[1])
+                assert np.allclose(ig, io, rtol=INFO_RTOL)
+
+
+def test_imported_reference_layout_frames(cf, cfg, imgs):
+    # frames built from reference-layout arrays (as MapBuilder holds them) give the same answer
+    a, b = oc.normalize_u8(imgs[0]), oc.normalize_u8(imgs[2])
+    Fa, Pa = oc.compute_intermedium(cfg, a)
+    Fb, Pb = oc.compute_intermedium(cfg, b)
+    fa, fb = cf.ImportFrame(a, Fa, Pa), cf.ImportFrame(b, Fb, Pb)
+    F2, P2 = fa.GetFFTResult()
+    assert np.array_equal(F2, Fa) and np.array_equal(P2, Pa)
+    io, po, pko = oc.compute_pose(cfg, Fa, b, Pa, Pb, True)
+    ig, pg, pkg = cf.ComputePose(fa, fb, True, return_peaks=True)
+    assert (pg[0], pg[1]) == (po[0], po[1]) == (11.0, -6.0)
+    assert np.allclose(ig, io, rtol=INFO_RTOL)
+
+
+def test_circular_roll_known_answers(cf, imgs):
+    a = imgs[0]
+    fa = cf.ComputeIntermedium(a)
+    base = None
+    for sy, sx in ((0, 0), (3, 0), (0, -9), (17, 25)):
+        fb = cf.ComputeIntermedium(np.roll(a, (sy, sx), axis=(0, 1)))
+        info, pose, pk = cf.ComputePose(fa, fb, True, return_peaks=True)
+        assert (pose[0], pose[1]) == (-sx, -sy)
+        assert abs(wrap_pi(pose[2])) < 1e-6
+        assert pk["polar"][0] % (D // 2) == 0
+        if base is None:
+            base = info
+            assert pk["trans"] == (H // 2, W // 2)
+        assert np.allclose(info, base, rtol=1e-3)
+
+
+def test_gaussian_kernel_and_invalid_kernel(golden_pairs, imgs):
+    import ni_slam_b200 as nis
+    c = nis.CorrelationFlow(nis.CFConfig(kernel=1), H, W)
+    fa, fb = c.ComputeIntermedium(imgs[0]), c.ComputeIntermedium(imgs[2])
+    info, pose = c.ComputePose(fa, fb, True)
+    r = golden_pairs["gauss_row"]
+    assert pose[0] == r[2] and pose[1] == r[3] and abs(wrap_pi(pose[2] - r[4])) < 1e-6
+    assert np.allclose(info, r[5:8], rtol=INFO_RTOL)
+    c.close()
+    bad = nis.CorrelationFlow(nis.CFConfig(kernel=7), H, W)          # ctor succeeds, EstimateTrans throws (:168)
+    fa, fb = bad.ComputeIntermedium(imgs[0]), bad.ComputeIntermedium(imgs[2])
+    with pytest.raises(ValueError, match="Received invalid kernel type"):
+        bad.ComputePose(fa, fb, True)
+    bad.close()
+
+
+def test_unsupported_sizes_are_rejected():
+    import ni_slam_b200 as nis
+    with pytest.raises(nis.NisError):
+        nis.CorrelationFlow(nis.CFConfig(), 481, 640)      # odd height
+    with pytest.raises(nis.NisError):
+        nis.CorrelationFlow(nis.CFConfig(), 500, 640)      # no instantiated column plan
+
+
+# ------------------------------------------------------------------ stream
+def test_track_stream_matches_oracle(cf, cfg, imgs):
+    frames = np.stack([imgs[0], imgs[1], imgs[2], imgs[3], imgs[0], imgs[5]])
+    poses, infos = cf.TrackStream(frames)
+    po, io = oc.track_stream(cfg, frames, threads=4)
+    assert poses.shape == (5, 3)
+    for t in range(5):
+        if io[t, 0] < 30 or io[t, 2] < 30:        # tracking lost in the oracle: peaks are noise (map_builder.cc:132)
+            continue
+        assert (poses[t, 0], poses[t, 1]) == (po[t, 0], po[t, 1]), t
+        assert abs(wrap_pi(poses[t, 2] - po[t, 2])) < 1e-6
+        assert np.allclose(infos[t], io[t], rtol=INFO_RTOL)
+    # batch-size independence: same stream, batch of 2 (ragged last batch)
+    cf.set_batch(2)
+    poses2, infos2 = cf.TrackStream(frames)
+    cf.set_batch(0)
+    assert np.array_equal(poses, poses2) and np.allclose(infos, infos2, rtol=1e-6)
+    # single frame: nothing to solve
+    p1, i1 = cf.TrackStream(frames[:1])
+    assert p1.shape == (0, 3)
+
+
+# ------------------------------------------------------------------ loop-closure scan
+def test_loop_scan_matches_oracle(cf, cfg, imgs):
+    import ni_slam_b200 as nis
+    lc = nis.LoopClosure(nis.LoopClosureConfig(position_response_thr=60, angle_response_thr=60), cf)
+    lc.clear()
+    order = [3, 0, 0, 5, 0, 6, 2]                       # three identical copies of keyframe 0: the FIRST must win
+    ids = [10 + k for k in range(len(order))]
+    dists = [float(k) for k in range(len(order))]
+    lc.AddImages(imgs[order], ids, dists)
+    assert lc.size() == len(order)
+    q = cf.ComputeIntermedium(imgs[1])
+    res, allr = lc.FindLoopClosure(q, 99, 50.0, return_all=True)
+    feats = [oc.compute_intermedium(cfg, oc.normalize_u8(imgs[i])) for i in order]
+    qi = oc.normalize_u8(imgs[1])
+    _, qP = oc.compute_intermedium(cfg, qi)
+    kfs = [(ids[k], feats[k][0], feats[k][1], dists[k]) for k in range(len(order))]
+    thr = oc.LoopConfigC(60.0, 60.0, 0, 0.0)
+    ro = oc.find_loop_closure(cfg, thr, qi, qP, 99, 50.0, kfs)
+    assert res.found and ro["found"]
+    assert res.loop_slot == ro["index"] == 1 and res.loop_frame_id == ro["frame_id"] == 11
+    assert tuple(res.relative_pose[:2]) == tuple(ro["relative_pose"][:2]) == (7.0, 0.0)
+    assert np.allclose(res.response, ro["response"], rtol=INFO_RTOL)
+    assert res.evaluated == len(order)
+    assert np.array_equal(allr[1], allr[2]) and np.array_equal(allr[1], allr[4])     # identical keyframes, identical bits
+    # explicit candidate list in a different order: iteration order decides ties
+    res2 = lc.FindLoopClosure(q, 99, 50.0, candidate_slots=[6, 4, 2, 1])
+    assert res2.loop_slot == 4
+    # filters (loop_closure.cc:43-53)
+    lc2 = nis.LoopClosure(nis.LoopClosureConfig(60, 60, frame_gap_thr=89, distance_thr=0.0), cf)
+    r3 = lc2.FindLoopClosure(q, 99, 50.0)
+    assert r3.loop_slot == 0 and r3.evaluated == 1
+    lc3 = nis.LoopClosure(nis.LoopClosureConfig(60, 60, frame_gap_thr=0, distance_thr=49.5), cf)
+    r4 = lc3.FindLoopClosure(q, 99, 50.0)
+    assert r4.loop_slot == 0 and r4.evaluated == 1
+    # everything filtered / empty list: initial best (-1,-1,-1), not found
+    lc4 = nis.LoopClosure(nis.LoopClosureConfig(60, 60, frame_gap_thr=1000), cf)
+    r5 = lc4.FindLoopClosure(q, 99, 50.0)
+    assert (not r5.found) and r5.loop_slot == -1 and np.array_equal(r5.response, [-1, -1, -1]) and r5.evaluated == 0
+    # batch-size independence
+    cf.set_batch(3)
+    res6 = lc.FindLoopClosure(q, 99, 50.0)
+    cf.set_batch(0)
+    assert res6.loop_slot == res.loop_slot and np.array_equal(res6.response, res.response)
+    # rank reduction helper: shard [0..3] and [4..6], global order = slot
+    ra = lc.FindLoopClosure(q, 99, 50.0, candidate_slots=[0, 1, 2, 3])
+    rb = lc.FindLoopClosure(q, 99, 50.0, candidate_slots=[4, 5, 6])
+    red, win = lc.Reduce([rb, ra], order=[rb.loop_slot, ra.loop_slot])
+    assert win == 1 and red.loop_slot == 1 and red.found and red.evaluated == 7
+    lc.clear()
+
+
+def test_large_rotation_loop_mode(cf, golden_pairs, imgs):
+    # image 6 is rotated by 152 degrees: only loop mode (two hypotheses) recovers it
+    fa, fb = cf.ComputeIntermedium(imgs[0]), cf.ComputeIntermedium(imgs[6])
+    info, pose, pk = cf.ComputePose(fa, fb, False, return_peaks=True)
+    assert (pose[0], pose[1]) == (-41.0, -17.0)
+    assert abs(wrap_pi(pose[2] - np.deg2rad(152.0))) < 1e-6
