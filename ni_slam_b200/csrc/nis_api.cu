@@ -116,6 +116,14 @@ static int fail(nis_ctx* c, int status, const char* what, int cuda_err = 0) {
     if (s_ != NIS_OK) return s_; \
   } while (0)
 
+// Host->device copies go on the context's (non-blocking) stream: a plain cudaMemcpy from pageable memory may return
+// before the DMA lands and is not ordered against kernels on a non-blocking stream.
+static cudaError_t h2d(nis_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(ctx->stream);
+}
+
 template <class T> static Src<T> src_slab(const T* base, long long stride, int shift = 0) {
   return Src<T>{base, stride, nullptr, 0, nullptr, shift};
 }
@@ -174,7 +182,7 @@ static int build_tables(nis_ctx* ctx) {
     plan_radices_row(z.C, r);        host_twiddles(r, tw, o[6 * s + 4], o[6 * s + 5]);
   }
   RESERVE(ctx->tw, tw.size() * sizeof(cpx));
-  CU(cudaMemcpy(ctx->tw.p, tw.data(), tw.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->tw.p, tw.data(), tw.size() * sizeof(cpx)));
   const cpx* base = ctx->tw.as<cpx>();
   for (int s = 0; s < 2; ++s) {
     SizeClass& z = ctx->sz[s];
@@ -186,7 +194,7 @@ static int build_tables(nis_ctx* ctx) {
   float lut[256];
   for (int u = 0; u < 256; ++u) lut[u] = (float)((double)(float)u / 255.0);
   RESERVE(ctx->lut, sizeof lut);
-  CU(cudaMemcpy(ctx->lut.p, lut, sizeof lut, cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->lut.p, lut, sizeof lut));
   // warpPolar angle / radius tables (correlation_flow.cc:228-236 -> cv::warpPolar)
   std::vector<double> cs(2 * (size_t)D);
   const double Kangle = 2.0 * M_PI / D;
@@ -196,8 +204,8 @@ static int build_tables(nis_ctx* ctx) {
   for (int q = 0; q < Cp; ++q) rho[q] = (float)(q * Kmag);
   RESERVE(ctx->cs, cs.size() * sizeof(double));
   RESERVE(ctx->rho, rho.size() * sizeof(float));
-  CU(cudaMemcpy(ctx->cs.p, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ctx->rho.p, rho.data(), rho.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->cs.p, cs.data(), cs.size() * sizeof(double)));
+  CU(h2d(ctx, ctx->rho.p, rho.data(), rho.size() * sizeof(float)));
   // per polar-peak-row angle tables (correlation_flow.cc:105-136): every float/double step of the reference, once
   std::vector<double> mats(3 * (size_t)D * 6), theta(3 * (size_t)D);
   for (int row = 0; row < D; ++row) {
@@ -221,8 +229,8 @@ static int build_tables(nis_ctx* ctx) {
   mats.resize(mats.size() + 6, 0.0);
   RESERVE(ctx->mats, mats.size() * sizeof(double));
   RESERVE(ctx->theta, theta.size() * sizeof(double));
-  CU(cudaMemcpy(ctx->mats.p, mats.data(), mats.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ctx->theta.p, theta.data(), theta.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->mats.p, mats.data(), mats.size() * sizeof(double)));
+  CU(h2d(ctx, ctx->theta.p, theta.data(), theta.size() * sizeof(double)));
   return NIS_OK;
 }
 
@@ -486,7 +494,7 @@ int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out)
   TRY(frame_alloc(ctx, false, &f));
   std::vector<float> rm(ctx->sz[0].real);
   transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());      // [W][H] lines -> [H][W]
-  cudaError_t e = cudaMemcpy(f->img_f32, rm.data(), rm.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaError_t e = h2d(ctx, f->img_f32, rm.data(), rm.size() * sizeof(float));
   int st = e == cudaSuccess ? features_batch(ctx, src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1,
                                               Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
                             : fail(ctx, NIS_ERR_CUDA, "cudaMemcpy image", (int)e);
@@ -518,12 +526,12 @@ int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft
   TRY(frame_alloc(ctx, false, &f));
   std::vector<float> rm(ctx->sz[0].real);
   transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());
-  cudaError_t e = cudaMemcpy(f->img_f32, rm.data(), rm.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaError_t e = h2d(ctx, f->img_f32, rm.data(), rm.size() * sizeof(float));
   for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
     const SizeClass& z = ctx->sz[s];
     std::vector<cpx> t(z.spec);
     transpose_to((const cpx*)(s == 0 ? fft_result : fft_polar), z.C, z.R / 2 + 1, t.data());
-    e = cudaMemcpy(s == 0 ? f->F : f->P, t.data(), z.spec * sizeof(cpx), cudaMemcpyHostToDevice);
+    e = h2d(ctx, s == 0 ? f->F : f->P, t.data(), z.spec * sizeof(cpx));
   }
   if (e != cudaSuccess) { nis_frame_free(ctx, f); return fail(ctx, NIS_ERR_CUDA, "frame import copy", (int)e); }
   *out = f;
@@ -618,9 +626,9 @@ static int db_reserve_slots(nis_ctx* ctx, int n_new, int* first) {
     CU(cudaStreamSynchronize(ctx->stream));
     RESERVE(ctx->d_slot_ptr, (size_t)cap * sizeof(cpx*));
     ctx->d_slot_cap = cap;
-    CU(cudaMemcpy(ctx->d_slot_ptr.p, ctx->slot_ptr.data(), (size_t)total * sizeof(cpx*), cudaMemcpyHostToDevice));
+    CU(h2d(ctx, ctx->d_slot_ptr.p, ctx->slot_ptr.data(), (size_t)total * sizeof(cpx*)));
   } else {
-    CU(cudaMemcpy(ctx->d_slot_ptr.as<cpx*>() + old, ctx->slot_ptr.data() + old, (size_t)n_new * sizeof(cpx*), cudaMemcpyHostToDevice));
+    CU(h2d(ctx, ctx->d_slot_ptr.as<cpx*>() + old, ctx->slot_ptr.data() + old, (size_t)n_new * sizeof(cpx*)));
   }
   return NIS_OK;
 }
@@ -779,7 +787,7 @@ int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_ou
   CU(cudaSetDevice(ctx->device));
   TRY(ensure_workspace(ctx, 1));
   const SizeClass& z = ctx->sz[which];
-  CU(cudaMemcpy(ctx->rk.p, real_in, z.real * sizeof(float), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->rk.p, real_in, z.real * sizeof(float)));
   TRY(fft2_batch(ctx, which, src_slab<float>(ctx->rk.as<float>(), 0), src_null<uint8_t>(), false, 1, Dst<cpx>{ctx->kxz.as<cpx>(), 0}));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpy(spec_out, ctx->kxz.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
@@ -791,12 +799,12 @@ int nis_debug_ifft2(nis_ctx* ctx, int which, const float* spec_in, float* real_o
   CU(cudaSetDevice(ctx->device));
   TRY(ensure_workspace(ctx, 1));
   const SizeClass& z = ctx->sz[which];
-  CU(cudaMemcpy(ctx->kxz.p, spec_in, z.spec * sizeof(cpx), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->kxz.p, spec_in, z.spec * sizeof(cpx)));
   Dst<cpx> t1{ctx->t1.as<cpx>(), 0};
   // the inverse row pass has no plain-load instantiation: multiply by conj(1) through ProMulConj instead
   {
     std::vector<cpx> ones(z.spec, make_float2(1.f, 0.f));
-    CU(cudaMemcpy(ctx->kzz.p, ones.data(), z.spec * sizeof(cpx), cudaMemcpyHostToDevice));
+    CU(h2d(ctx, ctx->kzz.p, ones.data(), z.spec * sizeof(cpx)));
   }
   LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(ctx->kxz.as<cpx>(), 0), src_slab<cpx>(ctx->kzz.as<cpx>(), 0)},
                                 EpiSpecStore{t1}, z.R / 2 + 1, 1, ctx->stream));
@@ -811,7 +819,7 @@ int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
   if (!ctx || !power_in || !polar_out) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   TRY(ensure_workspace(ctx, 1));
-  CU(cudaMemcpy(ctx->rk.p, power_in, ctx->sz[0].real * sizeof(float), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->rk.p, power_in, ctx->sz[0].real * sizeof(float)));
   LAUNCH(launch_polar(src_slab<float>(ctx->rk.as<float>(), 0), Dst<float>{ctx->rot.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
                       ctx->cs.as<double>(), ctx->rho.as<float>(), 1, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -826,9 +834,9 @@ int nis_debug_rotate(nis_ctx* ctx, const float* image_in, float degree, float* i
   double M[6];
   rotation_inverse(ctx->H, ctx->W, (double)degree, M);
   const int slot = 3 * ctx->D;
-  CU(cudaMemcpy(ctx->mats.as<double>() + 6 * (size_t)slot, M, sizeof M, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ctx->sel.p, &slot, sizeof(int), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ctx->rk.p, image_in, ctx->sz[0].real * sizeof(float), cudaMemcpyHostToDevice));
+  CU(h2d(ctx, ctx->mats.as<double>() + 6 * (size_t)slot, M, sizeof M));
+  CU(h2d(ctx, ctx->sel.p, &slot, sizeof(int)));
+  CU(h2d(ctx, ctx->rk.p, image_in, ctx->sz[0].real * sizeof(float)));
   LAUNCH(launch_rotate(src_slab<float>(ctx->rk.as<float>(), 0), src_null<uint8_t>(), ctx->lut.as<float>(), Dst<float>{ctx->rot.as<float>(), 0},
                        ctx->H, ctx->W, ctx->mats.as<double>(), ctx->sel.as<int>(), 1, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -847,8 +855,8 @@ int nis_debug_estimate_trans(nis_ctx* ctx, int which, const float* last_spec, co
   RESERVE(dz, z.spec * sizeof(cpx)); RESERVE(dx, z.spec * sizeof(cpx));
   if (g_out) RESERVE(dg, z.real * sizeof(float));
   int st = NIS_OK;
-  if (cudaMemcpy(dz.p, last_spec, z.spec * sizeof(cpx), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(dx.p, cur_spec, z.spec * sizeof(cpx), cudaMemcpyHostToDevice) != cudaSuccess)
+  if (h2d(ctx, dz.p, last_spec, z.spec * sizeof(cpx)) != cudaSuccess ||
+      h2d(ctx, dx.p, cur_spec, z.spec * sizeof(cpx)) != cudaSuccess)
     st = fail(ctx, NIS_ERR_CUDA, "debug copy", (int)cudaGetLastError());
   PeakStats ps;
   if (st == NIS_OK) st = estimate_trans_batch(ctx, which, src_slab<cpx>(dz.as<cpx>(), 0), 1, src_slab<cpx>(dz.as<cpx>(), 0),
