@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the NI-SLAM tracking / loop-closure hot path on B200.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): a synthetic 640x480 u8 stream, every frame a keyframe; one STEP =
+one pass of the hot path over the whole stream: per frame ComputeIntermedium + ComputePose(tracking) = one 3-DoF pose
+solve.  `value` = pose solves/s with the frames resident in HBM; `e2e` = the same through the public call with the
+frames in pinned HOST memory (H2D of the frames and D2H of the poses inside the timed region).
+Per-frame tracking does not shard: N > 1 runs N independent replicas (weak scaling, no collective).
+The loop-closure scan (configs[2..3]) is reported beside it in `loop_closure`: a keyframe DB sharded by index over the
+ranks, one broadcast query, one NCCL all-gather of the per-rank best records.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, D, CP = 480, 640, 720, 480
+BYTES_PER_SOLVE = H * W + 2 * ((H // 2 + 1) * W * 8 + (D // 2 + 1) * CP * 8)        # 5 547 520
+BYTES_PER_CANDIDATE = (H // 2 + 1) * W * 8 + (D // 2 + 1) * CP * 8                  # 2 620 160
+METRIC = "pose_solves_per_sec_640x480"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in self.tmp.read().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9 or p[0] != str(self.index):
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v == "Active":
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port; the reference cannot be compiled in
+# this image -- no Eigen / FFTW / OpenCV C++ -- see DESIGN.md) on all host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_frames(n, seed=0):
+    import torch
+    import bench_synth as bs
+    canvas = bs.make_canvas(2048, seed=seed, device="cpu")
+    cx, cy, ang = bs.stream_poses(n, seed=seed, size=2048)
+    return bs.crops(canvas, cx, cy, ang, H, W).numpy()
+
+
+def time_oracle_stream(frames, threads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c as oc
+    cfg = oc.make_cfg()
+    t0 = time.perf_counter()
+    oc.track_stream(cfg, frames, threads=threads)
+    dt = time.perf_counter() - t0
+    return (frames.shape[0] - 1) / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = cores
+    n = args.ref_frames
+    frames = cpu_frames(n)
+    for _ in range(max(args.warmup, 0) and 1):
+        time_oracle_stream(frames[:min(n, threads + 1)], threads)
+    times = []
+    for _ in range(args.steps):
+        _, dt = time_oracle_stream(frames, threads)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = (n - 1) / (ms / 1e3)
+    sample = "%d-frame 640x480 stream (%d solves) per step, oracle C port (oracle/nislam_oracle.c), %d OpenMP threads" % (n, n - 1, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "tracking stream 640x480 u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame",
+                       "frames_per_step": n, "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial"},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="frames per step (stream length)")
+    ap.add_argument("--batch", type=int, default=0, help="pairs in flight per kernel launch (0 = library default)")
+    ap.add_argument("--db", type=int, default=2048, help="loop-closure keyframes PER GPU (0 = skip the scan section)")
+    ap.add_argument("--queries", type=int, default=2)
+    ap.add_argument("--ref-frames", type=int, default=65, help="frames per step of the CPU reference arm")
+    ap.add_argument("--cpu-frames", type=int, default=65, help="frames of the cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import bench_synth as bs
+    import ni_slam_b200 as nis
+    from ni_slam_b200 import build as nis_build
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    nis_build.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cf = nis.CorrelationFlow(nis.CFConfig(), H, W, device=local_rank)
+    if args.batch:
+        cf.set_batch(args.batch)
+    ext = torch.cuda.ExternalStream(cf.stream, device=dev)
+
+    # ---- synthetic stream (different walk per rank)
+    n = args.frames
+    canvas = bs.make_canvas(4096, seed=0, device=dev)
+    cx, cy, ang = bs.stream_poses(n, seed=100 + rank)
+    frames = bs.crops(canvas, cx, cy, ang, H, W)                        # (n, H, W) u8 in HBM
+    frames_host = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    frames_host.copy_(frames)
+    torch.cuda.synchronize()
+
+    def step_dev():
+        return cf.TrackStreamPtr(frames.data_ptr(), n, on_device=True)
+
+    def step_host():
+        return cf.TrackStreamPtr(frames_host.data_ptr(), n, on_device=False)
+
+    for _ in range(args.warmup):
+        poses, infos = step_dev()
+
+    # sanity of the answers against the synthetic motion (not timed)
+    dth = np.deg2rad(np.diff(ang))
+    dmag = np.hypot(np.diff(cx), np.diff(cy))
+    ok = (np.abs((poses[:, 2] - dth + np.pi) % (2 * np.pi) - np.pi) < np.deg2rad(0.75)) & \
+         (np.abs(np.hypot(poses[:, 0], poses[:, 1]) - dmag) < 2.0)
+    pose_ok_frac = float(ok.mean())
+
+    # ---- timed region: HBM-resident inputs
+    clocks = ClockSampler(local_rank)
+    l0 = cf.kernel_launches()
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(ext)
+    barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = cf.kernel_launches() - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    solves_per_step = (n - 1) * world
+    value = solves_per_step / (ms_step / 1e3)
+
+    # ---- e2e: same call with HOST buffers (pinned), H2D + D2H inside
+    for _ in range(1):
+        step_host()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(ext)
+    t_host0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    e3.record(ext)
+    barrier()
+    wall_e2e = (time.perf_counter() - t_host0) / args.steps
+    t2 = torch.tensor([max(e2.elapsed_time(e3) / args.steps, wall_e2e * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = solves_per_step / (float(t2.item()) / 1e3)
+
+    # ---- per-kernel-family device time (one extra, untimed-for-value step with events around every launch)
+    cf.profile_begin()
+    step_dev()
+    prof = cf.profile_end()
+    tot = sum(v["ms"] for v in prof.values()) or 1.0
+    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / tot, 4)} for k, v in
+               sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = next(iter(kernels))
+    peak, peak_src = measured_peak()
+    achieved = (value / world) * BYTES_PER_SOLVE / 1e9                  # per GPU
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "definition": "per-GPU solves/s x %d algorithmic B/solve (SURVEY 8d) over the whole multi-kernel step" % BYTES_PER_SOLVE,
+                "peak_source": peak_src, "dominant_kernel": dom, "dominant_kernel_share": kernels[dom]["share"],
+                "dominant_kernel_avg_launch_ms": kernels[dom]["ms"] / max(kernels[dom]["launches"], 1), "kernels": kernels}
+
+    # ---- loop-closure scan: DB sharded by index over ranks, one NCCL all-gather of the per-rank best records
+    loop = None
+    if args.db > 0:
+        lc = nis.LoopClosure(nis.LoopClosureConfig(position_response_thr=60, angle_response_thr=60), cf)
+        nshard = args.db
+        gcx, gcy, gang = bs.db_poses(nshard * world, seed=1)
+        sl = slice(rank * nshard, (rank + 1) * nshard)
+        db_imgs = bs.crops(canvas, gcx[sl], gcy[sl], gang[sl], H, W)
+        ids = np.arange(rank * nshard, (rank + 1) * nshard, dtype=np.int32)
+        lc.AddImages(None, ids, None, ptr=db_imgs.data_ptr(), n=nshard, on_device=True)
+        del db_imgs
+        jstar = (nshard * world) // 2 + 3                                  # expected winner (global id)
+        q_img = bs.crops(canvas, [gcx[jstar] + 13], [gcy[jstar] - 7], [gang[jstar] + 4.5], H, W)
+        nbytes = C.sizeof(nis.LoopResultC)
+
+        def query():
+            qi = q_img.clone()
+            if world > 1:
+                dist.broadcast(qi, src=0)                                  # 307 KB u8 image; each rank recomputes its features
+            qf = cf.ComputeIntermedium(qi[0].cpu().numpy())
+            res = lc.FindLoopClosure(qf, current_frame_id=10 ** 9)
+            if world == 1:
+                return res
+            mine = torch.frombuffer(bytearray(bytes(res.raw)), dtype=torch.uint8).to(dev)
+            allb = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, mine)                       # the one collective of the path
+            raw = allb.cpu().numpy().tobytes()
+            recs = [nis.LoopResultC.from_buffer_copy(raw[i * nbytes:(i + 1) * nbytes]) for i in range(world)]
+            order = [r.frame_id if r.slot >= 0 else 2 ** 62 for r in recs]
+            red, _ = lc.Reduce(recs, order)
+            return red
+
+        res = query()
+        barrier()
+        l1 = cf.kernel_launches()
+        t0 = time.perf_counter()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record(ext)
+        for _ in range(args.queries):
+            res = query()
+        e5.record(ext)
+        barrier()
+        q_ms = max(e4.elapsed_time(e5), (time.perf_counter() - t0) * 1e3) / args.queries
+        tq = torch.tensor([q_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        q_ms = float(tq.item())
+        cand_per_s = nshard * world / (q_ms / 1e3)
+        loop = {"metric": "loop_closure_queries_per_sec", "db_keyframes": nshard * world, "keyframes_per_gpu": nshard,
+                "value": 1e3 / q_ms, "unit": "queries/s", "ms_per_query": q_ms, "candidates_per_sec": cand_per_s,
+                "queries_per_sec_over_100k_extrapolated": cand_per_s / 1e5, "winner_frame_id": int(res.loop_frame_id),
+                "expected_frame_id": int(jstar), "found": bool(res.found), "relative_pose": [float(x) for x in res.relative_pose],
+                "collective": "ncclAllGather of %d-byte records" % nbytes if world > 1 else "none (1 rank)",
+                "gpu_launches_per_query": (cf.kernel_launches() - l1) // max(args.queries, 1),
+                "roofline": {"bound": "hbm", "achieved": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9 / peak,
+                             "definition": "per-GPU candidates/s x %d algorithmic B/candidate (SURVEY 8d)" % BYTES_PER_CANDIDATE}}
+        lc.clear()
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample of the same stream
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_frames > 1:
+        try:
+            cores = os.cpu_count() or 1
+            sample = frames_host[:args.cpu_frames].numpy()
+            v_all, dt_all = time_oracle_stream(sample, cores)
+            sub = sample[:min(9, args.cpu_frames)]
+            v_1, dt_1 = time_oracle_stream(sub, 1)
+            cpu = {"value": v_all, "unit": "solves/s", "cores": cores, "kind": "port",
+                   "sample": "first %d frames of the same stream (%d solves, %.1f s), oracle/nislam_oracle.c, %d OpenMP threads; "
+                             "1 thread on %d frames: %.2f solves/s" % (args.cpu_frames, args.cpu_frames - 1, dt_all, cores, sub.shape[0], v_1),
+                   "value_1_thread": v_1}
+        except Exception as e:          # the checker must not take the bench down
+            cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "tracking stream 640x480 u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame "
+                                       "(BASELINE.json configs[1])", "frames_per_step_per_gpu": n, "solves_per_step": solves_per_step,
+                           "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial", "batch": args.batch or "default",
+                           "parallelism": "replicas only (tracking does not shard)" if world > 1 else "1 GPU",
+                           "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of features per step vs 126 MB L2" %
+                                 (n * H * W / 1e6, n * BYTES_PER_CANDIDATE / 1e6)},
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": n * H * W,
+                        "d2h_bytes_per_step": (n - 1) * 72},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "loop_closure": loop,
+                "pose_ok_frac": pose_ok_frac}
+        print(json.dumps(line), flush=True)
+    cf.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -126,6 +126,11 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
 int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n_ranks, const nis_loop_config* cfg,
                     nis_loop_result* out, int* winner_rank);
 
+/* ---- per-kernel-family timing: CUDA events around every launch between begin and end; `json_out` receives
+ *      {"family": {"launches": n, "ms": total}, ...}.  Measurement aid for bench.py (not on the reference surface). ---- */
+int nis_profile_begin(nis_ctx* ctx);
+int nis_profile_end(nis_ctx* ctx, char* json_out, int json_cap);
+
 /* ---- stage-level entry points used by the parity tests (host buffers, natural row-major numpy layout:
  *      real (R, C), spectrum (R/2+1, C) complex64).  which: 0 = image size H x W, 1 = polar size D x Cp. ---- */
 int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_out);

@@ -26,7 +26,8 @@ SYMBOLS = [
     "nis_set_batch", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
     "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
     "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_debug_fft2",
-    "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans",
+    "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
+    "nis_profile_end",
 ]
 
 
@@ -126,6 +127,8 @@ def load_library():
     lib.nis_db_clear.argtypes = [vp]
     lib.nis_loop_scan.argtypes = [vp, vp, i32, C.c_double, C.POINTER(_LoopConfigC), vp, i32, C.POINTER(LoopResultC), vp]
     lib.nis_loop_reduce.argtypes = [vp, vp, i32, C.POINTER(_LoopConfigC), C.POINTER(LoopResultC), C.POINTER(i32)]
+    lib.nis_profile_begin.argtypes = [vp]
+    lib.nis_profile_end.argtypes = [vp, C.c_char_p, i32]
     lib.nis_debug_fft2.argtypes = [vp, i32, vp, vp]
     lib.nis_debug_ifft2.argtypes = [vp, i32, vp, vp]
     lib.nis_debug_polar.argtypes = [vp, vp, vp]
@@ -213,6 +216,16 @@ class CorrelationFlow:
 
     def set_batch(self, b: int):
         self._check(self._lib.nis_set_batch(self._ctx, int(b)))
+
+    def profile_begin(self):
+        self._check(self._lib.nis_profile_begin(self._ctx))
+
+    def profile_end(self) -> dict:
+        """{kernel family: {"launches": n, "ms": total device time}} from CUDA events around every launch."""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.nis_profile_end(self._ctx, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     # ---- reference surface
     def ComputeIntermedium(self, image) -> Frame:

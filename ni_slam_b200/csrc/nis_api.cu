@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -80,7 +81,19 @@ struct nis_ctx {
   int d_slot_cap = 0;
   // pinned staging
   void* pin = nullptr; size_t pin_bytes = 0;
+  // optional per-kernel-family event timing (nis_profile_begin / nis_profile_end)
+  bool profiling = false;
+  struct ProfEv { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfEv> prof;
 };
+
+static void prof_before(nis_ctx* ctx, const char* name) {
+  nis_ctx::ProfEv ev{name, nullptr, nullptr};
+  cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+  cudaEventRecord(ev.a, ctx->stream);
+  ctx->prof.push_back(ev);
+}
+static void prof_after(nis_ctx* ctx) { cudaEventRecord(ctx->prof.back().b, ctx->stream); }
 
 static int fail(nis_ctx* c, int status, const char* what, int cuda_err = 0) {
   if (c) {
@@ -100,7 +113,9 @@ static int fail(nis_ctx* c, int status, const char* what, int cuda_err = 0) {
 // kernel launch through a launcher returning cudaError_t-as-int (or -1 for an unsupported size)
 #define LAUNCH(call)                                                                      \
   do {                                                                                    \
+    if (ctx->profiling) prof_before(ctx, #call);                                          \
     int e_ = (call);                                                                      \
+    if (ctx->profiling) prof_after(ctx);                                                  \
     if (e_ == -1) return fail(ctx, NIS_ERR_UNSUPPORTED_SIZE, "unsupported transform size: " #call); \
     if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, #call, e_);                                \
     ctx->launches++;                                                                      \
@@ -778,6 +793,48 @@ int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n
   out->evaluated = evaluated;
   out->found = (out->response[0] > cfg->position_response_thr) && (out->response[2] > cfg->angle_response_thr);
   if (winner_rank) *winner_rank = best;
+  return NIS_OK;
+}
+
+// ---- per-kernel-family timing (CUDA events around every launch; used by bench.py for the roofline line) ---------
+int nis_profile_begin(nis_ctx* ctx) {
+  if (!ctx) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  ctx->prof.clear();
+  ctx->profiling = true;
+  return NIS_OK;
+}
+
+int nis_profile_end(nis_ctx* ctx, char* json_out, int json_cap) {
+  if (!ctx || !json_out || json_cap <= 0) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  ctx->profiling = false;
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::map<std::string, std::pair<long long, double>> acc;      // family -> (launches, total ms)
+  for (auto& e : ctx->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    std::string name(e.name);
+    const size_t par = name.find('(');
+    if (par != std::string::npos) name = name.substr(0, par);
+    if (name.rfind("launch_", 0) == 0) name = name.substr(7);
+    auto& a = acc[name];
+    a.first++; a.second += ms;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  ctx->prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : acc) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+    js += buf; first = false;
+  }
+  js += "}";
+  if ((int)js.size() + 1 > json_cap) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "profile json buffer too small");
+  memcpy(json_out, js.c_str(), js.size() + 1);
   return NIS_OK;
 }
 
