@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per step (stream length)")
     ap.add_argument("--batch", type=int, default=0, help="pairs in flight per kernel launch (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent CUDA streams the batches are dealt to (0 = library default)")
     ap.add_argument("--db", type=int, default=2048, help="loop-closure keyframes PER GPU (0 = skip the scan section)")
     ap.add_argument("--queries", type=int, default=2)
     ap.add_argument("--ref-frames", type=int, default=65, help="frames per step of the CPU reference arm")
@@ -186,6 +187,8 @@ def main():
     cf = nis.CorrelationFlow(nis.CFConfig(), H, W, device=local_rank)
     if args.batch:
         cf.set_batch(args.batch)
+    if args.lanes:
+        cf.set_lanes(args.lanes)
     ext = torch.cuda.ExternalStream(cf.stream, device=dev)
 
     # ---- synthetic stream (different walk per rank)
@@ -252,9 +255,11 @@ def main():
     e2e_value = solves_per_step / (float(t2.item()) / 1e3)
 
     # ---- per-kernel-family device time (one extra, untimed-for-value step with events around every launch)
+    cf.set_lanes(1)                 # one lane so that the event pairs of different kernels do not overlap
     cf.profile_begin()
     step_dev()
     prof = cf.profile_end()
+    cf.set_lanes(args.lanes)
     tot = sum(v["ms"] for v in prof.values()) or 1.0
     kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / tot, 4)} for k, v in
                sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
@@ -347,7 +352,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "tracking stream 640x480 u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame "
                                        "(BASELINE.json configs[1])", "frames_per_step_per_gpu": n, "solves_per_step": solves_per_step,
-                           "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial", "batch": args.batch or "default",
+                           "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial", "batch": args.batch or "default", "lanes": args.lanes or "default",
                            "parallelism": "replicas only (tracking does not shard)" if world > 1 else "1 GPU",
                            "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of features per step vs 126 MB L2" %
                                  (n * H * W / 1e6, n * BYTES_PER_CANDIDATE / 1e6)},

@@ -80,6 +80,8 @@ int nis_synchronize(nis_ctx* ctx);
 long long nis_kernel_launches(const nis_ctx* ctx);
 /* work-batch size (pairs / candidates in flight per kernel launch); 0 = library default */
 int nis_set_batch(nis_ctx* ctx, int batch);
+/* number of concurrent CUDA streams ("lanes") the batches are dealt to; all fork from / join into nis_stream(); 0 = default */
+int nis_set_lanes(nis_ctx* ctx, int lanes);
 
 /* ---- features: MapBuilder::ComputeFFTResult = ConvertMatToNormalizedArray + CorrelationFlow::ComputeIntermedium
  *      (src/map_builder.cc:72-75, src/utils.cc:110-118, include/correlation_flow.h:12) ---- */

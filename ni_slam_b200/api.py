@@ -23,7 +23,7 @@ NIS_OK, NIS_ERR_INVALID_ARGUMENT, NIS_ERR_INVALID_KERNEL, NIS_ERR_UNSUPPORTED_SI
 
 SYMBOLS = [
     "nis_create", "nis_destroy", "nis_last_error", "nis_strerror", "nis_stream", "nis_synchronize", "nis_kernel_launches",
-    "nis_set_batch", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
+    "nis_set_batch", "nis_set_lanes", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
     "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
     "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_debug_fft2",
     "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
@@ -112,6 +112,7 @@ def load_library():
     lib.nis_synchronize.argtypes = [vp]
     lib.nis_kernel_launches.argtypes = [vp]; lib.nis_kernel_launches.restype = C.c_longlong
     lib.nis_set_batch.argtypes = [vp, i32]
+    lib.nis_set_lanes.argtypes = [vp, i32]
     lib.nis_features_u8.argtypes = [vp, vp, C.POINTER(vp)]
     lib.nis_features_f32.argtypes = [vp, vp, C.POINTER(vp)]
     lib.nis_frame_export.argtypes = [vp, vp, vp, vp]
@@ -216,6 +217,9 @@ class CorrelationFlow:
 
     def set_batch(self, b: int):
         self._check(self._lib.nis_set_batch(self._ctx, int(b)))
+
+    def set_lanes(self, n: int):
+        self._check(self._lib.nis_set_lanes(self._ctx, int(n)))
 
     def profile_begin(self):
         self._check(self._lib.nis_profile_begin(self._ctx))

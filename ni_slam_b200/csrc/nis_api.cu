@@ -53,9 +53,22 @@ struct SizeClass {             // one 2-D transform size: R rows (halved) x C co
   Twiddles colf, coli, row;
 };
 
+// One lane = one CUDA stream with its own workspace.  Batches are dealt round-robin to the lanes so that several small
+// (L2-resident) batches are in flight at once and the tail of one launch overlaps the head of another.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  int cap = 0;                 // workspace capacity in pairs
+  DevBuf t1, rk, kxz, kzz, rot, xs, maxzz, maxxz, stats_p, stats_t, sel, xxz, xxx;
+};
+
 struct nis_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // == lanes[0].stream: the stream callers time on; the other lanes fork from / join into it
+  std::vector<Lane> lanes;
+  int active_lanes = 1;            // lanes batches are dealt to (<= lanes.size())
+  cudaStream_t prof_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr;
   nis_cf_config cfg{};
   int H = 0, W = 0, D = 0, Cp = 0;
   SizeClass sz[2];             // 0: H x W, 1: D x Cp
@@ -65,9 +78,7 @@ struct nis_ctx {
   int batch = 16;
   // constant tables
   DevBuf tw, lut, cs, rho, mats, theta;
-  // workspace (capacity in pairs)
-  int cap = 0;
-  DevBuf t1, rk, kxz, kzz, rot, xs, maxzz, maxxz, stats_p, stats_t, sel, xxz, xxx, recs, best, cand;
+  DevBuf recs, best, cand;
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
   DevBuf sF, sP, sImg;
@@ -90,10 +101,10 @@ struct nis_ctx {
 static void prof_before(nis_ctx* ctx, const char* name) {
   nis_ctx::ProfEv ev{name, nullptr, nullptr};
   cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
-  cudaEventRecord(ev.a, ctx->stream);
+  cudaEventRecord(ev.a, ctx->prof_stream ? ctx->prof_stream : ctx->stream);
   ctx->prof.push_back(ev);
 }
-static void prof_after(nis_ctx* ctx) { cudaEventRecord(ctx->prof.back().b, ctx->stream); }
+static void prof_after(nis_ctx* ctx) { cudaEventRecord(ctx->prof.back().b, ctx->prof_stream ? ctx->prof_stream : ctx->stream); }
 
 static int fail(nis_ctx* c, int status, const char* what, int cuda_err = 0) {
   if (c) {
@@ -249,30 +260,47 @@ static int build_tables(nis_ctx* ctx) {
   return NIS_OK;
 }
 
-static int ensure_workspace(nis_ctx* ctx, int pairs) {
-  if (pairs <= ctx->cap) return NIS_OK;
+static int ensure_workspace(nis_ctx* ctx, Lane& L, int pairs) {
+  if (pairs <= L.cap) return NIS_OK;
+  CU(cudaStreamSynchronize(L.stream));
   const size_t E = 2 * (size_t)pairs;
-  RESERVE(ctx->t1, E * ctx->maxspec * sizeof(cpx));
-  RESERVE(ctx->rk, E * ctx->maxreal * sizeof(float));
-  RESERVE(ctx->kxz, E * ctx->maxspec * sizeof(cpx));
-  RESERVE(ctx->kzz, (size_t)pairs * ctx->maxspec * sizeof(cpx));
-  RESERVE(ctx->rot, E * ctx->maxreal * sizeof(float));
-  RESERVE(ctx->xs, E * ctx->sz[0].spec * sizeof(cpx));
-  RESERVE(ctx->maxzz, (size_t)pairs * sizeof(unsigned));
-  RESERVE(ctx->maxxz, E * sizeof(unsigned));
-  RESERVE(ctx->stats_p, (size_t)pairs * sizeof(PeakStats));
-  RESERVE(ctx->stats_t, E * sizeof(PeakStats));
-  RESERVE(ctx->sel, E * sizeof(int));
-  RESERVE(ctx->xxz, (size_t)pairs * sizeof(float));
-  RESERVE(ctx->xxx, E * sizeof(float));
-  RESERVE(ctx->best, sizeof(PoseRecord));
-  ctx->cap = pairs;
+  RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));
+  RESERVE(L.rk, E * ctx->maxreal * sizeof(float));
+  RESERVE(L.kxz, E * ctx->maxspec * sizeof(cpx));
+  RESERVE(L.kzz, (size_t)pairs * ctx->maxspec * sizeof(cpx));
+  RESERVE(L.rot, E * ctx->maxreal * sizeof(float));
+  RESERVE(L.xs, E * ctx->sz[0].spec * sizeof(cpx));
+  RESERVE(L.maxzz, (size_t)pairs * sizeof(unsigned));
+  RESERVE(L.maxxz, E * sizeof(unsigned));
+  RESERVE(L.stats_p, (size_t)pairs * sizeof(PeakStats));
+  RESERVE(L.stats_t, E * sizeof(PeakStats));
+  RESERVE(L.sel, E * sizeof(int));
+  RESERVE(L.xxz, (size_t)pairs * sizeof(float));
+  RESERVE(L.xxx, E * sizeof(float));
+  L.cap = pairs;
+  return NIS_OK;
+}
+
+// lanes 1.. start after everything already queued on the main stream; the main stream resumes after all lanes
+static int fork_lanes(nis_ctx* ctx) {
+  if (ctx->active_lanes <= 1) return NIS_OK;
+  CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int i = 1; i < ctx->active_lanes; ++i) CU(cudaStreamWaitEvent(ctx->lanes[i].stream, ctx->fork_ev, 0));
+  return NIS_OK;
+}
+static int join_lanes(nis_ctx* ctx) {
+  for (int i = 1; i < ctx->active_lanes; ++i) {
+    CU(cudaEventRecord(ctx->lanes[i].ev, ctx->lanes[i].stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->lanes[i].ev, 0));
+  }
   return NIS_OK;
 }
 
 static int ensure_recs(nis_ctx* ctx, int n) {
   if (n <= ctx->recs_cap) return NIS_OK;
+  CU(cudaDeviceSynchronize());
   RESERVE(ctx->recs, (size_t)n * sizeof(PoseRecord));
+  RESERVE(ctx->best, sizeof(PoseRecord));
   ctx->recs_cap = n;
   return NIS_OK;
 }
@@ -290,93 +318,98 @@ static int ensure_pinned(nis_ctx* ctx, size_t bytes) {
 // batched stages
 // -------------------------------------------------------------------------------------------------------------
 // 2-D r2c: real [B][R][C] (f32 slab or u8 source) -> spectrum
-static int fft2_batch(nis_ctx* ctx, int s, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> out) {
+static int fft2_batch(nis_ctx* ctx, Lane& L, int s, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> out) {
+  ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[s];
-  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)z.spec};
-  if (is_u8) LAUNCH(launch_col_fwd_u8(z.R, z.colf, ProRealU8{u8, z.C, ctx->lut.as<float>()}, t1, z.C, B, ctx->stream));
-  else LAUNCH(launch_col_fwd_f32(z.R, z.colf, ProRealF32{f32, z.C}, t1, z.C, B, ctx->stream));
-  LAUNCH(launch_row_fwd(z.C, z.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, z.R / 2 + 1, B, ctx->stream));
+  Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
+  if (is_u8) LAUNCH(launch_col_fwd_u8(z.R, z.colf, ProRealU8{u8, z.C, ctx->lut.as<float>()}, t1, z.C, B, L.stream));
+  else LAUNCH(launch_col_fwd_f32(z.R, z.colf, ProRealF32{f32, z.C}, t1, z.C, B, L.stream));
+  LAUNCH(launch_row_fwd(z.C, z.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, z.R / 2 + 1, B, L.stream));
   return NIS_OK;
 }
 
 // ComputeIntermedium (correlation_flow.cc:89-95) for B images
-static int features_batch(nis_ctx* ctx, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> F, Dst<cpx> P) {
-  TRY(ensure_workspace(ctx, B));
+static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> F, Dst<cpx> P) {
+  ctx->prof_stream = L.stream;
+  TRY(ensure_workspace(ctx, L, B));
   const SizeClass& zt = ctx->sz[0];
   const SizeClass& zp = ctx->sz[1];
-  TRY(fft2_batch(ctx, 0, f32, u8, is_u8, B, F));                                              // fft_result = FFT(image)
-  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)zt.spec};
-  Dst<float> power{ctx->rk.as<float>(), (long long)zt.real};
-  Dst<float> pol{ctx->rot.as<float>(), (long long)zp.real};
-  LAUNCH(launch_row_inv_abs(zt.C, zt.row, ProAbs{src_slab<cpx>(F.base, F.stride)}, EpiSpecStore{t1}, zt.R / 2 + 1, B, ctx->stream));
+  TRY(fft2_batch(ctx, L, 0, f32, u8, is_u8, B, F));                                              // fft_result = FFT(image)
+  Dst<cpx> t1{L.t1.as<cpx>(), (long long)zt.spec};
+  Dst<float> power{L.rk.as<float>(), (long long)zt.real};
+  Dst<float> pol{L.rot.as<float>(), (long long)zp.real};
+  LAUNCH(launch_row_inv_abs(zt.C, zt.row, ProAbs{src_slab<cpx>(F.base, F.stride)}, EpiSpecStore{t1}, zt.R / 2 + 1, B, L.stream));
   LAUNCH(launch_col_inv_store(zt.R, zt.coli, src_slab<cpx>(t1.base, t1.stride), EpiStore{power, zt.C, (float)zt.real}, zt.C, B,
-                              ctx->stream));                                                   // power = IFFT(|F|)
+                              L.stream));                                                   // power = IFFT(|F|)
   LAUNCH(launch_polar(src_slab<float>(power.base, power.stride), pol, ctx->H, ctx->W, ctx->D, ctx->Cp, ctx->cs.as<double>(),
-                      ctx->rho.as<float>(), B, ctx->stream));                                  // polar(fftshift(RemoveZero(power)))
-  TRY(fft2_batch(ctx, 1, src_slab<float>(pol.base, pol.stride), src_null<uint8_t>(), false, B, P));   // fft_polar
+                      ctx->rho.as<float>(), B, L.stream));                                  // polar(fftshift(RemoveZero(power)))
+  TRY(fft2_batch(ctx, L, 1, src_slab<float>(pol.base, pol.stride), src_null<uint8_t>(), false, B, P));   // fft_polar
   return NIS_OK;
 }
 
 // kernel(x, z) (polynomial / gaussian, correlation_flow.cc:181-226) for E entries, unnormalised spectrum + max
-static int kernel_batch(nis_ctx* ctx, int s, Src<cpx> X, Src<cpx> Z, int E, const float* xx, const float* zz, int zz_shift,
+static int kernel_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> X, Src<cpx> Z, int E, const float* xx, const float* zz, int zz_shift,
                         unsigned* maxbuf, Dst<cpx> out) {
+  ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[s];
   const nis_cf_config& c = ctx->cfg;
-  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)z.spec};
-  Dst<float> rk{ctx->rk.as<float>(), (long long)z.real};
-  CU(cudaMemsetAsync(maxbuf, 0, sizeof(unsigned) * E, ctx->stream));
-  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{X, Z}, EpiSpecStore{t1}, z.R / 2 + 1, E, ctx->stream));
+  Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
+  Dst<float> rk{L.rk.as<float>(), (long long)z.real};
+  CU(cudaMemsetAsync(maxbuf, 0, sizeof(unsigned) * E, L.stream));
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{X, Z}, EpiSpecStore{t1}, z.R / 2 + 1, E, L.stream));
   EpiKernel ek{rk, z.C, (float)z.real, c.kernel, c.offset, c.power, -1.f / (c.sigma * c.sigma), xx, zz, zz_shift, maxbuf};
-  LAUNCH(launch_col_inv_kernel(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ek, z.C, E, ctx->stream));
-  TRY(fft2_batch(ctx, s, src_slab<float>(rk.base, rk.stride), src_null<uint8_t>(), false, E, out));
+  LAUNCH(launch_col_inv_kernel(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ek, z.C, E, L.stream));
+  TRY(fft2_batch(ctx, L, s, src_slab<float>(rk.base, rk.stride), src_null<uint8_t>(), false, E, out));
   return NIS_OK;
 }
 
 // EstimateTrans (correlation_flow.cc:145-179) for E entries; entry e uses keyframe spectrum Z.at(e) and Kzz number e>>zshift
-static int estimate_trans_batch(nis_ctx* ctx, int s, Src<cpx> Zzz, int nzz, Src<cpx> Z, Src<cpx> X, int E, int zshift,
+static int estimate_trans_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> Zzz, int nzz, Src<cpx> Z, Src<cpx> X, int E, int zshift,
                                 PeakStats* stats, float* g_debug) {
+  ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[s];
   if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return fail(ctx, NIS_ERR_INVALID_KERNEL, "Received invalid kernel type");
   const float* xxz = nullptr; const float* xxx = nullptr;
   if (ctx->cfg.kernel == 1) {
-    LAUNCH(launch_spec_sqsum(Zzz, (int)z.spec, (float)(unsigned)z.real, ctx->xxz.as<float>(), nzz, ctx->stream));
-    LAUNCH(launch_spec_sqsum(X, (int)z.spec, (float)(unsigned)z.real, ctx->xxx.as<float>(), E, ctx->stream));
-    xxz = ctx->xxz.as<float>(); xxx = ctx->xxx.as<float>();
+    LAUNCH(launch_spec_sqsum(Zzz, (int)z.spec, (float)(unsigned)z.real, L.xxz.as<float>(), nzz, L.stream));
+    LAUNCH(launch_spec_sqsum(X, (int)z.spec, (float)(unsigned)z.real, L.xxx.as<float>(), E, L.stream));
+    xxz = L.xxz.as<float>(); xxx = L.xxx.as<float>();
   }
-  Dst<cpx> kzz{ctx->kzz.as<cpx>(), (long long)z.spec}, kxz{ctx->kxz.as<cpx>(), (long long)z.spec};
-  TRY(kernel_batch(ctx, s, Zzz, Zzz, nzz, xxz, xxz, 0, ctx->maxzz.as<unsigned>(), kzz));            // Kzz
-  TRY(kernel_batch(ctx, s, X, Z, E, xxx, xxz, zshift, ctx->maxxz.as<unsigned>(), kxz));             // Kxz
-  CU(cudaMemsetAsync(stats, 0, sizeof(PeakStats) * E, ctx->stream));
-  Dst<cpx> t1{ctx->t1.as<cpx>(), (long long)z.spec};
-  ProFilter pf{src_slab<cpx>(kzz.base, kzz.stride, zshift), src_slab<cpx>(kxz.base, kxz.stride), ctx->maxzz.as<unsigned>(),
-               ctx->maxxz.as<unsigned>(), zshift, ctx->cfg.lambda};
-  LAUNCH(launch_row_inv_filter(z.C, z.row, pf, EpiSpecStore{t1}, z.R / 2 + 1, E, ctx->stream));
+  Dst<cpx> kzz{L.kzz.as<cpx>(), (long long)z.spec}, kxz{L.kxz.as<cpx>(), (long long)z.spec};
+  TRY(kernel_batch(ctx, L, s, Zzz, Zzz, nzz, xxz, xxz, 0, L.maxzz.as<unsigned>(), kzz));            // Kzz
+  TRY(kernel_batch(ctx, L, s, X, Z, E, xxx, xxz, zshift, L.maxxz.as<unsigned>(), kxz));             // Kxz
+  CU(cudaMemsetAsync(stats, 0, sizeof(PeakStats) * E, L.stream));
+  Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
+  ProFilter pf{src_slab<cpx>(kzz.base, kzz.stride, zshift), src_slab<cpx>(kxz.base, kxz.stride), L.maxzz.as<unsigned>(),
+               L.maxxz.as<unsigned>(), zshift, ctx->cfg.lambda};
+  LAUNCH(launch_row_inv_filter(z.C, z.row, pf, EpiSpecStore{t1}, z.R / 2 + 1, E, L.stream));
   EpiPeak ep{stats, z.R, (float)z.real, g_debug, (long long)z.real, z.C};
-  LAUNCH(launch_col_inv_peak(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ep, z.C, E, ctx->stream));
+  LAUNCH(launch_col_inv_peak(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ep, z.C, E, L.stream));
   return NIS_OK;
 }
 
 // ComputePose (correlation_flow.cc:97-138) for B pairs -> device records
-static int compute_pose_batch(nis_ctx* ctx, bool loop_mode, Src<cpx> Fz, Src<cpx> Pz, Src<cpx> Px, Src<float> img_f32,
+static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz, Src<cpx> Pz, Src<cpx> Px, Src<float> img_f32,
                               Src<uint8_t> img_u8, bool is_u8, int B, int index0, PoseRecord* recs) {
-  TRY(ensure_workspace(ctx, B));
-  PeakStats* sp = ctx->stats_p.as<PeakStats>();
-  PeakStats* st = ctx->stats_t.as<PeakStats>();
-  TRY(estimate_trans_batch(ctx, 1, Pz, B, Pz, Px, B, 0, sp, nullptr));                              // rotation
-  LAUNCH(launch_polar_select(sp, ctx->D, loop_mode ? 1 : 0, ctx->sel.as<int>(), B, ctx->stream));
+  ctx->prof_stream = L.stream;
+  TRY(ensure_workspace(ctx, L, B));
+  PeakStats* sp = L.stats_p.as<PeakStats>();
+  PeakStats* st = L.stats_t.as<PeakStats>();
+  TRY(estimate_trans_batch(ctx, L, 1, Pz, B, Pz, Px, B, 0, sp, nullptr));                              // rotation
+  LAUNCH(launch_polar_select(sp, ctx->D, loop_mode ? 1 : 0, L.sel.as<int>(), B, L.stream));
   const int shift = loop_mode ? 1 : 0, E = B << shift;
-  Dst<float> rot{ctx->rot.as<float>(), (long long)ctx->sz[0].real};
+  Dst<float> rot{L.rot.as<float>(), (long long)ctx->sz[0].real};
   Src<float> i32 = img_f32; i32.shift = shift;
   Src<uint8_t> i8 = img_u8; i8.shift = shift;
   if (is_u8) i32 = src_null<float>(); else i8 = src_null<uint8_t>();
-  LAUNCH(launch_rotate(i32, i8, ctx->lut.as<float>(), rot, ctx->H, ctx->W, ctx->mats.as<double>(), ctx->sel.as<int>(), E,
-                       ctx->stream));                                                                // RotateArray(image, -deg[+180])
-  Dst<cpx> xs{ctx->xs.as<cpx>(), (long long)ctx->sz[0].spec};
-  TRY(fft2_batch(ctx, 0, src_slab<float>(rot.base, rot.stride), src_null<uint8_t>(), false, E, xs));
+  LAUNCH(launch_rotate(i32, i8, ctx->lut.as<float>(), rot, ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), E,
+                       L.stream));                                                                // RotateArray(image, -deg[+180])
+  Dst<cpx> xs{L.xs.as<cpx>(), (long long)ctx->sz[0].spec};
+  TRY(fft2_batch(ctx, L, 0, src_slab<float>(rot.base, rot.stride), src_null<uint8_t>(), false, E, xs));
   Src<cpx> Fze = Fz; Fze.shift = shift;
-  TRY(estimate_trans_batch(ctx, 0, Fz, B, Fze, src_slab<cpx>(xs.base, xs.stride), E, shift, st, nullptr));   // translation
+  TRY(estimate_trans_batch(ctx, L, 0, Fz, B, Fze, src_slab<cpx>(xs.base, xs.stride), E, shift, st, nullptr));   // translation
   AngleTables tabs{ctx->mats.as<double>(), ctx->theta.as<double>()};
-  LAUNCH(launch_pose_finalize(sp, st, tabs, ctx->H, ctx->W, ctx->D, ctx->Cp, loop_mode ? 1 : 0, index0, recs, B, ctx->stream));
+  LAUNCH(launch_pose_finalize(sp, st, tabs, ctx->H, ctx->W, ctx->D, ctx->Cp, loop_mode ? 1 : 0, index0, recs, B, L.stream));
   return NIS_OK;
 }
 
@@ -428,7 +461,16 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   }
   ctx->maxspec = std::max(ctx->sz[0].spec, ctx->sz[1].spec);
   ctx->maxreal = std::max(ctx->sz[0].real, ctx->sz[1].real);
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NIS_ERR_CUDA; }
+  const int nlanes = 8;
+  ctx->active_lanes = 3;
+  const char* el = getenv("NIS_LANES");
+  if (el && atoi(el) > 0) ctx->active_lanes = std::min(atoi(el), nlanes);
+  ctx->lanes.resize(nlanes);
+  for (Lane& L : ctx->lanes)
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
+  ctx->stream = ctx->lanes[0].stream;
+  if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
   const char* eb = getenv("NIS_BATCH");
   if (eb && atoi(eb) > 0) ctx->batch = atoi(eb);
   int st = build_tables(ctx);
@@ -440,14 +482,19 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
 int nis_destroy(nis_ctx* ctx) {
   if (!ctx) return NIS_OK;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
-  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->t1, &ctx->rk, &ctx->kxz, &ctx->kzz,
-                    &ctx->rot, &ctx->xs, &ctx->maxzz, &ctx->maxxz, &ctx->stats_p, &ctx->stats_t, &ctx->sel, &ctx->xxz, &ctx->xxx,
-                    &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF, &ctx->sP, &ctx->sImg, &ctx->d_slot_ptr};
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
+                    &ctx->sP, &ctx->sImg, &ctx->d_slot_ptr};
   for (DevBuf* b : bufs) b->release();
+  for (Lane& L : ctx->lanes) {
+    DevBuf* lb[] = {&L.t1, &L.rk, &L.kxz, &L.kzz, &L.rot, &L.xs, &L.maxzz, &L.maxxz, &L.stats_p, &L.stats_t, &L.sel, &L.xxz, &L.xxx};
+    for (DevBuf* b : lb) b->release();
+    if (L.ev) cudaEventDestroy(L.ev);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   for (void* c : ctx->chunks) cudaFree(c);
   if (ctx->pin) cudaFreeHost(ctx->pin);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NIS_OK;
 }
@@ -459,6 +506,13 @@ int nis_synchronize(nis_ctx* ctx) {
   return NIS_OK;
 }
 long long nis_kernel_launches(const nis_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int nis_set_lanes(nis_ctx* ctx, int lanes) {
+  if (!ctx || lanes < 0) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  ctx->active_lanes = lanes > 0 ? std::min(lanes, (int)ctx->lanes.size()) : 3;
+  return NIS_OK;
+}
 int nis_set_batch(nis_ctx* ctx, int batch) {
   if (!ctx || batch < 0) return NIS_ERR_INVALID_ARGUMENT;
   ctx->batch = batch > 0 ? batch : 16;
@@ -493,7 +547,7 @@ int nis_features_u8(nis_ctx* ctx, const uint8_t* image, nis_frame** out) {
   nis_frame* f = nullptr;
   TRY(frame_alloc(ctx, true, &f));
   cudaError_t e = cudaMemcpyAsync(f->img_u8, image, ctx->sz[0].real, cudaMemcpyHostToDevice, ctx->stream);
-  int st = e == cudaSuccess ? features_batch(ctx, src_null<float>(), src_slab<uint8_t>(f->img_u8, 0), true, 1,
+  int st = e == cudaSuccess ? features_batch(ctx, ctx->lanes[0], src_null<float>(), src_slab<uint8_t>(f->img_u8, 0), true, 1,
                                               Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
                             : fail(ctx, NIS_ERR_CUDA, "cudaMemcpyAsync image", (int)e);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
@@ -510,7 +564,7 @@ int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out)
   std::vector<float> rm(ctx->sz[0].real);
   transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());      // [W][H] lines -> [H][W]
   cudaError_t e = h2d(ctx, f->img_f32, rm.data(), rm.size() * sizeof(float));
-  int st = e == cudaSuccess ? features_batch(ctx, src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1,
+  int st = e == cudaSuccess ? features_batch(ctx, ctx->lanes[0], src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1,
                                               Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
                             : fail(ctx, NIS_ERR_CUDA, "cudaMemcpy image", (int)e);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
@@ -565,7 +619,7 @@ int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, 
   CU(cudaSetDevice(ctx->device));
   TRY(ensure_recs(ctx, 1));
   const bool u8 = cur->img_u8 != nullptr;
-  TRY(compute_pose_batch(ctx, !not_large_rotation, src_slab<cpx>(last->F, 0), src_slab<cpx>(last->P, 0), src_slab<cpx>(cur->P, 0),
+  TRY(compute_pose_batch(ctx, ctx->lanes[0], !not_large_rotation, src_slab<cpx>(last->F, 0), src_slab<cpx>(last->P, 0), src_slab<cpx>(cur->P, 0),
                          src_slab<float>(cur->img_f32, 0), src_slab<uint8_t>(cur->img_u8, 0), u8, 1, 0, ctx->recs.as<PoseRecord>()));
   PoseRecord r;
   CU(cudaMemcpyAsync(&r, ctx->recs.p, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));
@@ -589,19 +643,24 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   }
   TRY(ensure_recs(ctx, std::max(n - 1, 1)));
   const int B = ctx->batch;
+  const int NL = ctx->active_lanes;
   cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
-  for (int t0 = 0; t0 < n; t0 += B) {
+  TRY(fork_lanes(ctx));
+  for (int t0 = 0, k = 0; t0 < n; t0 += B, ++k) {
     const int nb = std::min(B, n - t0);
-    TRY(features_batch(ctx, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
+    TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
                        Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp}));
   }
-  for (int p0 = 0; p0 < n - 1; p0 += B) {
+  TRY(join_lanes(ctx));          // a pair needs the features of both of its frames
+  TRY(fork_lanes(ctx));
+  for (int p0 = 0, k = 0; p0 < n - 1; p0 += B, ++k) {
     const int nb = std::min(B, n - 1 - p0);
-    TRY(compute_pose_batch(ctx, false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt), src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp),
-                           src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp), src_null<float>(),
-                           src_slab<uint8_t>(d_frames + (size_t)(p0 + 1) * npx, (long long)npx), true, nb, p0,
+    TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt),
+                           src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp),
+                           src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)(p0 + 1) * npx, (long long)npx), true, nb, p0,
                            ctx->recs.as<PoseRecord>() + p0));
   }
+  TRY(join_lanes(ctx));
   if (n > 1) {
     TRY(ensure_pinned(ctx, (size_t)(n - 1) * sizeof(PoseRecord)));
     CU(cudaMemcpyAsync(ctx->pin, ctx->recs.p, (size_t)(n - 1) * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
@@ -671,22 +730,24 @@ static int db_add_images_impl(nis_ctx* ctx, const uint8_t* images, bool on_host,
   int s0 = 0;
   TRY(db_reserve_slots(ctx, n, &s0));
   const int B = ctx->batch;
-  if (on_host) RESERVE(ctx->sImg, (size_t)B * npx);
-  for (int i0 = 0; i0 < n;) {
+  const int NL = ctx->active_lanes;
+  const uint8_t* d_images = images;
+  if (on_host) {                      // stage the whole upload once (u8 images are 1/8.5 of the features they turn into)
+    RESERVE(ctx->sImg, (size_t)n * npx);
+    CU(cudaMemcpyAsync(ctx->sImg.p, images, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
+    d_images = ctx->sImg.as<uint8_t>();
+  }
+  TRY(fork_lanes(ctx));
+  for (int i0 = 0, k = 0; i0 < n; ++k) {
     const int slot = s0 + i0;
     const int room = ctx->chunk_slots - slot % ctx->chunk_slots;       // stay inside one chunk (contiguous records)
     const int nb = std::min(std::min(B, n - i0), room);
-    const uint8_t* src = images + (size_t)i0 * npx;
-    if (on_host) {
-      CU(cudaMemcpyAsync(ctx->sImg.p, src, (size_t)nb * npx, cudaMemcpyHostToDevice, ctx->stream));
-      src = ctx->sImg.as<uint8_t>();
-    }
     cpx* base = ctx->slot_ptr[slot];
-    TRY(features_batch(ctx, src_null<float>(), src_slab<uint8_t>(src, (long long)npx), true, nb, Dst<cpx>{base, (long long)rec},
-                       Dst<cpx>{base + spt, (long long)rec}));
-    if (on_host) CU(cudaStreamSynchronize(ctx->stream));                // staging buffer reuse
+    TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_images + (size_t)i0 * npx, (long long)npx), true, nb,
+                       Dst<cpx>{base, (long long)rec}, Dst<cpx>{base + spt, (long long)rec}));
     i0 += nb;
   }
+  TRY(join_lanes(ctx));
   CU(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n; ++i) {
     ctx->slot_frame_id.push_back(ids ? ids[i] : s0 + i);
@@ -739,14 +800,18 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   const bool u8 = query->img_u8 != nullptr;
   const int B = ctx->batch;
   const cpx* const* ptrs = ctx->d_slot_ptr.as<const cpx*>();
-  for (int b0 = 0; b0 < n; b0 += B) {
+  const int NL = ctx->active_lanes;
+  TRY(fork_lanes(ctx));
+  for (int b0 = 0, k = 0; b0 < n; b0 += B, ++k) {
     const int nb = std::min(B, n - b0);
     const int* idx = ctx->cand.as<int>() + b0;
     Src<cpx> Fz{nullptr, 0, ptrs, 0, idx, 0};
     Src<cpx> Pz{nullptr, 0, ptrs, (long long)ctx->sz[0].spec, idx, 0};
-    TRY(compute_pose_batch(ctx, true, Fz, Pz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
+    TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], true, Fz, Pz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
                            src_slab<uint8_t>(query->img_u8, 0), u8, nb, b0, ctx->recs.as<PoseRecord>() + b0));
   }
+  TRY(join_lanes(ctx));
+  ctx->prof_stream = ctx->stream;
   LAUNCH(launch_scan_reduce(ctx->recs.as<PoseRecord>(), n, ctx->best.as<PoseRecord>(), ctx->stream));
   PoseRecord best;
   CU(cudaMemcpyAsync(&best, ctx->best.p, sizeof best, cudaMemcpyDeviceToHost, ctx->stream));
@@ -842,62 +907,66 @@ int nis_profile_end(nis_ctx* ctx, char* json_out, int json_cap) {
 int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_out) {
   if (!ctx || !real_in || !spec_out || which < 0 || which > 1) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
-  TRY(ensure_workspace(ctx, 1));
+  Lane& L = ctx->lanes[0];
+  TRY(ensure_workspace(ctx, L, 1));
   const SizeClass& z = ctx->sz[which];
-  CU(h2d(ctx, ctx->rk.p, real_in, z.real * sizeof(float)));
-  TRY(fft2_batch(ctx, which, src_slab<float>(ctx->rk.as<float>(), 0), src_null<uint8_t>(), false, 1, Dst<cpx>{ctx->kxz.as<cpx>(), 0}));
+  CU(h2d(ctx, L.rk.p, real_in, z.real * sizeof(float)));
+  TRY(fft2_batch(ctx, L, which, src_slab<float>(L.rk.as<float>(), 0), src_null<uint8_t>(), false, 1, Dst<cpx>{L.kxz.as<cpx>(), 0}));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(spec_out, ctx->kxz.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(spec_out, L.kxz.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
   return NIS_OK;
 }
 
 int nis_debug_ifft2(nis_ctx* ctx, int which, const float* spec_in, float* real_out) {
   if (!ctx || !spec_in || !real_out || which < 0 || which > 1) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
-  TRY(ensure_workspace(ctx, 1));
+  Lane& L = ctx->lanes[0];
+  TRY(ensure_workspace(ctx, L, 1));
   const SizeClass& z = ctx->sz[which];
-  CU(h2d(ctx, ctx->kxz.p, spec_in, z.spec * sizeof(cpx)));
-  Dst<cpx> t1{ctx->t1.as<cpx>(), 0};
+  CU(h2d(ctx, L.kxz.p, spec_in, z.spec * sizeof(cpx)));
+  Dst<cpx> t1{L.t1.as<cpx>(), 0};
   // the inverse row pass has no plain-load instantiation: multiply by conj(1) through ProMulConj instead
   {
     std::vector<cpx> ones(z.spec, make_float2(1.f, 0.f));
-    CU(h2d(ctx, ctx->kzz.p, ones.data(), z.spec * sizeof(cpx)));
+    CU(h2d(ctx, L.kzz.p, ones.data(), z.spec * sizeof(cpx)));
   }
-  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(ctx->kxz.as<cpx>(), 0), src_slab<cpx>(ctx->kzz.as<cpx>(), 0)},
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(L.kxz.as<cpx>(), 0), src_slab<cpx>(L.kzz.as<cpx>(), 0)},
                                 EpiSpecStore{t1}, z.R / 2 + 1, 1, ctx->stream));
-  LAUNCH(launch_col_inv_store(z.R, z.coli, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{ctx->rk.as<float>(), 0}, z.C, (float)z.real},
+  LAUNCH(launch_col_inv_store(z.R, z.coli, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{L.rk.as<float>(), 0}, z.C, (float)z.real},
                               z.C, 1, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(real_out, ctx->rk.p, z.real * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(real_out, L.rk.p, z.real * sizeof(float), cudaMemcpyDeviceToHost));
   return NIS_OK;
 }
 
 int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
   if (!ctx || !power_in || !polar_out) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
-  TRY(ensure_workspace(ctx, 1));
-  CU(h2d(ctx, ctx->rk.p, power_in, ctx->sz[0].real * sizeof(float)));
-  LAUNCH(launch_polar(src_slab<float>(ctx->rk.as<float>(), 0), Dst<float>{ctx->rot.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
+  Lane& L = ctx->lanes[0];
+  TRY(ensure_workspace(ctx, L, 1));
+  CU(h2d(ctx, L.rk.p, power_in, ctx->sz[0].real * sizeof(float)));
+  LAUNCH(launch_polar(src_slab<float>(L.rk.as<float>(), 0), Dst<float>{L.rot.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
                       ctx->cs.as<double>(), ctx->rho.as<float>(), 1, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(polar_out, ctx->rot.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(polar_out, L.rot.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
   return NIS_OK;
 }
 
 int nis_debug_rotate(nis_ctx* ctx, const float* image_in, float degree, float* image_out) {
   if (!ctx || !image_in || !image_out) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
-  TRY(ensure_workspace(ctx, 1));
+  Lane& L = ctx->lanes[0];
+  TRY(ensure_workspace(ctx, L, 1));
   double M[6];
   rotation_inverse(ctx->H, ctx->W, (double)degree, M);
   const int slot = 3 * ctx->D;
   CU(h2d(ctx, ctx->mats.as<double>() + 6 * (size_t)slot, M, sizeof M));
-  CU(h2d(ctx, ctx->sel.p, &slot, sizeof(int)));
-  CU(h2d(ctx, ctx->rk.p, image_in, ctx->sz[0].real * sizeof(float)));
-  LAUNCH(launch_rotate(src_slab<float>(ctx->rk.as<float>(), 0), src_null<uint8_t>(), ctx->lut.as<float>(), Dst<float>{ctx->rot.as<float>(), 0},
-                       ctx->H, ctx->W, ctx->mats.as<double>(), ctx->sel.as<int>(), 1, ctx->stream));
+  CU(h2d(ctx, L.sel.p, &slot, sizeof(int)));
+  CU(h2d(ctx, L.rk.p, image_in, ctx->sz[0].real * sizeof(float)));
+  LAUNCH(launch_rotate(src_slab<float>(L.rk.as<float>(), 0), src_null<uint8_t>(), ctx->lut.as<float>(), Dst<float>{L.rot.as<float>(), 0},
+                       ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), 1, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(image_out, ctx->rot.p, ctx->sz[0].real * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(image_out, L.rot.p, ctx->sz[0].real * sizeof(float), cudaMemcpyDeviceToHost));
   return NIS_OK;
 }
 
@@ -905,7 +974,8 @@ int nis_debug_estimate_trans(nis_ctx* ctx, int which, const float* last_spec, co
                              float* g_out) {
   if (!ctx || !last_spec || !cur_spec || !peak_rc || !info || which < 0 || which > 1) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
-  TRY(ensure_workspace(ctx, 1));
+  Lane& L = ctx->lanes[0];
+  TRY(ensure_workspace(ctx, L, 1));
   const SizeClass& z = ctx->sz[which];
   // inputs parked in xs (Z) and the second half of rot (X); g in the first half of rot... keep it simple: two dedicated temporaries
   DevBuf dz, dx, dg;
@@ -916,10 +986,10 @@ int nis_debug_estimate_trans(nis_ctx* ctx, int which, const float* last_spec, co
       h2d(ctx, dx.p, cur_spec, z.spec * sizeof(cpx)) != cudaSuccess)
     st = fail(ctx, NIS_ERR_CUDA, "debug copy", (int)cudaGetLastError());
   PeakStats ps;
-  if (st == NIS_OK) st = estimate_trans_batch(ctx, which, src_slab<cpx>(dz.as<cpx>(), 0), 1, src_slab<cpx>(dz.as<cpx>(), 0),
-                                              src_slab<cpx>(dx.as<cpx>(), 0), 1, 0, ctx->stats_t.as<PeakStats>(), g_out ? dg.as<float>() : nullptr);
+  if (st == NIS_OK) st = estimate_trans_batch(ctx, L, which, src_slab<cpx>(dz.as<cpx>(), 0), 1, src_slab<cpx>(dz.as<cpx>(), 0),
+                                              src_slab<cpx>(dx.as<cpx>(), 0), 1, 0, L.stats_t.as<PeakStats>(), g_out ? dg.as<float>() : nullptr);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug sync", (int)cudaGetLastError());
-  if (st == NIS_OK && cudaMemcpy(&ps, ctx->stats_t.p, sizeof ps, cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug copy back");
+  if (st == NIS_OK && cudaMemcpy(&ps, L.stats_t.p, sizeof ps, cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug copy back");
   if (st == NIS_OK && g_out && cudaMemcpy(g_out, dg.p, z.real * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug g copy");
   dz.release(); dx.release(); dg.release();
   if (st != NIS_OK) return st;

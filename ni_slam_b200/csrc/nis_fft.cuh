@@ -393,7 +393,7 @@ template <int N, int R1, int R2, int L, int T> struct RowGeom {
   static NIS_HD int pad(int i) { return i + (i >> 4); }
 };
 
-// Pro::load(line, c) -> cpx for local line index `line` in [0,L) (caller guards valid lines); c in [0,N)
+// Pro::line(ln).load(c) -> cpx for local line index ln in [0,L) (caller guards valid lines); c in [0,N)
 template <int N, int R1, int R2, int L, int T, bool INV, class Pro>
 NIS_HD void row_phase0(int tid, cpx* smem, const Pro& pro, int nlines) {
   typedef RowGeom<N, R1, R2, L, T> Gm;
@@ -401,8 +401,9 @@ NIS_HD void row_phase0(int tid, cpx* smem, const Pro& pro, int nlines) {
     const int ln = w / Gm::M0, j = w % Gm::M0;
     if (ln >= nlines) break;
     cpx v[16];
+    const auto lc = pro.line(ln);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = pro.load(ln, j + r * Gm::M0);
+    for (int r = 0; r < 16; ++r) v[r] = lc.load(j + r * Gm::M0);
     Dft<16, INV>::run(v);
     cpx* s = smem + ln * Gm::PITCH + j * 17;     // pad(16 j + r) = 17 j + r
 #pragma unroll
@@ -446,7 +447,7 @@ NIS_HD void row_stage1_write(int tid, cpx* smem, int nlines, const CarryRegs<R1,
   }
 }
 
-// Epi::put(line, c, value)
+// Epi::line(ln).put(c, value)
 template <int N, int R1, int R2, int L, int T, bool INV, class Epi>
 NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines, Epi& epi) {
   typedef RowGeom<N, R1, R2, L, T> Gm;
@@ -463,8 +464,9 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
       v[r] = x;
     }
     Dft<R2, INV>::run(v);
+    const auto lc = epi.line(ln);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) epi.put(ln, j + r * NS2, v[r]);
+    for (int r = 0; r < R2; ++r) lc.put(j + r * NS2, v[r]);
   }
 }
 

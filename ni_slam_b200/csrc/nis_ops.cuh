@@ -157,7 +157,7 @@ struct EpiPeak {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// row-pass prologues: load(ln, c) for local line ln of this CTA; global line g = line0+ln -> (b, k1)
+// row-pass prologues / epilogue; local line ln of this CTA -> global line g = line0+ln -> (batch b, spectrum row k1)
 // ---------------------------------------------------------------------------------------------------------
 struct LineMap {
   int line0, nrows, W;     // nrows = R/2+1 spectrum rows per batch element
@@ -168,36 +168,37 @@ struct LineMap {
   }
 };
 
+// Each prologue exposes line(ln) -> per-line context (batch element, row offset, per-image scalars resolved once)
+// whose load(c) produces the input sample at column c.
 struct ProSpec {      // plain spectrum load
   Src<cpx> x;
+  struct Line { const cpx* p; NIS_HD cpx load(int c) const { return NIS_LDG(p + c); } };
   struct Bound {
     Src<cpx> x; LineMap m;
-    NIS_HD cpx load(int ln, int c) const { int b, k1; size_t off; m.map(ln, b, off, k1); return NIS_LDG(x.at(b) + off + c); }
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{x.at(b) + off}; }
   };
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
 };
 
 struct ProAbs {       // |F| (correlation_flow.cc:92: fft_result.abs())
   Src<cpx> x;
+  struct Line {
+    const cpx* p;
+    NIS_HD cpx load(int c) const { const cpx v = NIS_LDG(p + c); return make_float2(sqrtf(v.x * v.x + v.y * v.y), 0.f); }
+  };
   struct Bound {
     Src<cpx> x; LineMap m;
-    NIS_HD cpx load(int ln, int c) const {
-      int b, k1; size_t off; m.map(ln, b, off, k1);
-      const cpx v = NIS_LDG(x.at(b) + off + c);
-      return make_float2(hypotf(v.x, v.y), 0.f);
-    }
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{x.at(b) + off}; }
   };
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
 };
 
 struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:220-221)
   Src<cpx> x, z;
+  struct Line { const cpx* px; const cpx* pz; NIS_HD cpx load(int c) const { return cmulc(NIS_LDG(px + c), NIS_LDG(pz + c)); } };
   struct Bound {
     Src<cpx> x, z; LineMap m;
-    NIS_HD cpx load(int ln, int c) const {
-      int b, k1; size_t off; m.map(ln, b, off, k1);
-      return cmulc(NIS_LDG(x.at(b) + off + c), NIS_LDG(z.at(b) + off + c));
-    }
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{x.at(b) + off, z.at(b) + off}; }
   };
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, z, m}; }
 };
@@ -215,18 +216,21 @@ NIS_HD float bits2f(unsigned int u) {
 // max_zz is indexed by b >> zz_shift and kzz carries the same shift (two rotation hypotheses share one keyframe Kzz).
 struct ProFilter {
   Src<cpx> kzz, kxz; const unsigned int* max_zz; const unsigned int* max_xz; int zz_shift; float lambda;
+  struct Line {
+    const cpx* pz; const cpx* px; float izz, ixz, lambda; int k1;
+    NIS_HD cpx load(int c) const {
+      const cpx z = NIS_LDG(pz + c), x = NIS_LDG(px + c);
+      const float dr = z.x * izz + lambda, di = z.y * izz;
+      const float t = ((k1 + c) & 1) ? -ixz : ixz;
+      const float s = t / (dr * dr + di * di);
+      return cmul(make_float2(s * dr, -s * di), x);
+    }
+  };
   struct Bound {
     Src<cpx> kzz, kxz; const unsigned int* max_zz; const unsigned int* max_xz; int zz_shift; float lambda; LineMap m;
-    NIS_HD cpx load(int ln, int c) const {
+    NIS_HD Line line(int ln) const {
       int b, k1; size_t off; m.map(ln, b, off, k1);
-      const int bz = b >> zz_shift;
-      const float izz = 1.0f / bits2f(max_zz[bz]), ixz = 1.0f / bits2f(max_xz[b]);
-      const cpx z = NIS_LDG(kzz.at(b) + off + c), x = NIS_LDG(kxz.at(b) + off + c);
-      const float dr = z.x * izz + lambda, di = z.y * izz;
-      const float t = ((k1 + c) & 1) ? -1.f : 1.f;
-      const float den = dr * dr + di * di;
-      const cpx h = make_float2(t * dr / den, -t * di / den);
-      return cmul(h, make_float2(x.x * ixz, x.y * ixz));
+      return Line{kzz.at(b) + off, kxz.at(b) + off, 1.0f / bits2f(max_zz[b >> zz_shift]), 1.0f / bits2f(max_xz[b]), lambda, k1};
     }
   };
   NIS_HD Bound bind(const LineMap& m) const { return Bound{kzz, kxz, max_zz, max_xz, zz_shift, lambda, m}; }
@@ -235,9 +239,10 @@ struct ProFilter {
 // row-pass epilogue: store the spectrum line
 struct EpiSpecStore {
   Dst<cpx> dst;
+  struct Line { cpx* p; NIS_HD void put(int c, cpx v) const { p[c] = v; } };
   struct Bound {
     Dst<cpx> dst; LineMap m;
-    NIS_HD void put(int ln, int c, cpx v) { int b, k1; size_t off; m.map(ln, b, off, k1); dst.at(b)[off + c] = v; }
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{dst.at(b) + off}; }
   };
   NIS_HD Bound bind(const LineMap& m) const { return Bound{dst, m}; }
 };

@@ -124,3 +124,15 @@ def test_argmax_tiebreak_rule_in_kernel_key(emu):
     assert np.all(g == g[0, 0, 0])
     key = int(stats[0, 0])
     assert divmod(0xFFFFFFFF - (key & 0xFFFFFFFF), N) == (0, 0)
+
+
+def test_cpp_shim_compiles_against_the_abi():
+    """The reference-facing C++ shim (host/correlation_flow.hpp) and its driver compile and link against libnislam.so."""
+    from ni_slam_b200 import build
+    build.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "shim_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "shim_test.cc"), "-o", exe, "-L",
+                           os.path.join(ROOT, "ni_slam_b200", "lib"), "-lnislam",
+                           "-Wl,-rpath," + os.path.join(ROOT, "ni_slam_b200", "lib")])
+    assert os.path.exists(exe)

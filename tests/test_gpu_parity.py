@@ -284,3 +284,19 @@ def test_large_rotation_loop_mode(cf, golden_pairs, imgs):
     info, pose, pk = cf.ComputePose(fa, fb, False, return_peaks=True)
     assert (pose[0], pose[1]) == (-41.0, -17.0)
     assert abs(wrap_pi(pose[2] - np.deg2rad(152.0))) < 1e-6
+
+
+# ------------------------------------------------------------------ reference-facing C++ shim
+def test_cpp_shim_known_answers():
+    """ni_slam_b200/host/correlation_flow.hpp driven like MapBuilder drives the reference classes (tests/cpp/shim_test.cc)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "_build", "shim_test")
+    src = os.path.join(root, "tests", "cpp", "shim_test.cc")
+    if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", src, "-o", exe, "-L", os.path.join(root, "ni_slam_b200", "lib"), "-lnislam",
+                               "-Wl,-rpath," + os.path.join(root, "ni_slam_b200", "lib")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "shim_test ok" in out.stdout, out.stdout + out.stderr
