@@ -4,7 +4,7 @@ Only what the path needs: csrc/ (CUDA kernels + C ABI), host/ (C++ shim with the
 api.py (the same surface for Python) and build.py (in-tree nvcc build).  There is no CPU fallback.
 """
 from .api import (CFConfig, CorrelationFlow, Frame, LoopClosure, LoopClosureConfig, LoopClosureResult, LoopResultC, NisError,
-                  LIB_PATH, SYMBOLS, load_library)
+                  LIB_PATH, SYMBOLS, load_library, loop_reduce)
 
 __all__ = ["CFConfig", "CorrelationFlow", "Frame", "LoopClosure", "LoopClosureConfig", "LoopClosureResult", "LoopResultC",
-           "NisError", "LIB_PATH", "SYMBOLS", "load_library"]
+           "NisError", "LIB_PATH", "SYMBOLS", "load_library", "loop_reduce"]

@@ -379,14 +379,22 @@ class LoopClosure:
 
     def Reduce(self, per_rank, order=None):
         """Multi-GPU: pick the winner among per-rank results with the reference's rule (strict '>', first wins)."""
-        cf = self._cf
-        arr = (LoopResultC * len(per_rank))(*[r.raw if isinstance(r, LoopClosureResult) else r for r in per_rank])
-        o = np.ascontiguousarray(order, np.int64) if order is not None else None
-        out = LoopResultC()
-        win = C.c_int()
-        cfg = self._cfg_c()
-        cf._check(cf._lib.nis_loop_reduce(arr, _p(o), len(per_rank), C.byref(cfg), C.byref(out), C.byref(win)))
-        return _result_from_c(out), win.value
+        return loop_reduce(per_rank, order, self._loop_thr)
+
+
+def loop_reduce(per_rank, order, loop_cfg: LoopClosureConfig):
+    """nis_loop_reduce: merge the all-gathered per-rank best records (host-only, needs no GPU).  `order[i]` = position of
+    rank i's winner in the global iteration order (ties: smallest wins)."""
+    lib = load_library()
+    arr = (LoopResultC * len(per_rank))(*[r.raw if isinstance(r, LoopClosureResult) else r for r in per_rank])
+    o = np.ascontiguousarray(order, np.int64) if order is not None else None
+    out = LoopResultC()
+    win = C.c_int()
+    cfg = _LoopConfigC(loop_cfg.position_response_thr, loop_cfg.angle_response_thr, loop_cfg.frame_gap_thr, loop_cfg.distance_thr)
+    st = lib.nis_loop_reduce(arr, _p(o), len(per_rank), C.byref(cfg), C.byref(out), C.byref(win))
+    if st != NIS_OK:
+        raise NisError(st, lib.nis_strerror(st).decode())
+    return _result_from_c(out), win.value
 
 
 def _result_from_c(out: LoopResultC) -> LoopClosureResult:
