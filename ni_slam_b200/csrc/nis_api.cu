@@ -44,6 +44,8 @@ struct nis_frame {
   float* img_f32 = nullptr;
   cpx* F = nullptr;            // fft_result  [H/2+1][W]
   cpx* P = nullptr;            // fft_polar   [D/2+1][Cp]
+  cpx* Ht = nullptr;           // T/(kernel(F)/max + lambda): the keyframe-only factor of EstimateTrans, translation stage
+  cpx* Hp = nullptr;           // same for the polar stage
   void* block = nullptr;       // single allocation backing all of the above
 };
 
@@ -59,7 +61,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;
   int cap = 0;                 // workspace capacity in pairs
-  DevBuf t1, rk, kxz, kzz, rot, xs, maxzz, maxxz, stats_p, stats_t, sel, xxz, xxx;
+  DevBuf t1, real, maxp, maxt, maxh, stats_p, stats_t, sel, xx, zz;
 };
 
 struct nis_ctx {
@@ -81,10 +83,10 @@ struct nis_ctx {
   DevBuf recs, best, cand;
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
-  DevBuf sF, sP, sImg;
+  DevBuf sF, sP, sHt, sHp, sImg;
   // keyframe DB
   std::vector<void*> chunks;
-  int chunk_slots = 128;
+  int chunk_slots = 64;
   std::vector<cpx*> slot_ptr;          // host copy of the device pointer table
   std::vector<int> slot_frame_id;
   std::vector<double> slot_dist;
@@ -264,19 +266,16 @@ static int ensure_workspace(nis_ctx* ctx, Lane& L, int pairs) {
   if (pairs <= L.cap) return NIS_OK;
   CU(cudaStreamSynchronize(L.stream));
   const size_t E = 2 * (size_t)pairs;
-  RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));
-  RESERVE(L.rk, E * ctx->maxreal * sizeof(float));
-  RESERVE(L.kxz, E * ctx->maxspec * sizeof(cpx));
-  RESERVE(L.kzz, (size_t)pairs * ctx->maxspec * sizeof(cpx));
-  RESERVE(L.rot, E * ctx->maxreal * sizeof(float));
-  RESERVE(L.xs, E * ctx->sz[0].spec * sizeof(cpx));
-  RESERVE(L.maxzz, (size_t)pairs * sizeof(unsigned));
-  RESERVE(L.maxxz, E * sizeof(unsigned));
+  RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));          // the only full-size scratch: half-transformed spectra, in place
+  RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float));   // power = IFFT(|F|) feeding the polar gather
+  RESERVE(L.maxp, (size_t)pairs * sizeof(unsigned));
+  RESERVE(L.maxt, E * sizeof(unsigned));
+  RESERVE(L.maxh, (size_t)pairs * sizeof(unsigned));
   RESERVE(L.stats_p, (size_t)pairs * sizeof(PeakStats));
   RESERVE(L.stats_t, E * sizeof(PeakStats));
   RESERVE(L.sel, E * sizeof(int));
-  RESERVE(L.xxz, (size_t)pairs * sizeof(float));
-  RESERVE(L.xxx, E * sizeof(float));
+  RESERVE(L.xx, E * sizeof(double));
+  RESERVE(L.zz, (size_t)pairs * sizeof(double));
   L.cap = pairs;
   return NIS_OK;
 }
@@ -317,97 +316,119 @@ static int ensure_pinned(nis_ctx* ctx, size_t bytes) {
 // -------------------------------------------------------------------------------------------------------------
 // batched stages
 // -------------------------------------------------------------------------------------------------------------
-// 2-D r2c: real [B][R][C] (f32 slab or u8 source) -> spectrum
-static int fft2_batch(nis_ctx* ctx, Lane& L, int s, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> out) {
+// KernelFn for size class s (polynomial / gaussian, correlation_flow.cc:181-226)
+static KernelFn kernel_fn(const nis_ctx* ctx, int s, const double* xx, const double* zz, int zz_shift, unsigned* maxbuf) {
+  const nis_cf_config& c = ctx->cfg;
+  return KernelFn{(float)(unsigned)ctx->sz[s].real, c.kernel, c.offset, c.power, -1.f / (c.sigma * c.sigma), xx, zz, zz_shift, maxbuf};
+}
+
+// H = T / (kernel(Z)/max + lambda) for B keyframe spectra of size class s (the keyframe-only factor of EstimateTrans,
+// correlation_flow.cc:157-171: Kzz = kernel(z); H = output_fft/(Kzz + lambda)).  3 kernels, nothing real-valued is stored.
+static int hzz_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> Z, int B, Dst<cpx> Hout) {
   ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[s];
+  if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return fail(ctx, NIS_ERR_INVALID_KERNEL, "Received invalid kernel type");
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
-  if (is_u8) LAUNCH(launch_col_fwd_u8(z.R, z.colf, ProRealU8{u8, z.C, ctx->lut.as<float>()}, t1, z.C, B, L.stream));
-  else LAUNCH(launch_col_fwd_f32(z.R, z.colf, ProRealF32{f32, z.C}, t1, z.C, B, L.stream));
-  LAUNCH(launch_row_fwd(z.C, z.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, z.R / 2 + 1, B, L.stream));
+  Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
+  if (ctx->cfg.kernel == 1) LAUNCH(launch_spec_sqsum(Z, (int)z.spec, L.zz.as<double>(), B, L.stream));
+  CU(cudaMemsetAsync(L.maxh.p, 0, sizeof(unsigned) * B, L.stream));
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{Z, Z}, EpiSpecStore{t1}, z.R / 2 + 1, B, L.stream));
+  LAUNCH(launch_colcol(z.R, z.coli, z.colf, t1s, t1, kernel_fn(ctx, s, L.zz.as<double>(), L.zz.as<double>(), 0, L.maxh.as<unsigned>()),
+                       z.C, B, L.stream));
+  LAUNCH(launch_row_fwd_h(z.C, z.row, ProSpec{t1s}, EpiHStore{Hout, L.maxh.as<unsigned>(), ctx->cfg.lambda}, z.R / 2 + 1, B, L.stream));
   return NIS_OK;
 }
 
-// ComputeIntermedium (correlation_flow.cc:89-95) for B images
-static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> F, Dst<cpx> P) {
+// ComputeIntermedium (correlation_flow.cc:89-95) for B images, plus the cached H factors of both stages.
+// with_h = false skips the H factors (frames that are only ever "current").
+static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> F, Dst<cpx> P,
+                          Dst<cpx> Ht, Dst<cpx> Hp, bool with_h) {
   ctx->prof_stream = L.stream;
   TRY(ensure_workspace(ctx, L, B));
   const SizeClass& zt = ctx->sz[0];
   const SizeClass& zp = ctx->sz[1];
-  TRY(fft2_batch(ctx, L, 0, f32, u8, is_u8, B, F));                                              // fft_result = FFT(image)
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)zt.spec};
-  Dst<float> power{L.rk.as<float>(), (long long)zt.real};
-  Dst<float> pol{L.rot.as<float>(), (long long)zp.real};
-  LAUNCH(launch_row_inv_abs(zt.C, zt.row, ProAbs{src_slab<cpx>(F.base, F.stride)}, EpiSpecStore{t1}, zt.R / 2 + 1, B, L.stream));
-  LAUNCH(launch_col_inv_store(zt.R, zt.coli, src_slab<cpx>(t1.base, t1.stride), EpiStore{power, zt.C, (float)zt.real}, zt.C, B,
-                              L.stream));                                                   // power = IFFT(|F|)
-  LAUNCH(launch_polar(src_slab<float>(power.base, power.stride), pol, ctx->H, ctx->W, ctx->D, ctx->Cp, ctx->cs.as<double>(),
-                      ctx->rho.as<float>(), B, L.stream));                                  // polar(fftshift(RemoveZero(power)))
-  TRY(fft2_batch(ctx, L, 1, src_slab<float>(pol.base, pol.stride), src_null<uint8_t>(), false, B, P));   // fft_polar
+  Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
+  if (is_u8) LAUNCH(launch_col_fwd_u8(zt.R, zt.colf, ProRealU8{u8, zt.C, ctx->lut.as<float>()}, t1, zt.C, B, L.stream));
+  else LAUNCH(launch_col_fwd_f32(zt.R, zt.colf, ProRealF32{f32, zt.C}, t1, zt.C, B, L.stream));
+  // fft_result = FFT(image) stored from registers; the same kernel continues with IFFT(|fft_result|) along the rows
+  LAUNCH(launch_rowrow_storeabs(zt.C, zt.row, t1s, t1, MidStoreAbs{F}, zt.R / 2 + 1, B, L.stream));
+  Dst<float> power{L.real.as<float>(), (long long)zt.real};
+  LAUNCH(launch_col_inv_store(zt.R, zt.coli, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
+  // polar(fftshift(RemoveZeroComponent(power))) feeds the first FFT stage directly
+  Dst<cpx> t1p{L.t1.as<cpx>(), (long long)zp.spec};
+  PolarArgs pa{src_slab<float>(power.base, power.stride), ctx->H, ctx->W, ctx->cs.as<double>(), ctx->rho.as<float>()};
+  LAUNCH(launch_col_fwd_polar(zp.R, zp.colf, pa, t1p, zp.C, B, L.stream));
+  LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
+  if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
+    TRY(hzz_batch(ctx, L, 0, src_slab<cpx>(F.base, F.stride), B, Ht));
+    TRY(hzz_batch(ctx, L, 1, src_slab<cpx>(P.base, P.stride), B, Hp));
+  }
   return NIS_OK;
 }
 
-// kernel(x, z) (polynomial / gaussian, correlation_flow.cc:181-226) for E entries, unnormalised spectrum + max
-static int kernel_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> X, Src<cpx> Z, int E, const float* xx, const float* zz, int zz_shift,
-                        unsigned* maxbuf, Dst<cpx> out) {
-  ctx->prof_stream = L.stream;
+// the current-frame half of EstimateTrans (correlation_flow.cc:160, :171-178) on half-transformed input already in t1:
+//   [t1 holds row-inverse of X*conj(Z)] -> colcol (IFFT cols, kernel fn, FFT cols) -> rowrow (FFT rows, *H/max, IFFT rows)
+//   -> col_inv_peak (IFFT cols, arg-max + sums)
+static int correlate_tail(nis_ctx* ctx, Lane& L, int s, Src<cpx> Hz, int E, int zshift, unsigned* maxbuf, PeakStats* stats, float* g_debug) {
   const SizeClass& z = ctx->sz[s];
-  const nis_cf_config& c = ctx->cfg;
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
-  Dst<float> rk{L.rk.as<float>(), (long long)z.real};
-  CU(cudaMemsetAsync(maxbuf, 0, sizeof(unsigned) * E, L.stream));
-  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{X, Z}, EpiSpecStore{t1}, z.R / 2 + 1, E, L.stream));
-  EpiKernel ek{rk, z.C, (float)z.real, c.kernel, c.offset, c.power, -1.f / (c.sigma * c.sigma), xx, zz, zz_shift, maxbuf};
-  LAUNCH(launch_col_inv_kernel(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ek, z.C, E, L.stream));
-  TRY(fft2_batch(ctx, L, s, src_slab<float>(rk.base, rk.stride), src_null<uint8_t>(), false, E, out));
+  Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
+  LAUNCH(launch_colcol(z.R, z.coli, z.colf, t1s, t1, kernel_fn(ctx, s, L.xx.as<double>(), L.zz.as<double>(), zshift, maxbuf), z.C, E, L.stream));
+  Src<cpx> Hze = Hz; Hze.shift = zshift;
+  LAUNCH(launch_rowrow_filter(z.C, z.row, t1s, t1, MidFilterH{Hze, maxbuf}, z.R / 2 + 1, E, L.stream));
+  EpiPeak ep{stats, z.R, (float)z.real, g_debug, (long long)z.real, z.C};
+  LAUNCH(launch_col_inv_peak(z.R, z.coli, t1s, ep, z.C, E, L.stream));
   return NIS_OK;
 }
 
-// EstimateTrans (correlation_flow.cc:145-179) for E entries; entry e uses keyframe spectrum Z.at(e) and Kzz number e>>zshift
-static int estimate_trans_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> Zzz, int nzz, Src<cpx> Z, Src<cpx> X, int E, int zshift,
-                                PeakStats* stats, float* g_debug) {
+// EstimateTrans with both spectra stored (the polar stage): E == number of keyframes, no hypothesis sharing
+static int estimate_trans_stored(nis_ctx* ctx, Lane& L, int s, Src<cpx> Z, Src<cpx> Hz, Src<cpx> X, int B, unsigned* maxbuf,
+                                 PeakStats* stats, float* g_debug) {
   ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[s];
   if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return fail(ctx, NIS_ERR_INVALID_KERNEL, "Received invalid kernel type");
-  const float* xxz = nullptr; const float* xxx = nullptr;
   if (ctx->cfg.kernel == 1) {
-    LAUNCH(launch_spec_sqsum(Zzz, (int)z.spec, (float)(unsigned)z.real, L.xxz.as<float>(), nzz, L.stream));
-    LAUNCH(launch_spec_sqsum(X, (int)z.spec, (float)(unsigned)z.real, L.xxx.as<float>(), E, L.stream));
-    xxz = L.xxz.as<float>(); xxx = L.xxx.as<float>();
+    LAUNCH(launch_spec_sqsum(X, (int)z.spec, L.xx.as<double>(), B, L.stream));
+    LAUNCH(launch_spec_sqsum(Z, (int)z.spec, L.zz.as<double>(), B, L.stream));
   }
-  Dst<cpx> kzz{L.kzz.as<cpx>(), (long long)z.spec}, kxz{L.kxz.as<cpx>(), (long long)z.spec};
-  TRY(kernel_batch(ctx, L, s, Zzz, Zzz, nzz, xxz, xxz, 0, L.maxzz.as<unsigned>(), kzz));            // Kzz
-  TRY(kernel_batch(ctx, L, s, X, Z, E, xxx, xxz, zshift, L.maxxz.as<unsigned>(), kxz));             // Kxz
-  CU(cudaMemsetAsync(stats, 0, sizeof(PeakStats) * E, L.stream));
+  CU(cudaMemsetAsync(maxbuf, 0, sizeof(unsigned) * B, L.stream));
+  CU(cudaMemsetAsync(stats, 0, sizeof(PeakStats) * B, L.stream));
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
-  ProFilter pf{src_slab<cpx>(kzz.base, kzz.stride, zshift), src_slab<cpx>(kxz.base, kxz.stride), L.maxzz.as<unsigned>(),
-               L.maxxz.as<unsigned>(), zshift, ctx->cfg.lambda};
-  LAUNCH(launch_row_inv_filter(z.C, z.row, pf, EpiSpecStore{t1}, z.R / 2 + 1, E, L.stream));
-  EpiPeak ep{stats, z.R, (float)z.real, g_debug, (long long)z.real, z.C};
-  LAUNCH(launch_col_inv_peak(z.R, z.coli, src_slab<cpx>(t1.base, t1.stride), ep, z.C, E, L.stream));
-  return NIS_OK;
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{X, Z}, EpiSpecStore{t1}, z.R / 2 + 1, B, L.stream));
+  return correlate_tail(ctx, L, s, Hz, B, 0, maxbuf, stats, g_debug);
 }
 
 // ComputePose (correlation_flow.cc:97-138) for B pairs -> device records
-static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz, Src<cpx> Pz, Src<cpx> Px, Src<float> img_f32,
-                              Src<uint8_t> img_u8, bool is_u8, int B, int index0, PoseRecord* recs) {
+static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz, Src<cpx> Pz, Src<cpx> Htz, Src<cpx> Hpz, Src<cpx> Px,
+                              Src<float> img_f32, Src<uint8_t> img_u8, bool is_u8, int B, int index0, PoseRecord* recs) {
   ctx->prof_stream = L.stream;
   TRY(ensure_workspace(ctx, L, B));
   PeakStats* sp = L.stats_p.as<PeakStats>();
   PeakStats* st = L.stats_t.as<PeakStats>();
-  TRY(estimate_trans_batch(ctx, L, 1, Pz, B, Pz, Px, B, 0, sp, nullptr));                              // rotation
+  // rotation: EstimateTrans(last_fft_polar, fft_polar, ...)   (:103)
+  TRY(estimate_trans_stored(ctx, L, 1, Pz, Hpz, Px, B, L.maxp.as<unsigned>(), sp, nullptr));
   LAUNCH(launch_polar_select(sp, ctx->D, loop_mode ? 1 : 0, L.sel.as<int>(), B, L.stream));
+  // translation: FFT(RotateArray(image, -deg [+180])) never leaves the chip; one or two hypotheses per pair   (:107-132)
+  const SizeClass& zt = ctx->sz[0];
   const int shift = loop_mode ? 1 : 0, E = B << shift;
-  Dst<float> rot{L.rot.as<float>(), (long long)ctx->sz[0].real};
   Src<float> i32 = img_f32; i32.shift = shift;
   Src<uint8_t> i8 = img_u8; i8.shift = shift;
   if (is_u8) i32 = src_null<float>(); else i8 = src_null<uint8_t>();
-  LAUNCH(launch_rotate(i32, i8, ctx->lut.as<float>(), rot, ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), E,
-                       L.stream));                                                                // RotateArray(image, -deg[+180])
-  Dst<cpx> xs{L.xs.as<cpx>(), (long long)ctx->sz[0].spec};
-  TRY(fft2_batch(ctx, L, 0, src_slab<float>(rot.base, rot.stride), src_null<uint8_t>(), false, E, xs));
+  Dst<cpx> t1{L.t1.as<cpx>(), (long long)zt.spec};
+  Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
+  const bool gauss = ctx->cfg.kernel == 1;
+  if (gauss) {
+    CU(cudaMemsetAsync(L.xx.p, 0, sizeof(double) * E, L.stream));
+    LAUNCH(launch_spec_sqsum(Fz, (int)zt.spec, L.zz.as<double>(), B, L.stream));
+  }
+  CU(cudaMemsetAsync(L.maxt.p, 0, sizeof(unsigned) * E, L.stream));
+  CU(cudaMemsetAsync(st, 0, sizeof(PeakStats) * E, L.stream));
+  RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>()};
+  LAUNCH(launch_col_fwd_rotate(zt.R, zt.colf, ra, t1, zt.C, E, L.stream));
   Src<cpx> Fze = Fz; Fze.shift = shift;
-  TRY(estimate_trans_batch(ctx, L, 0, Fz, B, Fze, src_slab<cpx>(xs.base, xs.stride), E, shift, st, nullptr));   // translation
+  LAUNCH(launch_rowrow_mulconj(zt.C, zt.row, t1s, t1, MidMulConjZ{Fze, gauss ? L.xx.as<double>() : nullptr}, zt.R / 2 + 1, E, L.stream));
+  TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr));
   AngleTables tabs{ctx->mats.as<double>(), ctx->theta.as<double>()};
   LAUNCH(launch_pose_finalize(sp, st, tabs, ctx->H, ctx->W, ctx->D, ctx->Cp, loop_mode ? 1 : 0, index0, recs, B, L.stream));
   return NIS_OK;
@@ -484,10 +505,10 @@ int nis_destroy(nis_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
-                    &ctx->sP, &ctx->sImg, &ctx->d_slot_ptr};
+                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->d_slot_ptr};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {
-    DevBuf* lb[] = {&L.t1, &L.rk, &L.kxz, &L.kzz, &L.rot, &L.xs, &L.maxzz, &L.maxxz, &L.stats_p, &L.stats_t, &L.sel, &L.xxz, &L.xxx};
+    DevBuf* lb[] = {&L.t1, &L.real, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz};
     for (DevBuf* b : lb) b->release();
     if (L.ev) cudaEventDestroy(L.ev);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -524,11 +545,11 @@ static int frame_alloc(nis_ctx* ctx, bool u8, nis_frame** out) {
   nis_frame* f = new nis_frame();
   const size_t bF = ctx->sz[0].spec * sizeof(cpx), bP = ctx->sz[1].spec * sizeof(cpx);
   const size_t bI = ctx->sz[0].real * (u8 ? 1 : sizeof(float));
-  cudaError_t e = cudaMalloc(&f->block, bF + bP + bI);
+  cudaError_t e = cudaMalloc(&f->block, 2 * (bF + bP) + bI);
   if (e != cudaSuccess) { delete f; return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc frame", (int)e); }
   char* p = (char*)f->block;
-  f->F = (cpx*)p; f->P = (cpx*)(p + bF);
-  if (u8) f->img_u8 = (uint8_t*)(p + bF + bP); else f->img_f32 = (float*)(p + bF + bP);
+  f->F = (cpx*)p; f->P = (cpx*)(p + bF); f->Ht = (cpx*)(p + bF + bP); f->Hp = (cpx*)(p + 2 * bF + bP);
+  if (u8) f->img_u8 = (uint8_t*)(p + 2 * (bF + bP)); else f->img_f32 = (float*)(p + 2 * (bF + bP));
   *out = f;
   return NIS_OK;
 }
@@ -548,7 +569,7 @@ int nis_features_u8(nis_ctx* ctx, const uint8_t* image, nis_frame** out) {
   TRY(frame_alloc(ctx, true, &f));
   cudaError_t e = cudaMemcpyAsync(f->img_u8, image, ctx->sz[0].real, cudaMemcpyHostToDevice, ctx->stream);
   int st = e == cudaSuccess ? features_batch(ctx, ctx->lanes[0], src_null<float>(), src_slab<uint8_t>(f->img_u8, 0), true, 1,
-                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
+                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0}, Dst<cpx>{f->Ht, 0}, Dst<cpx>{f->Hp, 0}, true)
                             : fail(ctx, NIS_ERR_CUDA, "cudaMemcpyAsync image", (int)e);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
   if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
@@ -565,7 +586,7 @@ int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out)
   transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());      // [W][H] lines -> [H][W]
   cudaError_t e = h2d(ctx, f->img_f32, rm.data(), rm.size() * sizeof(float));
   int st = e == cudaSuccess ? features_batch(ctx, ctx->lanes[0], src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1,
-                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0})
+                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0}, Dst<cpx>{f->Ht, 0}, Dst<cpx>{f->Hp, 0}, true)
                             : fail(ctx, NIS_ERR_CUDA, "cudaMemcpy image", (int)e);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
   if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
@@ -603,6 +624,15 @@ int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft
     e = h2d(ctx, s == 0 ? f->F : f->P, t.data(), z.spec * sizeof(cpx));
   }
   if (e != cudaSuccess) { nis_frame_free(ctx, f); return fail(ctx, NIS_ERR_CUDA, "frame import copy", (int)e); }
+  // the keyframe-only factors H = T/(kernel(.)/max + lambda) of both stages (the kernel id is validated at ComputePose, like the reference)
+  if (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1) {
+    Lane& L = ctx->lanes[0];
+    int st = ensure_workspace(ctx, L, 1);
+    if (st == NIS_OK) st = hzz_batch(ctx, L, 0, src_slab<cpx>(f->F, 0), 1, Dst<cpx>{f->Ht, 0});
+    if (st == NIS_OK) st = hzz_batch(ctx, L, 1, src_slab<cpx>(f->P, 0), 1, Dst<cpx>{f->Hp, 0});
+    if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "import sync", (int)cudaGetLastError());
+    if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
+  }
   *out = f;
   return NIS_OK;
 }
@@ -619,7 +649,8 @@ int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, 
   CU(cudaSetDevice(ctx->device));
   TRY(ensure_recs(ctx, 1));
   const bool u8 = cur->img_u8 != nullptr;
-  TRY(compute_pose_batch(ctx, ctx->lanes[0], !not_large_rotation, src_slab<cpx>(last->F, 0), src_slab<cpx>(last->P, 0), src_slab<cpx>(cur->P, 0),
+  TRY(compute_pose_batch(ctx, ctx->lanes[0], !not_large_rotation, src_slab<cpx>(last->F, 0), src_slab<cpx>(last->P, 0),
+                         src_slab<cpx>(last->Ht, 0), src_slab<cpx>(last->Hp, 0), src_slab<cpx>(cur->P, 0),
                          src_slab<float>(cur->img_f32, 0), src_slab<uint8_t>(cur->img_u8, 0), u8, 1, 0, ctx->recs.as<PoseRecord>()));
   PoseRecord r;
   CU(cudaMemcpyAsync(&r, ctx->recs.p, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));
@@ -635,6 +666,8 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec;
   RESERVE(ctx->sF, (size_t)n * spt * sizeof(cpx));
   RESERVE(ctx->sP, (size_t)n * spp * sizeof(cpx));
+  RESERVE(ctx->sHt, (size_t)n * spt * sizeof(cpx));
+  RESERVE(ctx->sHp, (size_t)n * spp * sizeof(cpx));
   const uint8_t* d_frames = frames;
   if (on_host) {
     RESERVE(ctx->sImg, (size_t)n * npx);
@@ -645,18 +678,21 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   const int B = ctx->batch;
   const int NL = ctx->active_lanes;
   cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
+  cpx* Ht = ctx->sHt.as<cpx>(); cpx* Hp = ctx->sHp.as<cpx>();
   TRY(fork_lanes(ctx));
   for (int t0 = 0, k = 0; t0 < n; t0 += B, ++k) {
     const int nb = std::min(B, n - t0);
     TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
-                       Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp}));
+                       Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
+                       Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));
   }
   TRY(join_lanes(ctx));          // a pair needs the features of both of its frames
   TRY(fork_lanes(ctx));
   for (int p0 = 0, k = 0; p0 < n - 1; p0 += B, ++k) {
     const int nb = std::min(B, n - 1 - p0);
     TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt),
-                           src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp),
+                           src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(Ht + (size_t)p0 * spt, (long long)spt),
+                           src_slab<cpx>(Hp + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp),
                            src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)(p0 + 1) * npx, (long long)npx), true, nb, p0,
                            ctx->recs.as<PoseRecord>() + p0));
   }
@@ -678,8 +714,11 @@ int nis_track_stream_dev(nis_ctx* ctx, const uint8_t* frames_dev, int n, double*
 }
 
 // ---- keyframe DB ------------------------------------------------------------------------------------------------
+// keyframe record = [F][P][Ht][Hp]
+static size_t db_record(const nis_ctx* ctx) { return 2 * (ctx->sz[0].spec + ctx->sz[1].spec); }
+
 static int db_reserve_slots(nis_ctx* ctx, int n_new, int* first) {
-  const size_t rec = ctx->sz[0].spec + ctx->sz[1].spec;
+  const size_t rec = db_record(ctx);
   const int old = (int)ctx->slot_ptr.size();
   *first = old;
   for (int i = 0; i < n_new; ++i) {
@@ -713,8 +752,8 @@ int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distan
   int s0 = 0;
   TRY(db_reserve_slots(ctx, 1, &s0));
   cpx* dst = ctx->slot_ptr[s0];
-  CU(cudaMemcpyAsync(dst, f->F, ctx->sz[0].spec * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(dst + ctx->sz[0].spec, f->P, ctx->sz[1].spec * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+  // a frame's F, P, Ht, Hp are contiguous in the same order as a record
+  CU(cudaMemcpyAsync(dst, f->F, db_record(ctx) * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->slot_frame_id.push_back(frame_id);
   ctx->slot_dist.push_back(acc_distance);
@@ -726,7 +765,7 @@ static int db_add_images_impl(nis_ctx* ctx, const uint8_t* images, bool on_host,
   if (!ctx || (!images && n > 0) || n < 0) return NIS_ERR_INVALID_ARGUMENT;
   if (n == 0) return NIS_OK;
   CU(cudaSetDevice(ctx->device));
-  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, rec = ctx->sz[0].spec + ctx->sz[1].spec;
+  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec, rec = db_record(ctx);
   int s0 = 0;
   TRY(db_reserve_slots(ctx, n, &s0));
   const int B = ctx->batch;
@@ -744,7 +783,8 @@ static int db_add_images_impl(nis_ctx* ctx, const uint8_t* images, bool on_host,
     const int nb = std::min(std::min(B, n - i0), room);
     cpx* base = ctx->slot_ptr[slot];
     TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_images + (size_t)i0 * npx, (long long)npx), true, nb,
-                       Dst<cpx>{base, (long long)rec}, Dst<cpx>{base + spt, (long long)rec}));
+                       Dst<cpx>{base, (long long)rec}, Dst<cpx>{base + spt, (long long)rec}, Dst<cpx>{base + spt + spp, (long long)rec},
+                       Dst<cpx>{base + 2 * spt + spp, (long long)rec}, true));
     i0 += nb;
   }
   TRY(join_lanes(ctx));
@@ -805,9 +845,12 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   for (int b0 = 0, k = 0; b0 < n; b0 += B, ++k) {
     const int nb = std::min(B, n - b0);
     const int* idx = ctx->cand.as<int>() + b0;
+    const long long spt = (long long)ctx->sz[0].spec, spp = (long long)ctx->sz[1].spec;
     Src<cpx> Fz{nullptr, 0, ptrs, 0, idx, 0};
-    Src<cpx> Pz{nullptr, 0, ptrs, (long long)ctx->sz[0].spec, idx, 0};
-    TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], true, Fz, Pz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
+    Src<cpx> Pz{nullptr, 0, ptrs, spt, idx, 0};
+    Src<cpx> Htz{nullptr, 0, ptrs, spt + spp, idx, 0};
+    Src<cpx> Hpz{nullptr, 0, ptrs, 2 * spt + spp, idx, 0};
+    TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], true, Fz, Pz, Htz, Hpz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
                            src_slab<uint8_t>(query->img_u8, 0), u8, nb, b0, ctx->recs.as<PoseRecord>() + b0));
   }
   TRY(join_lanes(ctx));
@@ -909,11 +952,17 @@ int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_ou
   CU(cudaSetDevice(ctx->device));
   Lane& L = ctx->lanes[0];
   TRY(ensure_workspace(ctx, L, 1));
+  ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[which];
-  CU(h2d(ctx, L.rk.p, real_in, z.real * sizeof(float)));
-  TRY(fft2_batch(ctx, L, which, src_slab<float>(L.rk.as<float>(), 0), src_null<uint8_t>(), false, 1, Dst<cpx>{L.kxz.as<cpx>(), 0}));
+  DevBuf out;
+  RESERVE(out, z.spec * sizeof(cpx));
+  CU(h2d(ctx, L.real.p, real_in, z.real * sizeof(float)));
+  Dst<cpx> t1{L.t1.as<cpx>(), 0};
+  LAUNCH(launch_col_fwd_f32(z.R, z.colf, ProRealF32{src_slab<float>(L.real.as<float>(), 0), z.C}, t1, z.C, 1, L.stream));
+  LAUNCH(launch_row_fwd(z.C, z.row, ProSpec{src_slab<cpx>(t1.base, 0)}, EpiSpecStore{Dst<cpx>{out.as<cpx>(), 0}}, z.R / 2 + 1, 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(spec_out, L.kxz.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(spec_out, out.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
+  out.release();
   return NIS_OK;
 }
 
@@ -922,20 +971,25 @@ int nis_debug_ifft2(nis_ctx* ctx, int which, const float* spec_in, float* real_o
   CU(cudaSetDevice(ctx->device));
   Lane& L = ctx->lanes[0];
   TRY(ensure_workspace(ctx, L, 1));
+  ctx->prof_stream = L.stream;
   const SizeClass& z = ctx->sz[which];
-  CU(h2d(ctx, L.kxz.p, spec_in, z.spec * sizeof(cpx)));
-  Dst<cpx> t1{L.t1.as<cpx>(), 0};
-  // the inverse row pass has no plain-load instantiation: multiply by conj(1) through ProMulConj instead
+  DevBuf in, one;
+  RESERVE(in, z.spec * sizeof(cpx));
+  RESERVE(one, z.spec * sizeof(cpx));
+  CU(h2d(ctx, in.p, spec_in, z.spec * sizeof(cpx)));
   {
+    // the inverse row pass has no plain-load instantiation: multiply by conj(1) through ProMulConj instead
     std::vector<cpx> ones(z.spec, make_float2(1.f, 0.f));
-    CU(h2d(ctx, L.kzz.p, ones.data(), z.spec * sizeof(cpx)));
+    CU(h2d(ctx, one.p, ones.data(), z.spec * sizeof(cpx)));
   }
-  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(L.kxz.as<cpx>(), 0), src_slab<cpx>(L.kzz.as<cpx>(), 0)},
-                                EpiSpecStore{t1}, z.R / 2 + 1, 1, ctx->stream));
-  LAUNCH(launch_col_inv_store(z.R, z.coli, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{L.rk.as<float>(), 0}, z.C, (float)z.real},
-                              z.C, 1, ctx->stream));
+  Dst<cpx> t1{L.t1.as<cpx>(), 0};
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(in.as<cpx>(), 0), src_slab<cpx>(one.as<cpx>(), 0)}, EpiSpecStore{t1},
+                                z.R / 2 + 1, 1, L.stream));
+  LAUNCH(launch_col_inv_store(z.R, z.coli, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{L.real.as<float>(), 0}, z.C, (float)z.real}, z.C, 1,
+                              L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(real_out, L.rk.p, z.real * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(real_out, L.real.p, z.real * sizeof(float), cudaMemcpyDeviceToHost));
+  in.release(); one.release();
   return NIS_OK;
 }
 
@@ -944,11 +998,15 @@ int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
   CU(cudaSetDevice(ctx->device));
   Lane& L = ctx->lanes[0];
   TRY(ensure_workspace(ctx, L, 1));
-  CU(h2d(ctx, L.rk.p, power_in, ctx->sz[0].real * sizeof(float)));
-  LAUNCH(launch_polar(src_slab<float>(L.rk.as<float>(), 0), Dst<float>{L.rot.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
-                      ctx->cs.as<double>(), ctx->rho.as<float>(), 1, ctx->stream));
+  ctx->prof_stream = L.stream;
+  DevBuf out;
+  RESERVE(out, ctx->sz[1].real * sizeof(float));
+  CU(h2d(ctx, L.real.p, power_in, ctx->sz[0].real * sizeof(float)));
+  LAUNCH(launch_polar(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
+                      ctx->cs.as<double>(), ctx->rho.as<float>(), 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(polar_out, L.rot.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(polar_out, out.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
+  out.release();
   return NIS_OK;
 }
 
@@ -957,16 +1015,20 @@ int nis_debug_rotate(nis_ctx* ctx, const float* image_in, float degree, float* i
   CU(cudaSetDevice(ctx->device));
   Lane& L = ctx->lanes[0];
   TRY(ensure_workspace(ctx, L, 1));
+  ctx->prof_stream = L.stream;
   double M[6];
   rotation_inverse(ctx->H, ctx->W, (double)degree, M);
   const int slot = 3 * ctx->D;
+  DevBuf out;
+  RESERVE(out, ctx->sz[0].real * sizeof(float));
   CU(h2d(ctx, ctx->mats.as<double>() + 6 * (size_t)slot, M, sizeof M));
   CU(h2d(ctx, L.sel.p, &slot, sizeof(int)));
-  CU(h2d(ctx, L.rk.p, image_in, ctx->sz[0].real * sizeof(float)));
-  LAUNCH(launch_rotate(src_slab<float>(L.rk.as<float>(), 0), src_null<uint8_t>(), ctx->lut.as<float>(), Dst<float>{L.rot.as<float>(), 0},
-                       ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), 1, ctx->stream));
+  CU(h2d(ctx, L.real.p, image_in, ctx->sz[0].real * sizeof(float)));
+  LAUNCH(launch_rotate(src_slab<float>(L.real.as<float>(), 0), src_null<uint8_t>(), ctx->lut.as<float>(), Dst<float>{out.as<float>(), 0},
+                       ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(image_out, L.rot.p, ctx->sz[0].real * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(image_out, out.p, ctx->sz[0].real * sizeof(float), cudaMemcpyDeviceToHost));
+  out.release();
   return NIS_OK;
 }
 
@@ -977,21 +1039,21 @@ int nis_debug_estimate_trans(nis_ctx* ctx, int which, const float* last_spec, co
   Lane& L = ctx->lanes[0];
   TRY(ensure_workspace(ctx, L, 1));
   const SizeClass& z = ctx->sz[which];
-  // inputs parked in xs (Z) and the second half of rot (X); g in the first half of rot... keep it simple: two dedicated temporaries
-  DevBuf dz, dx, dg;
-  RESERVE(dz, z.spec * sizeof(cpx)); RESERVE(dx, z.spec * sizeof(cpx));
+  DevBuf dz, dx, dh, dg;
+  RESERVE(dz, z.spec * sizeof(cpx)); RESERVE(dx, z.spec * sizeof(cpx)); RESERVE(dh, z.spec * sizeof(cpx));
   if (g_out) RESERVE(dg, z.real * sizeof(float));
   int st = NIS_OK;
-  if (h2d(ctx, dz.p, last_spec, z.spec * sizeof(cpx)) != cudaSuccess ||
-      h2d(ctx, dx.p, cur_spec, z.spec * sizeof(cpx)) != cudaSuccess)
+  if (h2d(ctx, dz.p, last_spec, z.spec * sizeof(cpx)) != cudaSuccess || h2d(ctx, dx.p, cur_spec, z.spec * sizeof(cpx)) != cudaSuccess)
     st = fail(ctx, NIS_ERR_CUDA, "debug copy", (int)cudaGetLastError());
   PeakStats ps;
-  if (st == NIS_OK) st = estimate_trans_batch(ctx, L, which, src_slab<cpx>(dz.as<cpx>(), 0), 1, src_slab<cpx>(dz.as<cpx>(), 0),
-                                              src_slab<cpx>(dx.as<cpx>(), 0), 1, 0, L.stats_t.as<PeakStats>(), g_out ? dg.as<float>() : nullptr);
+  if (st == NIS_OK) st = hzz_batch(ctx, L, which, src_slab<cpx>(dz.as<cpx>(), 0), 1, Dst<cpx>{dh.as<cpx>(), 0});
+  if (st == NIS_OK) st = estimate_trans_stored(ctx, L, which, src_slab<cpx>(dz.as<cpx>(), 0), src_slab<cpx>(dh.as<cpx>(), 0),
+                                               src_slab<cpx>(dx.as<cpx>(), 0), 1, L.maxt.as<unsigned>(), L.stats_t.as<PeakStats>(),
+                                               g_out ? dg.as<float>() : nullptr);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug sync", (int)cudaGetLastError());
   if (st == NIS_OK && cudaMemcpy(&ps, L.stats_t.p, sizeof ps, cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug copy back");
   if (st == NIS_OK && g_out && cudaMemcpy(g_out, dg.p, z.real * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "debug g copy");
-  dz.release(); dx.release(); dg.release();
+  dz.release(); dx.release(); dh.release(); dg.release();
   if (st != NIS_OK) return st;
   const uint32_t idx = 0xffffffffu - (uint32_t)(ps.key & 0xffffffffull);
   const int col = (int)(idx / (uint32_t)z.R), row = (int)(idx % (uint32_t)z.R);

@@ -211,6 +211,7 @@ template <int N, int R0, int R1, int R2, int T> struct ColGeom {
   static constexpr int G = T / kColLanes;
   static constexpr int M0 = N / R0, M1 = N / R1, M2 = N / R2;   // butterflies per line per stage
   static constexpr int NS1 = R0, NS2 = R0 * R1;
+  static constexpr int ROUNDS0 = (M0 + G - 1) / G;
   static constexpr int ROUNDS1 = (M1 + G - 1) / G;
   static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)N * kColLanes;
 };
@@ -266,6 +267,36 @@ NIS_HD void col_fwd_phase0(int tid, cpx* smem, const Pro& pro) {
     Dft<R0, false>::run(v);
 #pragma unroll
     for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = v[r];
+  }
+}
+
+// phase 0 when the real pairs already sit in shared memory (fused inverse -> element-wise -> forward): in place,
+// read all -> barrier -> write all
+template <int N, int R0, int R1, int R2, int T>
+NIS_HD void col_fwd_phase0s_read(int tid, const cpx* smem, CarryRegs<R0, ColGeom<N, R0, R1, R2, T>::ROUNDS0>& st) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+#pragma unroll
+  for (int it = 0; it < Gm::ROUNDS0; ++it) {
+    const int j = gi + it * Gm::G;
+    if (j < Gm::M0) {
+#pragma unroll
+      for (int r = 0; r < R0; ++r) st.v[it][r] = smem[(j + r * Gm::M0) * kColLanes + l];
+      Dft<R0, false>::run(st.v[it]);
+    }
+  }
+}
+template <int N, int R0, int R1, int R2, int T>
+NIS_HD void col_fwd_phase0s_write(int tid, cpx* smem, const CarryRegs<R0, ColGeom<N, R0, R1, R2, T>::ROUNDS0>& st) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+#pragma unroll
+  for (int it = 0; it < Gm::ROUNDS0; ++it) {
+    const int j = gi + it * Gm::G;
+    if (j < Gm::M0) {
+#pragma unroll
+      for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = st.v[it][r];
+    }
   }
 }
 
@@ -378,6 +409,27 @@ NIS_HD void col_inv_phase2(int tid, const cpx* smem, const Twiddles& twd, Epi& e
   }
 }
 
+// phase 2 of the inverse pass kept in shared memory: every thread overwrites exactly the slots it read with
+// fn(re), fn(im) (the real pairs the following forward pass consumes), so no barrier is needed inside.
+template <int N, int R0, int R1, int R2, int T, class Fn>
+NIS_HD void col_inv_phase2_inplace(int tid, cpx* smem, const Twiddles& twd, Fn& fn) {
+  typedef ColGeom<N, R0, R1, R2, T> Gm;
+  constexpr int NS2 = Gm::NS2;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+  for (int j = gi; j < NS2; j += Gm::G) {
+    cpx v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      cpx x = smem[(j + r * NS2) * kColLanes + l];
+      if (r > 0) x = cmul(x, tw<true>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
+      v[r] = x;
+    }
+    Dft<R2, true>::run(v);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) smem[(j + r * NS2) * kColLanes + l] = fn.apply(v[r]);
+  }
+}
+
 // =========================================================================================================
 // ROW PASS: contiguous complex lines of length N = 16*R1*R2, L lines per CTA, lanes <-> butterfly index.
 // smem: cpx[L][N + N/16] (one pad slot per 16).
@@ -469,5 +521,37 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
     for (int r = 0; r < R2; ++r) lc.put(j + r * NS2, v[r]);
   }
 }
+
+// forward phase 2 kept in shared memory with an element-wise step (fused forward -> element-wise -> inverse):
+// Mid::line(ln).apply(c, value) -> value; every thread overwrites exactly the padded slots it read.
+template <int N, int R1, int R2, int L, int T, class Mid>
+NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, Mid& mid) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+  constexpr int NS2 = Gm::NS2;
+  for (int w = tid; w < L * NS2; w += T) {
+    const int ln = w / NS2, j = w % NS2;
+    if (ln >= nlines) break;
+    cpx* s = smem + ln * Gm::PITCH;
+    cpx v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      cpx x = s[Gm::pad(j + r * NS2)];
+      if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
+      v[r] = x;
+    }
+    Dft<R2, false>::run(v);
+    auto lc = mid.line(ln);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) s[Gm::pad(j + r * NS2)] = lc.apply(j + r * NS2, v[r]);
+    lc.flush();
+  }
+}
+
+// prologue reading a natural-order padded line out of shared memory (input of the fused inverse pass)
+template <int PITCH> struct SmemLinePro {
+  const cpx* base;
+  struct Line { const cpx* p; NIS_HD cpx load(int c) const { return p[c + (c >> 4)]; } };
+  NIS_HD Line line(int ln) const { return Line{base + ln * PITCH}; }
+};
 
 }  // namespace nis

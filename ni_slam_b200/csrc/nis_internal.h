@@ -28,15 +28,23 @@ void plan_radices_col(int N, bool inverse, int r[3]);
 void plan_radices_row(int N, int r[3]);
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
+struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; };
+struct PolarArgs { Src<float> power; int H, W; const double* cs; const float* rho; };
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
+int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int E, cudaStream_t s);   // RotateArray fused into stage 0
+int launch_col_fwd_polar(int N, Twiddles tw, PolarArgs pa, Dst<cpx> out, int W, int B, cudaStream_t s);     // warpPolar fused into stage 0
 int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, int B, cudaStream_t s);
-int launch_col_inv_kernel(int N, Twiddles tw, Src<cpx> in, EpiKernel epi, int W, int B, cudaStream_t s);
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s);
+// c2r -> kernel function -> r2c in one kernel (the real kernel image never leaves shared memory); in-place allowed
+int launch_colcol(int N, Twiddles twi, Twiddles twf, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s);
 int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
-int launch_row_inv_abs(int N, Twiddles tw, ProAbs pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+int launch_row_fwd_h(int N, Twiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s);
 int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
-int launch_row_inv_filter(int N, Twiddles tw, ProFilter pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+// forward -> element-wise -> inverse in one kernel; in-place allowed (a CTA reads and writes only its own lines)
+int launch_rowrow_mulconj(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s);
+int launch_rowrow_filter(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s);
+int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s);
 
 // ---- warps and bookkeeping kernels -----------------------------------------------------------------------
 // polar: power [B][H][W] (IFFT(|F|), unshifted) -> polar image [B][D][Cp]; RemoveZeroComponent + fftshift fused in the taps
@@ -45,8 +53,8 @@ int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, 
 // rotate: out[e] = warpAffine(image[e], rot_mats[sel[e]]) with BORDER_WRAP.  Exactly one of img_f32 / img_u8 is used.
 int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
                   const int* sel, int E, cudaStream_t s);
-// gaussian kernel helper: out[b] = (float)(sum over half spectrum |x^2|) / n
-int launch_spec_sqsum(Src<cpx> x, int count, float n, float* out, int B, cudaStream_t s);
+// gaussian kernel helper: out[b] = sum over the stored half spectrum of |x^2| (raw, double)
+int launch_spec_sqsum(Src<cpx> x, int count, double* out, int B, cudaStream_t s);
 // after the polar stage: per pair, pick the rotation-matrix slot(s) for the translation stage
 int launch_polar_select(const PeakStats* polar, int D, int loop_mode, int* sel, int B, cudaStream_t s);
 // per pair: info (GetInfo), hypothesis choice, pose

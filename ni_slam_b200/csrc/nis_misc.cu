@@ -7,50 +7,16 @@
 // fixed-point coordinates and the 4-tap sums equal OpenCV's scalar code bit for bit.
 #include "nis_device.cuh"
 #include "nis_internal.h"
+#include "nis_warp.cuh"
 
 namespace nis {
-
-__device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
-
-// OpenCV BilinearTab_f weights: {(1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy fx}, all exact in f32
-__device__ __forceinline__ float bilinear4(float v0, float v1, float v2, float v3, int fx, int fy) {
-  const float x = (float)fx * (1.f / 32.f), y = (float)fy * (1.f / 32.f);
-  const float x0 = 1.f - x, y0 = 1.f - y;
-  float acc = __fmul_rn(v0, y0 * x0);
-  acc = __fadd_rn(acc, __fmul_rn(v1, y0 * x));
-  acc = __fadd_rn(acc, __fmul_rn(v2, y * x0));
-  acc = __fadd_rn(acc, __fmul_rn(v3, y * x));
-  return acc;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// polar warp.  Source = fftshift(RemoveZeroComponent(power)) evaluated on the fly from `power`.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float shifted_tap(const float* __restrict__ p, int y, int x, int H, int W) {
-  if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) return 0.f;   // BORDER_CONSTANT(0) (WARP_FILL_OUTLIERS)
-  int r = y - H / 2; r += (r < 0) ? H : 0;                                     // circ_shift.h:238-244
-  int c = x - W / 2; c += (c < 0) ? W : 0;
-  if (c == 0) return __fadd_rn(__ldg(p + (size_t)r * W + 1), __ldg(p + (size_t)r * W + W - 1)) * 0.5f;   // col rule (incl. (0,0))
-  if (r == 0) return __fadd_rn(__ldg(p + (size_t)W + c), __ldg(p + (size_t)(H - 1) * W + c)) * 0.5f;      // row rule
-  return __ldg(p + (size_t)r * W + c);
-}
 
 __global__ void __launch_bounds__(256) polar_kernel(Src<float> power, Dst<float> out, int H, int W, int D, int Cp,
                                                     const double* __restrict__ cs, const float* __restrict__ rho_tab) {
   const int b = blockIdx.z, phi = blockIdx.y;
   const int rho = blockIdx.x * blockDim.x + threadIdx.x;
   if (rho >= Cp) return;
-  const float* p = power.at(b);
-  const double cp = cs[2 * phi], sp = cs[2 * phi + 1];
-  const double rf = (double)rho_tab[rho];
-  const float cx = (float)W / 2, cy = (float)H / 2;
-  const float mx = (float)__dadd_rn(__dmul_rn(rf, cp), (double)cx);
-  const float my = (float)__dadd_rn(__dmul_rn(rf, sp), (double)cy);
-  const int sx = __float2int_rn(mx * 32.f), sy = __float2int_rn(my * 32.f);   // cvRound: half to even
-  const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
-  const float v0 = shifted_tap(p, iy, ix, H, W), v1 = shifted_tap(p, iy, ix + 1, H, W);
-  const float v2 = shifted_tap(p, iy + 1, ix, H, W), v3 = shifted_tap(p, iy + 1, ix + 1, H, W);
-  out.at(b)[(size_t)phi * Cp + rho] = bilinear4(v0, v1, v2, v3, sx & 31, sy & 31);
+  out.at(b)[(size_t)phi * Cp + rho] = polar_pixel(power.at(b), H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho]);
 }
 
 int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
@@ -64,13 +30,6 @@ int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, 
 // ---------------------------------------------------------------------------------------------------------
 // rotation (warpAffine, INTER_LINEAR, BORDER_WRAP, AB_BITS = 10, INTER_BITS = 5)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int wrap_idx(int p, int len) {
-  if ((unsigned)p < (unsigned)len) return p;
-  if (p < 0) p -= ((p - len + 1) / len) * len;
-  if (p >= len) p %= len;
-  return p;
-}
-
 template <bool U8>
 __global__ void __launch_bounds__(256) rotate_kernel(Src<float> img_f32, Src<uint8_t> img_u8, const float* __restrict__ lut,
                                                      Dst<float> out, int H, int W, const double* __restrict__ mats,
@@ -79,24 +38,9 @@ __global__ void __launch_bounds__(256) rotate_kernel(Src<float> img_f32, Src<uin
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
   const double* M = mats + 6 * (size_t)sel[e];
-  const int X0 = __double2int_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]) * 1024.0) + 16;
-  const int Y0 = __double2int_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]) * 1024.0) + 16;
-  const int adelta = __double2int_rn(__dmul_rn(M[0], (double)x) * 1024.0);
-  const int bdelta = __double2int_rn(__dmul_rn(M[3], (double)x) * 1024.0);
-  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-  const int ix = sat_short(X >> 5), iy = sat_short(Y >> 5);
-  const int x0 = wrap_idx(ix, W), x1 = wrap_idx(ix + 1, W), y0 = wrap_idx(iy, H), y1 = wrap_idx(iy + 1, H);
-  float v0, v1, v2, v3;
-  if (U8) {
-    const uint8_t* p = img_u8.at(e);
-    v0 = __ldg(&lut[p[(size_t)y0 * W + x0]]); v1 = __ldg(&lut[p[(size_t)y0 * W + x1]]);
-    v2 = __ldg(&lut[p[(size_t)y1 * W + x0]]); v3 = __ldg(&lut[p[(size_t)y1 * W + x1]]);
-  } else {
-    const float* p = img_f32.at(e);
-    v0 = __ldg(p + (size_t)y0 * W + x0); v1 = __ldg(p + (size_t)y0 * W + x1);
-    v2 = __ldg(p + (size_t)y1 * W + x0); v3 = __ldg(p + (size_t)y1 * W + x1);
-  }
-  out.at(e)[(size_t)y * W + x] = bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
+  int X0, Y0;
+  rotate_row_setup(M, y, X0, Y0);
+  out.at(e)[(size_t)y * W + x] = rotate_pixel<U8>(U8 ? nullptr : img_f32.at(e), U8 ? img_u8.at(e) : nullptr, lut, H, W, M, X0, Y0, x);
 }
 
 int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
@@ -111,7 +55,7 @@ int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst
 // ---------------------------------------------------------------------------------------------------------
 // gaussian kernel helper: xf.square().abs().sum()/N over the stored half spectrum (correlation_flow.cc:184-185)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) spec_sqsum_kernel(Src<cpx> x, int count, float n, float* out) {
+__global__ void __launch_bounds__(256) spec_sqsum_kernel(Src<cpx> x, int count, double* out) {
   const int b = blockIdx.x;
   const cpx* p = x.at(b);
   double acc = 0.0;
@@ -126,12 +70,12 @@ __global__ void __launch_bounds__(256) spec_sqsum_kernel(Src<cpx> x, int count, 
   if (threadIdx.x == 0) {
     double t = 0;
     for (int i = 0; i < 8; ++i) t += red[i];
-    out[b] = (float)t / n;
+    out[b] = t;          // raw sum; the consumer divides by n in f32 like the reference
   }
 }
-int launch_spec_sqsum(Src<cpx> x, int count, float n, float* out, int B, cudaStream_t s) {
+int launch_spec_sqsum(Src<cpx> x, int count, double* out, int B, cudaStream_t s) {
   if (B <= 0) return 0;
-  spec_sqsum_kernel<<<B, 256, 0, s>>>(x, count, n, out);
+  spec_sqsum_kernel<<<B, 256, 0, s>>>(x, count, out);
   return (int)cudaGetLastError();
 }
 

@@ -44,6 +44,28 @@ NIS_HD float ord2f(uint32_t o) {
   union { float f; uint32_t u; } c; c.u = u; return c.f;
 #endif
 }
+NIS_HD void atomic_add_f(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+NIS_HD void atomic_add_d(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+NIS_HD float bits2f(unsigned int u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
 // key = (ordered value << 32) | (0xffffffff - column_major_index): max key = largest value, then the FIRST
 // element in column-major order (Eigen maxCoeff on a column-major array, correlation_flow.cc:175).
 NIS_HD unsigned long long peak_key(float v, int row, int col, int R) {
@@ -131,6 +153,33 @@ struct EpiKernel {
   }
 };
 
+// kernel function applied between the fused inverse and forward column passes (colcol kernel): same arithmetic as
+// EpiKernel, but the real pairs stay in shared memory.  Gaussian sums arrive as raw double sums over the half spectrum.
+struct KernelFn {
+  float n; int kernel; float offset; int power; float gcoef;
+  const double* xx_sum; const double* zz_sum; int zz_shift;
+  unsigned int* maxbuf;
+  struct Bound {
+    float n; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
+    NIS_HD float kfun(float v) const {
+      const float xz = v / n;
+      if (kernel == 0) return powi_double(xz + offset, power);
+      return expf(gcoef * ((xxzz - 2.f * xz) / n));
+    }
+    NIS_HD cpx apply(cpx v) {
+      const float a = kfun(v.x), b = kfun(v.y);
+      mx = fmaxf(mx, fmaxf(fabsf(a), fabsf(b)));
+      return make_float2(a, b);
+    }
+    template <class Sync> NIS_HD void finish(int tid, Sync& sync) { sync.block_max_to(maxp, mx, tid); }
+  };
+  NIS_HD Bound bind(int b) const {
+    float s = 0.f;
+    if (kernel == 1) s = (float)xx_sum[b] / n + (float)zz_sum[b >> zz_shift] / n;
+    return Bound{n, kernel, offset, power, gcoef, s, maxbuf + b, 0.f};
+  }
+};
+
 // final response (:173-178, :238-243): arg-max (column-major first), sum and sum of squares of g = v/n; g never stored
 struct EpiPeak {
   PeakStats* stats; int R; float n;
@@ -203,13 +252,6 @@ struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:2
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, z, m}; }
 };
 
-NIS_HD float bits2f(unsigned int u) {
-#if defined(__CUDA_ARCH__)
-  return __uint_as_float(u);
-#else
-  union { float f; uint32_t u; } c; c.u = u; return c.f;
-#endif
-}
 
 // G = T / (Kzz + lambda) * Kxz  (:171-172) with T = FFT(delta[R/2,C/2]) = (-1)^(k1+c) and the deferred
 // max-normalisation of both kernels (FFT is linear: FFT(k/max) = FFT(k)/max).
@@ -234,6 +276,82 @@ struct ProFilter {
     }
   };
   NIS_HD Bound bind(const LineMap& m) const { return Bound{kzz, kxz, max_zz, max_xz, zz_shift, lambda, m}; }
+};
+
+// ---- element-wise steps of the fused row kernel (forward FFT -> mid -> inverse FFT); Line::apply(c, x) -> y
+// y = x * conj(Z): X = FFT(rotated image) is consumed in registers and never stored (correlation_flow.cc:210-211).
+// With the gaussian kernel the half-spectrum sum of |x^2| (:184) is accumulated on the side.
+struct MidMulConjZ {
+  Src<cpx> z; double* xx_sum;       // xx_sum != nullptr only with the gaussian kernel
+  struct Line {
+    const cpx* pz; float* acc; float part;
+    NIS_HD cpx apply(int c, cpx x) {
+      if (acc) part += x.x * x.x + x.y * x.y;          // |x^2| = |x|^2
+      return cmulc(x, NIS_LDG(pz + c));
+    }
+    NIS_HD void flush() { if (acc) atomic_add_f(acc, part); }
+  };
+  struct Bound {
+    Src<cpx> z; double* xx_sum; LineMap m; float* scratch;       // scratch: one f32 accumulator per local line (shared memory)
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{z.at(b) + off, xx_sum ? scratch + ln : nullptr, 0.f}; }
+    NIS_HD void finish_line(int ln) const {
+      if (!xx_sum) return;
+      int b, k1; size_t off; m.map(ln, b, off, k1);
+      atomic_add_d(xx_sum + b, (double)scratch[ln]);
+    }
+  };
+  NIS_HD Bound bind(const LineMap& m, float* scratch) const { return Bound{z, xx_sum, m, scratch}; }
+};
+
+// y = H * x / max_xz with H = T/(Kzz/max_zz + lambda) cached per keyframe (G = H * Kxz, correlation_flow.cc:171-172)
+struct MidFilterH {
+  Src<cpx> h; const unsigned int* max_xz;
+  struct Line {
+    const cpx* ph; float ixz;
+    NIS_HD cpx apply(int c, cpx x) const { return cmul(NIS_LDG(ph + c), make_float2(x.x * ixz, x.y * ixz)); }
+    NIS_HD void flush() const {}
+  };
+  struct Bound {
+    Src<cpx> h; const unsigned int* max_xz; LineMap m;
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{h.at(b) + off, 1.0f / bits2f(max_xz[b])}; }
+    NIS_HD void finish_line(int) const {}
+  };
+  NIS_HD Bound bind(const LineMap& m, float*) const { return Bound{h, max_xz, m}; }
+};
+
+// store F = x, continue with |x| (ComputeIntermedium: fft_result = FFT(image); IFFT(fft_result.abs()), :91-92)
+struct MidStoreAbs {
+  Dst<cpx> f;
+  struct Line {
+    cpx* pf;
+    NIS_HD cpx apply(int c, cpx x) const { pf[c] = x; return make_float2(sqrtf(x.x * x.x + x.y * x.y), 0.f); }
+    NIS_HD void flush() const {}
+  };
+  struct Bound {
+    Dst<cpx> f; LineMap m;
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{f.at(b) + off}; }
+    NIS_HD void finish_line(int) const {}
+  };
+  NIS_HD Bound bind(const LineMap& m, float*) const { return Bound{f, m}; }
+};
+
+// row-pass epilogue: H = T / (Kzz/max + lambda), T = (-1)^(k1+c)  (the keyframe-only half of :171, cached per frame)
+struct EpiHStore {
+  Dst<cpx> dst; const unsigned int* max_zz; float lambda;
+  struct Line {
+    cpx* p; float izz, lambda; int k1;
+    NIS_HD void put(int c, cpx v) const {
+      const float dr = v.x * izz + lambda, di = v.y * izz;
+      const float t = ((k1 + c) & 1) ? -1.f : 1.f;
+      const float s = t / (dr * dr + di * di);
+      p[c] = make_float2(s * dr, -s * di);
+    }
+  };
+  struct Bound {
+    Dst<cpx> dst; const unsigned int* max_zz; float lambda; LineMap m;
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{dst.at(b) + off, 1.0f / bits2f(max_zz[b]), lambda, k1}; }
+  };
+  NIS_HD Bound bind(const LineMap& m) const { return Bound{dst, max_zz, lambda, m}; }
 };
 
 // row-pass epilogue: store the spectrum line

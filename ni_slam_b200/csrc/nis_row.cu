@@ -25,6 +25,62 @@ __global__ void __launch_bounds__(T) row_kernel(Pro pro, Epi epi, Twiddles twd, 
   row_phase2<N, R1, R2, L, T, INV>(tid, smem, twd, nl, be);
 }
 
+// fused forward row pass -> element-wise -> inverse row pass: K^xz, X = FFT(rotated image) and the filtered spectrum G
+// exist only in registers / shared memory.  Two padded line buffers (the inverse stage 0 cannot run in place).
+template <int N, int R1, int R2, int L, int T, class Mid>
+__global__ void __launch_bounds__(T) rowrow_kernel(Src<cpx> in, Dst<cpx> out, Mid mid, Twiddles twd, int nrows, int total_lines) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cpx* bufA = reinterpret_cast<cpx*>(smem_raw);
+  cpx* bufB = bufA + L * Gm::PITCH;
+  __shared__ float line_acc[L];
+  const int tid = threadIdx.x, line0 = blockIdx.x * L;
+  const int nl = min(L, total_lines - line0);
+  const LineMap m{line0, nrows, N};
+  if (tid < L) line_acc[tid] = 0.f;
+  {
+    const auto bp = ProSpec{in}.bind(m);
+    row_phase0<N, R1, R2, L, T, false>(tid, bufA, bp, nl);
+  }
+  __syncthreads();
+  {
+    CarryRegs<R1, Gm::ROUNDS1> st;
+    row_stage1_read<N, R1, R2, L, T, false>(tid, bufA, twd, nl, st);
+    __syncthreads();
+    row_stage1_write<N, R1, R2, L, T, false>(tid, bufA, nl, st);
+  }
+  __syncthreads();
+  auto bm = mid.bind(m, line_acc);
+  row_phase2_mid<N, R1, R2, L, T>(tid, bufA, twd, nl, bm);
+  __syncthreads();
+  {
+    const SmemLinePro<Gm::PITCH> sp{bufA};
+    row_phase0<N, R1, R2, L, T, true>(tid, bufB, sp, nl);
+  }
+  __syncthreads();
+  {
+    CarryRegs<R1, Gm::ROUNDS1> st;
+    row_stage1_read<N, R1, R2, L, T, true>(tid, bufB, twd, nl, st);
+    __syncthreads();
+    row_stage1_write<N, R1, R2, L, T, true>(tid, bufB, nl, st);
+  }
+  __syncthreads();
+  auto be = EpiSpecStore{out}.bind(m);
+  row_phase2<N, R1, R2, L, T, true>(tid, bufB, twd, nl, be);
+  if (tid < nl) bm.finish_line(tid);
+}
+
+template <int N, int R1, int R2, int L, int T, class Mid>
+static int run_rowrow(Twiddles tw, Src<cpx> in, Dst<cpx> out, Mid mid, int nrows, int B, cudaStream_t s) {
+  auto k = rowrow_kernel<N, R1, R2, L, T, Mid>;
+  const size_t smem = 2 * RowGeom<N, R1, R2, L, T>::kSmemBytes;
+  static int attr = set_smem(k, smem);
+  if (attr) return attr;
+  const int total = nrows * B;
+  k<<<(total + L - 1) / L, T, smem, s>>>(in, out, mid, tw, nrows, total);
+  return (int)cudaGetLastError();
+}
+
 template <int N, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
 static int run_row(Twiddles tw, Pro pro, Epi epi, int nrows, int B, cudaStream_t s) {
   auto k = row_kernel<N, R1, R2, L, T, INV, Pro, Epi>;
@@ -58,8 +114,18 @@ void plan_radices_row(int N, int r[3]) {
 #define ROW_CASE_false(n, r1, r2, l, t) case n: return run_row<n, r1, r2, l, t, false>(tw, pro, epi, nrows, B, s);
 #define ROW_CASE_true(n, r1, r2, l, t) case n: return run_row<n, r1, r2, l, t, true>(tw, pro, epi, nrows, B, s);
 int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
-int launch_row_inv_abs(int N, Twiddles tw, ProAbs pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
+int launch_row_fwd_h(int N, Twiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
 int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
-int launch_row_inv_filter(int N, Twiddles tw, ProFilter pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
+
+#define RR_DISPATCH                       \
+  if (B <= 0) return 0;                   \
+  switch (N) {                            \
+    NIS_ROW_PLANS(RR_CASE)                \
+    default: return -1;                   \
+  }
+#define RR_CASE(n, r1, r2, l, t) case n: return run_rowrow<n, r1, r2, l, t>(tw, in, out, mid, nrows, B, s);
+int launch_rowrow_mulconj(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
+int launch_rowrow_filter(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
+int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 
 }  // namespace nis

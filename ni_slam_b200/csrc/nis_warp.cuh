@@ -1,0 +1,110 @@
+// nis_warp.cuh -- device-only, OpenCV-exact resampling of one output pixel, shared by the standalone warp kernels
+// (nis_misc.cu) and by the column-pass prologues that fuse the warp into the first FFT stage (nis_col.cu).
+//   polar_pixel  : RemoveZeroComponent + fftshift + cv::warpPolar   (correlation_flow.cc:79-87, :94, :228-236)
+//   rotate_pixel : RotateArray = getRotationMatrix2D + warpAffine   (utils.cc:154-161)
+// Explicit round-to-nearest intrinsics everywhere: an FMA-contracted 4-tap sum differs from OpenCV's by 1 ulp.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "nis_ops.cuh"
+
+namespace nis {
+
+__device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
+
+// OpenCV BilinearTab_f weights: {(1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy fx}, all exact in f32
+__device__ __forceinline__ float bilinear4(float v0, float v1, float v2, float v3, int fx, int fy) {
+  const float x = (float)fx * (1.f / 32.f), y = (float)fy * (1.f / 32.f);
+  const float x0 = 1.f - x, y0 = 1.f - y;
+  float acc = __fmul_rn(v0, y0 * x0);
+  acc = __fadd_rn(acc, __fmul_rn(v1, y0 * x));
+  acc = __fadd_rn(acc, __fmul_rn(v2, y * x0));
+  acc = __fadd_rn(acc, __fmul_rn(v3, y * x));
+  return acc;
+}
+
+// tap of fftshift(RemoveZeroComponent(power)) at shifted coordinates (y, x); outside -> 0 (WARP_FILL_OUTLIERS)
+__device__ __forceinline__ float shifted_tap(const float* __restrict__ p, int y, int x, int H, int W) {
+  if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) return 0.f;
+  int r = y - H / 2; r += (r < 0) ? H : 0;                                     // circ_shift.h:238-244
+  int c = x - W / 2; c += (c < 0) ? W : 0;
+  if (c == 0) return __fadd_rn(__ldg(p + (size_t)r * W + 1), __ldg(p + (size_t)r * W + W - 1)) * 0.5f;   // column rule (incl. (0,0))
+  if (r == 0) return __fadd_rn(__ldg(p + (size_t)W + c), __ldg(p + (size_t)(H - 1) * W + c)) * 0.5f;      // row rule
+  return __ldg(p + (size_t)r * W + c);
+}
+
+// cs = (cos, sin) of the output row's angle (double, host libm); rf = (float)(rho * maxRadius / Cp)
+__device__ __forceinline__ float polar_pixel(const float* __restrict__ power, int H, int W, double cp, double sp, float rf) {
+  const float cx = (float)W / 2, cy = (float)H / 2;
+  const float mx = (float)__dadd_rn(__dmul_rn((double)rf, cp), (double)cx);
+  const float my = (float)__dadd_rn(__dmul_rn((double)rf, sp), (double)cy);
+  const int sx = __float2int_rn(mx * 32.f), sy = __float2int_rn(my * 32.f);   // cvRound: half to even
+  const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+  const float v0 = shifted_tap(power, iy, ix, H, W), v1 = shifted_tap(power, iy, ix + 1, H, W);
+  const float v2 = shifted_tap(power, iy + 1, ix, H, W), v3 = shifted_tap(power, iy + 1, ix + 1, H, W);
+  return bilinear4(v0, v1, v2, v3, sx & 31, sy & 31);
+}
+
+__device__ __forceinline__ int wrap_idx(int p, int len) {
+  if ((unsigned)p < (unsigned)len) return p;
+  if (p < 0) p -= ((p - len + 1) / len) * len;
+  if (p >= len) p %= len;
+  return p;
+}
+
+// per output row: X0, Y0 of warpAffine's fixed-point walk (AB_BITS = 10, round_delta = 16)
+__device__ __forceinline__ void rotate_row_setup(const double* __restrict__ M, int y, int& X0, int& Y0) {
+  X0 = __double2int_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]) * 1024.0) + 16;
+  Y0 = __double2int_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]) * 1024.0) + 16;
+}
+
+template <bool U8>
+__device__ __forceinline__ float rotate_pixel(const float* __restrict__ f32, const uint8_t* __restrict__ u8, const float* __restrict__ lut,
+                                              int H, int W, const double* __restrict__ M, int X0, int Y0, int x) {
+  const int adelta = __double2int_rn(__dmul_rn(M[0], (double)x) * 1024.0);
+  const int bdelta = __double2int_rn(__dmul_rn(M[3], (double)x) * 1024.0);
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int ix = sat_short(X >> 5), iy = sat_short(Y >> 5);
+  const int x0 = wrap_idx(ix, W), x1 = wrap_idx(ix + 1, W), y0 = wrap_idx(iy, H), y1 = wrap_idx(iy + 1, H);   // BORDER_WRAP
+  float v0, v1, v2, v3;
+  if (U8) {
+    v0 = __ldg(&lut[u8[(size_t)y0 * W + x0]]); v1 = __ldg(&lut[u8[(size_t)y0 * W + x1]]);
+    v2 = __ldg(&lut[u8[(size_t)y1 * W + x0]]); v3 = __ldg(&lut[u8[(size_t)y1 * W + x1]]);
+  } else {
+    v0 = __ldg(f32 + (size_t)y0 * W + x0); v1 = __ldg(f32 + (size_t)y0 * W + x1);
+    v2 = __ldg(f32 + (size_t)y1 * W + x0); v3 = __ldg(f32 + (size_t)y1 * W + x1);
+  }
+  return bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
+}
+
+// ---- column-pass prologues: the warp feeds the first FFT stage directly, the warped image is never stored ------
+struct ProPolar {
+  Src<float> power; int H, W; const double* cs; const float* rho;
+  struct Bound {
+    const float* p; int H, W, c0; const double* cs; const float* rho;
+    __device__ __forceinline__ cpx load(int phi, int l) const {
+      const double cp = __ldg(cs + 2 * phi), sp = __ldg(cs + 2 * phi + 1);
+      const int q = c0 + 2 * l;
+      return make_float2(polar_pixel(p, H, W, cp, sp, __ldg(rho + q)), polar_pixel(p, H, W, cp, sp, __ldg(rho + q + 1)));
+    }
+  };
+  __device__ __forceinline__ Bound bind(int b, int c0) const { return Bound{power.at(b), H, W, c0, cs, rho}; }
+};
+
+template <bool U8> struct ProRotate {
+  Src<float> f32; Src<uint8_t> u8; const float* lut; int H, W; const double* mats; const int* sel;
+  struct Bound {
+    const float* f; const uint8_t* u; const float* lut; int H, W, c0; const double* M;
+    __device__ __forceinline__ cpx load(int y, int l) const {
+      int X0, Y0;
+      rotate_row_setup(M, y, X0, Y0);
+      const int x = c0 + 2 * l;
+      return make_float2(rotate_pixel<U8>(f, u, lut, H, W, M, X0, Y0, x), rotate_pixel<U8>(f, u, lut, H, W, M, X0, Y0, x + 1));
+    }
+  };
+  __device__ __forceinline__ Bound bind(int e, int c0) const {
+    return Bound{U8 ? nullptr : f32.at(e), U8 ? u8.at(e) : nullptr, lut, H, W, c0, mats + 6 * (size_t)sel[e]};
+  }
+};
+
+}  // namespace nis

@@ -99,7 +99,100 @@ static void emu_row(const cpx* in, int total_lines, cpx* out) {
   }
 }
 
+// ---- fused: inverse column pass -> kernel function -> forward column pass (colcol kernel)
+template <int N, int I0, int I1, int I2, int F0, int F1, int F2, int T>
+static void emu_colcol(const cpx* in, int B, int W, cpx* out, KernelFn kfn) {
+  typedef ColGeom<N, I0, I1, I2, T> Gi;
+  typedef ColGeom<N, F0, F1, F2, T> Gf;
+  std::vector<cpx> ti1, ti2, tf1, tf2;
+  make_tw(I0, I1, I2, ti1, ti2); make_tw(F0, F1, F2, tf1, tf2);
+  Twiddles twi{ti1.data(), ti2.data()}, twf{tf1.data(), tf2.data()};
+  std::vector<cpx> smem((size_t)N * kColLanes);
+  std::vector<CarryRegs<I1, Gi::ROUNDS1>> si(T);
+  std::vector<CarryRegs<F0, Gf::ROUNDS0>> s0(T);
+  std::vector<CarryRegs<F1, Gf::ROUNDS1>> s1(T);
+  HostSync sync;
+  for (int b = 0; b < B; ++b)
+    for (int c0 = 0; c0 < W; c0 += 32) {
+      const cpx* src = in + (size_t)b * (N / 2 + 1) * W;
+      cpx* dst = out + (size_t)b * (N / 2 + 1) * W;
+      std::vector<KernelFn::Bound> fn(T, kfn.bind(b));
+      for (int t = 0; t < T; ++t) col_inv_phase0<N, I0, I1, I2, T>(t, smem.data(), src, W, c0);
+      for (int t = 0; t < T; ++t) col_stage1_read<N, I0, I1, I2, T, true>(t, smem.data(), twi, si[t]);
+      for (int t = 0; t < T; ++t) col_stage1_write<N, I0, I1, I2, T, true>(t, smem.data(), si[t]);
+      for (int t = 0; t < T; ++t) col_inv_phase2_inplace<N, I0, I1, I2, T>(t, smem.data(), twi, fn[t]);
+      for (int t = 0; t < T; ++t) col_fwd_phase0s_read<N, F0, F1, F2, T>(t, smem.data(), s0[t]);
+      for (int t = 0; t < T; ++t) col_fwd_phase0s_write<N, F0, F1, F2, T>(t, smem.data(), s0[t]);
+      for (int t = 0; t < T; ++t) col_stage1_read<N, F0, F1, F2, T, false>(t, smem.data(), twf, s1[t]);
+      for (int t = 0; t < T; ++t) col_stage1_write<N, F0, F1, F2, T, false>(t, smem.data(), s1[t]);
+      for (int t = 0; t < T; ++t) col_fwd_phase2<N, F0, F1, F2, T>(t, smem.data(), twf, dst, W, c0);
+      for (int t = 0; t < T; ++t) fn[t].finish(t, sync);
+    }
+}
+
+// ---- fused: forward row pass -> element-wise -> inverse row pass (rowrow kernel)
+template <int N, int R1, int R2, int L, int T, class Mid>
+static void emu_rowrow(const cpx* in, int nrows, int B, cpx* out, Mid mid) {
+  typedef RowGeom<N, R1, R2, L, T> Gm;
+  std::vector<cpx> t1, t2; make_tw(16, R1, R2, t1, t2);
+  Twiddles twd{t1.data(), t2.data()};
+  const int total = nrows * B;
+  std::vector<cpx> A((size_t)L * Gm::PITCH), Bb((size_t)L * Gm::PITCH);
+  std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
+  ProSpec pro{Src<cpx>{in, (long long)nrows * N, nullptr, 0, nullptr, 0}};
+  EpiSpecStore epi{Dst<cpx>{out, (long long)nrows * N}};
+  for (int line0 = 0; line0 < total; line0 += L) {
+    const int nl = total - line0 < L ? total - line0 : L;
+    LineMap m{line0, nrows, N};
+    float acc[L] = {0};
+    auto bp = pro.bind(m);
+    auto be = epi.bind(m);
+    auto bm = mid.bind(m, acc);
+    for (int t = 0; t < T; ++t) row_phase0<N, R1, R2, L, T, false>(t, A.data(), bp, nl);
+    for (int t = 0; t < T; ++t) row_stage1_read<N, R1, R2, L, T, false>(t, A.data(), twd, nl, st[t]);
+    for (int t = 0; t < T; ++t) row_stage1_write<N, R1, R2, L, T, false>(t, A.data(), nl, st[t]);
+    for (int t = 0; t < T; ++t) row_phase2_mid<N, R1, R2, L, T>(t, A.data(), twd, nl, bm);
+    SmemLinePro<Gm::PITCH> sp{A.data()};
+    for (int t = 0; t < T; ++t) row_phase0<N, R1, R2, L, T, true>(t, Bb.data(), sp, nl);
+    for (int t = 0; t < T; ++t) row_stage1_read<N, R1, R2, L, T, true>(t, Bb.data(), twd, nl, st[t]);
+    for (int t = 0; t < T; ++t) row_stage1_write<N, R1, R2, L, T, true>(t, Bb.data(), nl, st[t]);
+    for (int t = 0; t < T; ++t) row_phase2<N, R1, R2, L, T, true>(t, Bb.data(), twd, nl, be);
+    for (int t = 0; t < nl; ++t) bm.finish_line(t);
+  }
+}
+
 extern "C" {
+
+// in/out: [B][N/2+1][W] complex; maxbuf[B]; polynomial kernel (x/(N*W) + offset)^power
+int emu_colcol_poly(const float* in, int B, int N, int W, float* out, unsigned int* maxbuf, float offset, int power) {
+  memset(maxbuf, 0, sizeof(unsigned int) * B);
+  KernelFn kfn{(float)((long long)N * W), 0, offset, power, 0.f, nullptr, nullptr, 0, maxbuf};
+#define X(n, f0, f1, f2, i0, i1, i2, t) \
+  if (N == n) { emu_colcol<n, i0, i1, i2, f0, f1, f2, t>((const cpx*)in, B, W, (cpx*)out, kfn); return 0; }
+  NIS_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
+// in/out: [B][nrows][N]; z: [B][nrows][N]; out = IFFT_rows(FFT_rows(in) * conj(z)) (unnormalised); xx_sum[B] += sum |FFT_rows(in)|^2
+int emu_rowrow_mulconj(const float* in, const float* z, int B, int nrows, int N, float* out, double* xx_sum) {
+  MidMulConjZ mid{Src<cpx>{(const cpx*)z, (long long)nrows * N, nullptr, 0, nullptr, 0}, xx_sum};
+#define X(n, r1, r2, l, t) \
+  if (N == n) { emu_rowrow<n, r1, r2, l, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+  NIS_ROW_PLANS(X)
+#undef X
+  return -1;
+}
+
+// out = IFFT_rows(H * FFT_rows(in) / max[b])
+int emu_rowrow_filter(const float* in, const float* h, const unsigned int* maxbuf, int B, int nrows, int N, float* out) {
+  MidFilterH mid{Src<cpx>{(const cpx*)h, (long long)nrows * N, nullptr, 0, nullptr, 0}, maxbuf};
+#define X(n, r1, r2, l, t) \
+  if (N == n) { emu_rowrow<n, r1, r2, l, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+  NIS_ROW_PLANS(X)
+#undef X
+  return -1;
+}
 
 // returns 0 ok, -1 unsupported size
 int emu_col_fwd_f32(const float* x, int B, int N, int W, float* out) {

@@ -136,3 +136,41 @@ def test_cpp_shim_compiles_against_the_abi():
                            os.path.join(ROOT, "ni_slam_b200", "lib"), "-lnislam",
                            "-Wl,-rpath," + os.path.join(ROOT, "ni_slam_b200", "lib")])
     assert os.path.exists(exe)
+
+
+@pytest.mark.parametrize("N,W", [(480, 32), (720, 32), (96, 64)])
+def test_emulated_fused_colcol(emu, N, W):
+    """inverse column pass -> (x/n + offset)^3 -> forward column pass, the real kernel image only in shared memory"""
+    rng = np.random.default_rng(N + 1)
+    B = 2
+    real = rng.standard_normal((B, N, W)).astype(np.float32) * 50
+    spec = np.fft.rfft(real.astype(np.float64), axis=1).astype(np.complex64)
+    out = np.zeros_like(spec)
+    mx = np.zeros(B, np.uint32)
+    assert emu.emu_colcol_poly(P(spec), B, N, W, P(out), P(mx), C.c_float(0.1), 3) == 0
+    n = float(N * W)
+    k = ((real.astype(np.float64) * N / n).astype(np.float32) + np.float32(0.1)).astype(np.float64) ** 3
+    want = np.fft.rfft(k, axis=1)
+    assert np.abs(out - want).max() / np.abs(want).max() < 3e-6
+    assert np.allclose(mx.view(np.float32), np.abs(k).reshape(B, -1).max(axis=1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("N", [640, 480, 128])
+def test_emulated_fused_rowrow(emu, N):
+    """forward row pass -> element-wise (x conj z | H x / max) -> inverse row pass"""
+    rng = np.random.default_rng(N + 2)
+    B, nrows = 2, 7
+    x = (rng.standard_normal((B, nrows, N)) + 1j * rng.standard_normal((B, nrows, N))).astype(np.complex64)
+    z = (rng.standard_normal((B, nrows, N)) + 1j * rng.standard_normal((B, nrows, N))).astype(np.complex64)
+    out = np.zeros_like(x)
+    xx = np.zeros(B, np.float64)
+    assert emu.emu_rowrow_mulconj(P(x), P(z), B, nrows, N, P(out), P(xx)) == 0
+    X = np.fft.fft(x.astype(np.complex128), axis=2)
+    want = np.fft.ifft(X * np.conj(z), axis=2) * N
+    assert np.abs(out - want).max() / np.abs(want).max() < 3e-6
+    assert np.allclose(xx, (np.abs(X) ** 2).sum(axis=(1, 2)), rtol=1e-5)
+    mx = np.array([2.0, 0.5], np.float32).view(np.uint32)
+    out2 = np.zeros_like(x)
+    assert emu.emu_rowrow_filter(P(x), P(z), P(mx), B, nrows, N, P(out2)) == 0
+    want2 = np.fft.ifft(X * z / np.array([2.0, 0.5]).reshape(B, 1, 1), axis=2) * N
+    assert np.abs(out2 - want2).max() / np.abs(want2).max() < 3e-6
