@@ -79,7 +79,7 @@ struct nis_ctx {
   long long launches = 0;
   int batch = 16;
   // constant tables
-  DevBuf tw, lut, cs, rho, mats, theta;
+  DevBuf tw, lut, cs, rho, mats, theta, ptab;
   DevBuf recs, best, cand;
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
@@ -234,6 +234,12 @@ static int build_tables(nis_ctx* ctx) {
   RESERVE(ctx->rho, rho.size() * sizeof(float));
   CU(h2d(ctx, ctx->cs.p, cs.data(), cs.size() * sizeof(double)));
   CU(h2d(ctx, ctx->rho.p, rho.data(), rho.size() * sizeof(float)));
+  RESERVE(ctx->ptab, (size_t)D * Cp * sizeof(uint32_t));
+  {
+    int e_ = launch_polar_table(ctx->ptab.as<uint32_t>(), H, W, D, Cp, ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->stream);
+    if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_table", e_);
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   // per polar-peak-row angle tables (correlation_flow.cc:105-136): every float/double step of the reference, once
   std::vector<double> mats(3 * (size_t)D * 6), theta(3 * (size_t)D);
   for (int row = 0; row < D; ++row) {
@@ -357,7 +363,8 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
   LAUNCH(launch_col_inv_store(zt.R, zt.coli, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
   // polar(fftshift(RemoveZeroComponent(power))) feeds the first FFT stage directly
   Dst<cpx> t1p{L.t1.as<cpx>(), (long long)zp.spec};
-  PolarArgs pa{src_slab<float>(power.base, power.stride), ctx->H, ctx->W, ctx->cs.as<double>(), ctx->rho.as<float>()};
+  PolarArgs pa{src_slab<float>(power.base, power.stride), ctx->H, ctx->W, ctx->Cp, ctx->cs.as<double>(), ctx->rho.as<float>(),
+               ctx->ptab.as<uint32_t>()};
   LAUNCH(launch_col_fwd_polar(zp.R, zp.colf, pa, t1p, zp.C, B, L.stream));
   LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
   if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
@@ -504,7 +511,7 @@ int nis_destroy(nis_ctx* ctx) {
   if (!ctx) return NIS_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
+  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
                     &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->d_slot_ptr};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {

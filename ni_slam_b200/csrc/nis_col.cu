@@ -132,7 +132,7 @@ void plan_radices_col(int N, bool inverse, int r[3]) {
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealF32) }
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealU8) }
 int launch_col_fwd_polar(int N, Twiddles tw, PolarArgs pa, Dst<cpx> out, int W, int B, cudaStream_t s) {
-  ProPolar pro{pa.power, pa.H, pa.W, pa.cs, pa.rho};
+  ProPolar pro{pa.power, pa.H, pa.W, pa.Cp, pa.cs, pa.rho, pa.table};
   FWD_DISPATCH(ProPolar)
 }
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int B, cudaStream_t s) {

@@ -254,16 +254,18 @@ NIS_HD void col_stage1_write(int tid, cpx* smem, const CarryRegs<R1, ColGeom<N, 
 }
 
 // ---- forward r2c column pass ------------------------------------------------------------------------------
-// Pro::load(row, l) -> cpx (re = real column c0+2l, im = real column c0+2l+1 at image row `row`)
+// Pro::lane(l).load(row) -> cpx (re = real column c0+2l, im = real column c0+2l+1 at image row `row`); the per-lane
+// context lets a prologue hoist everything that depends only on the column pair
 // phase 0: stage 0 from global
 template <int N, int R0, int R1, int R2, int T, class Pro>
 NIS_HD void col_fwd_phase0(int tid, cpx* smem, const Pro& pro) {
   typedef ColGeom<N, R0, R1, R2, T> Gm;
   const int l = tid % kColLanes, gi = tid / kColLanes;
+  const auto ln = pro.lane(l);
   for (int j = gi; j < Gm::M0; j += Gm::G) {
     cpx v[R0];
 #pragma unroll
-    for (int r = 0; r < R0; ++r) v[r] = pro.load(j + r * Gm::M0, l);
+    for (int r = 0; r < R0; ++r) v[r] = ln.load(j + r * Gm::M0);
     Dft<R0, false>::run(v);
 #pragma unroll
     for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = v[r];

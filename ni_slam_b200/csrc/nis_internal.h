@@ -29,7 +29,7 @@ void plan_radices_row(int N, int r[3]);
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
 struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; };
-struct PolarArgs { Src<float> power; int H, W; const double* cs; const float* rho; };
+struct PolarArgs { Src<float> power; int H, W, Cp; const double* cs; const float* rho; const uint32_t* table; };
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int E, cudaStream_t s);   // RotateArray fused into stage 0
@@ -50,6 +50,8 @@ int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidSto
 // polar: power [B][H][W] (IFFT(|F|), unshifted) -> polar image [B][D][Cp]; RemoveZeroComponent + fftshift fused in the taps
 int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
                  int B, cudaStream_t s);
+// one-time polar gather table [D][Cp] (see nis_warp.cuh)
+int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s);
 // rotate: out[e] = warpAffine(image[e], rot_mats[sel[e]]) with BORDER_WRAP.  Exactly one of img_f32 / img_u8 is used.
 int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
                   const int* sel, int E, cudaStream_t s);

@@ -27,6 +27,17 @@ int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, 
   return (int)cudaGetLastError();
 }
 
+__global__ void polar_table_kernel(uint32_t* __restrict__ table, int H, int W, int D, int Cp, const double* __restrict__ cs,
+                                   const float* __restrict__ rho_tab) {
+  const int phi = blockIdx.y, rho = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rho >= Cp) return;
+  table[(size_t)phi * Cp + rho] = polar_table_entry(H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho]);
+}
+int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s) {
+  polar_table_kernel<<<dim3((Cp + 127) / 128, D), 128, 0, s>>>(table, H, W, D, Cp, cs_table, rho_table);
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // rotation (warpAffine, INTER_LINEAR, BORDER_WRAP, AB_BITS = 10, INTER_BITS = 5)
 // ---------------------------------------------------------------------------------------------------------

@@ -78,13 +78,14 @@ struct PeakStats {            // per batch element, zero-initialised before the 
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// column-pass prologues: load(row, l) -> (col c0+2l, col c0+2l+1) of a row-major real image
+// column-pass prologues: lane(l).load(row) -> (col c0+2l, col c0+2l+1) of a row-major real image
 // ---------------------------------------------------------------------------------------------------------
 struct ProRealF32 {
   Src<float> src; int W;
+  struct Lane { const float2* p; int W; NIS_HD cpx load(int row) const { return NIS_LDG(p + (size_t)row * (W / 2)); } };
   struct Bound {
     const float* img; int W, c0;
-    NIS_HD cpx load(int row, int l) const { return NIS_LDG(reinterpret_cast<const float2*>(img + (size_t)row * W + c0) + l); }
+    NIS_HD Lane lane(int l) const { return Lane{reinterpret_cast<const float2*>(img + c0) + l, W}; }
   };
   NIS_HD Bound bind(int b, int c0) const { return Bound{src.at(b), W, c0}; }
 };
@@ -92,12 +93,16 @@ struct ProRealF32 {
 // u8 image -> f32/255 through a 256-entry table (utils.cc:110-118: (float)((double)u/255.0))
 struct ProRealU8 {
   Src<uint8_t> src; int W; const float* lut;
+  struct Lane {
+    const uint8_t* p; int W; const float* lut;
+    NIS_HD cpx load(int row) const {
+      const uint8_t* q = p + (size_t)row * W;
+      return make_float2(NIS_LDG(&lut[q[0]]), NIS_LDG(&lut[q[1]]));
+    }
+  };
   struct Bound {
     const uint8_t* img; int W, c0; const float* lut;
-    NIS_HD cpx load(int row, int l) const {
-      const uint8_t* p = img + (size_t)row * W + c0 + 2 * l;
-      return make_float2(NIS_LDG(&lut[p[0]]), NIS_LDG(&lut[p[1]]));
-    }
+    NIS_HD Lane lane(int l) const { return Lane{img + c0 + 2 * l, W, lut}; }
   };
   NIS_HD Bound bind(int b, int c0) const { return Bound{src.at(b), W, c0, lut}; }
 };
@@ -105,20 +110,23 @@ struct ProRealU8 {
 // ---------------------------------------------------------------------------------------------------------
 // column-pass (c2r) epilogues: put(row, l, re, im), values unnormalised (divide by n = R*C like IFFT :76)
 // ---------------------------------------------------------------------------------------------------------
+// The reference divides by n = R*C (IFFT, :76); the kernels multiply by the f32 reciprocal instead (one FMUL instead of
+// an IEEE division sequence per element; the results differ by at most 1 ulp, far below the f32 FFT noise).
 struct EpiStore {
   Dst<float> dst; int W; float n;
   struct Bound {
-    float* img; int W, c0; float n;
+    float* img; int W, c0; float rn;
     NIS_HD void put(int row, int l, float re, float im) {
-      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = make_float2(re / n, im / n);
+      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = make_float2(re * rn, im * rn);
     }
     template <class Sync> NIS_HD void finish(int, Sync&) {}
   };
-  NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, n}; }
+  NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, 1.0f / n}; }
 };
 
 NIS_HD float powi_double(float x, int p) {
   // Eigen 3.3 ArrayBase::pow(int) -> std::pow(float,int) -> double pow, rounded to float (correlation_flow.cc:213,223)
+  if (p == 3) { const double b3 = (double)x; return (float)(b3 * b3 * b3); }      // the default of every shipped config
   double b = (double)x, r = 1.0;
   int e = p < 0 ? -p : p;
   for (int i = 0; i < e; ++i) r *= b;
@@ -160,9 +168,9 @@ struct KernelFn {
   const double* xx_sum; const double* zz_sum; int zz_shift;
   unsigned int* maxbuf;
   struct Bound {
-    float n; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
+    float n, rn; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
     NIS_HD float kfun(float v) const {
-      const float xz = v / n;
+      const float xz = v * rn;
       if (kernel == 0) return powi_double(xz + offset, power);
       return expf(gcoef * ((xxzz - 2.f * xz) / n));
     }
@@ -176,7 +184,7 @@ struct KernelFn {
   NIS_HD Bound bind(int b) const {
     float s = 0.f;
     if (kernel == 1) s = (float)xx_sum[b] / n + (float)zz_sum[b >> zz_shift] / n;
-    return Bound{n, kernel, offset, power, gcoef, s, maxbuf + b, 0.f};
+    return Bound{n, 1.0f / n, kernel, offset, power, gcoef, s, maxbuf + b, 0.f};
   }
 };
 
@@ -185,10 +193,10 @@ struct EpiPeak {
   PeakStats* stats; int R; float n;
   float* g_out; long long g_stride; int W;            // optional debug store (nullptr in production)
   struct Bound {
-    PeakStats* st; int R, c0; float n; float* g; int W;
+    PeakStats* st; int R, c0; float rn; float* g; int W;
     unsigned long long key; float s, q;
     NIS_HD void one(int row, int col, float v) {
-      const float x = v / n;
+      const float x = v * rn;
       const unsigned long long k = peak_key(x, row, col, R);
       key = k > key ? k : key;
       s += x; q += x * x;
@@ -201,7 +209,7 @@ struct EpiPeak {
     template <class Sync> NIS_HD void finish(int tid, Sync& sync) { sync.block_peak_to(st, key, (double)s, (double)q, tid); }
   };
   NIS_HD Bound bind(int b, int c0) const {
-    return Bound{stats + b, R, c0, n, g_out ? g_out + (long long)b * g_stride : nullptr, W, 0ull, 0.f, 0.f};
+    return Bound{stats + b, R, c0, 1.0f / n, g_out ? g_out + (long long)b * g_stride : nullptr, W, 0ull, 0.f, 0.f};
   }
 };
 

@@ -77,29 +77,86 @@ __device__ __forceinline__ float rotate_pixel(const float* __restrict__ f32, con
   return bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
 }
 
+// ---- polar gather table: the polar sampling grid does not depend on the image, so the fixed-point source position of
+// every output pixel is computed once per context.  entry = offset(r0*W + c0) | fx << 21 | fy << 26 when the 2x2 footprint
+// is an interior, unwrapped block of `power` (no RemoveZeroComponent row/column, no border); bit 31 = take the exact
+// general path.
+constexpr uint32_t kPolarSlow = 0x80000000u;
+__device__ __forceinline__ uint32_t polar_table_entry(int H, int W, double cp, double sp, float rf) {
+  const float cx = (float)W / 2, cy = (float)H / 2;
+  const float mx = (float)__dadd_rn(__dmul_rn((double)rf, cp), (double)cx);
+  const float my = (float)__dadd_rn(__dmul_rn((double)rf, sp), (double)cy);
+  const int sx = __float2int_rn(mx * 32.f), sy = __float2int_rn(my * 32.f);
+  const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+  if ((size_t)H * W > (1u << 21)) return kPolarSlow;
+  if (ix < 0 || iy < 0 || ix + 1 >= W || iy + 1 >= H) return kPolarSlow;
+  int r0 = iy - H / 2; r0 += (r0 < 0) ? H : 0;
+  int c0 = ix - W / 2; c0 += (c0 < 0) ? W : 0;
+  if (r0 < 1 || c0 < 1 || r0 + 1 >= H || c0 + 1 >= W) return kPolarSlow;
+  return (uint32_t)(r0 * W + c0) | ((uint32_t)(sx & 31) << 21) | ((uint32_t)(sy & 31) << 26);
+}
+__device__ __forceinline__ float polar_pixel_tab(const float* __restrict__ power, int H, int W, uint32_t e, double cp, double sp, float rf) {
+  if (e & kPolarSlow) return polar_pixel(power, H, W, cp, sp, rf);
+  const float* q = power + (e & 0x1fffffu);
+  return bilinear4(__ldg(q), __ldg(q + 1), __ldg(q + W), __ldg(q + W + 1), (e >> 21) & 31, (e >> 26) & 31);
+}
+
 // ---- column-pass prologues: the warp feeds the first FFT stage directly, the warped image is never stored ------
 struct ProPolar {
-  Src<float> power; int H, W; const double* cs; const float* rho;
-  struct Bound {
-    const float* p; int H, W, c0; const double* cs; const float* rho;
-    __device__ __forceinline__ cpx load(int phi, int l) const {
-      const double cp = __ldg(cs + 2 * phi), sp = __ldg(cs + 2 * phi + 1);
-      const int q = c0 + 2 * l;
-      return make_float2(polar_pixel(p, H, W, cp, sp, __ldg(rho + q)), polar_pixel(p, H, W, cp, sp, __ldg(rho + q + 1)));
+  Src<float> power; int H, W, Cp; const double* cs; const float* rho; const uint32_t* table;   // table [D][Cp]
+  struct Lane {
+    const float* p; int H, W, Cp, q; const double* cs; float rf0, rf1; const uint32_t* tab;
+    __device__ __forceinline__ cpx load(int phi) const {
+      const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + (size_t)phi * Cp + q));
+      double cp = 0.0, sp = 0.0;
+      if ((e.x | e.y) & kPolarSlow) { cp = __ldg(cs + 2 * phi); sp = __ldg(cs + 2 * phi + 1); }
+      return make_float2(polar_pixel_tab(p, H, W, e.x, cp, sp, rf0), polar_pixel_tab(p, H, W, e.y, cp, sp, rf1));
     }
   };
-  __device__ __forceinline__ Bound bind(int b, int c0) const { return Bound{power.at(b), H, W, c0, cs, rho}; }
+  struct Bound {
+    const float* p; int H, W, Cp, c0; const double* cs; const float* rho; const uint32_t* tab;
+    __device__ __forceinline__ Lane lane(int l) const {
+      const int q = c0 + 2 * l;
+      return Lane{p, H, W, Cp, q, cs, __ldg(rho + q), __ldg(rho + q + 1), tab};
+    }
+  };
+  __device__ __forceinline__ Bound bind(int b, int c0) const { return Bound{power.at(b), H, W, Cp, c0, cs, rho, table}; }
 };
 
 template <bool U8> struct ProRotate {
   Src<float> f32; Src<uint8_t> u8; const float* lut; int H, W; const double* mats; const int* sel;
-  struct Bound {
-    const float* f; const uint8_t* u; const float* lut; int H, W, c0; const double* M;
-    __device__ __forceinline__ cpx load(int y, int l) const {
+  struct Lane {
+    const float* f; const uint8_t* u; const float* lut; int H, W; const double* M; int a0, b0, a1, b1;   // adelta / bdelta of both columns
+    __device__ __forceinline__ float pixel(int X0, int Y0, int ad, int bd) const {
+      const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+      const int ix = sat_short(X >> 5), iy = sat_short(Y >> 5);
+      int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
+      if (!((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1))) {       // BORDER_WRAP
+        x0 = wrap_idx(x0, W); x1 = wrap_idx(x1, W); y0 = wrap_idx(y0, H); y1 = wrap_idx(y1, H);
+      }
+      float v0, v1, v2, v3;
+      if (U8) {
+        v0 = __ldg(&lut[u[(size_t)y0 * W + x0]]); v1 = __ldg(&lut[u[(size_t)y0 * W + x1]]);
+        v2 = __ldg(&lut[u[(size_t)y1 * W + x0]]); v3 = __ldg(&lut[u[(size_t)y1 * W + x1]]);
+      } else {
+        v0 = __ldg(f + (size_t)y0 * W + x0); v1 = __ldg(f + (size_t)y0 * W + x1);
+        v2 = __ldg(f + (size_t)y1 * W + x0); v3 = __ldg(f + (size_t)y1 * W + x1);
+      }
+      return bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
+    }
+    __device__ __forceinline__ cpx load(int y) const {
       int X0, Y0;
       rotate_row_setup(M, y, X0, Y0);
+      return make_float2(pixel(X0, Y0, a0, b0), pixel(X0, Y0, a1, b1));
+    }
+  };
+  struct Bound {
+    const float* f; const uint8_t* u; const float* lut; int H, W, c0; const double* M;
+    __device__ __forceinline__ Lane lane(int l) const {
       const int x = c0 + 2 * l;
-      return make_float2(rotate_pixel<U8>(f, u, lut, H, W, M, X0, Y0, x), rotate_pixel<U8>(f, u, lut, H, W, M, X0, Y0, x + 1));
+      return Lane{f, u, lut, H, W, M,
+                  __double2int_rn(__dmul_rn(M[0], (double)x) * 1024.0), __double2int_rn(__dmul_rn(M[3], (double)x) * 1024.0),
+                  __double2int_rn(__dmul_rn(M[0], (double)(x + 1)) * 1024.0), __double2int_rn(__dmul_rn(M[3], (double)(x + 1)) * 1024.0)};
     }
   };
   __device__ __forceinline__ Bound bind(int e, int c0) const {
