@@ -77,7 +77,7 @@ struct nis_ctx {
   size_t maxspec = 0, maxreal = 0;
   std::string err;
   long long launches = 0;
-  int batch = 16;
+  int batch = 16, default_batch = 16;
   // constant tables
   DevBuf tw, lut, cs, rho, mats, theta, ptab;
   DevBuf recs, best, cand;
@@ -499,6 +499,14 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
         cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
   ctx->stream = ctx->lanes[0].stream;
   if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
+  {
+    // default batch: one column-pass launch (W/32 CTAs per image, 2 resident CTAs per SM) should fill the GPU just once
+    cudaDeviceProp prop;
+    int sms = 148;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sms = prop.multiProcessorCount;
+    ctx->default_batch = std::max(4, std::min(64, (2 * sms) / std::max(1, W / 32)));
+    ctx->batch = ctx->default_batch;
+  }
   const char* eb = getenv("NIS_BATCH");
   if (eb && atoi(eb) > 0) ctx->batch = atoi(eb);
   int st = build_tables(ctx);
@@ -543,7 +551,7 @@ int nis_set_lanes(nis_ctx* ctx, int lanes) {
 }
 int nis_set_batch(nis_ctx* ctx, int batch) {
   if (!ctx || batch < 0) return NIS_ERR_INVALID_ARGUMENT;
-  ctx->batch = batch > 0 ? batch : 16;
+  ctx->batch = batch > 0 ? batch : ctx->default_batch;
   return NIS_OK;
 }
 
@@ -678,8 +686,7 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   const uint8_t* d_frames = frames;
   if (on_host) {
     RESERVE(ctx->sImg, (size_t)n * npx);
-    CU(cudaMemcpyAsync(ctx->sImg.p, frames, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
-    d_frames = ctx->sImg.as<uint8_t>();
+    d_frames = ctx->sImg.as<uint8_t>();      // uploaded batch by batch below, each on its lane, so copies overlap compute
   }
   TRY(ensure_recs(ctx, std::max(n - 1, 1)));
   const int B = ctx->batch;
@@ -689,6 +696,9 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   TRY(fork_lanes(ctx));
   for (int t0 = 0, k = 0; t0 < n; t0 += B, ++k) {
     const int nb = std::min(B, n - t0);
+    if (on_host)
+      CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames + (size_t)t0 * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
+                         ctx->lanes[k % NL].stream));
     TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
                        Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
                        Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));

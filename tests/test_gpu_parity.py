@@ -300,3 +300,33 @@ def test_cpp_shim_known_answers():
                                "-Wl,-rpath," + os.path.join(root, "ni_slam_b200", "lib")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "shim_test ok" in out.stdout, out.stdout + out.stderr
+
+
+# ------------------------------------------------------------------ other image sizes (BASELINE configs[4] = 1280x960; a tiny config)
+@pytest.mark.parametrize("h,w,d,cp", [(96, 128, 80, 64), (960, 1280, 720, 480)])
+def test_other_sizes_match_oracle(h, w, d, cp):
+    import ni_slam_b200 as nis
+    rng = np.random.default_rng(h)
+    base = rng.random((h + 64, w + 64)).astype(np.float32)
+    k = np.ones(5, np.float32) / 5                       # cheap separable blur so that shifts correlate
+    for ax in (0, 1):
+        base = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), ax, base)
+    base = (base - base.min()) / (base.max() - base.min())
+    a_u8 = np.clip(np.rint(base[32:32 + h, 32:32 + w] * 255), 0, 255).astype(np.uint8)
+    b_u8 = np.clip(np.rint(base[32 + 3:32 + 3 + h, 32 - 5:32 - 5 + w] * 255), 0, 255).astype(np.uint8)      # window moved by (-5, +3)
+    cfg = oc.make_cfg(height=h, width=w, rotation_divisor=d, rotation_channel=cp)
+    c = nis.CorrelationFlow(nis.CFConfig(rotation_divisor=d, rotation_channel=cp), h, w)
+    a, b = oc.normalize_u8(a_u8), oc.normalize_u8(b_u8)
+    Fa, Pa = oc.compute_intermedium(cfg, a)
+    Fb, Pb = oc.compute_intermedium(cfg, b)
+    fa, fb = c.ComputeIntermedium(a_u8), c.ComputeIntermedium(b_u8)
+    F, P = fa.GetFFTResult()
+    assert np.abs(F - Fa).max() / np.abs(Fa).max() < 2e-6 and np.abs(P - Pa).max() / np.abs(Pa).max() < 3e-6
+    for mode in (True, False):
+        io, po, pko = oc.compute_pose(cfg, Fa, b, Pa, Pb, mode)
+        ig, pg, pkg = c.ComputePose(fa, fb, mode, return_peaks=True)
+        assert pkg["polar"][0] % (d // 2) == pko["polar"][0] % (d // 2)
+        assert pkg["trans"] == pko["trans"] and (pg[0], pg[1]) == (po[0], po[1]) == (-5.0, 3.0)
+        assert abs(wrap_pi(pg[2] - po[2])) < 1e-6 or not mode
+        assert np.allclose(ig, io, rtol=1e-3)
+    c.close()
