@@ -61,7 +61,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;
   int cap = 0;                 // workspace capacity in pairs
-  DevBuf t1, real, maxp, maxt, maxh, stats_p, stats_t, sel, xx, zz;
+  DevBuf t1, real, pol, maxp, maxt, maxh, stats_p, stats_t, sel, xx, zz;
 };
 
 struct nis_ctx {
@@ -78,6 +78,7 @@ struct nis_ctx {
   std::string err;
   long long launches = 0;
   int batch = 16, default_batch = 16;
+  bool polar_fused = true;
   // constant tables
   DevBuf tw, lut, cs, rho, mats, theta, ptab;
   DevBuf recs, best, cand;
@@ -274,6 +275,7 @@ static int ensure_workspace(nis_ctx* ctx, Lane& L, int pairs) {
   const size_t E = 2 * (size_t)pairs;
   RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));          // the only full-size scratch: half-transformed spectra, in place
   RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float));   // power = IFFT(|F|) feeding the polar gather
+  RESERVE(L.pol, (size_t)pairs * ctx->sz[1].real * sizeof(float)); // polar image (when the gather is not fused into the FFT)
   RESERVE(L.maxp, (size_t)pairs * sizeof(unsigned));
   RESERVE(L.maxt, E * sizeof(unsigned));
   RESERVE(L.maxh, (size_t)pairs * sizeof(unsigned));
@@ -365,7 +367,14 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
   Dst<cpx> t1p{L.t1.as<cpx>(), (long long)zp.spec};
   PolarArgs pa{src_slab<float>(power.base, power.stride), ctx->H, ctx->W, ctx->Cp, ctx->cs.as<double>(), ctx->rho.as<float>(),
                ctx->ptab.as<uint32_t>()};
-  LAUNCH(launch_col_fwd_polar(zp.R, zp.colf, pa, t1p, zp.C, B, L.stream));
+  if (ctx->polar_fused) {
+    LAUNCH(launch_col_fwd_polar(zp.R, zp.colf, pa, t1p, zp.C, B, L.stream));
+  } else {
+    // the gather is latency bound: as its own full-occupancy kernel it beats riding in the register-limited FFT stage 0
+    Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
+    LAUNCH(launch_polar(pa.power, pol, ctx->H, ctx->W, ctx->D, ctx->Cp, pa.cs, pa.rho, pa.table, B, L.stream));
+    LAUNCH(launch_col_fwd_f32(zp.R, zp.colf, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
+  }
   LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
   if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
     TRY(hzz_batch(ctx, L, 0, src_slab<cpx>(F.base, F.stride), B, Ht));
@@ -507,6 +516,8 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
     ctx->default_batch = std::max(4, std::min(64, (2 * sms) / std::max(1, W / 32)));
     ctx->batch = ctx->default_batch;
   }
+  const char* ef = getenv("NIS_POLAR_FUSED");
+  if (ef) ctx->polar_fused = atoi(ef) != 0;
   const char* eb = getenv("NIS_BATCH");
   if (eb && atoi(eb) > 0) ctx->batch = atoi(eb);
   int st = build_tables(ctx);
@@ -523,7 +534,7 @@ int nis_destroy(nis_ctx* ctx) {
                     &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->d_slot_ptr};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {
-    DevBuf* lb[] = {&L.t1, &L.real, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz};
+    DevBuf* lb[] = {&L.t1, &L.real, &L.pol, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz};
     for (DevBuf* b : lb) b->release();
     if (L.ev) cudaEventDestroy(L.ev);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -1020,7 +1031,7 @@ int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
   RESERVE(out, ctx->sz[1].real * sizeof(float));
   CU(h2d(ctx, L.real.p, power_in, ctx->sz[0].real * sizeof(float)));
   LAUNCH(launch_polar(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
-                      ctx->cs.as<double>(), ctx->rho.as<float>(), 1, L.stream));
+                      ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->ptab.as<uint32_t>(), 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpy(polar_out, out.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
   out.release();

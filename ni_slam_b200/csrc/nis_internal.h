@@ -49,7 +49,7 @@ int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidSto
 // ---- warps and bookkeeping kernels -----------------------------------------------------------------------
 // polar: power [B][H][W] (IFFT(|F|), unshifted) -> polar image [B][D][Cp]; RemoveZeroComponent + fftshift fused in the taps
 int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
-                 int B, cudaStream_t s);
+                 const uint32_t* table, int B, cudaStream_t s);
 // one-time polar gather table [D][Cp] (see nis_warp.cuh)
 int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s);
 // rotate: out[e] = warpAffine(image[e], rot_mats[sel[e]]) with BORDER_WRAP.  Exactly one of img_f32 / img_u8 is used.

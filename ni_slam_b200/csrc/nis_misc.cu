@@ -11,19 +11,32 @@
 
 namespace nis {
 
+// one thread per pair of adjacent output pixels; `table` (may be null) is the per-context gather table of nis_warp.cuh
 __global__ void __launch_bounds__(256) polar_kernel(Src<float> power, Dst<float> out, int H, int W, int D, int Cp,
-                                                    const double* __restrict__ cs, const float* __restrict__ rho_tab) {
+                                                    const double* __restrict__ cs, const float* __restrict__ rho_tab,
+                                                    const uint32_t* __restrict__ table) {
   const int b = blockIdx.z, phi = blockIdx.y;
-  const int rho = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rho = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (rho >= Cp) return;
-  out.at(b)[(size_t)phi * Cp + rho] = polar_pixel(power.at(b), H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho]);
+  const float* p = power.at(b);
+  float2 v;
+  if (table) {
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(table + (size_t)phi * Cp + rho));
+    double cp = 0.0, sp = 0.0;
+    if ((e.x | e.y) & kPolarSlow) { cp = cs[2 * phi]; sp = cs[2 * phi + 1]; }
+    v = make_float2(polar_pixel_tab(p, H, W, e.x, cp, sp, rho_tab[rho]), polar_pixel_tab(p, H, W, e.y, cp, sp, rho_tab[rho + 1]));
+  } else {
+    v = make_float2(polar_pixel(p, H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho]),
+                    polar_pixel(p, H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho + 1]));
+  }
+  reinterpret_cast<float2*>(out.at(b) + (size_t)phi * Cp)[rho / 2] = v;
 }
 
 int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
-                 int B, cudaStream_t s) {
+                 const uint32_t* table, int B, cudaStream_t s) {
   if (B <= 0) return 0;
-  const int T = Cp >= 256 ? 256 : 128;
-  polar_kernel<<<dim3((Cp + T - 1) / T, D, B), T, 0, s>>>(power, out, H, W, D, Cp, cs_table, rho_table);
+  const int T = Cp >= 512 ? 256 : 128;
+  polar_kernel<<<dim3((Cp / 2 + T - 1) / T, D, B), T, 0, s>>>(power, out, H, W, D, Cp, cs_table, rho_table, table);
   return (int)cudaGetLastError();
 }
 

@@ -93,13 +93,13 @@ static int run_row(Twiddles tw, Pro pro, Epi epi, int nrows, int B, cudaStream_t
 }
 
 bool row_size_supported(int N) {
-#define X(n, r1, r2, l, t) if (N == n) return true;
+#define X(n, r1, r2, l, t, lr) if (N == n) return true;
   NIS_ROW_PLANS(X)
 #undef X
   return false;
 }
 void plan_radices_row(int N, int r[3]) {
-#define X(n, r1, r2, l, t) if (N == n) { r[0] = 16; r[1] = r1; r[2] = r2; return; }
+#define X(n, r1, r2, l, t, lr) if (N == n) { r[0] = 16; r[1] = r1; r[2] = r2; return; }
   NIS_ROW_PLANS(X)
 #undef X
   r[0] = r[1] = r[2] = 0;
@@ -111,8 +111,8 @@ void plan_radices_row(int N, int r[3]) {
     NIS_ROW_PLANS(ROW_CASE_##INV)        \
     default: return -1;                  \
   }
-#define ROW_CASE_false(n, r1, r2, l, t) case n: return run_row<n, r1, r2, l, t, false>(tw, pro, epi, nrows, B, s);
-#define ROW_CASE_true(n, r1, r2, l, t) case n: return run_row<n, r1, r2, l, t, true>(tw, pro, epi, nrows, B, s);
+#define ROW_CASE_false(n, r1, r2, l, t, lr) case n: return run_row<n, r1, r2, l, t, false>(tw, pro, epi, nrows, B, s);
+#define ROW_CASE_true(n, r1, r2, l, t, lr) case n: return run_row<n, r1, r2, l, t, true>(tw, pro, epi, nrows, B, s);
 int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
 int launch_row_fwd_h(int N, Twiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
 int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
@@ -123,7 +123,7 @@ int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi,
     NIS_ROW_PLANS(RR_CASE)                \
     default: return -1;                   \
   }
-#define RR_CASE(n, r1, r2, l, t) case n: return run_rowrow<n, r1, r2, l, t>(tw, in, out, mid, nrows, B, s);
+#define RR_CASE(n, r1, r2, l, t, lr) case n: return run_rowrow<n, r1, r2, lr, t>(tw, in, out, mid, nrows, B, s);
 int launch_rowrow_mulconj(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 int launch_rowrow_filter(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }

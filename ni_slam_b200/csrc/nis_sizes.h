@@ -2,7 +2,8 @@
 // Column pass (transform along image rows, the halved dimension: H, rotation_divisor):
 //   X(N, F0,F1,F2, I0,I1,I2, T)   forward radices (the paired, separating stage is F2), inverse radices (paired I0), threads
 // Row pass (transform along image columns: W, rotation_channel), first radix fixed at 16:
-//   X(N, R1, R2, L, T)            N = 16*R1*R2, L lines per CTA, threads
+//   X(N, R1, R2, L, T, LR)        N = 16*R1*R2, L lines per CTA, threads; LR = lines per CTA of the fused fwd->mid->inv kernel
+//                                 (two line buffers, so fewer lines keep more CTAs resident)
 // Image widths must also be multiples of 32 (one column-pass CTA owns 32 real columns).
 #pragma once
 #define NIS_COL_PLANS(X)              \
@@ -14,11 +15,11 @@
   X(80, 5, 4, 4, 4, 4, 5, 128)        \
   X(64, 4, 4, 4, 4, 4, 4, 128)
 
-#define NIS_ROW_PLANS(X)   \
-  X(640, 8, 5, 8, 256)     \
-  X(480, 6, 5, 8, 256)     \
-  X(1280, 8, 10, 4, 256)   \
-  X(1600, 10, 10, 4, 256)  \
-  X(128, 8, 1, 8, 128)     \
-  X(96, 6, 1, 8, 128)      \
-  X(64, 4, 1, 8, 128)
+#define NIS_ROW_PLANS(X)      \
+  X(640, 8, 5, 8, 256, 4)     \
+  X(480, 6, 5, 8, 256, 4)     \
+  X(1280, 8, 10, 4, 256, 2)   \
+  X(1600, 10, 10, 4, 256, 2)  \
+  X(128, 8, 1, 8, 128, 8)     \
+  X(96, 6, 1, 8, 128, 8)      \
+  X(64, 4, 1, 8, 128, 8)

@@ -177,8 +177,8 @@ int emu_colcol_poly(const float* in, int B, int N, int W, float* out, unsigned i
 // in/out: [B][nrows][N]; z: [B][nrows][N]; out = IFFT_rows(FFT_rows(in) * conj(z)) (unnormalised); xx_sum[B] += sum |FFT_rows(in)|^2
 int emu_rowrow_mulconj(const float* in, const float* z, int B, int nrows, int N, float* out, double* xx_sum) {
   MidMulConjZ mid{Src<cpx>{(const cpx*)z, (long long)nrows * N, nullptr, 0, nullptr, 0}, xx_sum};
-#define X(n, r1, r2, l, t) \
-  if (N == n) { emu_rowrow<n, r1, r2, l, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+#define X(n, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
   NIS_ROW_PLANS(X)
 #undef X
   return -1;
@@ -187,8 +187,8 @@ int emu_rowrow_mulconj(const float* in, const float* z, int B, int nrows, int N,
 // out = IFFT_rows(H * FFT_rows(in) / max[b])
 int emu_rowrow_filter(const float* in, const float* h, const unsigned int* maxbuf, int B, int nrows, int N, float* out) {
   MidFilterH mid{Src<cpx>{(const cpx*)h, (long long)nrows * N, nullptr, 0, nullptr, 0}, maxbuf};
-#define X(n, r1, r2, l, t) \
-  if (N == n) { emu_rowrow<n, r1, r2, l, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+#define X(n, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
   NIS_ROW_PLANS(X)
 #undef X
   return -1;
@@ -234,7 +234,7 @@ int emu_col_inv_kernel(const float* in, int B, int N, int W, float* out, unsigne
 }
 
 int emu_row(const float* in, int total_lines, int N, int inverse, float* out) {
-#define X(n, r1, r2, l, t)                                                              \
+#define X(n, r1, r2, l, t, lr)                                                          \
   if (N == n) {                                                                         \
     if (inverse) emu_row<n, r1, r2, l, t, true>((const cpx*)in, total_lines, (cpx*)out); \
     else emu_row<n, r1, r2, l, t, false>((const cpx*)in, total_lines, (cpx*)out);        \
