@@ -79,8 +79,8 @@ static const orc_plan *get_plan(int n) {
 }
 
 /* One Stockham stage: radix R, Ns = product of earlier radices.  sign=-1 forward, +1 inverse. */
-static void stage_generic(const orc_plan *p, int R, int Ns, int batch, int sign, const float *ir, const float *ii,
-                          float *or_, float *oi) {
+static inline __attribute__((always_inline)) void stage_generic(const orc_plan *p, int R, int Ns, int batch, int sign, const float *restrict ir, const float *restrict ii,
+                          float *restrict or_, float *restrict oi) {
   const int n = p->n, nb = n / R;
   float tr[32], ti[32];
   for (int j = 0; j < nb; ++j) {
@@ -110,20 +110,21 @@ static void stage_generic(const orc_plan *p, int R, int Ns, int batch, int sign,
   }
 }
 
+/* q*k*tstep <= (R-1)(Ns-1) n/(Ns R) < n: no modulo needed */
 #define LOAD_TW(q)                                                   \
-  const int t##q = (int)(((long)(q) * k * tstep) % n);               \
+  const int t##q = (q) * k * tstep;                                   \
   const float w##q##r = p->wr[t##q], w##q##i = sign < 0 ? p->wi[t##q] : -p->wi[t##q];
 
-static void stage2(const orc_plan *p, int Ns, int batch, int sign, const float *ir, const float *ii, float *or_,
-                   float *oi) {
+static inline __attribute__((always_inline)) void stage2(const orc_plan *p, int Ns, int batch, int sign, const float *restrict ir, const float *restrict ii,
+                   float *restrict or_, float *restrict oi) {
   const int n = p->n, nb = n / 2, tstep = n / (Ns * 2);
   for (int j = 0; j < nb; ++j) {
     const int k = j % Ns, j0 = (j / Ns) * Ns * 2 + k;
     LOAD_TW(1)
-    const float *a_r = ir + (size_t)j * batch, *a_i = ii + (size_t)j * batch;
-    const float *b_r = ir + (size_t)(j + nb) * batch, *b_i = ii + (size_t)(j + nb) * batch;
-    float *o0r = or_ + (size_t)j0 * batch, *o0i = oi + (size_t)j0 * batch;
-    float *o1r = or_ + (size_t)(j0 + Ns) * batch, *o1i = oi + (size_t)(j0 + Ns) * batch;
+    const float *restrict a_r = ir + (size_t)j * batch, *restrict a_i = ii + (size_t)j * batch;
+    const float *restrict b_r = ir + (size_t)(j + nb) * batch, *restrict b_i = ii + (size_t)(j + nb) * batch;
+    float *restrict o0r = or_ + (size_t)j0 * batch, *restrict o0i = oi + (size_t)j0 * batch;
+    float *restrict o1r = or_ + (size_t)(j0 + Ns) * batch, *restrict o1i = oi + (size_t)(j0 + Ns) * batch;
     for (int b = 0; b < batch; ++b) {
       const float xr = b_r[b] * w1r - b_i[b] * w1i, xi = b_r[b] * w1i + b_i[b] * w1r;
       o0r[b] = a_r[b] + xr; o0i[b] = a_i[b] + xi;
@@ -132,19 +133,19 @@ static void stage2(const orc_plan *p, int Ns, int batch, int sign, const float *
   }
 }
 
-static void stage3(const orc_plan *p, int Ns, int batch, int sign, const float *ir, const float *ii, float *or_,
-                   float *oi) {
+static inline __attribute__((always_inline)) void stage3(const orc_plan *p, int Ns, int batch, int sign, const float *restrict ir, const float *restrict ii,
+                   float *restrict or_, float *restrict oi) {
   const int n = p->n, nb = n / 3, tstep = n / (Ns * 3);
   const float c = -0.5f, s = (sign < 0 ? -1.f : 1.f) * 0.86602540378443864676f;
   for (int j = 0; j < nb; ++j) {
     const int k = j % Ns, j0 = (j / Ns) * Ns * 3 + k;
     LOAD_TW(1) LOAD_TW(2)
-    const float *x0r = ir + (size_t)j * batch, *x0i = ii + (size_t)j * batch;
-    const float *x1r = ir + (size_t)(j + nb) * batch, *x1i = ii + (size_t)(j + nb) * batch;
-    const float *x2r = ir + (size_t)(j + 2 * nb) * batch, *x2i = ii + (size_t)(j + 2 * nb) * batch;
-    float *o0r = or_ + (size_t)j0 * batch, *o0i = oi + (size_t)j0 * batch;
-    float *o1r = or_ + (size_t)(j0 + Ns) * batch, *o1i = oi + (size_t)(j0 + Ns) * batch;
-    float *o2r = or_ + (size_t)(j0 + 2 * Ns) * batch, *o2i = oi + (size_t)(j0 + 2 * Ns) * batch;
+    const float *restrict x0r = ir + (size_t)j * batch, *restrict x0i = ii + (size_t)j * batch;
+    const float *restrict x1r = ir + (size_t)(j + nb) * batch, *restrict x1i = ii + (size_t)(j + nb) * batch;
+    const float *restrict x2r = ir + (size_t)(j + 2 * nb) * batch, *restrict x2i = ii + (size_t)(j + 2 * nb) * batch;
+    float *restrict o0r = or_ + (size_t)j0 * batch, *restrict o0i = oi + (size_t)j0 * batch;
+    float *restrict o1r = or_ + (size_t)(j0 + Ns) * batch, *restrict o1i = oi + (size_t)(j0 + Ns) * batch;
+    float *restrict o2r = or_ + (size_t)(j0 + 2 * Ns) * batch, *restrict o2i = oi + (size_t)(j0 + 2 * Ns) * batch;
     for (int b = 0; b < batch; ++b) {
       const float ar = x0r[b], ai = x0i[b];
       const float br = x1r[b] * w1r - x1i[b] * w1i, bi = x1r[b] * w1i + x1i[b] * w1r;
@@ -158,21 +159,21 @@ static void stage3(const orc_plan *p, int Ns, int batch, int sign, const float *
   }
 }
 
-static void stage4(const orc_plan *p, int Ns, int batch, int sign, const float *ir, const float *ii, float *or_,
-                   float *oi) {
+static inline __attribute__((always_inline)) void stage4(const orc_plan *p, int Ns, int batch, int sign, const float *restrict ir, const float *restrict ii,
+                   float *restrict or_, float *restrict oi) {
   const int n = p->n, nb = n / 4, tstep = n / (Ns * 4);
   const float sg = sign < 0 ? 1.f : -1.f; /* forward: multiply by -i */
   for (int j = 0; j < nb; ++j) {
     const int k = j % Ns, j0 = (j / Ns) * Ns * 4 + k;
     LOAD_TW(1) LOAD_TW(2) LOAD_TW(3)
-    const float *x0r = ir + (size_t)j * batch, *x0i = ii + (size_t)j * batch;
-    const float *x1r = ir + (size_t)(j + nb) * batch, *x1i = ii + (size_t)(j + nb) * batch;
-    const float *x2r = ir + (size_t)(j + 2 * nb) * batch, *x2i = ii + (size_t)(j + 2 * nb) * batch;
-    const float *x3r = ir + (size_t)(j + 3 * nb) * batch, *x3i = ii + (size_t)(j + 3 * nb) * batch;
-    float *o0r = or_ + (size_t)j0 * batch, *o0i = oi + (size_t)j0 * batch;
-    float *o1r = or_ + (size_t)(j0 + Ns) * batch, *o1i = oi + (size_t)(j0 + Ns) * batch;
-    float *o2r = or_ + (size_t)(j0 + 2 * Ns) * batch, *o2i = oi + (size_t)(j0 + 2 * Ns) * batch;
-    float *o3r = or_ + (size_t)(j0 + 3 * Ns) * batch, *o3i = oi + (size_t)(j0 + 3 * Ns) * batch;
+    const float *restrict x0r = ir + (size_t)j * batch, *restrict x0i = ii + (size_t)j * batch;
+    const float *restrict x1r = ir + (size_t)(j + nb) * batch, *restrict x1i = ii + (size_t)(j + nb) * batch;
+    const float *restrict x2r = ir + (size_t)(j + 2 * nb) * batch, *restrict x2i = ii + (size_t)(j + 2 * nb) * batch;
+    const float *restrict x3r = ir + (size_t)(j + 3 * nb) * batch, *restrict x3i = ii + (size_t)(j + 3 * nb) * batch;
+    float *restrict o0r = or_ + (size_t)j0 * batch, *restrict o0i = oi + (size_t)j0 * batch;
+    float *restrict o1r = or_ + (size_t)(j0 + Ns) * batch, *restrict o1i = oi + (size_t)(j0 + Ns) * batch;
+    float *restrict o2r = or_ + (size_t)(j0 + 2 * Ns) * batch, *restrict o2i = oi + (size_t)(j0 + 2 * Ns) * batch;
+    float *restrict o3r = or_ + (size_t)(j0 + 3 * Ns) * batch, *restrict o3i = oi + (size_t)(j0 + 3 * Ns) * batch;
     for (int b = 0; b < batch; ++b) {
       const float ar = x0r[b], ai = x0i[b];
       const float br = x1r[b] * w1r - x1i[b] * w1i, bi = x1r[b] * w1i + x1i[b] * w1r;
@@ -189,8 +190,8 @@ static void stage4(const orc_plan *p, int Ns, int batch, int sign, const float *
   }
 }
 
-static void stage5(const orc_plan *p, int Ns, int batch, int sign, const float *ir, const float *ii, float *or_,
-                   float *oi) {
+static inline __attribute__((always_inline)) void stage5(const orc_plan *p, int Ns, int batch, int sign, const float *restrict ir, const float *restrict ii,
+                   float *restrict or_, float *restrict oi) {
   const int n = p->n, nb = n / 5, tstep = n / (Ns * 5);
   const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
   const float sg = sign < 0 ? -1.f : 1.f;
@@ -198,16 +199,16 @@ static void stage5(const orc_plan *p, int Ns, int batch, int sign, const float *
   for (int j = 0; j < nb; ++j) {
     const int k = j % Ns, j0 = (j / Ns) * Ns * 5 + k;
     LOAD_TW(1) LOAD_TW(2) LOAD_TW(3) LOAD_TW(4)
-    const float *x0r = ir + (size_t)j * batch, *x0i = ii + (size_t)j * batch;
-    const float *x1r = ir + (size_t)(j + nb) * batch, *x1i = ii + (size_t)(j + nb) * batch;
-    const float *x2r = ir + (size_t)(j + 2 * nb) * batch, *x2i = ii + (size_t)(j + 2 * nb) * batch;
-    const float *x3r = ir + (size_t)(j + 3 * nb) * batch, *x3i = ii + (size_t)(j + 3 * nb) * batch;
-    const float *x4r = ir + (size_t)(j + 4 * nb) * batch, *x4i = ii + (size_t)(j + 4 * nb) * batch;
-    float *o0r = or_ + (size_t)j0 * batch, *o0i = oi + (size_t)j0 * batch;
-    float *o1r = or_ + (size_t)(j0 + Ns) * batch, *o1i = oi + (size_t)(j0 + Ns) * batch;
-    float *o2r = or_ + (size_t)(j0 + 2 * Ns) * batch, *o2i = oi + (size_t)(j0 + 2 * Ns) * batch;
-    float *o3r = or_ + (size_t)(j0 + 3 * Ns) * batch, *o3i = oi + (size_t)(j0 + 3 * Ns) * batch;
-    float *o4r = or_ + (size_t)(j0 + 4 * Ns) * batch, *o4i = oi + (size_t)(j0 + 4 * Ns) * batch;
+    const float *restrict x0r = ir + (size_t)j * batch, *restrict x0i = ii + (size_t)j * batch;
+    const float *restrict x1r = ir + (size_t)(j + nb) * batch, *restrict x1i = ii + (size_t)(j + nb) * batch;
+    const float *restrict x2r = ir + (size_t)(j + 2 * nb) * batch, *restrict x2i = ii + (size_t)(j + 2 * nb) * batch;
+    const float *restrict x3r = ir + (size_t)(j + 3 * nb) * batch, *restrict x3i = ii + (size_t)(j + 3 * nb) * batch;
+    const float *restrict x4r = ir + (size_t)(j + 4 * nb) * batch, *restrict x4i = ii + (size_t)(j + 4 * nb) * batch;
+    float *restrict o0r = or_ + (size_t)j0 * batch, *restrict o0i = oi + (size_t)j0 * batch;
+    float *restrict o1r = or_ + (size_t)(j0 + Ns) * batch, *restrict o1i = oi + (size_t)(j0 + Ns) * batch;
+    float *restrict o2r = or_ + (size_t)(j0 + 2 * Ns) * batch, *restrict o2i = oi + (size_t)(j0 + 2 * Ns) * batch;
+    float *restrict o3r = or_ + (size_t)(j0 + 3 * Ns) * batch, *restrict o3i = oi + (size_t)(j0 + 3 * Ns) * batch;
+    float *restrict o4r = or_ + (size_t)(j0 + 4 * Ns) * batch, *restrict o4i = oi + (size_t)(j0 + 4 * Ns) * batch;
     for (int b = 0; b < batch; ++b) {
       const float ar = x0r[b], ai = x0i[b];
       const float br = x1r[b] * w1r - x1i[b] * w1i, bi = x1r[b] * w1i + x1i[b] * w1r;
@@ -230,29 +231,70 @@ static void stage5(const orc_plan *p, int Ns, int batch, int sign, const float *
   }
 }
 
-/* data in (re,im); scratch (sre,sim); result left in (re,im). */
+/* All stages of one transform for `batch` interleaved lanes held in a small contiguous block [n][batch], so the whole
+ * multi-stage transform stays in L1/L2.  Instantiated with a compile-time lane count (8 = one AVX2 vector) so that the
+ * inner lane loops of the always_inline stages become single vector operations. Result in (re,im). */
+#ifndef ORC_CHUNK
+#define ORC_CHUNK 8
+#endif
+#define ORC_DEFINE_CHUNK(NAME, WIDTH)                                                                             \
+  static void NAME(const orc_plan *p, int batch_rt, int sign, float *re, float *im, float *sre, float *sim) {     \
+    const int n = p->n, batch = (WIDTH) > 0 ? (WIDTH) : batch_rt;                                                 \
+    float *ar = re, *ai = im, *br = sre, *bi = sim;                                                               \
+    int Ns = 1;                                                                                                   \
+    for (int f = 0; f < p->nf; ++f) {                                                                             \
+      const int R = p->radix[f];                                                                                  \
+      switch (R) {                                                                                                \
+        case 2: stage2(p, Ns, batch, sign, ar, ai, br, bi); break;                                                \
+        case 3: stage3(p, Ns, batch, sign, ar, ai, br, bi); break;                                                \
+        case 4: stage4(p, Ns, batch, sign, ar, ai, br, bi); break;                                                \
+        case 5: stage5(p, Ns, batch, sign, ar, ai, br, bi); break;                                                \
+        default: stage_generic(p, R, Ns, batch, sign, ar, ai, br, bi); break;                                     \
+      }                                                                                                           \
+      Ns *= R;                                                                                                    \
+      float *t;                                                                                                   \
+      t = ar; ar = br; br = t;                                                                                    \
+      t = ai; ai = bi; bi = t;                                                                                    \
+    }                                                                                                             \
+    if (ar != re) {                                                                                               \
+      memcpy(re, ar, sizeof(float) * (size_t)n * batch);                                                          \
+      memcpy(im, ai, sizeof(float) * (size_t)n * batch);                                                          \
+    }                                                                                                             \
+  }
+ORC_DEFINE_CHUNK(fft1d_chunk8, ORC_CHUNK)
+ORC_DEFINE_CHUNK(fft1d_chunk_any, 0)
+
+/* data [n][batch] planar, in place; transforms are done ORC_CHUNK lanes at a time in a cache-resident scratch block */
 static void fft1d_batch(int n, int batch, int sign, float *re, float *im, float *sre, float *sim) {
   const orc_plan *p = get_plan(n);
-  float *ar = re, *ai = im, *br = sre, *bi = sim;
-  int Ns = 1;
-  for (int f = 0; f < p->nf; ++f) {
-    const int R = p->radix[f];
-    switch (R) {
-      case 2: stage2(p, Ns, batch, sign, ar, ai, br, bi); break;
-      case 3: stage3(p, Ns, batch, sign, ar, ai, br, bi); break;
-      case 4: stage4(p, Ns, batch, sign, ar, ai, br, bi); break;
-      case 5: stage5(p, Ns, batch, sign, ar, ai, br, bi); break;
-      default: stage_generic(p, R, Ns, batch, sign, ar, ai, br, bi); break;
+  (void)sre; (void)sim;
+  float *blk = (float *)aligned_alloc(64, sizeof(float) * 4 * (size_t)n * ORC_CHUNK);
+  float *cr = blk, *ci = blk + (size_t)n * ORC_CHUNK, *dr = ci + (size_t)n * ORC_CHUNK, *di = dr + (size_t)n * ORC_CHUNK;
+  for (int b0 = 0; b0 < batch; b0 += ORC_CHUNK) {
+    const int w = batch - b0 < ORC_CHUNK ? batch - b0 : ORC_CHUNK;
+    if (w == ORC_CHUNK) {
+      for (int i = 0; i < n; ++i) {
+        memcpy(cr + (size_t)i * ORC_CHUNK, re + (size_t)i * batch + b0, sizeof(float) * ORC_CHUNK);
+        memcpy(ci + (size_t)i * ORC_CHUNK, im + (size_t)i * batch + b0, sizeof(float) * ORC_CHUNK);
+      }
+      fft1d_chunk8(p, ORC_CHUNK, sign, cr, ci, dr, di);
+      for (int i = 0; i < n; ++i) {
+        memcpy(re + (size_t)i * batch + b0, cr + (size_t)i * ORC_CHUNK, sizeof(float) * ORC_CHUNK);
+        memcpy(im + (size_t)i * batch + b0, ci + (size_t)i * ORC_CHUNK, sizeof(float) * ORC_CHUNK);
+      }
+    } else {
+      for (int i = 0; i < n; ++i) {
+        memcpy(cr + (size_t)i * w, re + (size_t)i * batch + b0, sizeof(float) * w);
+        memcpy(ci + (size_t)i * w, im + (size_t)i * batch + b0, sizeof(float) * w);
+      }
+      fft1d_chunk_any(p, w, sign, cr, ci, dr, di);
+      for (int i = 0; i < n; ++i) {
+        memcpy(re + (size_t)i * batch + b0, cr + (size_t)i * w, sizeof(float) * w);
+        memcpy(im + (size_t)i * batch + b0, ci + (size_t)i * w, sizeof(float) * w);
+      }
     }
-    Ns *= R;
-    float *t;
-    t = ar; ar = br; br = t;
-    t = ai; ai = bi; bi = t;
   }
-  if (ar != re) {
-    memcpy(re, ar, sizeof(float) * (size_t)n * batch);
-    memcpy(im, ai, sizeof(float) * (size_t)n * batch);
-  }
+  free(blk);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -282,21 +324,27 @@ void orc_fft2(const float *x, int R, int C, float *xf) {
   const int half = R / 2 + 1, hb = (C + 1) / 2;
   ws_reserve(&t_ws, (size_t)(R > C ? R : C) * (size_t)((half > hb ? half : hb) + 1));
   float *zr = t_ws.a_re, *zi = t_ws.a_im;
-  /* pack line b into re, line b+hb into im, transposed to [r][b] */
-  for (int b = 0; b < hb; ++b) {
-    const float *la = x + (size_t)b * R;
-    const float *lb = (b + hb < C) ? x + (size_t)(b + hb) * R : NULL;
-    for (int r = 0; r < R; ++r) {
-      zr[(size_t)r * hb + b] = la[r];
-      zi[(size_t)r * hb + b] = lb ? lb[r] : 0.f;
+  /* pack line b into re, line b+hb into im, transposed to [r][b] (16x16 tiles keep both sides in cache lines) */
+  for (int b0 = 0; b0 < hb; b0 += 16)
+    for (int r0 = 0; r0 < R; r0 += 16) {
+      const int b1 = b0 + 16 < hb ? b0 + 16 : hb, r1 = r0 + 16 < R ? r0 + 16 : R;
+      for (int b = b0; b < b1; ++b) {
+        const float *la = x + (size_t)b * R;
+        const float *lb = (b + hb < C) ? x + (size_t)(b + hb) * R : NULL;
+        for (int r = r0; r < r1; ++r) {
+          zr[(size_t)r * hb + b] = la[r];
+          zi[(size_t)r * hb + b] = lb ? lb[r] : 0.f;
+        }
+      }
     }
-  }
   fft1d_batch(R, hb, -1, zr, zi, t_ws.b_re, t_ws.b_im);
   /* separate the two real lines, write transposed: S[c][k] planar */
   float *sr = t_ws.b_re, *si = t_ws.b_im;
-  for (int k = 0; k < half; ++k) {
+  for (int k0 = 0; k0 < half; k0 += 16)
+  for (int b0 = 0; b0 < hb; b0 += 16)
+  for (int k = k0; k < (k0 + 16 < half ? k0 + 16 : half); ++k) {
     const int km = (R - k) % R;
-    for (int b = 0; b < hb; ++b) {
+    for (int b = b0; b < (b0 + 16 < hb ? b0 + 16 : hb); ++b) {
       const float ar = zr[(size_t)k * hb + b], ai = zi[(size_t)k * hb + b];
       const float br = zr[(size_t)km * hb + b], bi = zi[(size_t)km * hb + b];
       sr[(size_t)b * half + k] = 0.5f * (ar + br);
@@ -326,11 +374,13 @@ void orc_ifft2(const float *xf, int R, int C, float *x) {
   fft1d_batch(C, half, +1, sr, si, t_ws.b_re, t_ws.b_im);
   /* z[k][b] = Xa[k] + i Xb[k], Hermitian-extended along k (c2r semantics: imag of k=0 and k=R/2 ignored) */
   float *zr = t_ws.b_re, *zi = t_ws.b_im;
-  for (int b = 0; b < hb; ++b) {
+  for (int b0 = 0; b0 < hb; b0 += 16)
+  for (int k0 = 0; k0 < half; k0 += 16)
+  for (int b = b0; b < (b0 + 16 < hb ? b0 + 16 : hb); ++b) {
     const float *ar = sr + (size_t)b * half, *ai = si + (size_t)b * half;
     const int has_b = (b + hb < C);
     const float *br = has_b ? sr + (size_t)(b + hb) * half : NULL, *bi = has_b ? si + (size_t)(b + hb) * half : NULL;
-    for (int k = 0; k < half; ++k) {
+    for (int k = k0; k < (k0 + 16 < half ? k0 + 16 : half); ++k) {
       float xar = ar[k], xai = ai[k], xbr = has_b ? br[k] : 0.f, xbi = has_b ? bi[k] : 0.f;
       if (k == 0 || 2 * k == R) { xai = 0.f; xbi = 0.f; }
       zr[(size_t)k * hb + b] = xar - xbi;
@@ -344,14 +394,16 @@ void orc_ifft2(const float *xf, int R, int C, float *x) {
   }
   fft1d_batch(R, hb, +1, zr, zi, t_ws.a_re, t_ws.a_im);
   const float inv = 1.0f / (float)((size_t)R * C);
-  for (int b = 0; b < hb; ++b) {
-    float *la = x + (size_t)b * R;
-    float *lb = (b + hb < C) ? x + (size_t)(b + hb) * R : NULL;
-    for (int r = 0; r < R; ++r) {
-      la[r] = zr[(size_t)r * hb + b] * inv;
-      if (lb) lb[r] = zi[(size_t)r * hb + b] * inv;
-    }
-  }
+  for (int b0 = 0; b0 < hb; b0 += 16)
+    for (int r0 = 0; r0 < R; r0 += 16)
+      for (int b = b0; b < (b0 + 16 < hb ? b0 + 16 : hb); ++b) {
+        float *la = x + (size_t)b * R;
+        float *lb = (b + hb < C) ? x + (size_t)(b + hb) * R : NULL;
+        for (int r = r0; r < (r0 + 16 < R ? r0 + 16 : R); ++r) {
+          la[r] = zr[(size_t)r * hb + b] * inv;
+          if (lb) lb[r] = zi[(size_t)r * hb + b] * inv;
+        }
+      }
 }
 
 /* ------------------------------------------------------------------------------------------ */
