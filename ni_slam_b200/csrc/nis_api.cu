@@ -85,6 +85,11 @@ struct nis_ctx {
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
   DevBuf sF, sP, sHt, sHp, sImg;
+  // scan: spectra of the query image rotated by every angle the polar stage can select (2 hypotheses x D rows), built once
+  // per query when the candidate list is long; indexed by the same `sel` the rotation matrices use (minus D)
+  DevBuf rotc, rotc_xx, rotc_sel;
+  bool use_rot_cache = false;
+  int rot_cache_min = 1024;
   // keyframe DB
   std::vector<void*> chunks;
   int chunk_slots = 64;
@@ -325,9 +330,10 @@ static int ensure_pinned(nis_ctx* ctx, size_t bytes) {
 // batched stages
 // -------------------------------------------------------------------------------------------------------------
 // KernelFn for size class s (polynomial / gaussian, correlation_flow.cc:181-226)
-static KernelFn kernel_fn(const nis_ctx* ctx, int s, const double* xx, const double* zz, int zz_shift, unsigned* maxbuf) {
+static KernelFn kernel_fn(const nis_ctx* ctx, int s, const double* xx, const double* zz, int zz_shift, unsigned* maxbuf,
+                          const int* xx_idx = nullptr) {
   const nis_cf_config& c = ctx->cfg;
-  return KernelFn{(float)(unsigned)ctx->sz[s].real, c.kernel, c.offset, c.power, -1.f / (c.sigma * c.sigma), xx, zz, zz_shift, maxbuf};
+  return KernelFn{(float)(unsigned)ctx->sz[s].real, c.kernel, c.offset, c.power, -1.f / (c.sigma * c.sigma), xx, zz, zz_shift, maxbuf, xx_idx};
 }
 
 // H = T / (kernel(Z)/max + lambda) for B keyframe spectra of size class s (the keyframe-only factor of EstimateTrans,
@@ -386,11 +392,14 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
 // the current-frame half of EstimateTrans (correlation_flow.cc:160, :171-178) on half-transformed input already in t1:
 //   [t1 holds row-inverse of X*conj(Z)] -> colcol (IFFT cols, kernel fn, FFT cols) -> rowrow (FFT rows, *H/max, IFFT rows)
 //   -> col_inv_peak (IFFT cols, arg-max + sums)
-static int correlate_tail(nis_ctx* ctx, Lane& L, int s, Src<cpx> Hz, int E, int zshift, unsigned* maxbuf, PeakStats* stats, float* g_debug) {
+static int correlate_tail(nis_ctx* ctx, Lane& L, int s, Src<cpx> Hz, int E, int zshift, unsigned* maxbuf, PeakStats* stats, float* g_debug,
+                          const double* xx_override = nullptr, const int* xx_idx = nullptr) {
   const SizeClass& z = ctx->sz[s];
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
   Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
-  LAUNCH(launch_colcol(z.R, z.coli, z.colf, t1s, t1, kernel_fn(ctx, s, L.xx.as<double>(), L.zz.as<double>(), zshift, maxbuf), z.C, E, L.stream));
+  LAUNCH(launch_colcol(z.R, z.coli, z.colf, t1s, t1,
+                       kernel_fn(ctx, s, xx_override ? xx_override : L.xx.as<double>(), L.zz.as<double>(), zshift, maxbuf, xx_idx), z.C, E,
+                       L.stream));
   Src<cpx> Hze = Hz; Hze.shift = zshift;
   LAUNCH(launch_rowrow_filter(z.C, z.row, t1s, t1, MidFilterH{Hze, maxbuf}, z.R / 2 + 1, E, L.stream));
   EpiPeak ep{stats, z.R, (float)z.real, g_debug, (long long)z.real, z.C};
@@ -413,6 +422,40 @@ static int estimate_trans_stored(nis_ctx* ctx, Lane& L, int s, Src<cpx> Z, Src<c
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
   LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{X, Z}, EpiSpecStore{t1}, z.R / 2 + 1, B, L.stream));
   return correlate_tail(ctx, L, s, Hz, B, 0, maxbuf, stats, g_debug);
+}
+
+// scan only: FFT(RotateArray(query, -deg)) and FFT(RotateArray(query, -deg+180)) for every polar row (2 D spectra), so that a
+// candidate's two hypotheses cost one spectrum read each.  Same kernels, same arithmetic as the per-candidate path.
+static int build_rot_cache(nis_ctx* ctx, Src<float> img_f32, Src<uint8_t> img_u8, bool is_u8) {
+  const SizeClass& zt = ctx->sz[0];
+  const int D = ctx->D, n = 2 * D;
+  RESERVE(ctx->rotc, (size_t)n * zt.spec * sizeof(cpx));
+  RESERVE(ctx->rotc_xx, (size_t)n * sizeof(double));
+  if (ctx->rotc_sel.bytes < (size_t)n * sizeof(int)) {
+    RESERVE(ctx->rotc_sel, (size_t)n * sizeof(int));
+    std::vector<int> sel(n);
+    for (int i = 0; i < n; ++i) sel[i] = D + i;          // matrix slots D..3D-1 = the two loop variants
+    CU(h2d(ctx, ctx->rotc_sel.p, sel.data(), (size_t)n * sizeof(int)));
+  }
+  const int NL = ctx->active_lanes, B = std::max(1, ctx->batch) * 2;
+  const bool gauss = ctx->cfg.kernel == 1;
+  TRY(fork_lanes(ctx));
+  for (int i0 = 0, k = 0; i0 < n; i0 += B, ++k) {
+    Lane& L = ctx->lanes[k % NL];
+    ctx->prof_stream = L.stream;
+    const int nb = std::min(B, n - i0);
+    TRY(ensure_workspace(ctx, L, (nb + 1) / 2));
+    Dst<cpx> t1{L.t1.as<cpx>(), (long long)zt.spec};
+    Src<float> i32 = img_f32; Src<uint8_t> i8 = img_u8;
+    if (is_u8) i32 = src_null<float>(); else i8 = src_null<uint8_t>();
+    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), ctx->rotc_sel.as<int>() + i0};
+    LAUNCH(launch_col_fwd_rotate(zt.R, zt.colf, ra, t1, zt.C, nb, L.stream));
+    Dst<cpx> out{ctx->rotc.as<cpx>() + (size_t)i0 * zt.spec, (long long)zt.spec};
+    LAUNCH(launch_row_fwd(zt.C, zt.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, zt.R / 2 + 1, nb, L.stream));
+    if (gauss) LAUNCH(launch_spec_sqsum(src_slab<cpx>(out.base, out.stride), (int)zt.spec, ctx->rotc_xx.as<double>() + i0, nb, L.stream));
+  }
+  TRY(join_lanes(ctx));
+  return NIS_OK;
 }
 
 // ComputePose (correlation_flow.cc:97-138) for B pairs -> device records
@@ -440,11 +483,18 @@ static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz
   }
   CU(cudaMemsetAsync(L.maxt.p, 0, sizeof(unsigned) * E, L.stream));
   CU(cudaMemsetAsync(st, 0, sizeof(PeakStats) * E, L.stream));
-  RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>()};
-  LAUNCH(launch_col_fwd_rotate(zt.R, zt.colf, ra, t1, zt.C, E, L.stream));
   Src<cpx> Fze = Fz; Fze.shift = shift;
-  LAUNCH(launch_rowrow_mulconj(zt.C, zt.row, t1s, t1, MidMulConjZ{Fze, gauss ? L.xx.as<double>() : nullptr}, zt.R / 2 + 1, E, L.stream));
-  TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr));
+  if (loop_mode && ctx->use_rot_cache) {
+    // FFT(RotateArray(query, angle)) comes from the per-query cache: one inverse row pass instead of warp + 3 passes
+    Src<cpx> Xc{ctx->rotc.as<cpx>() - (size_t)ctx->D * zt.spec, (long long)zt.spec, nullptr, 0, L.sel.as<int>(), 0};
+    LAUNCH(launch_row_inv_mulconj(zt.C, zt.row, ProMulConj{Xc, Fze}, EpiSpecStore{t1}, zt.R / 2 + 1, E, L.stream));
+    TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr, ctx->rotc_xx.as<double>() - ctx->D, L.sel.as<int>()));
+  } else {
+    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>()};
+    LAUNCH(launch_col_fwd_rotate(zt.R, zt.colf, ra, t1, zt.C, E, L.stream));
+    LAUNCH(launch_rowrow_mulconj(zt.C, zt.row, t1s, t1, MidMulConjZ{Fze, gauss ? L.xx.as<double>() : nullptr}, zt.R / 2 + 1, E, L.stream));
+    TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr));
+  }
   AngleTables tabs{ctx->mats.as<double>(), ctx->theta.as<double>()};
   LAUNCH(launch_pose_finalize(sp, st, tabs, ctx->H, ctx->W, ctx->D, ctx->Cp, loop_mode ? 1 : 0, index0, recs, B, L.stream));
   return NIS_OK;
@@ -513,9 +563,11 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
     cudaDeviceProp prop;
     int sms = 148;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sms = prop.multiProcessorCount;
-    ctx->default_batch = std::max(4, std::min(64, (2 * sms) / std::max(1, W / 32)));
+    ctx->default_batch = std::max(4, std::min(64, (2 * sms) / std::max(1, W / 32)));   // ~2 x 512 resident threads per SM
     ctx->batch = ctx->default_batch;
   }
+  const char* er = getenv("NIS_ROT_CACHE_MIN");      // candidates from which a scan builds the rotated-query cache (0 = never)
+  if (er) ctx->rot_cache_min = atoi(er);
   const char* ef = getenv("NIS_POLAR_FUSED");
   if (ef) ctx->polar_fused = atoi(ef) != 0;
   const char* eb = getenv("NIS_BATCH");
@@ -531,7 +583,7 @@ int nis_destroy(nis_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
-                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->d_slot_ptr};
+                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {
     DevBuf* lb[] = {&L.t1, &L.real, &L.pol, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz};
@@ -673,6 +725,7 @@ int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, 
                      double info[3], int32_t peak_rc[4]) {
   if (!ctx || !last || !cur || !pose || !info) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
+  ctx->use_rot_cache = false;
   TRY(ensure_recs(ctx, 1));
   const bool u8 = cur->img_u8 != nullptr;
   TRY(compute_pose_batch(ctx, ctx->lanes[0], !not_large_rotation, src_slab<cpx>(last->F, 0), src_slab<cpx>(last->P, 0),
@@ -869,6 +922,8 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   const int B = ctx->batch;
   const cpx* const* ptrs = ctx->d_slot_ptr.as<const cpx*>();
   const int NL = ctx->active_lanes;
+  ctx->use_rot_cache = ctx->rot_cache_min > 0 && n >= ctx->rot_cache_min;
+  if (ctx->use_rot_cache) TRY(build_rot_cache(ctx, src_slab<float>(query->img_f32, 0), src_slab<uint8_t>(query->img_u8, 0), u8));
   TRY(fork_lanes(ctx));
   for (int b0 = 0, k = 0; b0 < n; b0 += B, ++k) {
     const int nb = std::min(B, n - b0);
@@ -882,6 +937,7 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
                            src_slab<uint8_t>(query->img_u8, 0), u8, nb, b0, ctx->recs.as<PoseRecord>() + b0));
   }
   TRY(join_lanes(ctx));
+  ctx->use_rot_cache = false;
   ctx->prof_stream = ctx->stream;
   LAUNCH(launch_scan_reduce(ctx->recs.as<PoseRecord>(), n, ctx->best.as<PoseRecord>(), ctx->stream));
   PoseRecord best;

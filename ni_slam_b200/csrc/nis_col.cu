@@ -11,7 +11,7 @@ template <int N, int R0, int R1, int R2, int T, class Pro>
 __global__ void __launch_bounds__(T) col_fwd_kernel(Pro pro, Twiddles twd, Dst<cpx> out, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
-  const int b = blockIdx.y, c0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
   const auto bp = pro.bind(b, c0);
   col_fwd_phase0<N, R0, R1, R2, T>(tid, smem, bp);
   __syncthreads();
@@ -27,7 +27,7 @@ template <int N, int R0, int R1, int R2, int T, class Epi>
 __global__ void __launch_bounds__(T) col_inv_kernel(Src<cpx> in, Twiddles twd, Epi epi, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
-  const int b = blockIdx.y, c0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
   col_inv_phase0<N, R0, R1, R2, T>(tid, smem, in.at(b), W, c0);
   __syncthreads();
   CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1> st;
@@ -47,7 +47,7 @@ template <int N, int I0, int I1, int I2, int F0, int F1, int F2, int T>
 __global__ void __launch_bounds__(T) colcol_kernel(Src<cpx> in, Dst<cpx> out, Twiddles twi, Twiddles twf, KernelFn kfn, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
-  const int b = blockIdx.y, c0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
   col_inv_phase0<N, I0, I1, I2, T>(tid, smem, in.at(b), W, c0);
   __syncthreads();
   {
@@ -85,7 +85,7 @@ static int run_colcol(Twiddles twi, Twiddles twf, Src<cpx> in, Dst<cpx> out, Ker
   const size_t smem = ColGeom<N, F0, F1, F2, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / 32, B), T, smem, s>>>(in, out, twi, twf, fn, W);
+  k<<<dim3(W / kColTile, B), T, smem, s>>>(in, out, twi, twf, fn, W);
   return (int)cudaGetLastError();
 }
 
@@ -95,7 +95,7 @@ static int run_col_fwd(Twiddles tw, Pro pro, Dst<cpx> out, int W, int B, cudaStr
   const size_t smem = ColGeom<N, R0, R1, R2, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / 32, B), T, smem, s>>>(pro, tw, out, W);
+  k<<<dim3(W / kColTile, B), T, smem, s>>>(pro, tw, out, W);
   return (int)cudaGetLastError();
 }
 template <int N, int R0, int R1, int R2, int T, class Epi>
@@ -104,7 +104,7 @@ static int run_col_inv(Twiddles tw, Src<cpx> in, Epi epi, int W, int B, cudaStre
   const size_t smem = ColGeom<N, R0, R1, R2, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / 32, B), T, smem, s>>>(in, tw, epi, W);
+  k<<<dim3(W / kColTile, B), T, smem, s>>>(in, tw, epi, W);
   return (int)cudaGetLastError();
 }
 

@@ -203,11 +203,15 @@ struct Twiddles {
 // =========================================================================================================
 // COLUMN PASS: lanes <-> 16 complex lines (32 real columns).  smem: cpx[N][16].  T threads, G = T/16 groups.
 // =========================================================================================================
-constexpr int kColLanes = 16;
+#ifndef NIS_COL_LANES
+#define NIS_COL_LANES 8
+#endif
+constexpr int kColLanes = NIS_COL_LANES;          // complex lines per CTA
+constexpr int kColTile = 2 * kColLanes;           // real image columns per CTA
 
 template <int N, int R0, int R1, int R2, int T> struct ColGeom {
   static_assert(R0 * R1 * R2 == N, "bad factorisation");
-  static_assert(T % kColLanes == 0, "T must be a multiple of 16");
+  static_assert(T % kColLanes == 0, "T must be a multiple of the lane count");
   static constexpr int G = T / kColLanes;
   static constexpr int M0 = N / R0, M1 = N / R1, M2 = N / R2;   // butterflies per line per stage
   static constexpr int NS1 = R0, NS2 = R0 * R1;

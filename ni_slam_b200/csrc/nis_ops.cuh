@@ -167,6 +167,7 @@ struct KernelFn {
   float n; int kernel; float offset; int power; float gcoef;
   const double* xx_sum; const double* zz_sum; int zz_shift;
   unsigned int* maxbuf;
+  const int* xx_idx;            // optional: xx_sum[xx_idx[b]] (rotated-query cache of the scan)
   struct Bound {
     float n, rn; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
     NIS_HD float kfun(float v) const {
@@ -183,7 +184,7 @@ struct KernelFn {
   };
   NIS_HD Bound bind(int b) const {
     float s = 0.f;
-    if (kernel == 1) s = (float)xx_sum[b] / n + (float)zz_sum[b >> zz_shift] / n;
+    if (kernel == 1) s = (float)xx_sum[xx_idx ? xx_idx[b] : b] / n + (float)zz_sum[b >> zz_shift] / n;
     return Bound{n, 1.0f / n, kernel, offset, power, gcoef, s, maxbuf + b, 0.f};
   }
 };

@@ -6,14 +6,17 @@
 //                                 (two line buffers, so fewer lines keep more CTAs resident)
 // Image widths must also be multiples of 32 (one column-pass CTA owns 32 real columns).
 #pragma once
-#define NIS_COL_PLANS(X)              \
-  X(480, 10, 8, 6, 6, 8, 10, 512)     \
-  X(720, 10, 9, 8, 8, 9, 10, 512)     \
-  X(960, 10, 12, 8, 8, 12, 10, 512)   \
-  X(1200, 10, 12, 10, 10, 12, 10, 512) \
-  X(96, 4, 6, 4, 4, 6, 4, 128)        \
-  X(80, 5, 4, 4, 4, 4, 5, 128)        \
-  X(64, 4, 4, 4, 4, 4, 4, 128)
+#include "nis_fft.cuh"
+// T is given for 16 complex lanes per CTA and scaled with NIS_COL_LANES (nis_fft.cuh) so the butterflies per thread stay put
+#define NIS_CT(t) ((t) * NIS_COL_LANES / 16)
+#define NIS_COL_PLANS(X)                      \
+  X(480, 10, 8, 6, 6, 8, 10, NIS_CT(512))     \
+  X(720, 10, 9, 8, 8, 9, 10, NIS_CT(512))     \
+  X(960, 10, 12, 8, 8, 12, 10, NIS_CT(512))   \
+  X(1200, 10, 12, 10, 10, 12, 10, NIS_CT(512)) \
+  X(96, 4, 6, 4, 4, 6, 4, NIS_CT(128))        \
+  X(80, 5, 4, 4, 4, 4, 5, NIS_CT(128))        \
+  X(64, 4, 4, 4, 4, 4, 4, NIS_CT(128))
 
 #define NIS_ROW_PLANS(X)      \
   X(640, 8, 5, 8, 256, 4)     \

@@ -48,7 +48,7 @@ static void emu_col_fwd(const float* x, int B, int W, cpx* out) {
   std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
   ProRealF32 pro{Src<float>{x, (long long)N * W, nullptr, 0, nullptr, 0}, W};
   for (int b = 0; b < B; ++b)
-    for (int c0 = 0; c0 < W; c0 += 32) {
+    for (int c0 = 0; c0 < W; c0 += kColTile) {
       auto bp = pro.bind(b, c0);
       for (int t = 0; t < T; ++t) col_fwd_phase0<N, R0, R1, R2, T>(t, smem.data(), bp);
       for (int t = 0; t < T; ++t) col_stage1_read<N, R0, R1, R2, T, false>(t, smem.data(), twd, st[t]);
@@ -67,7 +67,7 @@ static void emu_col_inv(const cpx* in, int B, int W, Epi& epi) {
   std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
   HostSync sync;
   for (int b = 0; b < B; ++b)
-    for (int c0 = 0; c0 < W; c0 += 32) {
+    for (int c0 = 0; c0 < W; c0 += kColTile) {
       std::vector<typename Epi::Bound> eb(T, epi.bind(b, c0));
       for (int t = 0; t < T; ++t) col_inv_phase0<N, R0, R1, R2, T>(t, smem.data(), in + (size_t)b * (N / 2 + 1) * W, W, c0);
       for (int t = 0; t < T; ++t) col_stage1_read<N, R0, R1, R2, T, true>(t, smem.data(), twd, st[t]);
@@ -113,7 +113,7 @@ static void emu_colcol(const cpx* in, int B, int W, cpx* out, KernelFn kfn) {
   std::vector<CarryRegs<F1, Gf::ROUNDS1>> s1(T);
   HostSync sync;
   for (int b = 0; b < B; ++b)
-    for (int c0 = 0; c0 < W; c0 += 32) {
+    for (int c0 = 0; c0 < W; c0 += kColTile) {
       const cpx* src = in + (size_t)b * (N / 2 + 1) * W;
       cpx* dst = out + (size_t)b * (N / 2 + 1) * W;
       std::vector<KernelFn::Bound> fn(T, kfn.bind(b));
@@ -166,7 +166,7 @@ extern "C" {
 // in/out: [B][N/2+1][W] complex; maxbuf[B]; polynomial kernel (x/(N*W) + offset)^power
 int emu_colcol_poly(const float* in, int B, int N, int W, float* out, unsigned int* maxbuf, float offset, int power) {
   memset(maxbuf, 0, sizeof(unsigned int) * B);
-  KernelFn kfn{(float)((long long)N * W), 0, offset, power, 0.f, nullptr, nullptr, 0, maxbuf};
+  KernelFn kfn{(float)((long long)N * W), 0, offset, power, 0.f, nullptr, nullptr, 0, maxbuf, nullptr};
 #define X(n, f0, f1, f2, i0, i1, i2, t) \
   if (N == n) { emu_colcol<n, i0, i1, i2, f0, f1, f2, t>((const cpx*)in, B, W, (cpx*)out, kfn); return 0; }
   NIS_COL_PLANS(X)

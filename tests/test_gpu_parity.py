@@ -278,6 +278,29 @@ def test_loop_scan_matches_oracle(cf, cfg, imgs):
     lc.clear()
 
 
+def test_scan_rotated_query_cache_is_result_preserving(cf, imgs, monkeypatch):
+    """Long scans take FFT(RotateArray(query, angle)) from a per-query cache of all 2 D angles instead of re-rotating per
+    candidate; the responses must not change."""
+    import ni_slam_b200 as nis
+    order = [3, 0, 5, 6, 2, 4, 0, 7]
+    lc = nis.LoopClosure(nis.LoopClosureConfig(60, 60), cf)
+    lc.clear()
+    lc.AddImages(imgs[order])
+    q = cf.ComputeIntermedium(imgs[1])
+    res, allr = lc.FindLoopClosure(q, 99, 50.0, return_all=True)
+    lc.clear()
+    monkeypatch.setenv("NIS_ROT_CACHE_MIN", "1")
+    cf2 = nis.CorrelationFlow(nis.CFConfig(), H, W)
+    lc2 = nis.LoopClosure(nis.LoopClosureConfig(60, 60), cf2)
+    lc2.AddImages(imgs[order])
+    q2 = cf2.ComputeIntermedium(imgs[1])
+    res2, allr2 = lc2.FindLoopClosure(q2, 99, 50.0, return_all=True)
+    assert res2.loop_slot == res.loop_slot == 1 and res2.peak == res.peak and res2.hyp == res.hyp
+    assert np.array_equal(res2.relative_pose, res.relative_pose)
+    assert np.allclose(allr2, allr, rtol=2e-6)
+    cf2.close()
+
+
 def test_large_rotation_loop_mode(cf, golden_pairs, imgs):
     # image 6 is rotated by 152 degrees: only loop mode (two hypotheses) recovers it
     fa, fb = cf.ComputeIntermedium(imgs[0]), cf.ComputeIntermedium(imgs[6])
