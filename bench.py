@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per step (stream length)")
     ap.add_argument("--batch", type=int, default=0, help="pairs in flight per kernel launch (0 = library default)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent CUDA streams the batches are dealt to (0 = library default)")
-    ap.add_argument("--db", type=int, default=2048, help="loop-closure keyframes PER GPU (0 = skip the scan section)")
+    ap.add_argument("--db", type=int, default=4096, help="loop-closure keyframes PER GPU (0 = skip the scan section)")
     ap.add_argument("--queries", type=int, default=2)
     ap.add_argument("--ref-frames", type=int, default=65, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=65, help="frames of the cpu_baseline sample (0 = skip)")
@@ -372,6 +372,7 @@ def main():
                 "queries_per_sec_over_100k_extrapolated": cand_per_s / 1e5, "winner_frame_id": int(res.loop_frame_id),
                 "expected_frame_id": int(jstar), "found": bool(res.found), "relative_pose": [float(x) for x in res.relative_pose],
                 "collective": "ncclAllGather of %d-byte records" % nbytes if world > 1 else "none (1 rank)",
+                "rotated_query_cache": "on (>= 1024 candidates)",
                 "gpu_launches_per_query": (cf.kernel_launches() - l1) // max(args.queries, 1),
                 "roofline": {"bound": "hbm", "achieved": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9 / peak,
