@@ -36,6 +36,19 @@ BYTES_PER_CANDIDATE = (H // 2 + 1) * W * 8 + (D // 2 + 1) * CP * 8              
 METRIC = "pose_solves_per_sec_640x480"
 
 
+def ncu_traffic(kernel_family):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed ncu --set full
+    capture (profiles/ncu_r01_summary.json; cold-cache replay at the default batch).  None if no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_r01_summary.json")) as f:
+            cap = json.load(f)["full_capture"]
+        vals = [v["dram_bytes_per_launch"] for k, v in cap.items() if kernel_family.split("_")[0] in k and
+                (kernel_family in k.replace("_kernel", "") or kernel_family.startswith(k.split("_kernel")[0]))]
+        return float(np.mean(vals)) if vals else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -314,7 +327,9 @@ def main():
     dom = next(iter(kernels))
     peak, peak_src = measured_peak()
     achieved = (value / world) * BYTES_PER_SOLVE / 1e9                  # per GPU
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
+                "traffic_note": "bytes per launch of the dominant kernel family (ncu --set full, cold cache, default batch); the family "
+                                "moves its own tile in and out once, the multi-kernel step as a whole moves ~52 MB per solve",
                 "definition": "per-GPU solves/s x %d algorithmic B/solve (SURVEY 8d) over the whole multi-kernel step" % BYTES_PER_SOLVE,
                 "peak_source": peak_src, "dominant_kernel": dom, "dominant_kernel_share": kernels[dom]["share"],
                 "dominant_kernel_avg_launch_ms": kernels[dom]["ms"] / max(kernels[dom]["launches"], 1), "kernels": kernels}
