@@ -122,6 +122,17 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
                   const nis_loop_config* cfg, const int32_t* candidate_slots, int n_candidates, nis_loop_result* out,
                   double* all_responses);
 
+/* ---- candidate selection by prior pose: LoopClosure::FindLoopClosure(image, current_frame, prior_pose), src/loop_closure.cc:17-34
+ *      = Map::ComputeGridLocation + the 3x3 neighbourhood + Map::GetFramesInGrids (src/map.cc:81-101).
+ *      nis_db_set_position files a keyframe under its grid cell ((int)(x/grid_scale), (int)(y/grid_scale)) -- like Map::AddFrame
+ *      it is the pose at insertion time that counts.  nis_loop_scan_prior scans the keyframes of the 9 cells around the prior's cell,
+ *      cells in the reference's order (dx = -1..1 outer, dy = -1..1 inner), slots ascending inside a cell (the reference iterates
+ *      an unordered_set there, i.e. in no defined order).  candidates_out (may be NULL, capacity max_candidates) receives that list. ---- */
+int nis_db_set_position(nis_ctx* ctx, int slot, double x, double y, double grid_scale);
+int nis_loop_scan_prior(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance,
+                        const nis_loop_config* cfg, double prior_x, double prior_y, double grid_scale, nis_loop_result* out,
+                        int32_t* candidates_out, int max_candidates, int* n_candidates_out);
+
 /* Multi-GPU: every rank scans its own shard with nis_loop_scan, the ranks all-gather their nis_loop_result records
  * (NCCL), and each rank calls this to pick the winner with the reference's rule.  `order[i]` is the position of rank
  * i's winner in the global iteration order (ties: smallest wins); pass NULL to use the rank index. */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "nis_create", "nis_destroy", "nis_last_error", "nis_strerror", "nis_stream", "nis_synchronize", "nis_kernel_launches",
     "nis_set_batch", "nis_set_lanes", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
     "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
-    "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_debug_fft2",
+    "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_db_set_position", "nis_loop_scan_prior", "nis_debug_fft2",
     "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
     "nis_profile_end",
 ]
@@ -130,6 +130,9 @@ def load_library():
     lib.nis_loop_reduce.argtypes = [vp, vp, i32, C.POINTER(_LoopConfigC), C.POINTER(LoopResultC), C.POINTER(i32)]
     lib.nis_profile_begin.argtypes = [vp]
     lib.nis_profile_end.argtypes = [vp, C.c_char_p, i32]
+    lib.nis_db_set_position.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double]
+    lib.nis_loop_scan_prior.argtypes = [vp, vp, i32, C.c_double, C.POINTER(_LoopConfigC), C.c_double, C.c_double, C.c_double,
+                                        C.POINTER(LoopResultC), vp, i32, C.POINTER(i32)]
     lib.nis_debug_fft2.argtypes = [vp, i32, vp, vp]
     lib.nis_debug_ifft2.argtypes = [vp, i32, vp, vp]
     lib.nis_debug_polar.argtypes = [vp, vp, vp]
@@ -376,6 +379,25 @@ class LoopClosure:
                                         _p(cand), n, C.byref(out), _p(allr)))
         res = _result_from_c(out)
         return (res, allr) if return_all else res
+
+    def SetPosition(self, slot: int, x: float, y: float, grid_scale: float):
+        """Map::AddFrame's grid filing (src/map.cc:27-30): the keyframe's pose at insertion time picks its cell."""
+        self._cf._check(self._cf._lib.nis_db_set_position(self._cf._ctx, int(slot), float(x), float(y), float(grid_scale)))
+
+    def FindLoopClosurePrior(self, current_frame: Frame, prior_pose, grid_scale: float, current_frame_id: int = 0,
+                             current_distance: float = 0.0):
+        """LoopClosure::FindLoopClosure(image, current_frame, prior_pose) (loop_closure.cc:17-34): only the keyframes filed in
+        the 3x3 grid cells around the prior pose are scanned.  Returns (result, candidate slots in iteration order)."""
+        cf = self._cf
+        cap = max(self.size(), 1)
+        cand = np.zeros(cap, np.int32)
+        n = C.c_int()
+        out = LoopResultC()
+        cfg = self._cfg_c()
+        cf._check(cf._lib.nis_loop_scan_prior(cf._ctx, current_frame._h, int(current_frame_id), float(current_distance), C.byref(cfg),
+                                              float(prior_pose[0]), float(prior_pose[1]), float(grid_scale), C.byref(out), _p(cand),
+                                              cap, C.byref(n)))
+        return _result_from_c(out), cand[:n.value].copy()
 
     def Reduce(self, per_rank, order=None):
         """Multi-GPU: pick the winner among per-rank results with the reference's rule (strict '>', first wins)."""

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <climits>
 #include <map>
 #include <string>
 #include <vector>
@@ -96,6 +97,8 @@ struct nis_ctx {
   std::vector<cpx*> slot_ptr;          // host copy of the device pointer table
   std::vector<int> slot_frame_id;
   std::vector<double> slot_dist;
+  std::vector<std::pair<int, int>> slot_cell;    // grid cell at insertion time (Map::AddFrame), INT_MIN = not filed
+  std::map<std::pair<int, int>, std::vector<int>> grid;   // cell -> slots (ascending)
   DevBuf d_slot_ptr;
   int d_slot_cap = 0;
   // pinned staging
@@ -889,6 +892,7 @@ int nis_db_clear(nis_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   for (void* c : ctx->chunks) cudaFree(c);
   ctx->chunks.clear(); ctx->slot_ptr.clear(); ctx->slot_frame_id.clear(); ctx->slot_dist.clear();
+  ctx->slot_cell.clear(); ctx->grid.clear();
   return NIS_OK;
 }
 
@@ -960,6 +964,38 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   }
   out->found = (out->response[0] > cfg->position_response_thr) && (out->response[2] > cfg->angle_response_thr);        // :68-71
   return NIS_OK;
+}
+
+// Map::ComputeGridLocation (src/map.cc:81-85): static_cast<int>(x / grid_scale), truncation toward zero
+static std::pair<int, int> grid_cell(double x, double y, double scale) { return {(int)(x / scale), (int)(y / scale)}; }
+
+int nis_db_set_position(nis_ctx* ctx, int slot, double x, double y, double grid_scale) {
+  if (!ctx || slot < 0 || slot >= nis_db_size(ctx) || !(grid_scale > 0)) return NIS_ERR_INVALID_ARGUMENT;
+  ctx->slot_cell.resize(ctx->slot_frame_id.size(), {INT_MIN, INT_MIN});
+  if (ctx->slot_cell[slot].first != INT_MIN) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "slot already filed in the grid (Map::AddFrame files a frame once)");
+  const auto cell = grid_cell(x, y, grid_scale);
+  ctx->slot_cell[slot] = cell;
+  auto& v = ctx->grid[cell];
+  v.insert(std::upper_bound(v.begin(), v.end(), slot), slot);
+  return NIS_OK;
+}
+
+int nis_loop_scan_prior(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance, const nis_loop_config* cfg,
+                        double prior_x, double prior_y, double grid_scale, nis_loop_result* out, int32_t* candidates_out,
+                        int max_candidates, int* n_candidates_out) {
+  if (!ctx || !query || !cfg || !out || !(grid_scale > 0)) return NIS_ERR_INVALID_ARGUMENT;
+  const auto c0 = grid_cell(prior_x, prior_y, grid_scale);
+  std::vector<int32_t> cand;
+  for (int i = -1; i <= 1; ++i)               // loop_closure.cc:19-28
+    for (int j = -1; j <= 1; ++j) {
+      auto it = ctx->grid.find({c0.first + i, c0.second + j});
+      if (it != ctx->grid.end()) cand.insert(cand.end(), it->second.begin(), it->second.end());
+    }
+  if (n_candidates_out) *n_candidates_out = (int)cand.size();
+  if (candidates_out)
+    for (int i = 0; i < (int)cand.size() && i < max_candidates; ++i) candidates_out[i] = cand[i];
+  static const int32_t none = 0;
+  return nis_loop_scan(ctx, query, query_frame_id, query_acc_distance, cfg, cand.empty() ? &none : cand.data(), (int)cand.size(), out, nullptr);
 }
 
 int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n_ranks, const nis_loop_config* cfg,

@@ -150,6 +150,27 @@ class LoopClosureT {
                          const ArrayXXcf& current_fft_polar, double current_distance) {
     return Scan(image, current_frame_id, current_fft_result, current_fft_polar, current_distance, nullptr, 0);
   }
+  // Map::AddFrame's grid filing for slot (src/map.cc:27-30) and FindLoopClosure(image, current_frame, prior_pose) (:17-34)
+  void SetPosition(int slot, const Vector3d& pose, double grid_scale) {
+    nis_ctx* ctx = _correlation_flow->handle();
+    check(ctx, nis_db_set_position(ctx, slot, pose[0], pose[1], grid_scale));
+  }
+  Result FindLoopClosure(const ArrayXXf& image, int current_frame_id, const ArrayXXcf& current_fft_result,
+                         const ArrayXXcf& current_fft_polar, double current_distance, const Vector3d& prior_pose, double grid_scale) {
+    nis_ctx* ctx = _correlation_flow->handle();
+    nis_frame* q = nullptr;
+    check(ctx, nis_frame_import(ctx, image.data(), reinterpret_cast<const float*>(current_fft_result.data()),
+                                reinterpret_cast<const float*>(current_fft_polar.data()), &q));
+    nis_loop_config c{_loop_thr.position_response_thr, _loop_thr.angle_response_thr, _loop_thr.frame_gap_thr, _loop_thr.distance_thr};
+    nis_loop_result r;
+    int st = nis_loop_scan_prior(ctx, q, current_frame_id, current_distance, &c, prior_pose[0], prior_pose[1], grid_scale, &r, nullptr, 0, nullptr);
+    nis_frame_free(ctx, q);
+    check(ctx, st);
+    Result out;
+    out.found = r.found != 0; out.current_frame_id = current_frame_id; out.loop_slot = r.slot; out.loop_frame_id = r.frame_id;
+    for (int i = 0; i < 3; ++i) { out.response[i] = r.response[i]; out.relative_pose[i] = r.relative_pose[i]; }
+    return out;
+  }
   // FindLoopClosure(image, current_frame, frames) -- explicit candidate list, iteration order = list order (:36-73)
   Result FindLoopClosure(const ArrayXXf& image, int current_frame_id, const ArrayXXcf& current_fft_result,
                          const ArrayXXcf& current_fft_polar, double current_distance, const std::vector<int32_t>& candidate_slots) {

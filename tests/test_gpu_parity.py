@@ -301,6 +301,36 @@ def test_scan_rotated_query_cache_is_result_preserving(cf, imgs, monkeypatch):
     cf2.close()
 
 
+def test_prior_pose_candidate_selection(cf, imgs):
+    """FindLoopClosure(image, frame, prior_pose): Map::ComputeGridLocation + 3x3 cells + GetFramesInGrids (loop_closure.cc:17-34)."""
+    import ni_slam_b200 as nis
+    lc = nis.LoopClosure(nis.LoopClosureConfig(60, 60), cf)
+    lc.clear()
+    order = [3, 0, 5, 0, 2, 6]
+    lc.AddImages(imgs[order])
+    scale = 0.1
+    positions = [(0.05, 0.05), (0.12, 0.18), (0.35, 0.05), (0.26, 0.11), (-0.04, -0.08), (0.19, 0.29)]
+    for slot, (x, y) in enumerate(positions):
+        lc.SetPosition(slot, x, y, scale)
+    q = cf.ComputeIntermedium(imgs[1])
+    prior = (0.15, 0.15, 0.0)                                   # cell (1, 1): neighbourhood = cells 0..2 x 0..2
+
+    def cell(x, y):
+        return (int(x / scale), int(y / scale))                 # truncation toward zero like static_cast<int>
+    want = []
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            want += [s for s, (x, y) in enumerate(positions) if cell(x, y) == (1 + i, 1 + j)]
+    res, cand = lc.FindLoopClosurePrior(q, prior, scale, 99, 50.0)
+    assert list(cand) == want == [0, 4, 1, 5, 3]                # slot 2 is in cell (3, 0): outside; (-0.04,-0.08) truncates to (0, 0)
+    ref = lc.FindLoopClosure(q, 99, 50.0, candidate_slots=want)
+    assert res.loop_slot == ref.loop_slot == 1 and np.array_equal(res.response, ref.response)
+    # a prior far away: no candidates, initial result
+    res2, cand2 = lc.FindLoopClosurePrior(q, (5.0, 5.0, 0.0), scale, 99, 50.0)
+    assert len(cand2) == 0 and not res2.found and res2.loop_slot == -1
+    lc.clear()
+
+
 def test_large_rotation_loop_mode(cf, golden_pairs, imgs):
     # image 6 is rotated by 152 degrees: only loop mode (two hypotheses) recovers it
     fa, fb = cf.ComputeIntermedium(imgs[0]), cf.ComputeIntermedium(imgs[6])
