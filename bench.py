@@ -346,9 +346,11 @@ def main():
 
     # ---- timed region: HBM-resident inputs
     clocks = ClockSampler(local_rank)
+    clocks.start()
+    for _ in range(2):                 # keep the GPU under the same load while nvidia-smi spins up (samples every 100 ms)
+        step_dev()
     l0 = cf.kernel_launches()
     barrier()
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     for _ in range(args.steps):
@@ -449,10 +451,20 @@ def main():
             dist.all_reduce(tq, op=dist.ReduceOp.MAX)
         q_ms = float(tq.item())
         cand_per_s = nshard * world / (q_ms / 1e3)
+        # the store is dense (many keyframes overlap the query), so the winner need not be the planted one: check instead that the
+        # returned relative pose agrees with the winner's true pose (rotation to 0.75 deg, translation length to 2 px)
+        winner_ok = None
+        if res.loop_frame_id >= 0:
+            w = int(res.loop_frame_id)
+            qx, qy, qa = gcx[jstar] + 13, gcy[jstar] - 7, gang[jstar] + 4.5
+            dth = np.deg2rad(qa - gang[w])
+            winner_ok = bool(abs((res.relative_pose[2] - dth + np.pi) % (2 * np.pi) - np.pi) < np.deg2rad(0.75) and
+                             abs(np.hypot(res.relative_pose[0], res.relative_pose[1]) - np.hypot(qx - gcx[w], qy - gcy[w])) < 2.0)
         loop = {"metric": "loop_closure_queries_per_sec", "db_keyframes": nshard * world, "keyframes_per_gpu": nshard,
                 "value": 1e3 / q_ms, "unit": "queries/s", "ms_per_query": q_ms, "candidates_per_sec": cand_per_s,
                 "queries_per_sec_over_100k_extrapolated": cand_per_s / 1e5, "winner_frame_id": int(res.loop_frame_id),
-                "expected_frame_id": int(jstar), "found": bool(res.found), "relative_pose": [float(x) for x in res.relative_pose],
+                "planted_frame_id": int(jstar), "found": bool(res.found), "relative_pose": [float(x) for x in res.relative_pose],
+                "winner_consistent_with_ground_truth": winner_ok,
                 "collective": "ncclAllGather of %d-byte records" % nbytes if world > 1 else "none (1 rank)",
                 "rotated_query_cache": "on (>= 1024 candidates)",
                 "gpu_launches_per_query": (cf.kernel_launches() - l1) // max(args.queries, 1),
