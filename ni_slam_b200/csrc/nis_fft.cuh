@@ -19,7 +19,9 @@
 #if defined(__CUDACC__)
 #define NIS_HD __host__ __device__ __forceinline__
 #define NIS_HDC __host__ __device__ constexpr
+#define NIS_HD_NOINLINE static __host__ __device__ __noinline__
 #else
+#define NIS_HD_NOINLINE static
 #define NIS_HD inline
 #define NIS_HDC constexpr
 struct float2 { float x, y; };
@@ -448,6 +450,7 @@ template <int N, int R1, int R2, int L, int T> struct RowGeom {
   static constexpr int PITCH = N + N / 16;
   static constexpr int ROUNDS1 = (L * M1 + T - 1) / T;
   static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)L * PITCH;
+  static_assert(M1 % 16 == 0 && NS2 % 16 == 0, "stage strides must be multiples of the pad period");
   static NIS_HD int pad(int i) { return i + (i >> 4); }
 };
 
@@ -478,10 +481,11 @@ NIS_HD void row_stage1_read(int tid, const cpx* smem, const Twiddles& twd, int n
     const int ln = w / Gm::M1, j = w % Gm::M1;
     if (w < L * Gm::M1 && ln < nlines) {
       const int k = j & 15;
-      const cpx* s = smem + ln * Gm::PITCH;
+      // M1 is a multiple of 16, so pad(j + r*M1) = pad(j) + r*(M1 + M1/16): one padded base, constant offsets
+      const cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
-        cpx x = s[Gm::pad(j + r * Gm::M1)];
+        cpx x = s[r * (Gm::M1 + Gm::M1 / 16)];
         if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw1[(r - 1) * 16 + k])));
         st.v[it][r] = x;
       }
@@ -498,9 +502,9 @@ NIS_HD void row_stage1_write(int tid, cpx* smem, int nlines, const CarryRegs<R1,
     const int ln = w / Gm::M1, j = w % Gm::M1;
     if (w < L * Gm::M1 && ln < nlines) {
       const int k = j & 15, j0 = (j >> 4) * 16 * R1 + k;
-      cpx* s = smem + ln * Gm::PITCH;
+      cpx* s = smem + ln * Gm::PITCH + Gm::pad(j0);      // pad(j0 + 16 r) = pad(j0) + 17 r
 #pragma unroll
-      for (int r = 0; r < R1; ++r) s[Gm::pad(j0 + r * 16)] = st.v[it][r];
+      for (int r = 0; r < R1; ++r) s[r * 17] = st.v[it][r];
     }
   }
 }
@@ -513,11 +517,11 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
   for (int w = tid; w < L * NS2; w += T) {
     const int ln = w / NS2, j = w % NS2;
     if (ln >= nlines) break;
-    const cpx* s = smem + ln * Gm::PITCH;
+    const cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);    // NS2 is a multiple of 16: pad(j + r*NS2) = pad(j) + r*(NS2 + NS2/16)
     cpx v[R2];
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
-      cpx x = s[Gm::pad(j + r * NS2)];
+      cpx x = s[r * (NS2 + NS2 / 16)];
       if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
       v[r] = x;
     }
@@ -537,18 +541,18 @@ NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, 
   for (int w = tid; w < L * NS2; w += T) {
     const int ln = w / NS2, j = w % NS2;
     if (ln >= nlines) break;
-    cpx* s = smem + ln * Gm::PITCH;
+    cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);
     cpx v[R2];
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
-      cpx x = s[Gm::pad(j + r * NS2)];
+      cpx x = s[r * (NS2 + NS2 / 16)];
       if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, false>::run(v);
     auto lc = mid.line(ln);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) s[Gm::pad(j + r * NS2)] = lc.apply(j + r * NS2, v[r]);
+    for (int r = 0; r < R2; ++r) s[r * (NS2 + NS2 / 16)] = lc.apply(j + r * NS2, v[r]);
     lc.flush();
   }
 }

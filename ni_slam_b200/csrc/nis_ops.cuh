@@ -124,9 +124,12 @@ struct EpiStore {
   NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, 1.0f / n}; }
 };
 
+// rare kernel-function paths (general integer power, gaussian): kept out of line so the 20 inlined call sites of the fused
+// column kernel stay small (the cubic of every shipped config is the inline fast path)
+NIS_HD_NOINLINE float kernel_fn_slow(float xz, int kernel, float offset, int power, float gcoef, float xxzz, float n);
+
 NIS_HD float powi_double(float x, int p) {
   // Eigen 3.3 ArrayBase::pow(int) -> std::pow(float,int) -> double pow, rounded to float (correlation_flow.cc:213,223)
-  if (p == 3) { const double b3 = (double)x; return (float)(b3 * b3 * b3); }      // the default of every shipped config
   double b = (double)x, r = 1.0;
   int e = p < 0 ? -p : p;
   for (int i = 0; i < e; ++i) r *= b;
@@ -134,35 +137,14 @@ NIS_HD float powi_double(float x, int p) {
   return (float)r;
 }
 
-// polynomial kernel (:208-226): k = (xz/n + offset)^power, unnormalised; max|k| reduced into maxbuf[b]
-// gaussian kernel   (:181-206): k = exp(-1/sigma^2 * (xx + zz - 2 xz/n)/n)
-struct EpiKernel {
-  Dst<float> dst; int W; float n;
-  int kernel; float offset; int power; float gcoef;   // gcoef = -1/(sigma*sigma)
-  const float* xx; const float* zz; int zz_shift;     // gaussian: half-spectrum sums / n; zz indexed by b >> zz_shift
-  unsigned int* maxbuf;                               // per batch, float bits of max|k| (>= 0 so uint order = float order)
-  struct Bound {
-    float* img; int W, c0; float n; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
-    NIS_HD float kfun(float v) const {
-      const float xz = v / n;
-      if (kernel == 0) return powi_double(xz + offset, power);
-      return expf(gcoef * ((xxzz - 2.f * xz) / n));
-    }
-    NIS_HD void put(int row, int l, float re, float im) {
-      const float a = kfun(re), b = kfun(im);
-      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = make_float2(a, b);
-      mx = fmaxf(mx, fmaxf(fabsf(a), fabsf(b)));
-    }
-    template <class Sync> NIS_HD void finish(int tid, Sync& sync) { sync.block_max_to(maxp, mx, tid); }
-  };
-  NIS_HD Bound bind(int b, int c0) const {
-    const float s = (kernel == 1) ? (xx[b] + zz[b >> zz_shift]) : 0.f;
-    return Bound{dst.at(b), W, c0, n, kernel, offset, power, gcoef, s, maxbuf + b, 0.f};
-  }
-};
+NIS_HD_NOINLINE float kernel_fn_slow(float xz, int kernel, float offset, int power, float gcoef, float xxzz, float n) {
+  if (kernel == 0) return powi_double(xz + offset, power);
+  return expf(gcoef * ((xxzz - 2.f * xz) / n));
+}
 
-// kernel function applied between the fused inverse and forward column passes (colcol kernel): same arithmetic as
-// EpiKernel, but the real pairs stay in shared memory.  Gaussian sums arrive as raw double sums over the half spectrum.
+// kernel function applied between the fused inverse and forward column passes (colcol kernel); the real pairs stay in
+// shared memory.  polynomial (:208-226): k = (xz/n + offset)^power; gaussian (:181-206): k = exp(-1/sigma^2 (xx + zz - 2 xz/n)/n);
+// max|k| is reduced into maxbuf[b] and the division by it is deferred to the consumer.  Gaussian sums arrive as raw double sums over the half spectrum.
 struct KernelFn {
   float n; int kernel; float offset; int power; float gcoef;
   const double* xx_sum; const double* zz_sum; int zz_shift;
@@ -172,8 +154,8 @@ struct KernelFn {
     float n, rn; int kernel; float offset; int power; float gcoef, xxzz; unsigned int* maxp; float mx;
     NIS_HD float kfun(float v) const {
       const float xz = v * rn;
-      if (kernel == 0) return powi_double(xz + offset, power);
-      return expf(gcoef * ((xxzz - 2.f * xz) / n));
+      if (kernel == 0 && power == 3) { const double b3 = (double)(xz + offset); return (float)(b3 * b3 * b3); }
+      return kernel_fn_slow(xz, kernel, offset, power, gcoef, xxzz, n);
     }
     NIS_HD cpx apply(cpx v) {
       const float a = kfun(v.x), b = kfun(v.y);

@@ -45,10 +45,11 @@ __device__ __forceinline__ float polar_pixel(const float* __restrict__ power, in
   return bilinear4(v0, v1, v2, v3, sx & 31, sy & 31);
 }
 
+// BORDER_WRAP (cv::borderInterpolate): p mod len.  Written as add/subtract loops -- the coordinates of a rotation about the
+// image centre stay within a few image sizes, and an integer division sequence inlined at every tap bloats the kernel.
 __device__ __forceinline__ int wrap_idx(int p, int len) {
-  if ((unsigned)p < (unsigned)len) return p;
-  if (p < 0) p -= ((p - len + 1) / len) * len;
-  if (p >= len) p %= len;
+  while (p < 0) p += len;
+  while (p >= len) p -= len;
   return p;
 }
 

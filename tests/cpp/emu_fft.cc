@@ -223,16 +223,6 @@ int emu_col_inv_peak(const float* in, int B, int N, int W, void* stats, float* g
   return -1;
 }
 
-int emu_col_inv_kernel(const float* in, int B, int N, int W, float* out, unsigned int* maxbuf, float offset, int power) {
-  memset(maxbuf, 0, sizeof(unsigned int) * B);
-  EpiKernel epi{Dst<float>{out, (long long)N * W}, W, (float)((long long)N * W), 0, offset, power, 0.f, nullptr, nullptr, 0, maxbuf};
-#define X(n, f0, f1, f2, i0, i1, i2, t) \
-  if (N == n) { emu_col_inv<n, i0, i1, i2, t>((const cpx*)in, B, W, epi); return 0; }
-  NIS_COL_PLANS(X)
-#undef X
-  return -1;
-}
-
 int emu_row(const float* in, int total_lines, int N, int inverse, float* out) {
 #define X(n, r1, r2, l, t, lr)                                                          \
   if (N == n) {                                                                         \
