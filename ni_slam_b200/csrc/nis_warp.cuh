@@ -33,8 +33,9 @@ __device__ __forceinline__ float shifted_tap(const float* __restrict__ p, int y,
   return __ldg(p + (size_t)r * W + c);
 }
 
-// cs = (cos, sin) of the output row's angle (double, host libm); rf = (float)(rho * maxRadius / Cp)
-__device__ __forceinline__ float polar_pixel(const float* __restrict__ power, int H, int W, double cp, double sp, float rf) {
+// cs = (cos, sin) of the output row's angle (double, host libm); rf = (float)(rho * maxRadius / Cp).
+// General (border / RemoveZeroComponent-aware) path: out of line, the table-driven fast path covers almost every pixel.
+static __device__ __noinline__ float polar_pixel(const float* __restrict__ power, int H, int W, double cp, double sp, float rf) {
   const float cx = (float)W / 2, cy = (float)H / 2;
   const float mx = (float)__dadd_rn(__dmul_rn((double)rf, cp), (double)cx);
   const float my = (float)__dadd_rn(__dmul_rn((double)rf, sp), (double)cy);
@@ -135,13 +136,14 @@ template <bool U8> struct ProRotate {
       if (!((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1))) {       // BORDER_WRAP
         x0 = wrap_idx(x0, W); x1 = wrap_idx(x1, W); y0 = wrap_idx(y0, H); y1 = wrap_idx(y1, H);
       }
+      const int r0 = y0 * W, r1 = y1 * W;          // 32-bit indexing: an image has < 2^31 pixels
       float v0, v1, v2, v3;
       if (U8) {
-        v0 = __ldg(&lut[u[(size_t)y0 * W + x0]]); v1 = __ldg(&lut[u[(size_t)y0 * W + x1]]);
-        v2 = __ldg(&lut[u[(size_t)y1 * W + x0]]); v3 = __ldg(&lut[u[(size_t)y1 * W + x1]]);
+        v0 = __ldg(&lut[u[r0 + x0]]); v1 = __ldg(&lut[u[r0 + x1]]);
+        v2 = __ldg(&lut[u[r1 + x0]]); v3 = __ldg(&lut[u[r1 + x1]]);
       } else {
-        v0 = __ldg(f + (size_t)y0 * W + x0); v1 = __ldg(f + (size_t)y0 * W + x1);
-        v2 = __ldg(f + (size_t)y1 * W + x0); v3 = __ldg(f + (size_t)y1 * W + x1);
+        v0 = __ldg(f + r0 + x0); v1 = __ldg(f + r0 + x1);
+        v2 = __ldg(f + r1 + x0); v3 = __ldg(f + r1 + x1);
       }
       return bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
     }
