@@ -537,6 +537,9 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   if (H <= 0 || W <= 0 || D <= 0 || Cp <= 0 || (H & 1) || (D & 1) || (W % 32) || (Cp % 32)) return NIS_ERR_INVALID_ARGUMENT;
   if (!col_size_supported(H) || !col_size_supported(D) || !row_size_supported(W) || !row_size_supported(Cp))
     return NIS_ERR_UNSUPPORTED_SIZE;
+  // the fused rotation wraps source coordinates with one conditional add/subtract (exact while the half diagonal stays
+  // below 1.5 x the shorter side, i.e. aspect ratio <= 2.8)
+  if ((double)std::max(H, W) > 2.8 * (double)std::min(H, W)) return NIS_ERR_UNSUPPORTED_SIZE;
   // the kernel id is only checked when EstimateTrans runs, like the reference (correlation_flow.cc:157-169)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NIS_ERR_CUDA;

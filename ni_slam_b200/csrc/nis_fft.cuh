@@ -260,8 +260,9 @@ NIS_HD void col_stage1_write(int tid, cpx* smem, const CarryRegs<R1, ColGeom<N, 
 }
 
 // ---- forward r2c column pass ------------------------------------------------------------------------------
-// Pro::lane(l).load(row) -> cpx (re = real column c0+2l, im = real column c0+2l+1 at image row `row`); the per-lane
-// context lets a prologue hoist everything that depends only on the column pair
+// Pro::lane(l).load_all<R>(row0, stride, v): v[r] = (real column c0+2l, real column c0+2l+1) at image row row0 + r*stride;
+// the per-lane context lets a prologue hoist everything that depends only on the column pair, and handing it all R rows at
+// once lets gather-type prologues issue every independent load before the first use
 // phase 0: stage 0 from global
 template <int N, int R0, int R1, int R2, int T, class Pro>
 NIS_HD void col_fwd_phase0(int tid, cpx* smem, const Pro& pro) {
@@ -270,8 +271,7 @@ NIS_HD void col_fwd_phase0(int tid, cpx* smem, const Pro& pro) {
   const auto ln = pro.lane(l);
   for (int j = gi; j < Gm::M0; j += Gm::G) {
     cpx v[R0];
-#pragma unroll
-    for (int r = 0; r < R0; ++r) v[r] = ln.load(j + r * Gm::M0);
+    ln.template load_all<R0>(j, Gm::M0, v);        // v[r] = sample at row j + r*M0
     Dft<R0, false>::run(v);
 #pragma unroll
     for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = v[r];

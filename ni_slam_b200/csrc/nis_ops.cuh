@@ -82,7 +82,14 @@ struct PeakStats {            // per batch element, zero-initialised before the 
 // ---------------------------------------------------------------------------------------------------------
 struct ProRealF32 {
   Src<float> src; int W;
-  struct Lane { const float2* p; int W; NIS_HD cpx load(int row) const { return NIS_LDG(p + (size_t)row * (W / 2)); } };
+  struct Lane {
+    const float2* p; int W;
+    NIS_HD cpx load(int row) const { return NIS_LDG(p + (size_t)row * (W / 2)); }
+    template <int R> NIS_HD void load_all(int row0, int stride, cpx* v) const {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = load(row0 + r * stride);
+    }
+  };
   struct Bound {
     const float* img; int W, c0;
     NIS_HD Lane lane(int l) const { return Lane{reinterpret_cast<const float2*>(img + c0) + l, W}; }
@@ -98,6 +105,10 @@ struct ProRealU8 {
     NIS_HD cpx load(int row) const {
       const uint8_t* q = p + (size_t)row * W;
       return make_float2(NIS_LDG(&lut[q[0]]), NIS_LDG(&lut[q[1]]));
+    }
+    template <int R> NIS_HD void load_all(int row0, int stride, cpx* v) const {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = load(row0 + r * stride);
     }
   };
   struct Bound {

@@ -54,6 +54,12 @@ __device__ __forceinline__ int wrap_idx(int p, int len) {
   return p;
 }
 
+__device__ __forceinline__ int wrap1(int p, int len) {      // exact modulo for p in (-len, 2 len)
+  p += (p < 0) ? len : 0;
+  p -= (p >= len) ? len : 0;
+  return p;
+}
+
 // per output row: X0, Y0 of warpAffine's fixed-point walk (AB_BITS = 10, round_delta = 16)
 __device__ __forceinline__ void rotate_row_setup(const double* __restrict__ M, int y, int& X0, int& Y0) {
   X0 = __double2int_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]) * 1024.0) + 16;
@@ -108,11 +114,32 @@ struct ProPolar {
   Src<float> power; int H, W, Cp; const double* cs; const float* rho; const uint32_t* table;   // table [D][Cp]
   struct Lane {
     const float* p; int H, W, Cp, q; const double* cs; float rf0, rf1; const uint32_t* tab;
-    __device__ __forceinline__ cpx load(int phi) const {
-      const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + (size_t)phi * Cp + q));
-      double cp = 0.0, sp = 0.0;
-      if ((e.x | e.y) & kPolarSlow) { cp = __ldg(cs + 2 * phi); sp = __ldg(cs + 2 * phi + 1); }
-      return make_float2(polar_pixel_tab(p, H, W, e.x, cp, sp, rf0), polar_pixel_tab(p, H, W, e.y, cp, sp, rf1));
+    // branch-free table path for all R rows first (every gather is in flight before the first use), then the rare
+    // general-path pixels are patched
+    template <int R> __device__ __forceinline__ void load_all(int phi0, int stride, cpx* v) const {
+      uint2 e[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) e[r] = __ldg(reinterpret_cast<const uint2*>(tab + (phi0 + r * stride) * Cp + q));
+      uint32_t any = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        any |= e[r].x | e[r].y;
+        const float* q0 = p + ((e[r].x & kPolarSlow) ? 0u : (e[r].x & 0x1fffffu));
+        const float* q1 = p + ((e[r].y & kPolarSlow) ? 0u : (e[r].y & 0x1fffffu));
+        v[r] = make_float2(bilinear4(__ldg(q0), __ldg(q0 + 1), __ldg(q0 + W), __ldg(q0 + W + 1), (e[r].x >> 21) & 31, (e[r].x >> 26) & 31),
+                           bilinear4(__ldg(q1), __ldg(q1 + 1), __ldg(q1 + W), __ldg(q1 + W + 1), (e[r].y >> 21) & 31, (e[r].y >> 26) & 31));
+      }
+      if (any & kPolarSlow) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int phi = phi0 + r * stride;
+          if ((e[r].x | e[r].y) & kPolarSlow) {
+            const double cp = __ldg(cs + 2 * phi), sp = __ldg(cs + 2 * phi + 1);
+            if (e[r].x & kPolarSlow) v[r].x = polar_pixel(p, H, W, cp, sp, rf0);
+            if (e[r].y & kPolarSlow) v[r].y = polar_pixel(p, H, W, cp, sp, rf1);
+          }
+        }
+      }
     }
   };
   struct Bound {
@@ -132,10 +159,9 @@ template <bool U8> struct ProRotate {
     __device__ __forceinline__ float pixel(int X0, int Y0, int ad, int bd) const {
       const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
       const int ix = sat_short(X >> 5), iy = sat_short(Y >> 5);
-      int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
-      if (!((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1))) {       // BORDER_WRAP
-        x0 = wrap_idx(x0, W); x1 = wrap_idx(x1, W); y0 = wrap_idx(y0, H); y1 = wrap_idx(y1, H);
-      }
+      // BORDER_WRAP, branch-free: a rotation about the centre keeps every source coordinate inside (-len, 2 len) for the aspect
+      // ratios nis_create accepts (max(W,H) <= 2.8 min(W,H)), so one conditional add / subtract is the exact modulo
+      int x0 = wrap1(ix, W), x1 = wrap1(ix + 1, W), y0 = wrap1(iy, H), y1 = wrap1(iy + 1, H);
       const int r0 = y0 * W, r1 = y1 * W;          // 32-bit indexing: an image has < 2^31 pixels
       float v0, v1, v2, v3;
       if (U8) {
@@ -151,6 +177,10 @@ template <bool U8> struct ProRotate {
       int X0, Y0;
       rotate_row_setup(M, y, X0, Y0);
       return make_float2(pixel(X0, Y0, a0, b0), pixel(X0, Y0, a1, b1));
+    }
+    template <int R> __device__ __forceinline__ void load_all(int row0, int stride, cpx* v) const {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = load(row0 + r * stride);
     }
   };
   struct Bound {
