@@ -93,6 +93,15 @@ int nis_frame_export(nis_ctx* ctx, const nis_frame* f, float* fft_result, float*
 int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, nis_frame** out);
 int nis_frame_free(nis_ctx* ctx, nis_frame* f);
 
+/* ---- undistort front end: Camera::UndistortImage (src/camera.cc:92-93) = cv::remap(u8, _map1, _map2, INTER_LINEAR).
+ *      The caller's (unchanged) Camera computes the fixed-point maps once with initUndistortRectifyMap(..., CV_16SC2, ...)
+ *      (src/camera.cc:45-47) and hands them over: map1_xy = H x W x 2 int16 (x, y), map2 = H x W uint16 (fy*32 + fx).
+ *      While maps are set, every u8 image entering nis_features_u8 / nis_track_stream[_dev] / nis_db_add_images[_dev] is taken
+ *      as the RAW camera image and undistorted on the GPU first, exactly like MapBuilder::AddNewInput (src/map_builder.cc:31-33).
+ *      Pass NULL, NULL to switch the front end off.  nis_undistort_u8 runs the stage alone (host buffers). ---- */
+int nis_set_undistort_maps(nis_ctx* ctx, const int16_t* map1_xy, const uint16_t* map2);
+int nis_undistort_u8(nis_ctx* ctx, const uint8_t* raw_rowmajor, uint8_t* out_rowmajor);
+
 /* ---- solve: CorrelationFlow::ComputePose(last_fft_result, image, last_fft_polar, fft_polar, pose, not_large_rotation)
  *      include/correlation_flow.h:13, src/correlation_flow.cc:97-143; returns info in info[3], pose = (dx_px, dy_px, theta_rad).
  *      peak_rc (may be NULL) = polar row, polar col, translation row, translation col of the integer arg-max. ---- */

@@ -24,7 +24,7 @@ NIS_OK, NIS_ERR_INVALID_ARGUMENT, NIS_ERR_INVALID_KERNEL, NIS_ERR_UNSUPPORTED_SI
 SYMBOLS = [
     "nis_create", "nis_destroy", "nis_last_error", "nis_strerror", "nis_stream", "nis_synchronize", "nis_kernel_launches",
     "nis_set_batch", "nis_set_lanes", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
-    "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
+    "nis_set_undistort_maps", "nis_undistort_u8", "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
     "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_db_set_position", "nis_loop_scan_prior", "nis_debug_fft2",
     "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
     "nis_profile_end",
@@ -118,6 +118,8 @@ def load_library():
     lib.nis_frame_export.argtypes = [vp, vp, vp, vp]
     lib.nis_frame_import.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
     lib.nis_frame_free.argtypes = [vp, vp]
+    lib.nis_set_undistort_maps.argtypes = [vp, vp, vp]
+    lib.nis_undistort_u8.argtypes = [vp, vp, vp]
     lib.nis_compute_pose.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.nis_track_stream.argtypes = [vp, vp, i32, vp, vp]
     lib.nis_track_stream_dev.argtypes = [vp, vp, i32, vp, vp]
@@ -249,6 +251,25 @@ class CorrelationFlow:
             img = np.ascontiguousarray(image.astype(np.float32).T)          # reference layout (column-major)
             self._check(self._lib.nis_features_f32(self._ctx, _p(img), C.byref(h)))
         return Frame(self, h)
+
+    def SetUndistortMaps(self, map1, map2):
+        """Hand over the Camera's fixed-point remap maps (initUndistortRectifyMap(..., CV_16SC2), src/camera.cc:45-47): map1
+        (H, W, 2) int16, map2 (H, W) uint16.  From then on every u8 image is treated as the RAW camera image and undistorted on
+        the GPU first (Camera::UndistortImage, src/camera.cc:92-93).  Pass None, None to switch the front end off."""
+        if map1 is None:
+            self._check(self._lib.nis_set_undistort_maps(self._ctx, None, None))
+            return
+        m1 = np.ascontiguousarray(map1, np.int16)
+        m2 = np.ascontiguousarray(map2, np.uint16)
+        assert m1.shape == (self.H, self.W, 2) and m2.shape == (self.H, self.W)
+        self._check(self._lib.nis_set_undistort_maps(self._ctx, _p(m1), _p(m2)))
+
+    def UndistortImage(self, raw_u8):
+        raw = np.ascontiguousarray(raw_u8, np.uint8)
+        assert raw.shape == (self.H, self.W)
+        out = np.empty_like(raw)
+        self._check(self._lib.nis_undistort_u8(self._ctx, _p(raw), _p(out)))
+        return out
 
     def ImportFrame(self, image_f32, fft_result, fft_polar) -> Frame:
         img = np.ascontiguousarray(np.asarray(image_f32, np.float32).T)

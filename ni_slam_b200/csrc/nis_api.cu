@@ -85,7 +85,10 @@ struct nis_ctx {
   DevBuf recs, best, cand;
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
-  DevBuf sF, sP, sHt, sHp, sImg;
+  DevBuf sF, sP, sHt, sHp, sImg, sUnd;
+  // undistort front end (Camera::UndistortImage): fixed-point remap maps handed over by the caller
+  DevBuf umap1, umap2;
+  bool undistort = false;
   // scan: spectra of the query image rotated by every angle the polar stage can select (2 hypotheses x D rows), built once
   // per query when the candidate list is long; indexed by the same `sel` the rotation matrices use (minus D)
   DevBuf rotc, rotc_xx, rotc_sel;
@@ -589,7 +592,7 @@ int nis_destroy(nis_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
-                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel};
+                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->sUnd, &ctx->umap1, &ctx->umap2, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {
     DevBuf* lb[] = {&L.t1, &L.real, &L.pol, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz};
@@ -646,12 +649,56 @@ int nis_frame_free(nis_ctx* ctx, nis_frame* f) {
   return NIS_OK;
 }
 
+int nis_set_undistort_maps(nis_ctx* ctx, const int16_t* map1_xy, const uint16_t* map2) {
+  if (!ctx || ((map1_xy == nullptr) != (map2 == nullptr))) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  if (!map1_xy) { ctx->undistort = false; return NIS_OK; }
+  const size_t npx = ctx->sz[0].real;
+  RESERVE(ctx->umap1, npx * 2 * sizeof(int16_t));
+  RESERVE(ctx->umap2, npx * sizeof(uint16_t));
+  CU(h2d(ctx, ctx->umap1.p, map1_xy, npx * 2 * sizeof(int16_t)));
+  CU(h2d(ctx, ctx->umap2.p, map2, npx * sizeof(uint16_t)));
+  ctx->undistort = true;
+  return NIS_OK;
+}
+
+// undistort B raw u8 images on stream `st` (batched Camera::UndistortImage)
+static int undistort_batch(nis_ctx* ctx, cudaStream_t st, const uint8_t* raw, uint8_t* out, int B) {
+  ctx->prof_stream = st;
+  const long long npx = (long long)ctx->sz[0].real;
+  LAUNCH(launch_undistort(src_slab<uint8_t>(raw, npx), Dst<uint8_t>{out, npx}, ctx->H, ctx->W, ctx->umap1.p, ctx->umap2.p, B, st));
+  return NIS_OK;
+}
+
+int nis_undistort_u8(nis_ctx* ctx, const uint8_t* raw, uint8_t* out) {
+  if (!ctx || !raw || !out) return NIS_ERR_INVALID_ARGUMENT;
+  if (!ctx->undistort) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "no undistort maps set");
+  CU(cudaSetDevice(ctx->device));
+  const size_t npx = ctx->sz[0].real;
+  RESERVE(ctx->sImg, 2 * npx);
+  uint8_t* d = ctx->sImg.as<uint8_t>();
+  CU(h2d(ctx, d, raw, npx));
+  TRY(undistort_batch(ctx, ctx->stream, d, d + npx, 1));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(out, d + npx, npx, cudaMemcpyDeviceToHost));
+  return NIS_OK;
+}
+
 int nis_features_u8(nis_ctx* ctx, const uint8_t* image, nis_frame** out) {
   if (!ctx || !image || !out) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   nis_frame* f = nullptr;
   TRY(frame_alloc(ctx, true, &f));
-  cudaError_t e = cudaMemcpyAsync(f->img_u8, image, ctx->sz[0].real, cudaMemcpyHostToDevice, ctx->stream);
+  cudaError_t e;
+  if (ctx->undistort) {                       // raw camera image: undistort into the frame's image buffer first
+    const size_t npx = ctx->sz[0].real;
+    if (ctx->sImg.reserve(npx)) { nis_frame_free(ctx, f); return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc raw staging"); }
+    e = cudaMemcpyAsync(ctx->sImg.p, image, npx, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && undistort_batch(ctx, ctx->stream, ctx->sImg.as<uint8_t>(), f->img_u8, 1) != NIS_OK) e = cudaErrorUnknown;
+  } else {
+    e = cudaMemcpyAsync(f->img_u8, image, ctx->sz[0].real, cudaMemcpyHostToDevice, ctx->stream);
+  }
   int st = e == cudaSuccess ? features_batch(ctx, ctx->lanes[0], src_null<float>(), src_slab<uint8_t>(f->img_u8, 0), true, 1,
                                               Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0}, Dst<cpx>{f->Ht, 0}, Dst<cpx>{f->Hp, 0}, true)
                             : fail(ctx, NIS_ERR_CUDA, "cudaMemcpyAsync image", (int)e);
@@ -758,6 +805,11 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
     RESERVE(ctx->sImg, (size_t)n * npx);
     d_frames = ctx->sImg.as<uint8_t>();      // uploaded batch by batch below, each on its lane, so copies overlap compute
   }
+  const uint8_t* d_raw = d_frames;
+  if (ctx->undistort) {                        // raw camera frames: undistorted batch by batch into their own slab
+    RESERVE(ctx->sUnd, (size_t)n * npx);
+    d_frames = ctx->sUnd.as<uint8_t>();
+  }
   TRY(ensure_recs(ctx, std::max(n - 1, 1)));
   const int B = ctx->batch;
   const int NL = ctx->active_lanes;
@@ -769,6 +821,8 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
     if (on_host)
       CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames + (size_t)t0 * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
                          ctx->lanes[k % NL].stream));
+    if (ctx->undistort)
+      TRY(undistort_batch(ctx, ctx->lanes[k % NL].stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
     TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
                        Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
                        Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));
@@ -863,12 +917,19 @@ static int db_add_images_impl(nis_ctx* ctx, const uint8_t* images, bool on_host,
     CU(cudaMemcpyAsync(ctx->sImg.p, images, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
     d_images = ctx->sImg.as<uint8_t>();
   }
+  const uint8_t* d_raw = d_images;
+  if (ctx->undistort) {
+    RESERVE(ctx->sUnd, (size_t)n * npx);
+    d_images = ctx->sUnd.as<uint8_t>();
+  }
   TRY(fork_lanes(ctx));
   for (int i0 = 0, k = 0; i0 < n; ++k) {
     const int slot = s0 + i0;
     const int room = ctx->chunk_slots - slot % ctx->chunk_slots;       // stay inside one chunk (contiguous records)
     const int nb = std::min(std::min(B, n - i0), room);
     cpx* base = ctx->slot_ptr[slot];
+    if (ctx->undistort)
+      TRY(undistort_batch(ctx, ctx->lanes[k % NL].stream, d_raw + (size_t)i0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)i0 * npx, nb));
     TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_images + (size_t)i0 * npx, (long long)npx), true, nb,
                        Dst<cpx>{base, (long long)rec}, Dst<cpx>{base + spt, (long long)rec}, Dst<cpx>{base + spt + spp, (long long)rec},
                        Dst<cpx>{base + 2 * spt + spp, (long long)rec}, true));

@@ -55,6 +55,8 @@ int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const doubl
 // rotate: out[e] = warpAffine(image[e], rot_mats[sel[e]]) with BORDER_WRAP.  Exactly one of img_f32 / img_u8 is used.
 int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
                   const int* sel, int E, cudaStream_t s);
+// Camera::UndistortImage: exact u8 cv::remap with the fixed-point maps the caller's Camera computed (CV_16SC2 + CV_16UC1)
+int launch_undistort(Src<uint8_t> raw, Dst<uint8_t> out, int H, int W, const void* map1, const void* map2, int B, cudaStream_t s);
 // gaussian kernel helper: out[b] = sum over the stored half spectrum of |x^2| (raw, double)
 int launch_spec_sqsum(Src<cpx> x, int count, double* out, int B, cudaStream_t s);
 // after the polar stage: per pair, pick the rotation-matrix slot(s) for the translation stage

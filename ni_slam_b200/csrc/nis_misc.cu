@@ -77,6 +77,34 @@ int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Camera::UndistortImage (src/camera.cc:92-93): cv::remap(u8, map1 CV_16SC2, map2 CV_16UC1, INTER_LINEAR), BORDER_CONSTANT(0).
+// OpenCV's u8 path is pure integer: weights (1-fy)(1-fx)... scaled to 2^15 (exact multiples of 32), rounded with
+// (sum + 2^14) >> 15 -- reproduced bit for bit.  map1 = (x, y) integer source position, map2 = fy*32 + fx.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) undistort_kernel(Src<uint8_t> raw, Dst<uint8_t> out, int H, int W,
+                                                        const short2* __restrict__ map1, const unsigned short* __restrict__ map2) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const short2 xy = __ldg(map1 + (size_t)y * W + x);
+  const int a = __ldg(map2 + (size_t)y * W + x) & 1023;
+  const int fx = a & 31, fy = a >> 5;
+  const int sx = xy.x, sy = xy.y;
+  const uint8_t* p = raw.at(b);
+  auto tap = [&](int yy, int xx) -> int {
+    return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? (int)__ldg(p + yy * W + xx) : 0;
+  };
+  const int w0 = (32 - fy) * (32 - fx) * 32, w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32, w3 = fy * fx * 32;
+  const int v = tap(sy, sx) * w0 + tap(sy, sx + 1) * w1 + tap(sy + 1, sx) * w2 + tap(sy + 1, sx + 1) * w3;
+  out.at(b)[(size_t)y * W + x] = (uint8_t)min(255, max(0, (v + (1 << 14)) >> 15));
+}
+int launch_undistort(Src<uint8_t> raw, Dst<uint8_t> out, int H, int W, const void* map1, const void* map2, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  undistort_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, s>>>(raw, out, H, W, (const short2*)map1, (const unsigned short*)map2);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // gaussian kernel helper: xf.square().abs().sum()/N over the stored half spectrum (correlation_flow.cc:184-185)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) spec_sqsum_kernel(Src<cpx> x, int count, double* out) {

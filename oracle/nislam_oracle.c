@@ -531,6 +531,25 @@ void orc_rotate(const float *src, int H, int W, float degree, float *dst) {
   }
 }
 
+/* Camera::UndistortImage (camera.cc:92-93): cv::remap(u8, map1 CV_16SC2, map2 CV_16UC1, INTER_LINEAR), BORDER_CONSTANT(0).
+ * OpenCV's u8 bilinear remap is integer: BilinearTab_i weights = round(w * 2^15) (exact multiples of 32 for 1/32 fractions),
+ * FixedPtCast: (sum + 2^14) >> 15.  raw/out row-major H x W; map1 = (x,y) int16 pairs; map2 = fy*32 + fx. */
+void orc_undistort_u8(const uint8_t *raw, int H, int W, const int16_t *map1, const uint16_t *map2, uint8_t *out) {
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const int sx = map1[2 * ((size_t)y * W + x)], sy = map1[2 * ((size_t)y * W + x) + 1];
+      const int a = map2[(size_t)y * W + x] & 1023, fx = a & 31, fy = a >> 5;
+      const int w0 = (32 - fy) * (32 - fx) * 32, w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32, w3 = fy * fx * 32;
+      int t[4];
+      for (int k = 0; k < 4; ++k) {
+        const int xx = sx + (k & 1), yy = sy + (k >> 1);
+        t[k] = ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? raw[(size_t)yy * W + xx] : 0;
+      }
+      int v = (t[0] * w0 + t[1] * w1 + t[2] * w2 + t[3] * w3 + (1 << 14)) >> 15;
+      out[(size_t)y * W + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* CorrelationFlow                                                                             */
 /* ------------------------------------------------------------------------------------------ */

@@ -131,6 +131,14 @@ def rotate(x, degree):
     return from_colmajor(out)
 
 
+def undistort_u8(raw, map1, map2):
+    H, W = raw.shape
+    out = np.zeros((H, W), np.uint8)
+    lib().orc_undistort_u8(_p(np.ascontiguousarray(raw, np.uint8)), H, W, _p(np.ascontiguousarray(map1, np.int16)),
+                           _p(np.ascontiguousarray(map2, np.uint16)), _p(out))
+    return out
+
+
 def rotation_inverse(H, W, degree):
     m = np.zeros(6, np.float64)
     lib().orc_rotation_inverse(H, W, float(degree), _p(m))

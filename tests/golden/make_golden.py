@@ -80,7 +80,17 @@ def main():
         mats.append(cv2.invertAffineTransform(m).reshape(-1))
     st["inv_mats_640x480"] = np.stack(mats)
     np.savez_compressed(os.path.join(HERE, "golden_stages.npz"), **st)
-    print("wrote golden_pairs.npz, golden_stages.npz")
+    # --- undistort front end: Camera::UndistortImage = remap with the CV_16SC2 maps of initUndistortRectifyMap (camera.cc:45-47,92-93)
+    und = {}
+    hs, ws = 96, 128
+    Ks = np.array([[104.0, 0, 63.2], [0, 103.0, 48.7], [0, 0, 1]])
+    Ds = np.array([-0.28, 0.09, 0.0007, -0.0004, -0.012])
+    newK, _ = cv2.getOptimalNewCameraMatrix(Ks, Ds, (ws, hs), 0, (ws, hs))
+    m1, m2 = cv2.initUndistortRectifyMap(Ks, Ds, None, newK, (ws, hs), cv2.CV_16SC2)
+    raw = np.random.default_rng(77).integers(0, 256, (hs, ws)).astype(np.uint8)
+    und.update(K=Ks, D=Ds, map1=m1, map2=m2, raw=raw, out=cv2.remap(raw, m1, m2, cv2.INTER_LINEAR))
+    np.savez_compressed(os.path.join(HERE, "golden_undistort.npz"), **und)
+    print("wrote golden_pairs.npz, golden_stages.npz, golden_undistort.npz")
     print(out["pose_rows"])
 
 

@@ -383,3 +383,53 @@ def test_other_sizes_match_oracle(h, w, d, cp):
         assert abs(wrap_pi(pg[2] - po[2])) < 1e-6 or not mode
         assert np.allclose(ig, io, rtol=1e-3)
     c.close()
+
+
+# ------------------------------------------------------------------ undistort front end (Camera::UndistortImage)
+def _synthetic_maps(h, w):
+    """fixed-point remap maps of a mild radial distortion, built without cv2: (x, y) int16 + (fy*32 + fx) uint16"""
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    xn, yn = (xs - w / 2) / (0.8 * w), (ys - h / 2) / (0.8 * w)
+    r2 = xn * xn + yn * yn
+    f = 1 - 0.25 * r2 + 0.08 * r2 * r2
+    sx = np.rint(((xn * f) * 0.8 * w + w / 2) * 32).astype(np.int64)
+    sy = np.rint(((yn * f) * 0.8 * w + h / 2) * 32).astype(np.int64)
+    m1 = np.stack([sx >> 5, sy >> 5], axis=-1).astype(np.int16)
+    m2 = ((sy & 31) * 32 + (sx & 31)).astype(np.uint16)
+    return m1, m2
+
+
+def test_undistort_front_end(imgs):
+    import os
+    import ni_slam_b200 as nis
+    # stage: bit-exact against the cv2-generated golden (small camera) and the C oracle (full size)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_undistort.npz"))
+    small = nis.CorrelationFlow(nis.CFConfig(rotation_divisor=80, rotation_channel=64), 96, 128)
+    small.SetUndistortMaps(g["map1"], g["map2"])
+    assert np.array_equal(small.UndistortImage(g["raw"]), g["out"])
+    small.close()
+    c = nis.CorrelationFlow(nis.CFConfig(), H, W)
+    m1, m2 = _synthetic_maps(H, W)
+    c.SetUndistortMaps(m1, m2)
+    raw = imgs[:4]
+    und = np.stack([oc.undistort_u8(r, m1, m2) for r in raw])
+    for r, u in zip(raw, und):
+        assert np.array_equal(c.UndistortImage(r), u)
+    # end to end: raw frames through the front end == undistorted frames without it (features, stream poses, scan)
+    F_raw, P_raw = c.ComputeIntermedium(raw[0]).GetFFTResult()
+    poses_raw, infos_raw = c.TrackStream(raw)
+    lc = nis.LoopClosure(nis.LoopClosureConfig(60, 60), c)
+    lc.clear()
+    lc.AddImages(raw[[2, 0, 3]])
+    res_raw = lc.FindLoopClosure(c.ComputeIntermedium(raw[1]), 99, 50.0)
+    lc.clear()
+    c.SetUndistortMaps(None, None)
+    F_u, P_u = c.ComputeIntermedium(und[0]).GetFFTResult()
+    poses_u, infos_u = c.TrackStream(und)
+    lc.AddImages(und[[2, 0, 3]])
+    res_u = lc.FindLoopClosure(c.ComputeIntermedium(und[1]), 99, 50.0)
+    assert np.array_equal(F_raw, F_u) and np.array_equal(P_raw, P_u)
+    assert np.array_equal(poses_raw, poses_u) and np.allclose(infos_raw, infos_u, rtol=1e-6)
+    assert res_raw.loop_slot == res_u.loop_slot and np.allclose(res_raw.response, res_u.response, rtol=1e-6)
+    lc.clear()
+    c.close()

@@ -194,3 +194,18 @@ def test_python_restatement_agrees(golden_pairs):
     # match stands ~150 std above it, so argmax and info are stable although g itself is only comparable to ~1e-2 std
     assert np.sqrt(np.mean((g_r - g_c) ** 2)) / g_r.std() < 2e-2
     assert abs(i_r - i_c) / i_r < 3e-4
+
+
+# ---------------------------------------------------------------- undistort front end (camera.cc:92-93)
+def test_undistort_bit_exact_vs_cv2_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_undistort.npz"))
+    assert np.array_equal(oc.undistort_u8(g["raw"], g["map1"], g["map2"]), g["out"])
+    cv2 = pytest.importorskip("cv2")
+    H, W = 480, 640
+    K = np.array([[520., 0, 318.], [0, 515., 243.], [0, 0, 1]])
+    Dm = np.array([-0.28, 0.09, 0.0007, -0.0004, -0.012])
+    newK, _ = cv2.getOptimalNewCameraMatrix(K, Dm, (W, H), 0, (W, H))
+    m1, m2 = cv2.initUndistortRectifyMap(K, Dm, None, newK, (W, H), cv2.CV_16SC2)
+    raw = np.random.default_rng(5).integers(0, 256, (H, W)).astype(np.uint8)
+    assert np.array_equal(oc.undistort_u8(raw, m1, m2), cv2.remap(raw, m1, m2, cv2.INTER_LINEAR))
