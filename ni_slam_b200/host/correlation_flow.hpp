@@ -82,6 +82,20 @@ class CorrelationFlowT {
     check(ctx_, st);
   }
 
+  // Optional GPU front end for MapBuilder::AddNewInput (src/map_builder.cc:31-33): hand over Camera's fixed-point maps once
+  // (_map1.ptr<short>(), _map2.ptr<ushort>() of initUndistortRectifyMap(..., CV_16SC2), src/camera.cc:45-47) and feed the RAW
+  // u8 cv::Mat; Camera::UndistortImage + ConvertMatToNormalizedArray + ComputeIntermedium then all run on the GPU.
+  void SetUndistortMaps(const int16_t* map1_xy, const uint16_t* map2) { check(ctx_, nis_set_undistort_maps(ctx_, map1_xy, map2)); }
+  void ComputeIntermediumU8(const uint8_t* image_rowmajor, ArrayXXcf& fft_result, ArrayXXcf& fft_polar) {
+    nis_frame* f = nullptr;
+    check(ctx_, nis_features_u8(ctx_, image_rowmajor, &f));
+    fft_result.resize(cfg.height / 2 + 1, cfg.width);
+    fft_polar.resize(cfg.rotation_divisor / 2 + 1, cfg.rotation_channel);
+    int st = nis_frame_export(ctx_, f, reinterpret_cast<float*>(fft_result.data()), reinterpret_cast<float*>(fft_polar.data()));
+    nis_frame_free(ctx_, f);
+    check(ctx_, st);
+  }
+
   // Vector3d ComputePose(last_fft_result, image, last_fft_polar, fft_polar, pose, not_large_rotation)   correlation_flow.h:13
   Vector3d ComputePose(const ArrayXXcf& last_fft_result, const ArrayXXf& image, const ArrayXXcf& last_fft_polar,
                        const ArrayXXcf& fft_polar, Vector3d& pose, bool not_large_rotation) {
