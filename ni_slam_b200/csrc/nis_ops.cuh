@@ -231,19 +231,6 @@ struct ProSpec {      // plain spectrum load
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
 };
 
-struct ProAbs {       // |F| (correlation_flow.cc:92: fft_result.abs())
-  Src<cpx> x;
-  struct Line {
-    const cpx* p;
-    NIS_HD cpx load(int c) const { const cpx v = NIS_LDG(p + c); return make_float2(sqrtf(v.x * v.x + v.y * v.y), 0.f); }
-  };
-  struct Bound {
-    Src<cpx> x; LineMap m;
-    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{x.at(b) + off}; }
-  };
-  NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
-};
-
 struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:220-221)
   Src<cpx> x, z;
   struct Line { const cpx* px; const cpx* pz; NIS_HD cpx load(int c) const { return cmulc(NIS_LDG(px + c), NIS_LDG(pz + c)); } };
@@ -254,31 +241,6 @@ struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:2
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, z, m}; }
 };
 
-
-// G = T / (Kzz + lambda) * Kxz  (:171-172) with T = FFT(delta[R/2,C/2]) = (-1)^(k1+c) and the deferred
-// max-normalisation of both kernels (FFT is linear: FFT(k/max) = FFT(k)/max).
-// max_zz is indexed by b >> zz_shift and kzz carries the same shift (two rotation hypotheses share one keyframe Kzz).
-struct ProFilter {
-  Src<cpx> kzz, kxz; const unsigned int* max_zz; const unsigned int* max_xz; int zz_shift; float lambda;
-  struct Line {
-    const cpx* pz; const cpx* px; float izz, ixz, lambda; int k1;
-    NIS_HD cpx load(int c) const {
-      const cpx z = NIS_LDG(pz + c), x = NIS_LDG(px + c);
-      const float dr = z.x * izz + lambda, di = z.y * izz;
-      const float t = ((k1 + c) & 1) ? -ixz : ixz;
-      const float s = t / (dr * dr + di * di);
-      return cmul(make_float2(s * dr, -s * di), x);
-    }
-  };
-  struct Bound {
-    Src<cpx> kzz, kxz; const unsigned int* max_zz; const unsigned int* max_xz; int zz_shift; float lambda; LineMap m;
-    NIS_HD Line line(int ln) const {
-      int b, k1; size_t off; m.map(ln, b, off, k1);
-      return Line{kzz.at(b) + off, kxz.at(b) + off, 1.0f / bits2f(max_zz[b >> zz_shift]), 1.0f / bits2f(max_xz[b]), lambda, k1};
-    }
-  };
-  NIS_HD Bound bind(const LineMap& m) const { return Bound{kzz, kxz, max_zz, max_xz, zz_shift, lambda, m}; }
-};
 
 // ---- element-wise steps of the fused row kernel (forward FFT -> mid -> inverse FFT); Line::apply(c, x) -> y
 // y = x * conj(Z): X = FFT(rotated image) is consumed in registers and never stored (correlation_flow.cc:210-211).
