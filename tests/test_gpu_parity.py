@@ -468,3 +468,36 @@ def test_abi_edge_cases(cf, imgs):
     assert np.all(np.isfinite(p2)) and np.all(np.isfinite(i2))
     # launches are counted (the driver reads this as evidence that the CUDA path ran)
     assert cf.kernel_launches() > 0
+
+
+# ------------------------------------------------------------------ seeded random pairs (SURVEY 8d synthetic inputs)
+def test_random_pairs_match_oracle(cf, cfg):
+    """12 seeded pairs (|d| <= 60 px, |ang| <= 15 deg) cropped from the SURVEY App. C canvas: translation peak bit-exact, polar
+    row equal mod D/2, dx/dy exact, info within tolerance, in both modes."""
+    ref = pytest.importorskip("nislam_ref")
+    if ref.cv2 is None:
+        pytest.skip("cv2 missing")
+    canvas = ref.make_canvas(0)
+    rng = np.random.default_rng(2024)
+    a_u8 = ref.crop(canvas, 640, 480, 0)
+    a = oc.normalize_u8(a_u8)
+    Fa, Pa = oc.compute_intermedium(cfg, a)
+    fa = cf.ComputeIntermedium(a_u8)
+    n_checked = 0
+    for _ in range(12):
+        dx, dy = rng.integers(-60, 61, 2)
+        ang = rng.integers(-30, 31) * 0.5
+        b_u8 = ref.crop(canvas, 640 + dx, 480 + dy, ang)
+        b = oc.normalize_u8(b_u8)
+        Fb, Pb = oc.compute_intermedium(cfg, b)
+        fb = cf.ComputeIntermedium(b_u8)
+        for mode in (True, False):
+            io, po, pko = oc.compute_pose(cfg, Fa, b, Pa, Pb, mode)
+            ig, pg, pkg = cf.ComputePose(fa, fb, mode, return_peaks=True)
+            assert pkg["polar"][0] % (D // 2) == pko["polar"][0] % (D // 2), (dx, dy, ang, mode)
+            assert pkg["trans"] == pko["trans"], (dx, dy, ang, mode)
+            assert (pg[0], pg[1]) == (po[0], po[1]) == (float(dx), float(dy)), (dx, dy, ang, mode, pg, po)
+            assert abs(wrap_pi(pg[2] - np.deg2rad(ang))) < 1e-6
+            assert np.allclose(ig, io, rtol=INFO_RTOL), (ig, io)
+            n_checked += 1
+    assert n_checked == 24
