@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnislam.so")
+# NIS_LIB: alternative build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("NIS_LIB") or os.path.join(_HERE, "lib", "libnislam.so")
 
 NIS_OK, NIS_ERR_INVALID_ARGUMENT, NIS_ERR_INVALID_KERNEL, NIS_ERR_UNSUPPORTED_SIZE, NIS_ERR_CUDA, NIS_ERR_OOM = range(6)
 

@@ -34,18 +34,49 @@ namespace nis {
 
 typedef float2 cpx;
 
+// ---------------------------------------------------------------------------------------------------------
+// complex primitives.  On sm_100a every one of them is ONE or TWO packed f32x2 instructions (FADD2 / FMUL2 / FFMA2 work on an
+// aligned register pair = one complex number; operand modifiers swap the halves, negate one half or broadcast a scalar,
+// so multiplying by +-i and conjugating are free).  Measured on B200 (tools/ubench/f32x2.cu): FFMA2 has the flop rate of FFMA
+// at half the issue slots, and the FFT passes are issue bound.  The host build (tests/cpp emulation) uses the scalar forms.
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && !defined(NIS_NO_F32X2)
+typedef unsigned long long pk64;
+NIS_HD pk64 pk2(float x, float y) { pk64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+NIS_HD cpx upk2(pk64 v) { cpx r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+NIS_HD pk64 add2(pk64 a, pk64 b) { pk64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+NIS_HD pk64 sub2(pk64 a, pk64 b) { pk64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+NIS_HD pk64 mul2(pk64 a, pk64 b) { pk64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+NIS_HD pk64 fma2(pk64 a, pk64 b, pk64 c) { pk64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+NIS_HD cpx cadd(cpx a, cpx b) { return upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+NIS_HD cpx csub(cpx a, cpx b) { return upk2(sub2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+NIS_HD cpx cscale(cpx a, float s) { return upk2(mul2(pk2(s, s), pk2(a.x, a.y))); }
+// s*a + b, s real
+NIS_HD cpx cfma(float s, cpx a, cpx b) { return upk2(fma2(pk2(s, s), pk2(a.x, a.y), pk2(b.x, b.y))); }
+NIS_HD cpx cmul(cpx a, cpx b) {                       // a*b: (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
+  const cpx t = upk2(mul2(pk2(b.y, b.y), pk2(a.y, a.x)));
+  return upk2(fma2(pk2(b.x, b.x), pk2(a.x, a.y), pk2(-t.x, t.y)));
+}
+NIS_HD cpx cmulc(cpx a, cpx b) {                      // a*conj(b): (a.x b.x + a.y b.y, a.y b.x - a.x b.y)
+  const cpx t = upk2(mul2(pk2(b.y, b.y), pk2(a.y, a.x)));
+  return upk2(fma2(pk2(b.x, b.x), pk2(a.x, a.y), pk2(t.x, -t.y)));
+}
+#else
 NIS_HD cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
 NIS_HD cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
-NIS_HD cpx cmul(cpx a, cpx b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-NIS_HD cpx cmulc(cpx a, cpx b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
 NIS_HD cpx cscale(cpx a, float s) { return make_float2(a.x * s, a.y * s); }
+NIS_HD cpx cfma(float s, cpx a, cpx b) { return make_float2(s * a.x + b.x, s * a.y + b.y); }
+NIS_HD cpx cmul(cpx a, cpx b) { return make_float2(a.x * b.x - a.y * b.y, a.y * b.x + a.x * b.y); }
+NIS_HD cpx cmulc(cpx a, cpx b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+#endif
+NIS_HD cpx cconj(cpx a) { return make_float2(a.x, -a.y); }
 // multiply by -i (forward) / +i (inverse)
 template <bool INV> NIS_HD cpx mul_mi(cpx a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
-// twiddle as stored (forward, exp(-i..)) or conjugated (inverse)
-template <bool INV> NIS_HD cpx tw(cpx w) { return INV ? make_float2(w.x, -w.y) : w; }
+// x times the stored (forward, exp(-i..)) twiddle, or its conjugate for the inverse transform
+template <bool INV> NIS_HD cpx ctw(cpx x, cpx w) { return INV ? cmulc(x, w) : cmul(x, w); }
 
 // ---------------------------------------------------------------------------------------------------------
-// in-register DFTs.  dft<R,INV>(v): v[k] <- sum_n v[n] exp(-/+ 2 pi i n k / R)
+// in-register DFTs.  dft<R,INV>(v): v[k] <- sum_n v[n] exp(-/+ 2 pi i n k / R); written with the complex primitives only
 // ---------------------------------------------------------------------------------------------------------
 template <int R, bool INV> struct Dft;
 
@@ -61,16 +92,16 @@ template <bool INV> struct Dft<2, INV> {
 template <bool INV> struct Dft<3, INV> {
   static NIS_HD void run(cpx* v) {
     const float s3 = 0.86602540378443864676f;
-    cpx a = v[0], s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
-    cpx m = make_float2(a.x - 0.5f * s.x, a.y - 0.5f * s.y);
-    cpx t = cscale(mul_mi<INV>(d), s3);
+    const cpx a = v[0], s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+    const cpx m = cfma(-0.5f, s, a);
+    const cpx t = mul_mi<INV>(cscale(d, s3));
     v[0] = cadd(a, s); v[1] = cadd(m, t); v[2] = csub(m, t);
   }
 };
 
 template <bool INV> struct Dft<4, INV> {
   static NIS_HD void run(cpx* v) {
-    cpx s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]), s2 = cadd(v[1], v[3]), s3 = mul_mi<INV>(csub(v[1], v[3]));
+    const cpx s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]), s2 = cadd(v[1], v[3]), s3 = mul_mi<INV>(csub(v[1], v[3]));
     v[0] = cadd(s0, s2); v[2] = csub(s0, s2); v[1] = cadd(s1, s3); v[3] = csub(s1, s3);
   }
 };
@@ -79,31 +110,30 @@ template <bool INV> struct Dft<5, INV> {
   static NIS_HD void run(cpx* v) {
     const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    cpx a = v[0];
-    cpx p1 = cadd(v[1], v[4]), m1 = csub(v[1], v[4]), p2 = cadd(v[2], v[3]), m2 = csub(v[2], v[3]);
-    cpx t1 = make_float2(a.x + c1 * p1.x + c2 * p2.x, a.y + c1 * p1.y + c2 * p2.y);
-    cpx t2 = make_float2(a.x + c2 * p1.x + c1 * p2.x, a.y + c2 * p1.y + c1 * p2.y);
-    cpx u = mul_mi<INV>(make_float2(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y));
-    cpx w = mul_mi<INV>(make_float2(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y));
-    v[0] = make_float2(a.x + p1.x + p2.x, a.y + p1.y + p2.y);
+    const cpx a = v[0];
+    const cpx p1 = cadd(v[1], v[4]), m1 = csub(v[1], v[4]), p2 = cadd(v[2], v[3]), m2 = csub(v[2], v[3]);
+    const cpx t1 = cfma(c2, p2, cfma(c1, p1, a));
+    const cpx t2 = cfma(c1, p2, cfma(c2, p1, a));
+    const cpx u = mul_mi<INV>(cfma(s2, m2, cscale(m1, s1)));
+    const cpx w = mul_mi<INV>(cfma(-s1, m2, cscale(m1, s2)));
+    v[0] = cadd(cadd(a, p1), p2);
     v[1] = cadd(t1, u); v[4] = csub(t1, u); v[2] = cadd(t2, w); v[3] = csub(t2, w);
   }
 };
 
-// radix 8 = 2 x 4 with W8 twiddles
+// radix 8 = 2 x 4 with W8 twiddles:  w8^1 x = h (x + (-/+ i) x),  w8^3 x = -h (x + (+/- i) x)
 template <bool INV> struct Dft<8, INV> {
   static NIS_HD void run(cpx* v) {
     const float h = 0.70710678118654752440f;
     cpx e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
     Dft<4, INV>::run(e); Dft<4, INV>::run(o);
-    // w8^1 = (1 -/+ i)/sqrt2, w8^2 = -/+ i, w8^3 = (-1 -/+ i)/sqrt2
-    cpx o1 = INV ? make_float2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y)) : make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
-    cpx o2 = mul_mi<INV>(o[2]);
-    cpx o3 = INV ? make_float2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y)) : make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+    const cpx q1 = cadd(o[1], mul_mi<INV>(o[1]));
+    const cpx o2 = mul_mi<INV>(o[2]);
+    const cpx q3 = cadd(o[3], mul_mi<!INV>(o[3]));
     v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
-    v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+    v[1] = cfma(h, q1, e[1]); v[5] = cfma(-h, q1, e[1]);
     v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
-    v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+    v[3] = cfma(-h, q3, e[3]); v[7] = cfma(h, q3, e[3]);
   }
 };
 
@@ -120,8 +150,10 @@ template <bool INV> struct Dft<16, INV> {
     const float wi[8] = {0.f, -s, -h, -c, -1.f, -c, -h, -s};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      cpx w = make_float2(wr[k], INV ? -wi[k] : wi[k]);
-      cpx t = (k == 0) ? o[0] : cmul(o[k], w);
+      cpx t;
+      if (k == 0) t = o[0];
+      else if (k == 4) t = mul_mi<INV>(o[4]);
+      else t = ctw<INV>(o[k], make_float2(wr[k], wi[k]));
       v[k] = cadd(e[k], t); v[k + 8] = csub(e[k], t);
     }
   }
@@ -140,10 +172,10 @@ template <bool INV> struct Dft<9, INV> {
       Dft<3, INV>::run(t);
       y[n2][0] = t[0]; y[n2][1] = t[1]; y[n2][2] = t[2];
     }
-    y[1][1] = cmul(y[1][1], make_float2(c1, INV ? s1 : -s1));
-    y[1][2] = cmul(y[1][2], make_float2(c2, INV ? s2 : -s2));
-    y[2][1] = cmul(y[2][1], make_float2(c2, INV ? s2 : -s2));
-    y[2][2] = cmul(y[2][2], make_float2(c4, INV ? s4 : -s4));
+    y[1][1] = ctw<INV>(y[1][1], make_float2(c1, -s1));
+    y[1][2] = ctw<INV>(y[1][2], make_float2(c2, -s2));
+    y[2][1] = ctw<INV>(y[2][1], make_float2(c2, -s2));
+    y[2][2] = ctw<INV>(y[2][2], make_float2(c4, -s4));
 #pragma unroll
     for (int k1 = 0; k1 < 3; ++k1) {
       cpx t[3] = {y[0][k1], y[1][k1], y[2][k1]};
@@ -237,7 +269,7 @@ NIS_HD void col_stage1_read(int tid, const cpx* smem, const Twiddles& twd, Carry
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         cpx x = smem[(j + r * Gm::M1) * kColLanes + l];
-        if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + k])));
+        if (r > 0) x = ctw<INV>(x, NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + k]));
         st.v[it][r] = x;
       }
       Dft<R1, INV>::run(st.v[it]);
@@ -310,7 +342,8 @@ NIS_HD void col_fwd_phase0s_write(int tid, cpx* smem, const CarryRegs<R0, ColGeo
 
 // separation of the two real lines packed in Z:  A[k] = (Z[k]+conj Z[N-k])/2,  B[k] = (Z[k]-conj Z[N-k])/(2i)
 NIS_HD float4 r2c_split(cpx zk, cpx zn) {
-  return make_float4(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y), 0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+  const cpx a = cscale(cadd(zk, cconj(zn)), 0.5f), b = cscale(mul_mi<false>(csub(zk, cconj(zn))), 0.5f);
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 // phase 2: stage 2, butterflies j and NS2-j handled by one thread so Z[k] and Z[N-k] meet in registers.
@@ -380,8 +413,9 @@ NIS_HD void col_inv_phase0(int tid, cpx* smem, const cpx* in, int pitch, int c0)
       const int kk = lo ? k : N - k;
       float4 ab = NIS_LDG(&in4[((size_t)kk * pitch + c0) / 2 + l]);
       if (kk == 0 || 2 * kk == N) { ab.y = 0.f; ab.w = 0.f; }     // c2r ignores these imaginary parts
-      const cpx zlo = make_float2(ab.x - ab.w, ab.y + ab.z);       // A + iB        = Z[kk]
-      const cpx zhi = make_float2(ab.x + ab.w, ab.z - ab.y);       // conjA + i conjB = Z[N-kk]
+      const cpx ca = make_float2(ab.x, ab.y), ib = mul_mi<true>(make_float2(ab.z, ab.w));
+      const cpx zlo = cadd(ca, ib);                                // A + iB        = Z[kk]
+      const cpx zhi = cconj(csub(ca, ib));                         // conjA + i conjB = Z[N-kk]
       v[r] = lo ? zlo : zhi;
       if (!single) u[R0 - 1 - r] = lo ? zhi : zlo;
     }
@@ -408,7 +442,7 @@ NIS_HD void col_inv_phase2(int tid, const cpx* smem, const Twiddles& twd, Epi& e
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
       cpx x = smem[(j + r * NS2) * kColLanes + l];
-      if (r > 0) x = cmul(x, tw<true>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
+      if (r > 0) x = ctw<true>(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, true>::run(v);
@@ -429,7 +463,7 @@ NIS_HD void col_inv_phase2_inplace(int tid, cpx* smem, const Twiddles& twd, Fn& 
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
       cpx x = smem[(j + r * NS2) * kColLanes + l];
-      if (r > 0) x = cmul(x, tw<true>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
+      if (r > 0) x = ctw<true>(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, true>::run(v);
@@ -486,7 +520,7 @@ NIS_HD void row_stage1_read(int tid, const cpx* smem, const Twiddles& twd, int n
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         cpx x = s[r * (Gm::M1 + Gm::M1 / 16)];
-        if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw1[(r - 1) * 16 + k])));
+        if (r > 0) x = ctw<INV>(x, NIS_LDG(&twd.tw1[(r - 1) * 16 + k]));
         st.v[it][r] = x;
       }
       Dft<R1, INV>::run(st.v[it]);
@@ -522,7 +556,7 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
       cpx x = s[r * (NS2 + NS2 / 16)];
-      if (r > 0) x = cmul(x, tw<INV>(NIS_LDG(&twd.tw2[(r - 1) * NS2 + j])));
+      if (r > 0) x = ctw<INV>(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, INV>::run(v);

@@ -128,7 +128,7 @@ struct EpiStore {
   struct Bound {
     float* img; int W, c0; float rn;
     NIS_HD void put(int row, int l, float re, float im) {
-      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = make_float2(re * rn, im * rn);
+      reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = cscale(make_float2(re, im), rn);
     }
     template <class Sync> NIS_HD void finish(int, Sync&) {}
   };
@@ -272,7 +272,7 @@ struct MidFilterH {
   Src<cpx> h; const unsigned int* max_xz;
   struct Line {
     const cpx* ph; float ixz;
-    NIS_HD cpx apply(int c, cpx x) const { return cmul(NIS_LDG(ph + c), make_float2(x.x * ixz, x.y * ixz)); }
+    NIS_HD cpx apply(int c, cpx x) const { return cmul(cscale(x, ixz), NIS_LDG(ph + c)); }
     NIS_HD void flush() const {}
   };
   struct Bound {

@@ -501,7 +501,8 @@ def test_random_pairs_match_oracle(cf, cfg):
             assert pkg["polar"][0] % (D // 2) == pko["polar"][0] % (D // 2), (dx, dy, ang, mode)
             assert pkg["trans"] == pko["trans"], (dx, dy, ang, mode)
             assert (pg[0], pg[1]) == (po[0], po[1]) == (float(dx), float(dy)), (dx, dy, ang, mode, pg, po)
-            assert abs(wrap_pi(pg[2] - np.deg2rad(ang))) < 1e-6
+            assert abs(wrap_pi(pg[2] - po[2])) < 1e-6, (dx, dy, ang, mode, pg, po)
+            assert abs(wrap_pi(pg[2] - np.deg2rad(ang))) < np.deg2rad(0.5) + 1e-6      # ground truth to one polar bin (360/D)
             assert np.allclose(ig[:2], io[:2], rtol=INFO_RTOL), (ig, io)
             assert np.allclose(ig[2], io[2], rtol=INFO_ROT_RTOL), (ig, io)
             n_checked += 1
