@@ -80,8 +80,10 @@ struct nis_ctx {
   long long launches = 0;
   int batch = 16, default_batch = 16;
   bool polar_fused = true;
+  bool polar_tiled = true;          // tiled shared-memory polar gather (default); NIS_POLAR_TILED=0 falls back to the fused / direct gathers
+  int ptile_pitch = 0, ptile_rows = 0;
   // constant tables
-  DevBuf tw, lut, cs, rho, mats, theta, ptab;
+  DevBuf tw, lut, cs, rho, mats, theta, ptab, ptiles, ptab2;
   DevBuf recs, best, cand;
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
@@ -252,6 +254,28 @@ static int build_tables(nis_ctx* ctx) {
     if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_table", e_);
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  if (ctx->polar_tiled) {
+    const int tr = (Cp + kPolarTR - 1) / kPolarTR, ta = (D + kPolarTA - 1) / kPolarTA;
+    RESERVE(ctx->ptiles, (size_t)tr * ta * sizeof(int4));
+    RESERVE(ctx->ptab2, (size_t)D * Cp * sizeof(uint32_t));
+    int e_ = launch_polar_tile_bbox(ctx->ptiles.as<int4>(), H, W, D, Cp, ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->stream);
+    if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_tile_bbox", e_);
+    std::vector<int4> tiles((size_t)tr * ta);
+    CU(cudaMemcpyAsync(tiles.data(), ctx->ptiles.p, tiles.size() * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int bh = 1, bw = 1;
+    for (const int4& t : tiles) { bh = std::max(bh, t.z); bw = std::max(bw, t.w); }
+    ctx->ptile_pitch = bw | 1;
+    ctx->ptile_rows = bh + 1;                                      // the tap at (dy+1, dx+1) of the last row stays inside the allocation
+    if ((size_t)ctx->ptile_rows * ctx->ptile_pitch > 65535 || (size_t)ctx->ptile_rows * ctx->ptile_pitch * sizeof(float) > 48 * 1024) {
+      ctx->polar_tiled = false;                                    // cell footprint too large for this geometry: direct gathers
+    } else {
+      e_ = launch_polar_tile_table(ctx->ptab2.as<uint32_t>(), ctx->ptiles.as<int4>(), ctx->ptile_pitch, H, W, D, Cp, ctx->cs.as<double>(),
+                                   ctx->rho.as<float>(), ctx->stream);
+      if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_tile_table", e_);
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
   // per polar-peak-row angle tables (correlation_flow.cc:105-136): every float/double step of the reference, once
   std::vector<double> mats(3 * (size_t)D * 6), theta(3 * (size_t)D);
   for (int row = 0; row < D; ++row) {
@@ -285,7 +309,7 @@ static int ensure_workspace(nis_ctx* ctx, Lane& L, int pairs) {
   CU(cudaStreamSynchronize(L.stream));
   const size_t E = 2 * (size_t)pairs;
   RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));          // the only full-size scratch: half-transformed spectra, in place
-  RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float));   // power = IFFT(|F|) feeding the polar gather
+  RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float2));  // power = IFFT(|F|) feeding the polar gather (pair-duplicated: 8 B / pixel)
   RESERVE(L.pol, (size_t)pairs * ctx->sz[1].real * sizeof(float)); // polar image (when the gather is not fused into the FFT)
   RESERVE(L.maxp, (size_t)pairs * sizeof(unsigned));
   RESERVE(L.maxt, E * sizeof(unsigned));
@@ -374,12 +398,20 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
   // fft_result = FFT(image) stored from registers; the same kernel continues with IFFT(|fft_result|) along the rows
   LAUNCH(launch_rowrow_storeabs(zt.C, zt.row, t1s, t1, MidStoreAbs{F}, zt.R / 2 + 1, B, L.stream));
   Dst<float> power{L.real.as<float>(), (long long)zt.real};
-  LAUNCH(launch_col_inv_store(zt.R, zt.coli, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
+  Dst<float2> power2{L.real.as<float2>(), (long long)zt.real};
+  if (ctx->polar_fused && !ctx->polar_tiled) LAUNCH(launch_col_inv_store_pairs(zt.R, zt.coli, t1s, EpiStorePairs{power2, zt.C, (float)zt.real}, zt.C, B, L.stream));
+  else LAUNCH(launch_col_inv_store(zt.R, zt.coli, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
   // polar(fftshift(RemoveZeroComponent(power))) feeds the first FFT stage directly
   Dst<cpx> t1p{L.t1.as<cpx>(), (long long)zp.spec};
-  PolarArgs pa{src_slab<float>(power.base, power.stride), ctx->H, ctx->W, ctx->Cp, ctx->cs.as<double>(), ctx->rho.as<float>(),
-               ctx->ptab.as<uint32_t>()};
-  if (ctx->polar_fused) {
+  PolarArgs pa{src_slab<float>(power.base, power.stride), src_slab<float2>(power2.base, power2.stride), ctx->H, ctx->W, ctx->Cp,
+               ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->ptab.as<uint32_t>()};
+  if (ctx->polar_tiled) {
+    // cell-tiled gather from shared memory, then a plain r2c column pass over the polar image (it stays in L2)
+    Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
+    LAUNCH(launch_polar_tiled(pa.power, pol, ctx->H, ctx->W, ctx->D, ctx->Cp, ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch,
+                              ctx->ptile_rows, B, L.stream));
+    LAUNCH(launch_col_fwd_f32(zp.R, zp.colf, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
+  } else if (ctx->polar_fused) {
     LAUNCH(launch_col_fwd_polar(zp.R, zp.colf, pa, t1p, zp.C, B, L.stream));
   } else {
     // the gather is latency bound: as its own full-occupancy kernel it beats riding in the register-limited FFT stage 0
@@ -579,6 +611,8 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   if (er) ctx->rot_cache_min = atoi(er);
   const char* ef = getenv("NIS_POLAR_FUSED");
   if (ef) ctx->polar_fused = atoi(ef) != 0;
+  ef = getenv("NIS_POLAR_TILED");
+  if (ef) ctx->polar_tiled = atoi(ef) != 0;
   const char* eb = getenv("NIS_BATCH");
   if (eb && atoi(eb) > 0) ctx->batch = atoi(eb);
   int st = build_tables(ctx);
@@ -591,7 +625,7 @@ int nis_destroy(nis_ctx* ctx) {
   if (!ctx) return NIS_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
+  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->ptiles, &ctx->ptab2, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
                     &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->sUnd, &ctx->umap1, &ctx->umap2, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {
@@ -1186,8 +1220,12 @@ int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
   DevBuf out;
   RESERVE(out, ctx->sz[1].real * sizeof(float));
   CU(h2d(ctx, L.real.p, power_in, ctx->sz[0].real * sizeof(float)));
-  LAUNCH(launch_polar(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
-                      ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->ptab.as<uint32_t>(), 1, L.stream));
+  if (ctx->polar_tiled)           // the production gather
+    LAUNCH(launch_polar_tiled(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
+                              ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch, ctx->ptile_rows, 1, L.stream));
+  else
+    LAUNCH(launch_polar(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
+                        ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->ptab.as<uint32_t>(), 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpy(polar_out, out.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
   out.release();

@@ -132,7 +132,7 @@ void plan_radices_col(int N, bool inverse, int r[3]) {
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealF32) }
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealU8) }
 int launch_col_fwd_polar(int N, Twiddles tw, PolarArgs pa, Dst<cpx> out, int W, int B, cudaStream_t s) {
-  ProPolar pro{pa.power, pa.H, pa.W, pa.Cp, pa.cs, pa.rho, pa.table};
+  ProPolar pro{pa.power2, pa.H, pa.W, pa.Cp, pa.cs, pa.rho, pa.table};
   FWD_DISPATCH(ProPolar)
 }
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int B, cudaStream_t s) {
@@ -154,6 +154,7 @@ int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W
   }
 #define INV_CASE(n, f0, f1, f2, i0, i1, i2, t) case n: return run_col_inv<n, i0, i1, i2, t>(tw, in, epi, W, B, s);
 int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
+int launch_col_inv_store_pairs(int N, Twiddles tw, Src<cpx> in, EpiStorePairs epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 #undef INV_CASE
 

@@ -5,6 +5,8 @@
 //   (correlation_flow.cc:97-138, loop_closure.cc:61-71) kept on the device so a batch never syncs with the host.
 // All interpolation arithmetic is written with explicit round-to-nearest intrinsics (no FMA contraction) so the
 // fixed-point coordinates and the 4-tap sums equal OpenCV's scalar code bit for bit.
+#include <limits.h>
+
 #include "nis_device.cuh"
 #include "nis_internal.h"
 #include "nis_warp.cuh"
@@ -48,6 +50,91 @@ __global__ void polar_table_kernel(uint32_t* __restrict__ table, int H, int W, i
 }
 int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s) {
   polar_table_kernel<<<dim3((Cp + 127) / 128, D), 128, 0, s>>>(table, H, W, D, Cp, cs_table, rho_table);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tiled polar gather.  The direct gathers above touch ~8 different 128-byte lines per warp request (a ray crosses image rows),
+// which makes the L1 tag stage the limiter.  Here one CTA owns a polar cell of kPolarTA angles x kPolarTR radii, stages the
+// bounding box of its source footprint -- already fftshift-ed, RemoveZeroComponent-ed and zero-filled outside the image, so the
+// gather has no special cases -- in shared memory with row-contiguous loads, and gathers the four taps from there.
+// Per-context tables (built once): tiles[t] = {y0, x0, bh, bw} of the cell's box in shifted coordinates, and per output pixel
+// (dy * pitch + dx) | fx << 16 | fy << 21 relative to that box.  Same fixed-point arithmetic as polar_pixel, bit for bit.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void polar_fixed_point(int H, int W, double cp, double sp, float rf, int& ix, int& iy, int& fx, int& fy) {
+  const float cx = (float)W / 2, cy = (float)H / 2;
+  const float mx = (float)__dadd_rn(__dmul_rn((double)rf, cp), (double)cx);
+  const float my = (float)__dadd_rn(__dmul_rn((double)rf, sp), (double)cy);
+  const int sx = __float2int_rn(mx * 32.f), sy = __float2int_rn(my * 32.f);
+  ix = sat_short(sx >> 5); iy = sat_short(sy >> 5); fx = sx & 31; fy = sy & 31;
+}
+
+__global__ void __launch_bounds__(256) polar_tile_bbox_kernel(int4* __restrict__ tiles, int H, int W, int D, int Cp,
+                                                              const double* __restrict__ cs, const float* __restrict__ rho_tab) {
+  __shared__ int red[4];
+  if (threadIdx.x == 0) { red[0] = INT_MAX; red[1] = INT_MAX; red[2] = INT_MIN; red[3] = INT_MIN; }
+  __syncthreads();
+  int ymin = INT_MAX, xmin = INT_MAX, ymax = INT_MIN, xmax = INT_MIN;
+  for (int i = threadIdx.x; i < kPolarTA * kPolarTR; i += blockDim.x) {
+    const int phi = blockIdx.y * kPolarTA + i / kPolarTR, rho = blockIdx.x * kPolarTR + i % kPolarTR;
+    if (phi >= D || rho >= Cp) continue;
+    int ix, iy, fx, fy;
+    polar_fixed_point(H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho], ix, iy, fx, fy);
+    ymin = min(ymin, iy); xmin = min(xmin, ix); ymax = max(ymax, iy + 1); xmax = max(xmax, ix + 1);
+  }
+  atomicMin(&red[0], ymin); atomicMin(&red[1], xmin); atomicMax(&red[2], ymax); atomicMax(&red[3], xmax);
+  __syncthreads();
+  if (threadIdx.x == 0) tiles[blockIdx.y * gridDim.x + blockIdx.x] = make_int4(red[0], red[1], red[2] - red[0] + 1, red[3] - red[1] + 1);
+}
+
+__global__ void polar_tile_table_kernel(uint32_t* __restrict__ table, const int4* __restrict__ tiles, int tiles_r, int pitch, int H, int W,
+                                        int D, int Cp, const double* __restrict__ cs, const float* __restrict__ rho_tab) {
+  const int phi = blockIdx.y, rho = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rho >= Cp) return;
+  int ix, iy, fx, fy;
+  polar_fixed_point(H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho], ix, iy, fx, fy);
+  const int4 t = tiles[(phi / kPolarTA) * tiles_r + rho / kPolarTR];
+  table[(size_t)phi * Cp + rho] = (uint32_t)((iy - t.x) * pitch + (ix - t.y)) | ((uint32_t)fx << 16) | ((uint32_t)fy << 21);
+}
+
+__global__ void __launch_bounds__(256) polar_tile_kernel(Src<float> power, Dst<float> out, int H, int W, int D, int Cp,
+                                                         const int4* __restrict__ tiles, const uint32_t* __restrict__ table, int pitch) {
+  extern __shared__ float box[];
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const float* p = power.at(b);
+  const int4 t = __ldg(&tiles[blockIdx.y * gridDim.x + blockIdx.x]);        // y0, x0, bh, bw
+  for (int i = tid; i < t.z * t.w; i += 256) {
+    const int ly = i / t.w, lx = i - ly * t.w;
+    box[ly * pitch + lx] = shifted_tap(p, t.x + ly, t.y + lx, H, W);
+  }
+  __syncthreads();
+  const int rho = blockIdx.x * kPolarTR + (tid % kPolarTR);
+  if (rho >= Cp) return;
+  float* o = out.at(b);
+#pragma unroll
+  for (int k = 0; k < kPolarTA * kPolarTR / 256; ++k) {
+    const int phi = blockIdx.y * kPolarTA + tid / kPolarTR + k * (256 / kPolarTR);
+    if (phi >= D) break;
+    const uint32_t e = __ldg(table + (size_t)phi * Cp + rho);
+    const float* q = box + (e & 0xffffu);
+    o[(size_t)phi * Cp + rho] = bilinear4(q[0], q[1], q[pitch], q[pitch + 1], (e >> 16) & 31, (e >> 21) & 31);
+  }
+}
+
+int launch_polar_tile_bbox(int4* tiles, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s) {
+  polar_tile_bbox_kernel<<<dim3((Cp + kPolarTR - 1) / kPolarTR, (D + kPolarTA - 1) / kPolarTA), 256, 0, s>>>(tiles, H, W, D, Cp, cs_table, rho_table);
+  return (int)cudaGetLastError();
+}
+int launch_polar_tile_table(uint32_t* table, const int4* tiles, int pitch, int H, int W, int D, int Cp, const double* cs_table,
+                            const float* rho_table, cudaStream_t s) {
+  polar_tile_table_kernel<<<dim3((Cp + 127) / 128, D), 128, 0, s>>>(table, tiles, (Cp + kPolarTR - 1) / kPolarTR, pitch, H, W, D, Cp, cs_table, rho_table);
+  return (int)cudaGetLastError();
+}
+int launch_polar_tiled(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const int4* tiles, const uint32_t* table, int pitch,
+                       int box_rows, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  const size_t smem = (size_t)box_rows * pitch * sizeof(float);
+  polar_tile_kernel<<<dim3((Cp + kPolarTR - 1) / kPolarTR, (D + kPolarTA - 1) / kPolarTA, B), 256, smem, s>>>(power, out, H, W, D, Cp, tiles, table, pitch);
   return (int)cudaGetLastError();
 }
 

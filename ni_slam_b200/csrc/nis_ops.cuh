@@ -97,14 +97,28 @@ struct ProRealF32 {
   NIS_HD Bound bind(int b, int c0) const { return Bound{src.at(b), W, c0}; }
 };
 
-// u8 image -> f32/255 through a 256-entry table (utils.cc:110-118: (float)((double)u/255.0))
+// u8 -> f32/255 (utils.cc:110-118: (float)((double)u/255.0)).  The correctly rounded f32 quotient u/255.f equals the double
+// quotient rounded to f32 for all 256 inputs, and so does one FMA-corrected step from u * fl(1/255) (both checked exhaustively
+// in exact rational arithmetic by the CPU test suite), so the conversion is three FP instructions: a table lookup per tap costs
+// the L1 data pipe -- the bottleneck of these kernels -- up to 8 wavefronts per warp.
+NIS_HD float u8_to_unit(unsigned int u) {
+#if defined(__CUDA_ARCH__)
+  const float x = (float)u, r = 1.0f / 255.0f;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
+#else
+  return (float)u / 255.0f;
+#endif
+}
+
+// u8 image -> f32/255
 struct ProRealU8 {
   Src<uint8_t> src; int W; const float* lut;
   struct Lane {
     const uint8_t* p; int W; const float* lut;
     NIS_HD cpx load(int row) const {
-      const uint8_t* q = p + (size_t)row * W;
-      return make_float2(NIS_LDG(&lut[q[0]]), NIS_LDG(&lut[q[1]]));
+      const unsigned int w = NIS_LDG(reinterpret_cast<const unsigned short*>(p + (size_t)row * W));   // columns c0+2l (low byte), c0+2l+1
+      return make_float2(u8_to_unit(w & 0xffu), u8_to_unit(w >> 8));
     }
     template <int R> NIS_HD void load_all(int row0, int stride, cpx* v) const {
 #pragma unroll
@@ -129,6 +143,26 @@ struct EpiStore {
     float* img; int W, c0; float rn;
     NIS_HD void put(int row, int l, float re, float im) {
       reinterpret_cast<float2*>(img + (size_t)row * W + c0)[l] = cscale(make_float2(re, im), rn);
+    }
+    template <class Sync> NIS_HD void finish(int, Sync&) {}
+  };
+  NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, 1.0f / n}; }
+};
+
+// power = IFFT(|F|) in the pair-duplicated layout the fused polar gather reads: entry[r][c] = (p[r][c], p[r][c+1]), so one
+// 8-byte load fetches both horizontal taps of a bilinear footprint (half the gather wavefronts on the L1 data pipe).  Each
+// thread owns columns c = c0+2l and c+1: it writes entry[c] whole, the .x half of entry[c+1] and the .y half of entry[c-1].
+struct EpiStorePairs {
+  Dst<float2> dst; int W; float n;
+  struct Bound {
+    float2* img; int W, c0; float rn;
+    NIS_HD void put(int row, int l, float re, float im) {
+      const int c = c0 + 2 * l;
+      float2* rowp = img + (size_t)row * W + c;
+      const cpx v = cscale(make_float2(re, im), rn);
+      rowp[0] = v;
+      rowp[1].x = v.y;
+      if (c > 0) rowp[-1].y = v.x;
     }
     template <class Sync> NIS_HD void finish(int, Sync&) {}
   };

@@ -8,19 +8,31 @@
 #pragma once
 #include "nis_fft.cuh"
 // T is given for 16 complex lanes per CTA and scaled with NIS_COL_LANES (nis_fft.cuh) so the butterflies per thread stay put
+#ifndef NIS_COL_TBASE
+#define NIS_COL_TBASE 256     // 128-thread column CTAs at 8 lanes: measured +3.5% over 256 (more, smaller CTAs hide barrier stalls)
+#endif
 #define NIS_CT(t) ((t) * NIS_COL_LANES / 16)
 #define NIS_COL_PLANS(X)                      \
-  X(480, 10, 8, 6, 6, 8, 10, NIS_CT(512))     \
-  X(720, 10, 9, 8, 8, 9, 10, NIS_CT(512))     \
-  X(960, 10, 12, 8, 8, 12, 10, NIS_CT(512))   \
-  X(1200, 10, 12, 10, 10, 12, 10, NIS_CT(512)) \
+  X(480, 10, 8, 6, 6, 8, 10, NIS_CT(NIS_COL_TBASE))     \
+  X(720, 10, 9, 8, 8, 9, 10, NIS_CT(NIS_COL_TBASE))     \
+  X(960, 10, 12, 8, 8, 12, 10, NIS_CT(NIS_COL_TBASE))   \
+  X(1200, 10, 12, 10, 10, 12, 10, NIS_CT(NIS_COL_TBASE)) \
   X(96, 4, 6, 4, 4, 6, 4, NIS_CT(128))        \
   X(80, 5, 4, 4, 4, 4, 5, NIS_CT(128))        \
   X(64, 4, 4, 4, 4, 4, 4, NIS_CT(128))
 
+#ifndef NIS_ROW_L
+#define NIS_ROW_L 8
+#endif
+#ifndef NIS_ROW_T
+#define NIS_ROW_T 256
+#endif
+#ifndef NIS_ROW_LR
+#define NIS_ROW_LR 4
+#endif
 #define NIS_ROW_PLANS(X)      \
-  X(640, 8, 5, 8, 256, 4)     \
-  X(480, 6, 5, 8, 256, 4)     \
+  X(640, 8, 5, NIS_ROW_L, NIS_ROW_T, NIS_ROW_LR)     \
+  X(480, 6, 5, NIS_ROW_L, NIS_ROW_T, NIS_ROW_LR)     \
   X(1280, 8, 10, 4, 256, 2)   \
   X(1600, 10, 10, 4, 256, 2)  \
   X(128, 8, 1, 8, 128, 8)     \

@@ -23,19 +23,25 @@ __device__ __forceinline__ float bilinear4(float v0, float v1, float v2, float v
   return acc;
 }
 
+// element i of the power image: plain f32 [H][W], or the pair-duplicated layout of EpiStorePairs (.x of entry i)
+__device__ __forceinline__ float power_at(const float* __restrict__ p, size_t i) { return __ldg(p + i); }
+__device__ __forceinline__ float power_at(const float2* __restrict__ p, size_t i) { return __ldg(&p[i].x); }
+
 // tap of fftshift(RemoveZeroComponent(power)) at shifted coordinates (y, x); outside -> 0 (WARP_FILL_OUTLIERS)
-__device__ __forceinline__ float shifted_tap(const float* __restrict__ p, int y, int x, int H, int W) {
+template <class P>
+__device__ __forceinline__ float shifted_tap(const P* __restrict__ p, int y, int x, int H, int W) {
   if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) return 0.f;
   int r = y - H / 2; r += (r < 0) ? H : 0;                                     // circ_shift.h:238-244
   int c = x - W / 2; c += (c < 0) ? W : 0;
-  if (c == 0) return __fadd_rn(__ldg(p + (size_t)r * W + 1), __ldg(p + (size_t)r * W + W - 1)) * 0.5f;   // column rule (incl. (0,0))
-  if (r == 0) return __fadd_rn(__ldg(p + (size_t)W + c), __ldg(p + (size_t)(H - 1) * W + c)) * 0.5f;      // row rule
-  return __ldg(p + (size_t)r * W + c);
+  if (c == 0) return __fadd_rn(power_at(p, (size_t)r * W + 1), power_at(p, (size_t)r * W + W - 1)) * 0.5f;   // column rule (incl. (0,0))
+  if (r == 0) return __fadd_rn(power_at(p, (size_t)W + c), power_at(p, (size_t)(H - 1) * W + c)) * 0.5f;      // row rule
+  return power_at(p, (size_t)r * W + c);
 }
 
 // cs = (cos, sin) of the output row's angle (double, host libm); rf = (float)(rho * maxRadius / Cp).
 // General (border / RemoveZeroComponent-aware) path: out of line, the table-driven fast path covers almost every pixel.
-static __device__ __noinline__ float polar_pixel(const float* __restrict__ power, int H, int W, double cp, double sp, float rf) {
+template <class P>
+static __device__ __noinline__ float polar_pixel(const P* __restrict__ power, int H, int W, double cp, double sp, float rf) {
   const float cx = (float)W / 2, cy = (float)H / 2;
   const float mx = (float)__dadd_rn(__dmul_rn((double)rf, cp), (double)cx);
   const float my = (float)__dadd_rn(__dmul_rn((double)rf, sp), (double)cy);
@@ -76,8 +82,8 @@ __device__ __forceinline__ float rotate_pixel(const float* __restrict__ f32, con
   const int x0 = wrap_idx(ix, W), x1 = wrap_idx(ix + 1, W), y0 = wrap_idx(iy, H), y1 = wrap_idx(iy + 1, H);   // BORDER_WRAP
   float v0, v1, v2, v3;
   if (U8) {
-    v0 = __ldg(&lut[u8[(size_t)y0 * W + x0]]); v1 = __ldg(&lut[u8[(size_t)y0 * W + x1]]);
-    v2 = __ldg(&lut[u8[(size_t)y1 * W + x0]]); v3 = __ldg(&lut[u8[(size_t)y1 * W + x1]]);
+    v0 = u8_to_unit(__ldg(u8 + (size_t)y0 * W + x0)); v1 = u8_to_unit(__ldg(u8 + (size_t)y0 * W + x1));
+    v2 = u8_to_unit(__ldg(u8 + (size_t)y1 * W + x0)); v3 = u8_to_unit(__ldg(u8 + (size_t)y1 * W + x1));
   } else {
     v0 = __ldg(f32 + (size_t)y0 * W + x0); v1 = __ldg(f32 + (size_t)y0 * W + x1);
     v2 = __ldg(f32 + (size_t)y1 * W + x0); v3 = __ldg(f32 + (size_t)y1 * W + x1);
@@ -111,9 +117,9 @@ __device__ __forceinline__ float polar_pixel_tab(const float* __restrict__ power
 
 // ---- column-pass prologues: the warp feeds the first FFT stage directly, the warped image is never stored ------
 struct ProPolar {
-  Src<float> power; int H, W, Cp; const double* cs; const float* rho; const uint32_t* table;   // table [D][Cp]
+  Src<float2> power; int H, W, Cp; const double* cs; const float* rho; const uint32_t* table;   // table [D][Cp]
   struct Lane {
-    const float* p; int H, W, Cp, q; const double* cs; float rf0, rf1; const uint32_t* tab;
+    const float2* p; int H, W, Cp, q; const double* cs; float rf0, rf1; const uint32_t* tab;
     // branch-free table path for all R rows first (every gather is in flight before the first use), then the rare
     // general-path pixels are patched
     template <int R> __device__ __forceinline__ void load_all(int phi0, int stride, cpx* v) const {
@@ -124,10 +130,11 @@ struct ProPolar {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         any |= e[r].x | e[r].y;
-        const float* q0 = p + ((e[r].x & kPolarSlow) ? 0u : (e[r].x & 0x1fffffu));
-        const float* q1 = p + ((e[r].y & kPolarSlow) ? 0u : (e[r].y & 0x1fffffu));
-        v[r] = make_float2(bilinear4(__ldg(q0), __ldg(q0 + 1), __ldg(q0 + W), __ldg(q0 + W + 1), (e[r].x >> 21) & 31, (e[r].x >> 26) & 31),
-                           bilinear4(__ldg(q1), __ldg(q1 + 1), __ldg(q1 + W), __ldg(q1 + W + 1), (e[r].y >> 21) & 31, (e[r].y >> 26) & 31));
+        const float2* q0 = p + ((e[r].x & kPolarSlow) ? 0u : (e[r].x & 0x1fffffu));
+        const float2* q1 = p + ((e[r].y & kPolarSlow) ? 0u : (e[r].y & 0x1fffffu));
+        const float2 a0 = __ldg(q0), b0 = __ldg(q0 + W), a1 = __ldg(q1), b1 = __ldg(q1 + W);     // (tap, tap+1) of both footprint rows
+        v[r] = make_float2(bilinear4(a0.x, a0.y, b0.x, b0.y, (e[r].x >> 21) & 31, (e[r].x >> 26) & 31),
+                           bilinear4(a1.x, a1.y, b1.x, b1.y, (e[r].y >> 21) & 31, (e[r].y >> 26) & 31));
       }
       if (any & kPolarSlow) {
 #pragma unroll
@@ -143,7 +150,7 @@ struct ProPolar {
     }
   };
   struct Bound {
-    const float* p; int H, W, Cp, c0; const double* cs; const float* rho; const uint32_t* tab;
+    const float2* p; int H, W, Cp, c0; const double* cs; const float* rho; const uint32_t* tab;
     __device__ __forceinline__ Lane lane(int l) const {
       const int q = c0 + 2 * l;
       return Lane{p, H, W, Cp, q, cs, __ldg(rho + q), __ldg(rho + q + 1), tab};
@@ -165,8 +172,8 @@ template <bool U8> struct ProRotate {
       const int r0 = y0 * W, r1 = y1 * W;          // 32-bit indexing: an image has < 2^31 pixels
       float v0, v1, v2, v3;
       if (U8) {
-        v0 = __ldg(&lut[u[r0 + x0]]); v1 = __ldg(&lut[u[r0 + x1]]);
-        v2 = __ldg(&lut[u[r1 + x0]]); v3 = __ldg(&lut[u[r1 + x1]]);
+        v0 = u8_to_unit(__ldg(u + r0 + x0)); v1 = u8_to_unit(__ldg(u + r0 + x1));
+        v2 = u8_to_unit(__ldg(u + r1 + x0)); v3 = u8_to_unit(__ldg(u + r1 + x1));
       } else {
         v0 = __ldg(f + r0 + x0); v1 = __ldg(f + r0 + x1);
         v2 = __ldg(f + r1 + x0); v3 = __ldg(f + r1 + x1);

@@ -209,3 +209,35 @@ def test_undistort_bit_exact_vs_cv2_golden():
     m1, m2 = cv2.initUndistortRectifyMap(K, Dm, None, newK, (W, H), cv2.CV_16SC2)
     raw = np.random.default_rng(5).integers(0, 256, (H, W)).astype(np.uint8)
     assert np.array_equal(oc.undistort_u8(raw, m1, m2), cv2.remap(raw, m1, m2, cv2.INTER_LINEAR))
+
+
+def test_u8_normalisation_is_reproducible_in_f32():
+    """utils.cc:110-118 computes (float)((double)u / 255.0).  The CUDA prologues do the conversion arithmetically in f32
+    (nis_ops.cuh u8_to_unit); check in exact rational arithmetic that both f32 forms give the reference's value for all 256 inputs."""
+    import math
+    from fractions import Fraction as Fr
+
+    def rn32(x):                       # round a rational to the nearest float32 (ties to even), as a Fraction
+        if x == 0:
+            return Fr(0)
+        s, x = (1 if x > 0 else -1), abs(x)
+        e = math.floor(math.log2(x)) - 23
+        while x / Fr(2) ** e >= 2 ** 24:
+            e += 1
+        while x / Fr(2) ** e < 2 ** 23:
+            e -= 1
+        q = x / Fr(2) ** e
+        n = q.numerator // q.denominator
+        rem = q - n
+        if rem > Fr(1, 2) or (rem == Fr(1, 2) and n % 2 == 1):
+            n += 1
+        return s * n * Fr(2) ** e
+
+    r = rn32(Fr(1, 255))
+    for u in range(256):
+        ref = Fr(float(np.float32(np.float64(u) / 255.0)))
+        assert rn32(Fr(u, 255)) == ref                       # correctly rounded f32 division
+        q = rn32(Fr(u) * r)
+        rem = rn32(Fr(u) - q * 255)                          # fmaf(-q, 255, u), exact
+        assert rn32(rem * r + q) == ref                      # fmaf(rem, 1/255, q): the device form
+        assert float(ref) == float(oc.normalize_u8(np.full((2, 2), u, np.uint8))[0, 0])
