@@ -72,6 +72,8 @@ struct nis_ctx {
   int active_lanes = 1;            // lanes batches are dealt to (<= lanes.size())
   cudaStream_t prof_stream = nullptr;
   cudaEvent_t fork_ev = nullptr;
+  cudaStream_t copy_stream = nullptr;          // host->device uploads of a stream run back to back here, ahead of the compute lanes
+  std::vector<cudaEvent_t> up_ev, feat_ev;     // per batch of a stream: upload done / features done
   nis_cf_config cfg{};
   int H = 0, W = 0, D = 0, Cp = 0;
   SizeClass sz[2];             // 0: H x W, 1: D x Cp
@@ -599,6 +601,7 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
         cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
   ctx->stream = ctx->lanes[0].stream;
   if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { nis_destroy(ctx); return NIS_ERR_CUDA; }
   {
     // default batch: one column-pass launch (W/32 CTAs per image, 2 resident CTAs per SM) should fill the GPU just once
     cudaDeviceProp prop;
@@ -635,6 +638,9 @@ int nis_destroy(nis_ctx* ctx) {
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->feat_ev) cudaEventDestroy(e);
   for (void* c : ctx->chunks) cudaFree(c);
   if (ctx->pin) cudaFreeHost(ctx->pin);
   delete ctx;
@@ -849,28 +855,52 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   const int NL = ctx->active_lanes;
   cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
   cpx* Ht = ctx->sHt.as<cpx>(); cpx* Hp = ctx->sHp.as<cpx>();
+  const int nbatch = (n + B - 1) / B;
+  while ((int)ctx->up_ev.size() < nbatch) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    ctx->up_ev.push_back(a);
+    CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    ctx->feat_ev.push_back(b);
+  }
+  // One software pipeline over the batches: uploads run back to back on the copy stream from the start; batch k's features go to
+  // lane k % NL as soon as its upload has landed; the pose solves of batch k-1 (which need the first frame of batch k) follow on
+  // the same lane, so copies overlap ALL of the compute and a batch's features are still in L2 when its solves read them.
   TRY(fork_lanes(ctx));
-  for (int t0 = 0, k = 0; t0 < n; t0 += B, ++k) {
-    const int nb = std::min(B, n - t0);
-    if (on_host)
+  if (on_host) {
+    CU(cudaEventRecord(ctx->fork_ev, ctx->stream));               // the copy stream, too, starts after everything already queued
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+    for (int k = 0; k < nbatch; ++k) {
+      const int t0 = k * B, nb = std::min(B, n - t0);
       CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames + (size_t)t0 * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
-                         ctx->lanes[k % NL].stream));
-    if (ctx->undistort)
-      TRY(undistort_batch(ctx, ctx->lanes[k % NL].stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
-    TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
+                         ctx->copy_stream));
+      CU(cudaEventRecord(ctx->up_ev[k], ctx->copy_stream));
+    }
+  }
+  auto pose_of_batch = [&](int j, Lane& L) -> int {                 // pairs (t, t+1) with t in batch j
+    const int p0 = j * B, nb = std::min(B, n - 1 - p0);
+    if (nb <= 0) return NIS_OK;
+    return compute_pose_batch(ctx, L, false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt),
+                              src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(Ht + (size_t)p0 * spt, (long long)spt),
+                              src_slab<cpx>(Hp + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp),
+                              src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)(p0 + 1) * npx, (long long)npx), true, nb, p0,
+                              ctx->recs.as<PoseRecord>() + p0);
+  };
+  for (int k = 0; k < nbatch; ++k) {
+    const int t0 = k * B, nb = std::min(B, n - t0);
+    Lane& L = ctx->lanes[k % NL];
+    if (on_host) CU(cudaStreamWaitEvent(L.stream, ctx->up_ev[k], 0));
+    if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
+    TRY(features_batch(ctx, L, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
                        Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
                        Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));
+    CU(cudaEventRecord(ctx->feat_ev[k], L.stream));
+    if (k >= 1) {                                                   // solves of batch k-1: features of batches k-1 (other lane) and k (this lane)
+      if (NL > 1) CU(cudaStreamWaitEvent(L.stream, ctx->feat_ev[k - 1], 0));
+      TRY(pose_of_batch(k - 1, L));
+    }
   }
-  TRY(join_lanes(ctx));          // a pair needs the features of both of its frames
-  TRY(fork_lanes(ctx));
-  for (int p0 = 0, k = 0; p0 < n - 1; p0 += B, ++k) {
-    const int nb = std::min(B, n - 1 - p0);
-    TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt),
-                           src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(Ht + (size_t)p0 * spt, (long long)spt),
-                           src_slab<cpx>(Hp + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(P + (size_t)(p0 + 1) * spp, (long long)spp),
-                           src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)(p0 + 1) * npx, (long long)npx), true, nb, p0,
-                           ctx->recs.as<PoseRecord>() + p0));
-  }
+  TRY(pose_of_batch(nbatch - 1, ctx->lanes[(nbatch - 1) % NL]));    // the last batch's own pairs
   TRY(join_lanes(ctx));
   if (n > 1) {
     TRY(ensure_pinned(ctx, (size_t)(n - 1) * sizeof(PoseRecord)));
