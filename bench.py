@@ -267,11 +267,32 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner / NCCL_DEBUG output to
+    stdout), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the
+    original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -532,7 +553,7 @@ def main():
                         "d2h_bytes_per_step": (n - 1) * 72},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "loop_closure": loop, "undistort_front_end": front,
                 "pose_ok_frac": pose_ok_frac}
-        print(json.dumps(line), flush=True)
+        emit(line)
     cf.close()
     if world > 1:
         dist.destroy_process_group()
