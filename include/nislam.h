@@ -115,6 +115,38 @@ int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, 
 int nis_track_stream(nis_ctx* ctx, const uint8_t* frames_host, int n, double* poses, double* infos);
 int nis_track_stream_dev(nis_ctx* ctx, const uint8_t* frames_dev, int n, double* poses, double* infos);
 
+/* ---- tracking of a stream under the reference's keyframe policy: MapBuilder::AddNewInput without loop closure, optimisation
+ *      and stitching (src/map_builder.cc:30-70): Tracking against the LAST KEYFRAME (:127-138), the confidence gate, pose
+ *      composition (UpdateCurrentPose :118-125, ComputeAbsolutePose / ComputeRelativePose src/utils.cc:133-152,
+ *      Camera::ConvertCenterToPrincipal / ConvertImagePlanePoseToCamera / ConvertCameraPoseToRobot src/camera.cc:148-218),
+ *      ComputeRelativeDA (:157-166) and the keyframe test c1..c4 (:47-53).  Frames after a keyframe are solved against it
+ *      speculatively in batches; the solves behind the first frame that becomes a keyframe are redone against the new one, so the
+ *      results are exactly those of the frame-by-frame loop. ---- */
+typedef struct {           /* KeyframeSelectionConfig, include/read_configs.h:27-32 */
+  double max_distance;
+  double max_angle;
+  double lower_response_thr;
+  double upper_response_thr;
+} nis_kfs_config;
+typedef struct {           /* the parts of Camera the pose conversions read (src/camera.cc:148-218) */
+  double fx, fy, cx, cy;   /* _new_K(0,0), (1,1), (0,2), (1,2) */
+  double height;           /* _height */
+  double extrinsics[9];    /* _extrinsics, row-major 3 x 3 */
+} nis_camera_model;
+typedef struct {
+  int32_t tracked;         /* good_tracking (map_builder.cc:132); 1 for the first frame */
+  int32_t inserted;        /* return value of AddNewInput: the frame became a keyframe */
+  int32_t keyframe;        /* index of the keyframe this frame was solved against (-1 for the first frame) */
+  int32_t reserved;
+  double response[3];      /* ComputePose return value */
+  double relative_pose[3]; /* ComputePose pose after ConvertCenterToPrincipal (map_builder.cc:131) */
+  double cf_pose[3];       /* _current_cf_pose after this frame */
+  double pose[3];          /* _current_pose (robot frame) after this frame */
+  double distance;         /* _distance after this frame */
+} nis_track_result;
+int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, const nis_kfs_config* kfs,
+                               const nis_camera_model* cam, nis_track_result* out /* n records */);
+
 /* ---- keyframe database = Map::AddFrame for the arrays the scan reads (include/frame.h:35-36, src/map.cc) ---- */
 int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distance, int* slot);
 /* bulk insert: n u8 images (host or device), features computed on the GPU straight into the DB */

@@ -25,7 +25,7 @@ NIS_OK, NIS_ERR_INVALID_ARGUMENT, NIS_ERR_INVALID_KERNEL, NIS_ERR_UNSUPPORTED_SI
 SYMBOLS = [
     "nis_create", "nis_destroy", "nis_last_error", "nis_strerror", "nis_stream", "nis_synchronize", "nis_kernel_launches",
     "nis_set_batch", "nis_set_lanes", "nis_features_u8", "nis_features_f32", "nis_frame_export", "nis_frame_import", "nis_frame_free",
-    "nis_set_undistort_maps", "nis_undistort_u8", "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_db_add", "nis_db_add_images",
+    "nis_set_undistort_maps", "nis_undistort_u8", "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_track_stream_keyframes", "nis_db_add", "nis_db_add_images",
     "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_db_set_position", "nis_loop_scan_prior", "nis_debug_fft2",
     "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
     "nis_profile_end",
@@ -52,6 +52,42 @@ class LoopResultC(C.Structure):
     _fields_ = [("found", C.c_int32), ("slot", C.c_int32), ("frame_id", C.c_int32), ("hyp", C.c_int32),
                 ("relative_pose", C.c_double * 3), ("response", C.c_double * 3), ("peak", C.c_int32 * 4),
                 ("evaluated", C.c_int32)]
+
+
+class _KfsConfigC(C.Structure):       # nis_kfs_config = KeyframeSelectionConfig (include/read_configs.h:27-32)
+    _fields_ = [("max_distance", C.c_double), ("max_angle", C.c_double), ("lower_response_thr", C.c_double),
+                ("upper_response_thr", C.c_double)]
+
+
+class _CameraModelC(C.Structure):     # nis_camera_model: the parts of Camera the pose conversions read (src/camera.cc:148-218)
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("height", C.c_double),
+                ("extrinsics", C.c_double * 9)]
+
+
+# nis_track_result, one record per frame
+TRACK_RESULT_DTYPE = np.dtype([("tracked", np.int32), ("inserted", np.int32), ("keyframe", np.int32), ("reserved", np.int32),
+                               ("response", np.float64, 3), ("relative_pose", np.float64, 3), ("cf_pose", np.float64, 3),
+                               ("pose", np.float64, 3), ("distance", np.float64)])
+
+
+@dataclass
+class KeyframeSelectionConfig:
+    """include/read_configs.h:27-32; defaults = configs/config_ntu.yaml:19-23."""
+    max_distance: float = 0.4
+    max_angle: float = 0.052359877
+    lower_response_thr: float = 30.0
+    upper_response_thr: float = 90.0
+
+
+@dataclass
+class CameraModel:
+    """What Camera's pose conversions read: new_K, height above ground, camera->robot extrinsics (src/camera.cc:148-218)."""
+    fx: float = 1000.0
+    fy: float = 1000.0
+    cx: float = 320.0
+    cy: float = 240.0
+    height: float = 1.0
+    extrinsics: tuple = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
 
 
 @dataclass
@@ -114,6 +150,7 @@ def load_library():
     lib.nis_kernel_launches.argtypes = [vp]; lib.nis_kernel_launches.restype = C.c_longlong
     lib.nis_set_batch.argtypes = [vp, i32]
     lib.nis_set_lanes.argtypes = [vp, i32]
+    lib.nis_track_stream_keyframes.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.nis_features_u8.argtypes = [vp, vp, C.POINTER(vp)]
     lib.nis_features_f32.argtypes = [vp, vp, C.POINTER(vp)]
     lib.nis_frame_export.argtypes = [vp, vp, vp, vp]
@@ -300,6 +337,17 @@ class CorrelationFlow:
         infos = np.zeros((max(n - 1, 0), 3), np.float64)
         self._check(self._lib.nis_track_stream(self._ctx, _p(frames), n, _p(poses), _p(infos)))
         return poses, infos
+
+    def TrackStreamKeyframes(self, frames_u8, kfs: "KeyframeSelectionConfig", cam: "CameraModel"):
+        """MapBuilder::AddNewInput (tracking against the last keyframe, gate, pose composition, keyframe test; no loop closure)
+        over a host stream -> structured array of n nis_track_result records (TRACK_RESULT_DTYPE)."""
+        frames = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+        n = frames.shape[0]
+        out = np.zeros(n, TRACK_RESULT_DTYPE)
+        k = _KfsConfigC(kfs.max_distance, kfs.max_angle, kfs.lower_response_thr, kfs.upper_response_thr)
+        c = _CameraModelC(cam.fx, cam.fy, cam.cx, cam.cy, cam.height, (C.c_double * 9)(*cam.extrinsics))
+        self._check(self._lib.nis_track_stream_keyframes(self._ctx, _p(frames), n, C.byref(k), C.byref(c), _p(out)))
+        return out
 
     def TrackStreamPtr(self, ptr: int, n: int, on_device: bool):
         """Same, frames given by raw pointer (pinned host or device memory, e.g. torch tensor .data_ptr())."""

@@ -16,6 +16,7 @@
 
 #include "../../include/nislam.h"
 #include "nis_internal.h"
+#include "../host/pose_math.hpp"
 
 using namespace nis;
 
@@ -917,6 +918,100 @@ int nis_track_stream(nis_ctx* ctx, const uint8_t* frames_host, int n, double* po
 }
 int nis_track_stream_dev(nis_ctx* ctx, const uint8_t* frames_dev, int n, double* poses, double* infos) {
   return track_stream_impl(ctx, frames_dev, false, n, poses, infos);
+}
+
+// ---- stream tracking under the reference's keyframe policy (map_builder.cc:30-70 without loop closure / optimisation) ----
+int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, const nis_kfs_config* kfs, const nis_camera_model* cam,
+                               nis_track_result* out) {
+  if (!ctx || !frames_host || n < 1 || !kfs || !cam || !out || cam->height < 0 || cam->fx == 0 || cam->fy == 0) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec;
+  RESERVE(ctx->sF, (size_t)n * spt * sizeof(cpx));
+  RESERVE(ctx->sP, (size_t)n * spp * sizeof(cpx));
+  RESERVE(ctx->sHt, (size_t)n * spt * sizeof(cpx));
+  RESERVE(ctx->sHp, (size_t)n * spp * sizeof(cpx));
+  RESERVE(ctx->sImg, (size_t)n * npx);
+  const uint8_t* d_raw = ctx->sImg.as<uint8_t>();
+  const uint8_t* d_frames = d_raw;
+  if (ctx->undistort) {
+    RESERVE(ctx->sUnd, (size_t)n * npx);
+    d_frames = ctx->sUnd.as<uint8_t>();
+  }
+  const int B = ctx->batch, NL = ctx->active_lanes;
+  TRY(ensure_recs(ctx, B));
+  TRY(ensure_pinned(ctx, (size_t)B * sizeof(PoseRecord)));
+  cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
+  cpx* Ht = ctx->sHt.as<cpx>(); cpx* Hp = ctx->sHp.as<cpx>();
+  // features of every frame (no keyframe factors yet: only frames that become keyframes need H), uploads on the copy stream
+  const int nbatch = (n + B - 1) / B;
+  while ((int)ctx->up_ev.size() < nbatch) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    ctx->up_ev.push_back(a);
+    CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    ctx->feat_ev.push_back(b);
+  }
+  TRY(fork_lanes(ctx));
+  CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+  for (int k = 0; k < nbatch; ++k) {
+    const int t0 = k * B, nb = std::min(B, n - t0);
+    CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames_host + (size_t)t0 * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
+                       ctx->copy_stream));
+    CU(cudaEventRecord(ctx->up_ev[k], ctx->copy_stream));
+  }
+  for (int k = 0; k < nbatch; ++k) {
+    const int t0 = k * B, nb = std::min(B, n - t0);
+    Lane& L = ctx->lanes[k % NL];
+    CU(cudaStreamWaitEvent(L.stream, ctx->up_ev[k], 0));
+    if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
+    TRY(features_batch(ctx, L, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
+                       Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
+                       Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, false));
+  }
+  TRY(join_lanes(ctx));
+  Lane& L0 = ctx->lanes[0];
+  auto keyframe_factors = [&](int K) -> int {       // H = T/(Kzz+lambda) of both stages for keyframe K (correlation_flow.cc:157-171)
+    TRY(ensure_workspace(ctx, L0, 1));
+    TRY(hzz_batch(ctx, L0, 0, src_slab<cpx>(F + (size_t)K * spt, (long long)spt), 1, Dst<cpx>{Ht + (size_t)K * spt, (long long)spt}));
+    return hzz_batch(ctx, L0, 1, src_slab<cpx>(P + (size_t)K * spp, (long long)spp), 1, Dst<cpx>{Hp + (size_t)K * spp, (long long)spp});
+  };
+  pose::TrackerState st;
+  pose::initialize(*cam, st, out[0]);
+  pose::snapshot(st, out[0]);
+  int K = 0;
+  TRY(keyframe_factors(K));
+  int t = 1, spec = std::min(B, 8), since_kf = 0;
+  while (t < n) {
+    const int nb = std::min(spec, n - t);
+    // frames t .. t+nb-1 against keyframe K: the keyframe operands are one slab with stride 0
+    TRY(compute_pose_batch(ctx, L0, false, src_slab<cpx>(F + (size_t)K * spt, 0), src_slab<cpx>(P + (size_t)K * spp, 0),
+                           src_slab<cpx>(Ht + (size_t)K * spt, 0), src_slab<cpx>(Hp + (size_t)K * spp, 0),
+                           src_slab<cpx>(P + (size_t)t * spp, (long long)spp), src_null<float>(),
+                           src_slab<uint8_t>(d_frames + (size_t)t * npx, (long long)npx), true, nb, t, ctx->recs.as<PoseRecord>()));
+    CU(cudaMemcpyAsync(ctx->pin, ctx->recs.p, (size_t)nb * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const PoseRecord* r = (const PoseRecord*)ctx->pin;
+    int used = nb;
+    for (int i = 0; i < nb; ++i) {
+      nis_track_result& o = out[t + i];
+      o.keyframe = K;
+      const bool ins = pose::step(*cam, *kfs, ctx->W, ctx->H, r[i].pose, r[i].info, st, o);
+      pose::snapshot(st, o);
+      ++since_kf;
+      if (ins) {                                   // frames behind it were solved against the wrong keyframe: redo them
+        K = t + i;
+        used = i + 1;
+        spec = std::max(4, std::min(B, 2 * since_kf));
+        since_kf = 0;
+        if (K + 1 < n) TRY(keyframe_factors(K));
+        break;
+      }
+    }
+    if (used == nb && since_kf >= spec) spec = std::min(B, 2 * spec);
+    t += used;
+  }
+  return NIS_OK;
 }
 
 // ---- keyframe DB ------------------------------------------------------------------------------------------------

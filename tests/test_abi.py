@@ -167,3 +167,39 @@ def test_emulated_fused_rowrow(emu, N):
     assert emu.emu_rowrow_filter(P(x), P(z), P(mx), B, nrows, N, P(out2)) == 0
     want2 = np.fft.ifft(X * z / np.array([2.0, 0.5]).reshape(B, 1, 1), axis=2) * N
     assert np.abs(out2 - want2).max() / np.abs(want2).max() < 3e-6
+
+
+def test_host_pose_math_matches_tracker_restatement():
+    """ni_slam_b200/host/pose_math.hpp (gate, pose composition, keyframe test of nis_track_stream_keyframes) against the Python
+    restatement of map_builder.cc:30-70 on 300 scripted ComputePose outputs: decisions identical, poses to 1e-12."""
+    import numpy as np
+    import tracker_ref as tr
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "pose_math_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "pose_math_test.cc"), "-o", exe])
+    rng = np.random.default_rng(7)
+    n = 300
+    E = [0.6, -0.8, 0.1, 0.8, 0.6, -0.2, 0.0, 0.0, 1.0]
+    cam = dict(fx=812.5, fy=790.25, cx=331.5, cy=236.25, height=0.37)
+    kfs = (0.02, 0.03, 30.0, 90.0)
+    resp = np.stack([rng.uniform(5, 200, n), np.zeros(n), rng.uniform(5, 200, n)], 1)
+    resp[:, 1] = resp[:, 0]
+    pose = np.stack([rng.integers(-25, 26, n), rng.integers(-25, 26, n), np.deg2rad(rng.integers(-720, 721, n) * 0.5)], 1).astype(np.float64)
+    text = "%r %r %r %r %r " % (cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["height"]) + " ".join(repr(e) for e in E)
+    text += " %r %r %r %r 640 480 %d\n" % (kfs + (n,))
+    text += "\n".join(" ".join(repr(float(v)) for v in list(resp[i]) + list(pose[i])) for i in range(n)) + "\n"
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.split("\n")
+    it = iter(range(n))
+    trk = tr.MapBuilderTracker(tr.Camera(extrinsics=E, image_width=640, image_height=480, **cam), *kfs, lambda img: (None, None),
+                               lambda *a: (lambda i: (resp[i], pose[i]))(next(it)))
+    n_ins = 0
+    for i in range(n + 1):
+        o = trk.add_new_input(None)
+        v = [float(x) for x in out[i].split()]
+        assert (int(v[0]), int(v[1]), int(v[2])) == (int(o["tracked"]), int(o["inserted"]), o["keyframe"]), i
+        assert np.allclose(v[3:6], o["cf_pose"], rtol=0, atol=1e-9) and np.allclose(v[6:9], o["pose"], rtol=0, atol=1e-9), i
+        assert abs(v[9] - o["distance"]) < 1e-12
+        if i:
+            assert np.allclose(v[10:13], o["relative_pose"], rtol=0, atol=1e-9)
+        n_ins += int(o["inserted"])
+    assert 10 < n_ins < n

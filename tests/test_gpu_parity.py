@@ -507,3 +507,51 @@ def test_random_pairs_match_oracle(cf, cfg):
             assert np.allclose(ig[2], io[2], rtol=INFO_ROT_RTOL), (ig, io)
             n_checked += 1
     assert n_checked == 24
+
+
+# ------------------------------------------------------------------ keyframe-policy tracking (map_builder.cc:30-70)
+def test_track_stream_keyframes_matches_map_builder_restatement(cf, cfg):
+    """nis_track_stream_keyframes (speculative batches against the last keyframe) against the frame-by-frame restatement of
+    MapBuilder::AddNewInput driven by the C oracle: same tracked / inserted / keyframe sequence, integer pixel shifts exact, angles
+    equal mod 2 pi, composed poses to 1e-9, confidences within the info tolerances."""
+    ref = pytest.importorskip("nislam_ref")
+    if ref.cv2 is None:
+        pytest.skip("cv2 missing")
+    import ni_slam_b200 as nis
+    import tracker_ref as tr
+    canvas = ref.make_canvas(0)
+    rng = np.random.default_rng(11)
+    n = 36
+    steps = np.stack([rng.integers(-7, 8, n), rng.integers(-7, 8, n)], 1)
+    steps[0] = 0
+    xy = np.cumsum(steps, 0)
+    ang = np.cumsum(np.r_[0, rng.integers(-2, 3, n - 1) * 0.5])
+    frames = np.stack([ref.crop(canvas, 640 + int(xy[t, 0]), 480 + int(xy[t, 1]), float(ang[t])) for t in range(n)])
+    E = [0.0, -1.0, 0.1, 1.0, 0.0, 0.2, 0.0, 0.0, 1.0]
+    cam = nis.CameraModel(fx=800.0, fy=820.0, cx=330.0, cy=235.0, height=0.5, extrinsics=tuple(E))
+    kfs = nis.KeyframeSelectionConfig(max_distance=0.02, max_angle=0.03, lower_response_thr=30.0, upper_response_thr=90.0)
+    got = cf.TrackStreamKeyframes(frames, kfs, cam)
+    assert got.shape == (n,)
+
+    def cpose(lF, img, lP, P):
+        info, pose, _ = oc.compute_pose(cfg, lF, img, lP, P, True)
+        return info, pose
+    trk = tr.MapBuilderTracker(tr.Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.height, E, W, H), kfs.max_distance, kfs.max_angle,
+                               kfs.lower_response_thr, kfs.upper_response_thr, lambda img: oc.compute_intermedium(cfg, img), cpose)
+    n_kf = 0
+    for t in range(n):
+        o = trk.add_new_input(oc.normalize_u8(frames[t]))
+        g = got[t]
+        assert (bool(g["tracked"]), bool(g["inserted"]), int(g["keyframe"])) == (o["tracked"], o["inserted"], o["keyframe"]), t
+        if t:
+            assert np.allclose(g["response"][:2], o["response"][:2], rtol=INFO_RTOL) and np.allclose(g["response"][2], o["response"][2], rtol=INFO_ROT_RTOL), t
+            assert abs(wrap_pi(g["relative_pose"][2] - o["relative_pose"][2])) < 1e-6, t
+            assert np.allclose(g["relative_pose"][:2], o["relative_pose"][:2], rtol=0, atol=1e-9), t
+        assert np.allclose(g["cf_pose"][:2], o["cf_pose"][:2], rtol=0, atol=1e-9) and abs(wrap_pi(g["cf_pose"][2] - o["cf_pose"][2])) < 1e-9, t
+        assert np.allclose(g["pose"][:2], o["pose"][:2], rtol=0, atol=1e-9) and abs(wrap_pi(g["pose"][2] - o["pose"][2])) < 1e-9, t
+        assert abs(g["distance"] - o["distance"]) < 1e-12
+        n_kf += int(o["inserted"])
+    assert 3 <= n_kf < n            # the policy really alternates between keyframes and tracked-only frames
+    # a one-frame stream is just Initialize
+    one = cf.TrackStreamKeyframes(frames[:1], kfs, cam)
+    assert one.shape == (1,) and one[0]["inserted"] == 1 and one[0]["keyframe"] == -1

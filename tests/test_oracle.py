@@ -241,3 +241,54 @@ def test_u8_normalisation_is_reproducible_in_f32():
         rem = rn32(Fr(u) - q * 255)                          # fmaf(-q, 255, u), exact
         assert rn32(rem * r + q) == ref                      # fmaf(rem, 1/255, q): the device form
         assert float(ref) == float(oc.normalize_u8(np.full((2, 2), u, np.uint8))[0, 0])
+
+
+# ---------------------------------------------------------------- tracker restatement (map_builder.cc:30-70) known answers
+def _cam(**kw):
+    import tracker_ref as tr
+    d = dict(fx=800.0, fy=820.0, cx=330.0, cy=235.0, height=0.5, extrinsics=[0, -1, 0.1, 1, 0, 0.2, 0, 0, 1], image_width=W, image_height=H)
+    d.update(kw)
+    return tr.Camera(**d)
+
+
+def test_pose_algebra_known_answers():
+    import tracker_ref as tr
+    # NormalizeAngle: [-pi, pi)
+    assert tr.normalize_angle(np.pi) == -np.pi and abs(tr.normalize_angle(3 * np.pi / 2) + np.pi / 2) < 1e-15
+    # absolute(relative) round trip and a hand-computed composition: p1 = (1, 2, 90 deg), rel = (1, 0, 0) -> (1, 3, 90 deg)
+    p1, p2 = np.array([1.0, 2.0, np.pi / 2]), np.array([-3.0, 0.5, -2.0])
+    assert np.allclose(tr.compute_absolute_pose(p1, np.array([1.0, 0.0, 0.0])), [1.0, 3.0, np.pi / 2], atol=1e-15)
+    rel = tr.compute_relative_pose(p1, p2)
+    back = tr.compute_absolute_pose(p1, rel)
+    assert np.allclose(back[:2], p2[:2], atol=1e-14) and abs(wrap_pi(back[2] - p2[2])) < 1e-14
+    cam = _cam()
+    # ConvertCenterToPrincipal: no rotation -> unchanged; 180 deg -> + 2 * O_bias with O_bias = (W/2 - cx, H/2 - cy) = (-10, 5)
+    assert np.array_equal(cam.convert_center_to_principal(np.array([3.0, 4.0, 0.0])), [3.0, 4.0, 0.0])
+    assert np.allclose(cam.convert_center_to_principal(np.array([3.0, 4.0, np.pi])), [3.0 - 20.0, 4.0 + 10.0, np.pi], atol=1e-12)
+    # image plane -> camera -> robot: (80, 82, 0.3) -> (0.1, 0.1, 0.3) -> E * (0.05, 0.05, 0.3)
+    assert np.allclose(cam.image_plane_to_robot(np.array([80.0, 82.0, 0.3])), [-0.05 + 0.03, 0.05 + 0.06, 0.3], atol=1e-15)
+
+
+def test_tracker_keyframe_policy_with_scripted_poses():
+    """AddNewInput's control flow with ComputePose scripted: gate, c1..c4, tracking against the LAST KEYFRAME, stale state on a
+    lost frame (map_builder.cc:42-57)."""
+    import tracker_ref as tr
+    script = [  # (response, pose_center) returned by ComputePose for frames 1..
+        ((150.0, 150.0, 120.0), (4.0, 0.0, 0.0)),     # small motion, confident: not a keyframe
+        ((150.0, 150.0, 120.0), (20.0, 0.0, 0.0)),    # 20 px / 800 = 0.025 > max_distance 0.02: keyframe
+        ((10.0, 10.0, 120.0), (3.0, 3.0, 0.0)),       # lost (response(0) < 30): state stays
+        ((150.0, 150.0, 50.0), (1.0, 0.0, 0.0)),      # response(2) inside (30, 90): keyframe by c4
+        ((150.0, 150.0, 120.0), (0.0, 0.0, 0.05)),    # rotation 0.05 > max_angle 0.03: keyframe by c2
+    ]
+    it = iter(script)
+    trk = tr.MapBuilderTracker(_cam(cx=320.0, cy=240.0), 0.02, 0.03, 30.0, 90.0, lambda img: (None, None), lambda *a: next(it))
+    outs = [trk.add_new_input(None) for _ in range(6)]
+    assert [o["inserted"] for o in outs] == [True, False, True, False, True, True]
+    assert [o["tracked"] for o in outs] == [True, True, True, False, True, True]
+    assert [o["keyframe"] for o in outs] == [-1, 0, 0, 2, 2, 4]
+    assert np.allclose(outs[1]["cf_pose"], [4, 0, 0]) and np.allclose(outs[2]["cf_pose"], [20, 0, 0])     # both against keyframe 0
+    assert np.allclose(outs[3]["cf_pose"], [20, 0, 0])                                                    # lost: stale
+    assert np.allclose(outs[4]["cf_pose"], [21, 0, 0]) and np.allclose(outs[5]["cf_pose"], [21, 0, 0.05])
+    assert abs(outs[5]["distance"] - (0.025 + 1 / 800)) < 1e-15
+    # robot pose: extrinsics rotate by +90 deg, scale by height 0.5: cf (21, 0) px -> camera (0.02625, 0) -> robot delta (0, 0.013125)
+    assert np.allclose(outs[4]["pose"][:2] - outs[0]["pose"][:2], [0.0, 0.5 * 21 / 800], atol=1e-15)
