@@ -301,7 +301,8 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per step (stream length)")
     ap.add_argument("--batch", type=int, default=0, help="pairs in flight per kernel launch (0 = library default)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent CUDA streams the batches are dealt to (0 = library default)")
-    ap.add_argument("--db", type=int, default=4096, help="loop-closure keyframes PER GPU (0 = skip the scan section)")
+    ap.add_argument("--db", type=int, default=-1, help="loop-closure keyframes PER GPU (0 = skip the scan section; -1 = BASELINE configs: 10k on one GPU, "
+                                                     "100k sharded over N GPUs, capped by free HBM)")
     ap.add_argument("--queries", type=int, default=5)
     ap.add_argument("--ref-frames", type=int, default=129, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=129, help="frames of the cpu_baseline sample (0 = skip)")
@@ -466,15 +467,31 @@ def main():
 
     # ---- loop-closure scan: DB sharded by index over ranks, one NCCL all-gather of the per-rank best records
     loop = None
-    if args.db > 0:
+    if args.db != 0:
         lc = nis.LoopClosure(nis.LoopClosureConfig(position_response_thr=60, angle_response_thr=60), cf)
         nshard = args.db
+        db_note = "--db"
+        if nshard < 0:
+            # BASELINE.json configs[2] (1 query vs 10k keyframes, 1 GPU) / configs[3] (100k keyframes sharded over the GPUs); a keyframe
+            # record (F, P, Ht, Hp) is 5.24 MB, so 2 GPUs cannot hold 100k: the shard is capped by free HBM and the total reported
+            want = 10000 if world == 1 else -(-100000 // world)
+            free_b = torch.cuda.mem_get_info(dev)[0]
+            cap = int(0.7 * free_b / (2 * BYTES_PER_CANDIDATE + H * W))
+            if world > 1:
+                tcap = torch.tensor([cap], dtype=torch.int64, device=dev)
+                dist.all_reduce(tcap, op=dist.ReduceOp.MIN)
+                cap = int(tcap.item())
+            nshard = max(64, min(want, cap))
+            db_note = "configs[2]: 10k keyframes on one GPU" if world == 1 else (
+                "configs[3]: 100k keyframes over %d GPUs" % world if nshard == want else
+                "configs[3] capped by HBM: %d of 100k keyframes fit %d GPUs (5.24 MB per keyframe record)" % (nshard * world, world))
         gcx, gcy, gang = bs.db_poses(nshard * world, seed=1)
-        sl = slice(rank * nshard, (rank + 1) * nshard)
-        db_imgs = bs.crops(canvas, gcx[sl], gcy[sl], gang[sl], H, W)
-        ids = np.arange(rank * nshard, (rank + 1) * nshard, dtype=np.int32)
-        lc.AddImages(None, ids, None, ptr=db_imgs.data_ptr(), n=nshard, on_device=True)
-        del db_imgs
+        for c0 in range(0, nshard, 2048):                                  # keyframes are generated and added in chunks (bounded temporaries)
+            c1 = min(nshard, c0 + 2048)
+            g0 = rank * nshard
+            db_imgs = bs.crops(canvas, gcx[g0 + c0:g0 + c1], gcy[g0 + c0:g0 + c1], gang[g0 + c0:g0 + c1], H, W)
+            lc.AddImages(None, np.arange(g0 + c0, g0 + c1, dtype=np.int32), None, ptr=db_imgs.data_ptr(), n=c1 - c0, on_device=True)
+            del db_imgs
         jstar = (nshard * world) // 2 + 3                                  # expected winner (global id)
         q_img = bs.crops(canvas, [gcx[jstar] + 13], [gcy[jstar] - 7], [gang[jstar] + 4.5], H, W)
         nbytes = C.sizeof(nis.LoopResultC)
@@ -525,7 +542,7 @@ def main():
             dth = np.deg2rad(qa - gang[w])
             winner_ok = bool(abs((res.relative_pose[2] - dth + np.pi) % (2 * np.pi) - np.pi) < np.deg2rad(0.75) and
                              abs(np.hypot(res.relative_pose[0], res.relative_pose[1]) - np.hypot(qx - gcx[w], qy - gcy[w])) < 2.0)
-        loop = {"metric": "loop_closure_queries_per_sec", "db_keyframes": nshard * world, "keyframes_per_gpu": nshard,
+        loop = {"metric": "loop_closure_queries_per_sec", "db_keyframes": nshard * world, "keyframes_per_gpu": nshard, "workload": db_note,
                 "value": 1e3 / q_ms, "unit": "queries/s", "ms_per_query": q_ms, "ms_per_query_all": [round(x, 3) for x in per_query], "candidates_per_sec": cand_per_s,
                 "queries_per_sec_over_100k_extrapolated": cand_per_s / 1e5, "winner_frame_id": int(res.loop_frame_id),
                 "planted_frame_id": int(jstar), "found": bool(res.found), "relative_pose": [float(x) for x in res.relative_pose],

@@ -73,6 +73,7 @@ struct nis_ctx {
   int active_lanes = 1;            // lanes batches are dealt to (<= lanes.size())
   cudaStream_t prof_stream = nullptr;
   cudaEvent_t fork_ev = nullptr;
+  std::vector<void*> frame_pool;               // freed nis_frame blocks, reused by the next frame_alloc
   cudaStream_t copy_stream = nullptr;          // host->device uploads of a stream run back to back here, ahead of the compute lanes
   std::vector<cudaEvent_t> up_ev, feat_ev;     // per batch of a stream: upload done / features done
   nis_cf_config cfg{};
@@ -641,6 +642,7 @@ int nis_destroy(nis_ctx* ctx) {
   }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (void* b : ctx->frame_pool) cudaFree(b);
   for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->feat_ev) cudaEventDestroy(e);
   for (void* c : ctx->chunks) cudaFree(c);
@@ -674,8 +676,15 @@ static int frame_alloc(nis_ctx* ctx, bool u8, nis_frame** out) {
   nis_frame* f = new nis_frame();
   const size_t bF = ctx->sz[0].spec * sizeof(cpx), bP = ctx->sz[1].spec * sizeof(cpx);
   const size_t bI = ctx->sz[0].real * (u8 ? 1 : sizeof(float));
-  cudaError_t e = cudaMalloc(&f->block, 2 * (bF + bP) + bI);
-  if (e != cudaSuccess) { delete f; return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc frame", (int)e); }
+  // every frame block has room for an f32 image, so freed blocks are interchangeable and come back from a small pool: cudaMalloc /
+  // cudaFree per frame cost up to hundreds of ms next to a large keyframe store (measured), the per-frame MapBuilder loop hits both
+  if (!ctx->frame_pool.empty()) {
+    f->block = ctx->frame_pool.back();
+    ctx->frame_pool.pop_back();
+  } else {
+    cudaError_t e = cudaMalloc(&f->block, 2 * (bF + bP) + ctx->sz[0].real * sizeof(float));
+    if (e != cudaSuccess) { delete f; return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc frame", (int)e); }
+  }
   char* p = (char*)f->block;
   f->F = (cpx*)p; f->P = (cpx*)(p + bF); f->Ht = (cpx*)(p + bF + bP); f->Hp = (cpx*)(p + 2 * bF + bP);
   if (u8) f->img_u8 = (uint8_t*)(p + 2 * (bF + bP)); else f->img_f32 = (float*)(p + 2 * (bF + bP));
@@ -686,7 +695,10 @@ static int frame_alloc(nis_ctx* ctx, bool u8, nis_frame** out) {
 int nis_frame_free(nis_ctx* ctx, nis_frame* f) {
   if (!f) return NIS_OK;
   if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  if (f->block) cudaFree(f->block);
+  if (f->block) {
+    if (ctx && ctx->frame_pool.size() < 16) ctx->frame_pool.push_back(f->block);
+    else cudaFree(f->block);
+  }
   delete f;
   return NIS_OK;
 }
@@ -942,7 +954,8 @@ int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, 
   TRY(ensure_pinned(ctx, (size_t)B * sizeof(PoseRecord)));
   cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
   cpx* Ht = ctx->sHt.as<cpx>(); cpx* Hp = ctx->sHp.as<cpx>();
-  // features of every frame (no keyframe factors yet: only frames that become keyframes need H), uploads on the copy stream
+  // features AND keyframe factors H of every frame in full batches (any frame may become a keyframe; one frame's H computed on demand
+  // inside the sequential loop below would cost six latency-bound launches per keyframe), uploads on the copy stream
   const int nbatch = (n + B - 1) / B;
   while ((int)ctx->up_ev.size() < nbatch) {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -967,20 +980,14 @@ int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, 
     if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
     TRY(features_batch(ctx, L, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
                        Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
-                       Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, false));
+                       Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));
   }
   TRY(join_lanes(ctx));
   Lane& L0 = ctx->lanes[0];
-  auto keyframe_factors = [&](int K) -> int {       // H = T/(Kzz+lambda) of both stages for keyframe K (correlation_flow.cc:157-171)
-    TRY(ensure_workspace(ctx, L0, 1));
-    TRY(hzz_batch(ctx, L0, 0, src_slab<cpx>(F + (size_t)K * spt, (long long)spt), 1, Dst<cpx>{Ht + (size_t)K * spt, (long long)spt}));
-    return hzz_batch(ctx, L0, 1, src_slab<cpx>(P + (size_t)K * spp, (long long)spp), 1, Dst<cpx>{Hp + (size_t)K * spp, (long long)spp});
-  };
   pose::TrackerState st;
   pose::initialize(*cam, st, out[0]);
   pose::snapshot(st, out[0]);
   int K = 0;
-  TRY(keyframe_factors(K));
   int t = 1, spec = std::min(B, 8), since_kf = 0;
   while (t < n) {
     const int nb = std::min(spec, n - t);
@@ -1004,7 +1011,6 @@ int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, 
         used = i + 1;
         spec = std::max(4, std::min(B, 2 * since_kf));
         since_kf = 0;
-        if (K + 1 < n) TRY(keyframe_factors(K));
         break;
       }
     }
