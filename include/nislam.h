@@ -147,6 +147,28 @@ typedef struct {
 int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, const nis_kfs_config* kfs,
                                const nis_camera_model* cam, nis_track_result* out /* n records */);
 
+/* ---- MapStitcher (src/map_stitcher.cc, include/map_stitcher.h): the occupancy mosaic of keyframe images.  InsertFrame (:14-22:
+ *      image * 100/255 as u8, kept for later) + AddImageToOccupancy (:36-133: every pixel lands on the integer ground position
+ *      (int)(R (i - W/2, j - H/2) + t), truncated toward zero; per-frame sums and counts are merged into the cells with the
+ *      reference's integer rules, including storing the raw per-frame SUM when a cell is first created) and RecomputeOccupancy
+ *      (:135-145) after a pose-graph optimisation.  The reference keeps an unbounded hash of cell_size x cell_size cells; here the
+ *      cells live in a dense window [cell_x0, cell_x0 + cells_x) x [cell_y0, cell_y0 + cells_y) in HBM, pixels outside it are counted
+ *      (nis_stitcher_dropped) and otherwise ignored.  Frames are replayed in insertion order by nis_stitcher_recompute (the reference
+ *      iterates an unordered_map keyed by pointer, i.e. in no defined order, although its merge rule is order dependent). ---- */
+typedef struct nis_stitcher nis_stitcher;
+int nis_stitcher_create(int device, int image_height, int image_width, int cell_size, int cell_x0, int cell_y0, int cells_x, int cells_y,
+                        nis_stitcher** out);
+int nis_stitcher_destroy(nis_stitcher* st);
+/* InsertFrame(frame, image): image = the undistorted u8 frame (host, row-major H x W), robot_pose = Frame::GetPose */
+int nis_stitcher_insert(nis_stitcher* st, const uint8_t* image_u8, const double robot_pose[3], const nis_camera_model* cam, int* frame_slot);
+/* RecomputeOccupancy with the poses after optimisation: robot_poses = frames x 3 doubles in insertion order */
+int nis_stitcher_recompute(nis_stitcher* st, const double* robot_poses, const nis_camera_model* cam);
+int nis_stitcher_frames(const nis_stitcher* st);
+/* one cell of GetOccupancyData(): data / weight = cell_size x cell_size int32, [in-cell y][in-cell x]; *present = 0 when the cell was
+ * never created (buffers untouched) */
+int nis_stitcher_cell(nis_stitcher* st, int cell_x, int cell_y, int32_t* data, int32_t* weight, int* present);
+int nis_stitcher_dropped(nis_stitcher* st, long long* pixels_outside_window);
+
 /* ---- keyframe database = Map::AddFrame for the arrays the scan reads (include/frame.h:35-36, src/map.cc) ---- */
 int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distance, int* slot);
 /* bulk insert: n u8 images (host or device), features computed on the GPU straight into the DB */

@@ -28,7 +28,8 @@ SYMBOLS = [
     "nis_set_undistort_maps", "nis_undistort_u8", "nis_compute_pose", "nis_track_stream", "nis_track_stream_dev", "nis_track_stream_keyframes", "nis_db_add", "nis_db_add_images",
     "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_db_set_position", "nis_loop_scan_prior", "nis_debug_fft2",
     "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
-    "nis_profile_end",
+    "nis_profile_end", "nis_stitcher_create", "nis_stitcher_destroy", "nis_stitcher_insert", "nis_stitcher_recompute",
+    "nis_stitcher_frames", "nis_stitcher_cell", "nis_stitcher_dropped",
 ]
 
 
@@ -151,6 +152,13 @@ def load_library():
     lib.nis_set_batch.argtypes = [vp, i32]
     lib.nis_set_lanes.argtypes = [vp, i32]
     lib.nis_track_stream_keyframes.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.nis_stitcher_create.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    lib.nis_stitcher_destroy.argtypes = [vp]
+    lib.nis_stitcher_insert.argtypes = [vp, vp, vp, vp, vp]
+    lib.nis_stitcher_recompute.argtypes = [vp, vp, vp]
+    lib.nis_stitcher_frames.argtypes = [vp]
+    lib.nis_stitcher_cell.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.nis_stitcher_dropped.argtypes = [vp, vp]
     lib.nis_features_u8.argtypes = [vp, vp, C.POINTER(vp)]
     lib.nis_features_f32.argtypes = [vp, vp, C.POINTER(vp)]
     lib.nis_frame_export.argtypes = [vp, vp, vp, vp]
@@ -472,6 +480,63 @@ class LoopClosure:
     def Reduce(self, per_rank, order=None):
         """Multi-GPU: pick the winner among per-rank results with the reference's rule (strict '>', first wins)."""
         return loop_reduce(per_rank, order, self._loop_thr)
+
+
+class MapStitcher:
+    """MapStitcher (include/map_stitcher.h:24-41) on the GPU: InsertFrame / RecomputeOccupancy / GetOccupancyData over a dense window
+    of cells [cell_x0, cell_x0 + cells_x) x [cell_y0, cell_y0 + cells_y)."""
+
+    def __init__(self, cell_size: int, cam: CameraModel, image_height: int, image_width: int, cell_x0: int = -2, cell_y0: int = -2,
+                 cells_x: int = 4, cells_y: int = 4, device: int = 0):
+        self._lib = load_library()
+        self._st = C.c_void_p()
+        self.cs, self.H, self.W = int(cell_size), int(image_height), int(image_width)
+        self._cam = _CameraModelC(cam.fx, cam.fy, cam.cx, cam.cy, cam.height, (C.c_double * 9)(*cam.extrinsics))
+        self._check(self._lib.nis_stitcher_create(device, self.H, self.W, self.cs, cell_x0, cell_y0, cells_x, cells_y, C.byref(self._st)))
+
+    def _check(self, status):
+        if status != 0:
+            raise NisError(status, self._lib.nis_strerror(status).decode())
+
+    def InsertFrame(self, image_u8, robot_pose) -> int:
+        img = np.ascontiguousarray(image_u8, np.uint8)
+        assert img.shape == (self.H, self.W)
+        pose = (C.c_double * 3)(*[float(v) for v in robot_pose])
+        slot = C.c_int(-1)
+        self._check(self._lib.nis_stitcher_insert(self._st, _p(img), pose, C.byref(self._cam), C.byref(slot)))
+        return slot.value
+
+    def RecomputeOccupancy(self, robot_poses):
+        poses = np.ascontiguousarray(robot_poses, np.float64).reshape(-1, 3)
+        assert poses.shape[0] == self.frames()
+        self._check(self._lib.nis_stitcher_recompute(self._st, _p(poses), C.byref(self._cam)))
+
+    def frames(self) -> int:
+        return int(self._lib.nis_stitcher_frames(self._st))
+
+    def cell(self, cell_x: int, cell_y: int):
+        """-> (data, weight) int32 [cs, cs] indexed [in-cell y, in-cell x], or None when the cell does not exist."""
+        data = np.zeros((self.cs, self.cs), np.int32)
+        weight = np.zeros((self.cs, self.cs), np.int32)
+        present = C.c_int(0)
+        self._check(self._lib.nis_stitcher_cell(self._st, cell_x, cell_y, _p(data), _p(weight), C.byref(present)))
+        return (data, weight) if present.value else None
+
+    def dropped(self) -> int:
+        v = C.c_longlong(0)
+        self._check(self._lib.nis_stitcher_dropped(self._st, C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if self._st:
+            self._lib.nis_stitcher_destroy(self._st)
+            self._st = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def loop_reduce(per_rank, order, loop_cfg: LoopClosureConfig):

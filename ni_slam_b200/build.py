@@ -2,7 +2,7 @@
 
     python -m ni_slam_b200.build [--force]
 
-The four translation units are compiled in parallel; the shared object links the static CUDA runtime so it has no
+The five translation units are compiled in parallel; the shared object links the static CUDA runtime so it has no
 dependency beyond the driver.
 """
 from __future__ import annotations
@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libnislam.so")
-UNITS = ["nis_col.cu", "nis_row.cu", "nis_misc.cu", "nis_api.cu"]
+UNITS = ["nis_col.cu", "nis_row.cu", "nis_misc.cu", "nis_api.cu", "nis_stitch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--threads", "4"]
 

@@ -40,6 +40,28 @@ inline P3 camera_to_robot(const nis_camera_model& cam, const P3& p) {
 }
 inline P3 image_plane_to_robot(const nis_camera_model& cam, const P3& p) { return camera_to_robot(cam, image_plane_to_camera(cam, p)); }
 
+// Camera::ConvertRobotPoseToImagePlane (src/camera.cc:211-222, :177-194, :233-241) and ConvertPrincipalToCenter (:136-146): the pose
+// MapStitcher::AddImageToOccupancy places an image with (map_stitcher.cc:38-41)
+inline void inverse3(const double* E, double* I) {       // cofactor inverse, like Eigen's fixed-size 3x3 inverse()
+  const double c00 = E[4] * E[8] - E[5] * E[7], c01 = E[5] * E[6] - E[3] * E[8], c02 = E[3] * E[7] - E[4] * E[6];
+  const double det = E[0] * c00 + E[1] * c01 + E[2] * c02, id = 1.0 / det;
+  I[0] = c00 * id; I[1] = (E[2] * E[7] - E[1] * E[8]) * id; I[2] = (E[1] * E[5] - E[2] * E[4]) * id;
+  I[3] = c01 * id; I[4] = (E[0] * E[8] - E[2] * E[6]) * id; I[5] = (E[2] * E[3] - E[0] * E[5]) * id;
+  I[6] = c02 * id; I[7] = (E[1] * E[6] - E[0] * E[7]) * id; I[8] = (E[0] * E[4] - E[1] * E[3]) * id;
+}
+inline P3 robot_to_image_plane(const nis_camera_model& cam, const P3& r) {
+  double I[9];
+  inverse3(cam.extrinsics, I);
+  P3 c{I[0] * r.x + I[1] * r.y + I[2] * r.th, I[3] * r.x + I[4] * r.y + I[5] * r.th, I[6] * r.x + I[7] * r.y + I[8] * r.th};
+  c.x /= cam.height; c.y /= cam.height;
+  return P3{cam.fx * c.x, cam.fy * c.y, c.th};
+}
+inline P3 principal_to_center(const nis_camera_model& cam, int W, int H, const P3& p) {   // p - (I - R(th)) O_bias
+  const double c = cos(p.th), s = sin(p.th);
+  const double ox = W * 0.5 - cam.cx, oy = H * 0.5 - cam.cy;
+  return P3{p.x - ((1.0 - c) * ox + s * oy), p.y - (-s * ox + (1.0 - c) * oy), p.th};
+}
+
 // MapBuilder state that AddNewInput carries from frame to frame (include/map_builder.h)
 struct TrackerState {
   bool init = false;

@@ -555,3 +555,58 @@ def test_track_stream_keyframes_matches_map_builder_restatement(cf, cfg):
     # a one-frame stream is just Initialize
     one = cf.TrackStreamKeyframes(frames[:1], kfs, cam)
     assert one.shape == (1,) and one[0]["inserted"] == 1 and one[0]["keyframe"] == -1
+
+
+# ------------------------------------------------------------------ MapStitcher (map_stitcher.cc): integer work, bit-exact
+def _stitch_compare(st_gpu, st_ref, x0, y0, nx, ny):
+    seen = 0
+    for cy in range(y0, y0 + ny):
+        for cx in range(x0, x0 + nx):
+            got = st_gpu.cell(cx, cy)
+            exp = st_ref.cells.get((cx, cy))
+            assert (got is None) == (exp is None), (cx, cy)
+            if got is not None:
+                assert np.array_equal(got[1], exp[1]), ("weight", cx, cy)
+                assert np.array_equal(got[0], exp[0]), ("data", cx, cy)
+                seen += 1
+    assert seen == len(st_ref.cells)
+
+
+def test_map_stitcher_bit_exact():
+    import ni_slam_b200 as nis
+    import stitcher_ref as sr
+    import tracker_ref as tr
+    rng = np.random.default_rng(5)
+    E = [0.6, -0.8, 0.05, 0.8, 0.6, -0.02, 0.0, 0.0, 1.0]
+    for (Hs, Ws, cs, nfr, spread) in ((96, 128, 50, 14, 0.12), (480, 640, 1000, 4, 0.9)):
+        camd = dict(fx=410.0, fy=395.0, cx=Ws / 2 - 3.5, cy=Hs / 2 + 2.25, height=0.8)
+        cam = nis.CameraModel(extrinsics=tuple(E), **camd)
+        ref = sr.MapStitcher(cs, tr.Camera(extrinsics=E, image_width=Ws, image_height=Hs, **camd))
+        gpu = nis.MapStitcher(cs, cam, Hs, Ws, cell_x0=-4, cell_y0=-4, cells_x=8, cells_y=8)
+        poses = []
+        for f in range(nfr):
+            img = rng.integers(0, 256, (Hs, Ws), dtype=np.uint8)
+            pose = [rng.uniform(-spread, spread), rng.uniform(-spread, spread), rng.uniform(-np.pi, np.pi)]
+            if f == 0:
+                pose = [0.0, 0.0, 0.0]                  # Initialize: exact integer ground positions
+            if f == 3:
+                pose = list(poses[2])                   # a revisit: every element of the footprint merges
+            poses.append(pose)
+            assert gpu.InsertFrame(img, pose) == f
+            ref.insert_frame(img, pose)
+        assert gpu.frames() == nfr and gpu.dropped() == 0
+        _stitch_compare(gpu, ref, -4, -4, 8, 8)
+        # RecomputeOccupancy after "optimisation": perturbed poses, frames replayed in insertion order
+        poses2 = [[p[0] + rng.normal(0, 0.01), p[1] + rng.normal(0, 0.01), p[2] + rng.normal(0, 0.02)] for p in poses]
+        gpu.RecomputeOccupancy(poses2)
+        ref.recompute_occupancy(poses2)
+        assert gpu.dropped() == 0
+        _stitch_compare(gpu, ref, -4, -4, 8, 8)
+        gpu.close()
+    # a window that is too small: pixels outside are counted, cells outside do not exist
+    cam = nis.CameraModel(fx=400.0, fy=400.0, cx=64.0, cy=48.0, height=1.0)
+    small = nis.MapStitcher(50, cam, 96, 128, cell_x0=0, cell_y0=0, cells_x=1, cells_y=1)
+    small.InsertFrame(np.full((96, 128), 255, np.uint8), [0.0, 0.0, 0.0])
+    d, w = small.cell(0, 0)
+    assert w.sum() == 50 * 48 and small.dropped() == 96 * 128 - 50 * 48 and small.cell(-1, 0) is None and d.max() == 100
+    small.close()

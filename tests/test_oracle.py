@@ -292,3 +292,47 @@ def test_tracker_keyframe_policy_with_scripted_poses():
     assert abs(outs[5]["distance"] - (0.025 + 1 / 800)) < 1e-15
     # robot pose: extrinsics rotate by +90 deg, scale by height 0.5: cf (21, 0) px -> camera (0.02625, 0) -> robot delta (0, 0.013125)
     assert np.allclose(outs[4]["pose"][:2] - outs[0]["pose"][:2], [0.0, 0.5 * 21 / 800], atol=1e-15)
+
+
+# ---------------------------------------------------------------- MapStitcher restatement (map_stitcher.cc) known answers
+def test_stitcher_scaling_matches_opencv():
+    """InsertFrame's `image * (100.0/255.0)` on a u8 cv::Mat = convertTo with a float alpha and cvRound; cv2.convertScaleAbs runs the
+    same scale-convert path (|.| is the identity on non-negative input)."""
+    import stitcher_ref as sr
+    v = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    ours = sr.normalize_image(v)
+    assert ours[0, 0] == 0 and ours[15, 15] == 100 and ours[7, 15] == 50          # 127 * 100/255 = 49.8 -> 50
+    cv2 = pytest.importorskip("cv2")
+    assert np.array_equal(ours, cv2.convertScaleAbs(v, alpha=100.0 / 255.0))
+
+
+def test_stitcher_known_answers():
+    import stitcher_ref as sr
+    import tracker_ref as tr
+    Hs, Ws, cs = 6, 8, 5
+    cam = tr.Camera(fx=2.0, fy=2.0, cx=Ws / 2, cy=Hs / 2, height=0.5, extrinsics=np.eye(3), image_width=Ws, image_height=Hs)
+    img = (np.arange(Hs * Ws, dtype=np.uint8).reshape(Hs, Ws) * 5)
+    st = sr.MapStitcher(cs, cam)
+    # robot pose (0.25, 0.5, 0): camera = pose / height = (0.5, 1), image plane = f * camera = (1, 2) px; the principal point is the centre
+    st.insert_frame(img, [0.25, 0.5, 0.0])
+    norm = sr.normalize_image(img).astype(np.int32)
+    # pixel (j, i) lands on x = trunc(i - 4 + 1), y = trunc(j - 3 + 2): x in [-3, 4], y in [-1, 4] -> cells x in {-1, 0}, y in {-1, 0}
+    assert set(st.cells) == {(-1, -1), (0, -1), (-1, 0), (0, 0)}
+    d, w = st.cells[(0, 0)]
+    assert w[0, 0] == 1 and d[0, 0] == norm[1, 3] and d[4, 4] == norm[5, 7]       # (x, y) = (0, 0) <- (i, j) = (3, 1); first insert: raw sums
+    d, w = st.cells[(-1, -1)]
+    assert d[4, 2] == norm[0, 0] and w[4, 2] == 1 and w.sum() == 3                # x = -3 -> cell -1, in-cell 2; y = -1 -> in-cell 4
+    # same frame again: existing cells merge as (data*weight + sum*count) / (weight + count) = (d + d) / 2 = d, weights double
+    st.insert_frame(img, [0.25, 0.5, 0.0])
+    d2, w2 = st.cells[(0, 0)]
+    assert np.array_equal(d2, st.cells[(0, 0)][0]) and w2[0, 0] == 2 and d2[0, 0] == norm[1, 3]
+    # truncation toward zero: a pose shifted by half a pixel (image plane x = 0.5) makes x = trunc(i - 4 + 0.5): -3.5 -> -3 and 0.5 -> 0,
+    # so the two source columns i = 3 and i = 4 collide on x = 0 (count 2, sum of both) and x = -3 ... 4 as before
+    st3 = sr.MapStitcher(cs, cam)
+    st3.insert_frame(img, [0.125, 0.5, 0.0])
+    d3, w3 = st3.cells[(0, 0)]
+    assert w3[0, 0] == 2 and d3[0, 0] == norm[1, 3] + norm[1, 4]
+    # recompute with the same poses reproduces the state; with a moved pose the mosaic moves
+    before = {k: (v[0].copy(), v[1].copy()) for k, v in st.cells.items()}
+    st.recompute_occupancy([[0.25, 0.5, 0.0], [0.25, 0.5, 0.0]])
+    assert all(np.array_equal(before[k][0], st.cells[k][0]) and np.array_equal(before[k][1], st.cells[k][1]) for k in before)
