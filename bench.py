@@ -465,6 +465,33 @@ def main():
     except Exception as e:                                   # a next-row extra must never take the headline down
         policy = {"error": str(e)[:200]}
 
+    # ---- next-row measurement: MapStitcher -- InsertFrame of keyframes into the occupancy mosaic, then one
+    # RecomputeOccupancy (what follows every pose-graph optimisation); integer work, HBM bound
+    stitch = None
+    try:
+        nst = 64
+        cam_s = nis.CameraModel(fx=1000.0, fy=1000.0, cx=W / 2, cy=H / 2, height=1.0)
+        ms_ = nis.MapStitcher(1000, cam_s, H, W, cell_x0=-3, cell_y0=-3, cells_x=6, cells_y=6, device=local_rank)
+        imgs_s = frames_host.numpy()[:nst]
+        rs = np.random.default_rng(3)
+        poses_s = np.stack([rs.uniform(-1.5, 1.5, nst), rs.uniform(-1.5, 1.5, nst), rs.uniform(-np.pi, np.pi, nst)], 1)
+        t0 = time.perf_counter()
+        for f in range(nst):
+            ms_.InsertFrame(imgs_s[f], poses_s[f])
+        t_ins = time.perf_counter() - t0
+        ms_.RecomputeOccupancy(poses_s)
+        t0 = time.perf_counter()
+        ms_.RecomputeOccupancy(poses_s)
+        t_rec = time.perf_counter() - t0
+        bytes_frame = H * W * (1 + 16)                       # u8 image in + read-modify-write of data and weight (2 x int32 x 2) per pixel
+        stitch = {"what": "MapStitcher: %d keyframes 640x480 into 1000x1000-cell mosaic; InsertFrame from host memory (synchronous per "
+                          "frame, like the reference) and RecomputeOccupancy from the stored images" % nst,
+                  "insert_frames_per_sec": nst / t_ins, "recompute_frames_per_sec": nst / t_rec,
+                  "recompute_algorithmic_GBps": nst / t_rec * bytes_frame / 1e9, "dropped_pixels": ms_.dropped()}
+        ms_.close()
+    except Exception as e:
+        stitch = {"error": str(e)[:200]}
+
     # ---- loop-closure scan: DB sharded by index over ranks, one NCCL all-gather of the per-rank best records
     loop = None
     if args.db != 0:
@@ -585,7 +612,7 @@ def main():
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": n * H * W,
                         "d2h_bytes_per_step": (n - 1) * 72},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "loop_closure": loop, "undistort_front_end": front, "keyframe_policy": policy,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "loop_closure": loop, "undistort_front_end": front, "keyframe_policy": policy, "map_stitcher": stitch,
                 "pose_ok_frac": pose_ok_frac}
         emit(line)
     cf.close()
