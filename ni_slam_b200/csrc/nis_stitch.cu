@@ -1,6 +1,6 @@
 // nis_stitch.cu -- MapStitcher on the GPU (src/map_stitcher.cc:14-145): the occupancy mosaic of keyframe images, sm_100a.
-// Integer / byte work bound by HBM: per frame one u8 image in, its bounding box of per-frame sums / counts (two int32 planes) zeroed,
-// scattered with atomics and merged into the dense cell window with the reference's integer rules.
+// Integer / byte work: per frame one u8 image in, per-frame (sum, count) pairs scattered with one 64-bit atomic per pixel into the
+// frame's bounding box (which the merge kernel leaves zeroed again), merged into the dense cell window with the reference's integer rules.
 //   stitch_normalize_kernel : InsertFrame's  image * (100.0 / 255.0)  as u8 (cv::Mat scaling: float multiply, round half to even)
 //   stitch_scatter_kernel   : the pixel loop of AddImageToOccupancy (:95-111): x = (int)(Wx(i) + Hx(j)), y = (int)(Wy(i) + Hy(j))
 //   stitch_merge_kernel     : the per-cell merge (:113-132), element-wise; untouched elements are provably unchanged by it
@@ -38,14 +38,18 @@ __device__ __forceinline__ void ground_xy(const PlaceArgs& a, int i, int j, int&
   y = __double2int_rz(__dadd_rn(wy, hy));
 }
 
-__global__ void stitch_scatter_kernel(const uint8_t* __restrict__ img, int H, int W, PlaceArgs a, int* __restrict__ tsum, int* __restrict__ tcnt) {
+// also commits the PREVIOUS frame's touched cells (this kernel does not read `present`; the merge kernel that does runs after it)
+__global__ void stitch_scatter_kernel(const uint8_t* __restrict__ img, int H, int W, PlaceArgs a, unsigned long long* __restrict__ tbox,
+                                      int* __restrict__ present, int* __restrict__ touched, int ncells) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (j == 0)
+    for (int c = i; c < ncells; c += gridDim.x * blockDim.x)
+      if (touched[c]) { present[c] = 1; touched[c] = 0; }
   if (i >= W) return;
   int x, y;
   ground_xy(a, i, j, x, y);
   const int b = (y - a.min_y) * a.bw + (x - a.min_x);
-  atomicAdd(&tsum[b], (int)img[(size_t)j * W + i]);
-  atomicAdd(&tcnt[b], 1);
+  atomicAdd(&tbox[b], ((unsigned long long)img[(size_t)j * W + i] << 32) | 1ull);      // per-frame (sum, count) in one 64-bit atomic
 }
 
 __device__ __forceinline__ int cell_of(int x, int cs, int& in) {      // ComputeCellPosition (:24-34): floor division
@@ -54,14 +58,15 @@ __device__ __forceinline__ int cell_of(int x, int cs, int& in) {      // Compute
   return c;
 }
 
-__global__ void stitch_merge_kernel(PlaceArgs a, const int* __restrict__ tsum, const int* __restrict__ tcnt, int cs, int cell_x0, int cell_y0,
+__global__ void stitch_merge_kernel(PlaceArgs a, unsigned long long* __restrict__ tbox, int cs, int cell_x0, int cell_y0,
                                     int cells_x, int cells_y, int* __restrict__ data, int* __restrict__ weight, const int* __restrict__ present,
                                     int* __restrict__ touched, unsigned long long* __restrict__ dropped) {
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   if (bx >= a.bw) return;
-  const int cnt = tcnt[by * a.bw + bx];
+  const unsigned long long t = tbox[by * a.bw + bx];
+  const int cnt = (int)(unsigned)(t & 0xffffffffull), sum = (int)(unsigned)(t >> 32);
   if (cnt == 0) return;                           // untouched elements: (d*w + 0*0)/w = d for w >= 1, and d = 0 where w = 0
-  const int sum = tsum[by * a.bw + bx];
+  tbox[by * a.bw + bx] = 0ull;                    // the box is all zero again for the next frame: no per-frame memset
   int inx, iny;
   const int ccx = cell_of(a.min_x + bx, cs, inx) - cell_x0, ccy = cell_of(a.min_y + by, cs, iny) - cell_y0;
   if (ccx < 0 || ccy < 0 || ccx >= cells_x || ccy >= cells_y) { atomicAdd(dropped, (unsigned long long)cnt); return; }
@@ -90,7 +95,7 @@ __global__ void stitch_commit_kernel(int* __restrict__ present, int* __restrict_
 struct nis_stitcher {
   int device = 0, H = 0, W = 0, cs = 0, cell_x0 = 0, cell_y0 = 0, cells_x = 0, cells_y = 0;
   int* data = nullptr; int* weight = nullptr; int* present = nullptr; int* touched = nullptr;
-  int* tsum = nullptr; int* tcnt = nullptr; size_t tcap = 0;
+  unsigned long long* tbox = nullptr; size_t tcap = 0;   // per-frame (sum << 32 | count) over the frame's bounding box
   unsigned long long* dropped = nullptr;
   uint8_t* staging = nullptr;
   std::vector<uint8_t*> chunks;        // normalised images, kFramesPerChunk per allocation (_raw_images)
@@ -103,6 +108,12 @@ static const int kFramesPerChunk = 256;
 
 static const uint8_t* frame_ptr(const nis_stitcher* st, int slot) {
   return st->chunks[slot / kFramesPerChunk] + (size_t)(slot % kFramesPerChunk) * st->H * st->W;
+}
+
+static cudaError_t commit(nis_stitcher* st) {      // cells touched by the last frame exist from now on
+  const int nc = st->cells_x * st->cells_y;
+  stitch_commit_kernel<<<(nc + 255) / 256, 256, 0, st->stream>>>(st->present, st->touched, nc);
+  return cudaGetLastError();
 }
 
 // AddImageToOccupancy(frame) for the stored image `slot` placed at `robot_pose`
@@ -127,18 +138,16 @@ static int add_image(nis_stitcher* st, int slot, const double robot_pose[3], con
   a.bw = *std::max_element(xs, xs + 4) - a.min_x + 1; a.bh = *std::max_element(ys, ys + 4) - a.min_y + 1;
   const size_t need = (size_t)a.bw * a.bh;
   if (need > st->tcap) {
-    if (st->tsum) { cudaFree(st->tsum); cudaFree(st->tcnt); st->tsum = st->tcnt = nullptr; st->tcap = 0; }
-    SCU(cudaMalloc(&st->tsum, need * sizeof(int)));
-    SCU(cudaMalloc(&st->tcnt, need * sizeof(int)));
+    SCU(cudaStreamSynchronize(st->stream));
+    if (st->tbox) { cudaFree(st->tbox); st->tbox = nullptr; st->tcap = 0; }
+    SCU(cudaMalloc(&st->tbox, need * sizeof(unsigned long long)));
+    SCU(cudaMemsetAsync(st->tbox, 0, need * sizeof(unsigned long long), st->stream));     // zeroed once; the merge kernel restores the zeros it consumed
     st->tcap = need;
   }
-  SCU(cudaMemsetAsync(st->tsum, 0, need * sizeof(int), st->stream));
-  SCU(cudaMemsetAsync(st->tcnt, 0, need * sizeof(int), st->stream));
-  stitch_scatter_kernel<<<dim3((W + 255) / 256, H), 256, 0, st->stream>>>(frame_ptr(st, slot), H, W, a, st->tsum, st->tcnt);
-  stitch_merge_kernel<<<dim3((a.bw + 255) / 256, a.bh), 256, 0, st->stream>>>(a, st->tsum, st->tcnt, st->cs, st->cell_x0, st->cell_y0, st->cells_x,
-                                                                              st->cells_y, st->data, st->weight, st->present, st->touched, st->dropped);
   const int nc = st->cells_x * st->cells_y;
-  stitch_commit_kernel<<<(nc + 255) / 256, 256, 0, st->stream>>>(st->present, st->touched, nc);
+  stitch_scatter_kernel<<<dim3((W + 255) / 256, H), 256, 0, st->stream>>>(frame_ptr(st, slot), H, W, a, st->tbox, st->present, st->touched, nc);
+  stitch_merge_kernel<<<dim3((a.bw + 255) / 256, a.bh), 256, 0, st->stream>>>(a, st->tbox, st->cs, st->cell_x0, st->cell_y0, st->cells_x,
+                                                                              st->cells_y, st->data, st->weight, st->present, st->touched, st->dropped);
   SCU(cudaGetLastError());
   return NIS_OK;
 }
@@ -173,7 +182,7 @@ int nis_stitcher_destroy(nis_stitcher* st) {
   if (!st) return NIS_OK;
   cudaSetDevice(st->device);
   if (st->stream) cudaStreamSynchronize(st->stream);
-  void* bufs[] = {st->data, st->weight, st->present, st->touched, st->tsum, st->tcnt, st->dropped, st->staging};
+  void* bufs[] = {st->data, st->weight, st->present, st->touched, st->tbox, st->dropped, st->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   for (uint8_t* c : st->chunks) cudaFree(c);
   if (st->stream) cudaStreamDestroy(st->stream);
@@ -196,6 +205,7 @@ int nis_stitcher_insert(nis_stitcher* st, const uint8_t* image_u8, const double 
   st->frames = slot + 1;
   const int rc = add_image(st, slot, robot_pose, cam);
   if (rc != NIS_OK) return rc;
+  SCU(commit(st));
   SCU(cudaStreamSynchronize(st->stream));          // the caller's image buffer is free again, like the reference's synchronous call
   if (frame_slot) *frame_slot = slot;
   return NIS_OK;
@@ -208,11 +218,13 @@ int nis_stitcher_recompute(nis_stitcher* st, const double* robot_poses, const ni
   SCU(cudaMemsetAsync(st->data, 0, n * sizeof(int), st->stream));            // _occupancy_data.clear() (:137)
   SCU(cudaMemsetAsync(st->weight, 0, n * sizeof(int), st->stream));
   SCU(cudaMemsetAsync(st->present, 0, nc * sizeof(int), st->stream));
+  SCU(cudaMemsetAsync(st->touched, 0, nc * sizeof(int), st->stream));
   SCU(cudaMemsetAsync(st->dropped, 0, sizeof(unsigned long long), st->stream));
   for (int f = 0; f < st->frames; ++f) {
     const int rc = add_image(st, f, robot_poses + 3 * f, cam);
     if (rc != NIS_OK) return rc;
   }
+  SCU(commit(st));
   SCU(cudaStreamSynchronize(st->stream));
   return NIS_OK;
 }
