@@ -4,10 +4,14 @@
 #include "nis_internal.h"
 #include "nis_sizes.h"
 
+#ifndef NIS_ROW_THREADS_PER_SM
+#define NIS_ROW_THREADS_PER_SM 1024     // resident row-pass threads per SM the register budget is sized for (64 registers / thread)
+#endif
+
 namespace nis {
 
 template <int N, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
-__global__ void __launch_bounds__(T, (T <= 256 ? 1024 / T : 1)) row_kernel(Pro pro, Epi epi, Twiddles twd, int nrows, int total_lines) {
+__global__ void __launch_bounds__(T, (T <= 256 ? NIS_ROW_THREADS_PER_SM / T : 1)) row_kernel(Pro pro, Epi epi, Twiddles twd, int nrows, int total_lines) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
   const int tid = threadIdx.x, line0 = blockIdx.x * L;
@@ -28,7 +32,7 @@ __global__ void __launch_bounds__(T, (T <= 256 ? 1024 / T : 1)) row_kernel(Pro p
 // fused forward row pass -> element-wise -> inverse row pass: K^xz, X = FFT(rotated image) and the filtered spectrum G
 // exist only in registers / shared memory.  Two padded line buffers (the inverse stage 0 cannot run in place).
 template <int N, int R1, int R2, int L, int T, class Mid>
-__global__ void __launch_bounds__(T, (T <= 256 ? 1024 / T : 1)) rowrow_kernel(Src<cpx> in, Dst<cpx> out, Mid mid, Twiddles twd, int nrows, int total_lines) {
+__global__ void __launch_bounds__(T, (T <= 256 ? NIS_ROW_THREADS_PER_SM / T : 1)) rowrow_kernel(Src<cpx> in, Dst<cpx> out, Mid mid, Twiddles twd, int nrows, int total_lines) {
   typedef RowGeom<N, R1, R2, L, T> Gm;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* bufA = reinterpret_cast<cpx*>(smem_raw);
