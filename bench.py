@@ -121,7 +121,7 @@ def cpu_frames(n, seed=0):
 def time_oracle_stream(frames, threads):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c as oc
-    cfg = oc.make_cfg()
+    cfg = oc.make_cfg(height=H, width=W)
     t0 = time.perf_counter()
     oc.track_stream(cfg, frames, threads=threads)
     dt = time.perf_counter() - t0
@@ -257,12 +257,12 @@ def run_reference(args, rank):
         pool.join()
     ms = 1e3 * float(np.mean(times))
     value = (n - 1) / (ms / 1e3)
-    sample = "%d-frame 640x480 stream (%d solves) per step, %s, %d threads; warm-up solves/s of both restatements: %s" % (
+    sample = "%d-frame stream (%d solves) per step, %s, %d threads; warm-up solves/s of both restatements: %s" % (
         n, n - 1, label, threads, json.dumps(both))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "tracking stream 640x480 u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame",
+            "config": {"workload": "tracking stream %dx%d u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame" % (W, H),
                        "frames_per_step": n, "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial"},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -291,6 +291,15 @@ def emit(line):
     out.flush()
 
 
+def set_size(size):
+    """Image geometry of the run (module globals: every helper reads them at call time)."""
+    global H, W, BYTES_PER_SOLVE, BYTES_PER_CANDIDATE, METRIC
+    W, H = (int(v) for v in size.lower().split("x"))
+    BYTES_PER_CANDIDATE = (H // 2 + 1) * W * 8 + (D // 2 + 1) * CP * 8
+    BYTES_PER_SOLVE = H * W + 2 * BYTES_PER_CANDIDATE
+    METRIC = "pose_solves_per_sec_%dx%d" % (W, H)
+
+
 def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
@@ -298,6 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="640x480", help="image size WxH: 640x480 (BASELINE configs[1..3], the headline) or 1280x960 (configs[4])")
     ap.add_argument("--frames", type=int, default=1000, help="frames per step (stream length)")
     ap.add_argument("--batch", type=int, default=0, help="pairs in flight per kernel launch (0 = library default)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent CUDA streams the batches are dealt to (0 = library default)")
@@ -307,6 +317,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=129, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=129, help="frames of the cpu_baseline sample (0 = skip)")
     args = ap.parse_args()
+    set_size(args.size)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -502,7 +513,8 @@ def main():
         if nshard < 0:
             # BASELINE.json configs[2] (1 query vs 10k keyframes, 1 GPU) / configs[3] (100k keyframes sharded over the GPUs); a keyframe
             # record (F, P, Ht, Hp) is 5.24 MB, so 2 GPUs cannot hold 100k: the shard is capped by free HBM and the total reported
-            want = 10000 if world == 1 else -(-100000 // world)
+            total = 100000 if (W, H) == (640, 480) else 50000            # configs[3] / configs[4]
+            want = 10000 if (world == 1 and total == 100000) else -(-total // world)
             free_b = torch.cuda.mem_get_info(dev)[0]
             cap = int(0.7 * free_b / (2 * BYTES_PER_CANDIDATE + H * W))
             if world > 1:
@@ -510,9 +522,13 @@ def main():
                 dist.all_reduce(tcap, op=dist.ReduceOp.MIN)
                 cap = int(tcap.item())
             nshard = max(64, min(want, cap))
-            db_note = "configs[2]: 10k keyframes on one GPU" if world == 1 else (
-                "configs[3]: 100k keyframes over %d GPUs" % world if nshard == want else
-                "configs[3] capped by HBM: %d of 100k keyframes fit %d GPUs (5.24 MB per keyframe record)" % (nshard * world, world))
+            if nshard < want:
+                db_note = "capped by HBM: %d of %dk keyframes fit %d GPU(s) (%.2f MB per keyframe record)" % (
+                    nshard * world, want * world // 1000, world, 2 * BYTES_PER_CANDIDATE / 1e6)
+            elif world == 1 and total == 100000:
+                db_note = "configs[2]: 10k keyframes on one GPU"
+            else:
+                db_note = "configs[%d]: %dk keyframes over %d GPU(s)" % (3 if total == 100000 else 4, total // 1000, world)
         gcx, gcy, gang = bs.db_poses(nshard * world, seed=1)
         for c0 in range(0, nshard, 2048):                                  # keyframes are generated and added in chunks (bounded temporaries)
             c1 = min(nshard, c0 + 2048)
@@ -604,7 +620,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "tracking stream 640x480 u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame "
+                "config": {"workload": "tracking stream %dx%d u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame " % (W, H) +
                                        "(BASELINE.json configs[1])", "frames_per_step_per_gpu": n, "solves_per_step": solves_per_step,
                            "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial", "batch": args.batch or "default", "lanes": args.lanes or "default",
                            "parallelism": "replicas only (tracking does not shard)" if world > 1 else "1 GPU",
