@@ -267,7 +267,14 @@ struct ProSpec {      // plain spectrum load
 
 struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:220-221)
   Src<cpx> x, z;
-  struct Line { const cpx* px; const cpx* pz; NIS_HD cpx load(int c) const { return cmulc(NIS_LDG(px + c), NIS_LDG(pz + c)); } };
+  struct Line {
+    const cpx* px; const cpx* pz;
+    NIS_HD cpx load(int c) const {
+      const cpx x = NIS_LDG(px + c);
+      if (px == pz) return make_float2(x.x * x.x + x.y * x.y, 0.f);     // auto form z * conj(z): one load, imaginary part exactly 0
+      return cmulc(x, NIS_LDG(pz + c));
+    }
+  };
   struct Bound {
     Src<cpx> x, z; LineMap m;
     NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{x.at(b) + off, z.at(b) + off}; }
