@@ -103,9 +103,17 @@ __global__ void __launch_bounds__(256) polar_tile_kernel(Src<float> power, Dst<f
   const int b = blockIdx.z, tid = threadIdx.x;
   const float* p = power.at(b);
   const int4 t = __ldg(&tiles[blockIdx.y * gridDim.x + blockIdx.x]);        // y0, x0, bh, bw
+  // staging, flat over the box (full lanes): the row index comes from a multiply-high with the per-tile reciprocal instead of an
+  // integer division; interior elements cost two wraps and a load, the RemoveZeroComponent row / column (r == 0, c == 0) and
+  // everything outside the image go through the exact general tap
+  const unsigned rcp = 0xffffffffu / (unsigned)t.w + 1u;        // floor(i / w) == umulhi(i, rcp) for i * w < 2^32
   for (int i = tid; i < t.z * t.w; i += 256) {
-    const int ly = i / t.w, lx = i - ly * t.w;
-    box[ly * pitch + lx] = shifted_tap(p, t.x + ly, t.y + lx, H, W);
+    const int ly = (int)__umulhi((unsigned)i, rcp), lx = i - ly * t.w;
+    const int y = t.x + ly, x = t.y + lx;
+    int r = y - H / 2; r += (r < 0) ? H : 0;
+    int c = x - W / 2; c += (c < 0) ? W : 0;
+    const bool plain = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W && r != 0 && c != 0;
+    box[ly * pitch + lx] = plain ? __ldg(p + (size_t)r * W + c) : shifted_tap(p, y, x, H, W);
   }
   __syncthreads();
   const int rho = blockIdx.x * kPolarTR + (tid % kPolarTR);
