@@ -516,7 +516,10 @@ def main():
             total = 100000 if (W, H) == (640, 480) else 50000            # configs[3] / configs[4]
             want = 10000 if (world == 1 and total == 100000) else -(-total // world)
             free_b = torch.cuda.mem_get_info(dev)[0]
-            cap = int(0.7 * free_b / (2 * BYTES_PER_CANDIDATE + H * W))
+            per_kf = 2 * BYTES_PER_CANDIDATE + H * W
+            cap = int(0.7 * free_b / per_kf)
+            if want * per_kf <= 0.85 * free_b:              # the configured shard fits with >= 15 % of HBM to spare: take it whole
+                cap = want
             if world > 1:
                 tcap = torch.tensor([cap], dtype=torch.int64, device=dev)
                 dist.all_reduce(tcap, op=dist.ReduceOp.MIN)
