@@ -610,3 +610,26 @@ def test_map_stitcher_bit_exact():
     d, w = small.cell(0, 0)
     assert w.sum() == 50 * 48 and small.dropped() == 96 * 128 - 50 * 48 and small.cell(-1, 0) is None and d.max() == 100
     small.close()
+
+
+def test_map_stitcher_conservation_full_size():
+    """Size-independent property at the full 640x480 / 1000-cell geometry: every source pixel lands in exactly one cell element, so
+    after one InsertFrame the weights sum to H*W (none dropped) and the data to the sum of the scaled image, for any pose."""
+    import ni_slam_b200 as nis
+    import stitcher_ref as sr
+    rng = np.random.default_rng(17)
+    cam = nis.CameraModel(fx=900.0, fy=880.0, cx=W / 2 + 6.0, cy=H / 2 - 3.0, height=1.3, extrinsics=(0.0, -1.0, 0.3, 1.0, 0.0, -0.1, 0.0, 0.0, 1.0))
+    for trial in range(3):
+        st = nis.MapStitcher(1000, cam, H, W, cell_x0=-2, cell_y0=-2, cells_x=4, cells_y=4)
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        st.InsertFrame(img, [rng.uniform(-0.8, 0.8), rng.uniform(-0.8, 0.8), rng.uniform(-np.pi, np.pi)])
+        assert st.dropped() == 0
+        wsum = dsum = 0
+        for cy in range(-2, 2):
+            for cx in range(-2, 2):
+                c = st.cell(cx, cy)
+                if c is not None:
+                    dsum += int(c[0].astype(np.int64).sum())
+                    wsum += int(c[1].astype(np.int64).sum())
+        assert wsum == H * W and dsum == int(sr.normalize_image(img).astype(np.int64).sum())
+        st.close()

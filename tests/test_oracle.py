@@ -336,3 +336,54 @@ def test_stitcher_known_answers():
     before = {k: (v[0].copy(), v[1].copy()) for k, v in st.cells.items()}
     st.recompute_occupancy([[0.25, 0.5, 0.0], [0.25, 0.5, 0.0]])
     assert all(np.array_equal(before[k][0], st.cells[k][0]) and np.array_equal(before[k][1], st.cells[k][1]) for k in before)
+
+
+# ---------------------------------------------------------------- size-independent properties (hypothesis)
+def test_pose_algebra_properties():
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    import tracker_ref as tr
+    coord = st.floats(-500, 500, allow_nan=False)
+    ang = st.floats(-10, 10, allow_nan=False)
+
+    @settings(max_examples=200, deadline=None)
+    @given(coord, coord, ang, coord, coord, ang)
+    def check(x1, y1, a1, x2, y2, a2):
+        p1, p2 = np.array([x1, y1, a1]), np.array([x2, y2, a2])
+        rel = tr.compute_relative_pose(p1, p2)
+        back = tr.compute_absolute_pose(p1, rel)
+        assert np.allclose(back[:2], p2[:2], atol=1e-9) and abs(wrap_pi(back[2] - p2[2])) < 1e-9
+        assert -np.pi <= rel[2] < np.pi and -np.pi <= back[2] < np.pi                 # NormalizeAngle range
+        cam = _cam()
+        c = np.array([x1, y1, wrap_pi(a1)])
+        pp = cam.convert_center_to_principal(c)
+        assert pp[2] == c[2]
+        # ConvertPrincipalToCenter (camera.cc:136-146) undoes ConvertCenterToPrincipal
+        import stitcher_ref as sr
+        assert np.allclose(sr.principal_to_center(cam, pp), c, atol=1e-9)
+        # robot -> image plane undoes image plane -> robot
+        assert np.allclose(sr.robot_to_image_plane(cam, cam.image_plane_to_robot(c)), c, atol=1e-6)
+    check()
+
+
+def test_stitcher_conservation_properties():
+    """Every source pixel lands in exactly one cell element: after one InsertFrame the weights sum to H*W and the raw sums to the sum
+    of the normalised image, whatever the pose; replaying the same poses reproduces the mosaic."""
+    import stitcher_ref as sr
+    import tracker_ref as tr
+    rng = np.random.default_rng(3)
+    Hs, Ws = 24, 32
+    cam = tr.Camera(fx=40.0, fy=38.0, cx=17.0, cy=11.5, height=0.7, extrinsics=[0.8, -0.6, 0.01, 0.6, 0.8, 0.02, 0, 0, 1], image_width=Ws, image_height=Hs)
+    for trial in range(20):
+        img = rng.integers(0, 256, (Hs, Ws), dtype=np.uint8)
+        pose = [rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-np.pi, np.pi)]
+        st = sr.MapStitcher(int(rng.integers(5, 40)), cam)
+        st.insert_frame(img, pose)
+        assert sum(int(w.sum()) for _, w in st.cells.values()) == Hs * Ws
+        assert sum(int(d.sum()) for d, _ in st.cells.values()) == int(sr.normalize_image(img).astype(np.int64).sum())
+        pose2 = [pose[0] + 0.05, pose[1] - 0.03, pose[2] + 0.4]
+        st.insert_frame(img[::-1].copy(), pose2)
+        snap = {k: (d.copy(), w.copy()) for k, (d, w) in st.cells.items()}
+        st.recompute_occupancy([pose, pose2])
+        assert set(snap) == set(st.cells)
+        assert all(np.array_equal(snap[k][0], st.cells[k][0]) and np.array_equal(snap[k][1], st.cells[k][1]) for k in snap)
