@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../ni_slam_b200/host/correlation_flow.hpp"
+#include "../../ni_slam_b200/host/map_stitcher.hpp"
 
 template <class T> struct ColMajor {           // minimal Eigen::Array<T,Dynamic,Dynamic> stand-in (column-major)
   int r = 0, c = 0;
@@ -109,6 +110,34 @@ int main() {
   LoopClosure lc2(far, cf);
   auto res3 = lc2.FindLoopClosure(b, 99, Fb, Pb, 50.0);
   EXPECT(!res3.found && res3.loop_slot == -1 && res3.response[0] == -1.0);
+  // MapStitcher shim (host/map_stitcher.hpp) driven like MapBuilder drives the reference (map_builder.cc:37, :62, :113): identity pose,
+  // principal point at the centre -> pixel (i, j) lands on ground (i - W/2, j - H/2); first insert stores the scaled pixel itself
+  {
+    struct FakeFrame { Vec3 p; void GetPose(Vec3& out) const { out = p; } };
+    typedef nislam::MapStitcherT<Vec3, ColMajor<int>> MapStitcher;
+    nis_camera_model cam{500.0, 500.0, W / 2.0, H / 2.0, 1.0, {1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    MapStitcher ms(1000, true, cam, H, W, -1, -1, 2, 2);
+    std::vector<uint8_t> img((size_t)H * W);
+    for (int j = 0; j < H; ++j) for (int i = 0; i < W; ++i) img[(size_t)j * W + i] = (uint8_t)((i + 2 * j) & 255);
+    FakeFrame f0{{{0.0, 0.0, 0.0}}};
+    const FakeFrame* fp = &f0;
+    ms.InsertFrame(fp, img.data());
+    ColMajor<int> d, wgt;
+    EXPECT(ms.GetCell(0, 0, d, wgt) && ms.DroppedPixels() == 0);
+    // ground (0, 0) <- pixel (i, j) = (W/2, H/2); scaled value = rint(v * 100/255)
+    const int v = img[(size_t)(H / 2) * W + W / 2];
+    EXPECT(wgt(0, 0) == 1 && d(0, 0) == (int)std::lrint((float)v * (float)(100.0 / 255.0)));
+    EXPECT(ms.GetCell(-1, -1, d, wgt) && wgt(999, 999) == 1 && wgt(0, 0) == 0);      // ground (-1, -1) <- pixel (W/2 - 1, H/2 - 1)
+    // second identical insert: existing cells average, (d*1 + d*1) / 2 = d, weight 2
+    ms.InsertFrame(fp, img.data());
+    EXPECT(ms.GetCell(0, 0, d, wgt) && wgt(0, 0) == 2 && d(0, 0) == (int)std::lrint((float)v * (float)(100.0 / 255.0)));
+    std::vector<const FakeFrame*> frames{fp, fp};
+    ms.RecomputeOccupancy(frames);
+    EXPECT(ms.GetCell(0, 0, d, wgt) && wgt(0, 0) == 2);
+    MapStitcher off(1000, false, cam, H, W, -1, -1, 2, 2);                           // stitch_map: false -> every call is a no-op (:15)
+    off.InsertFrame(fp, img.data());
+    EXPECT(!off.GetCell(0, 0, d, wgt));
+  }
   printf("shim_test ok\n");
   return 0;
 }
