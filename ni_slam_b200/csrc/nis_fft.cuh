@@ -509,18 +509,23 @@ NIS_HD void row_phase0(int tid, cpx* smem, const Pro& pro, int nlines) {
 template <int N, int R1, int R2, int L, int T, bool INV>
 NIS_HD void row_stage1_read(int tid, const cpx* smem, const Twiddles& twd, int nlines, CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1>& st) {
   typedef RowGeom<N, R1, R2, L, T> Gm;
+  static_assert(T % 16 == 0, "the stage-1 twiddle index j & 15 must not depend on the round");
+  // k = j & 15 with j = (tid + it*T) % M1; T and M1 are multiples of 16, so k = tid & 15 in every round: the R1-1 twiddles are
+  // loaded once per thread instead of once per round (they were two thirds of this kernel's global loads)
+  cpx twv[R1 > 1 ? R1 - 1 : 1];
+#pragma unroll
+  for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * 16 + (tid & 15)]);
 #pragma unroll
   for (int it = 0; it < Gm::ROUNDS1; ++it) {
     const int w = tid + it * T;
     const int ln = w / Gm::M1, j = w % Gm::M1;
     if (w < L * Gm::M1 && ln < nlines) {
-      const int k = j & 15;
       // M1 is a multiple of 16, so pad(j + r*M1) = pad(j) + r*(M1 + M1/16): one padded base, constant offsets
       const cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         cpx x = s[r * (Gm::M1 + Gm::M1 / 16)];
-        if (r > 0) x = ctw<INV>(x, NIS_LDG(&twd.tw1[(r - 1) * 16 + k]));
+        if (r > 0) x = ctw<INV>(x, twv[r - 1]);
         st.v[it][r] = x;
       }
       Dft<R1, INV>::run(st.v[it]);
@@ -548,6 +553,13 @@ template <int N, int R1, int R2, int L, int T, bool INV, class Epi>
 NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines, Epi& epi) {
   typedef RowGeom<N, R1, R2, L, T> Gm;
   constexpr int NS2 = Gm::NS2;
+  // when T is a multiple of NS2 the butterfly index j = w % NS2 is the same in every round: hoist the R2-1 twiddles
+  constexpr bool kHoist = (T % NS2 == 0);
+  cpx twv[R2 > 1 ? R2 - 1 : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int r = 1; r < R2; ++r) twv[r - 1] = NIS_LDG(&twd.tw2[(r - 1) * NS2 + tid % NS2]);
+  }
   for (int w = tid; w < L * NS2; w += T) {
     const int ln = w / NS2, j = w % NS2;
     if (ln >= nlines) break;
@@ -556,7 +568,7 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
       cpx x = s[r * (NS2 + NS2 / 16)];
-      if (r > 0) x = ctw<INV>(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
+      if (r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, INV>::run(v);
@@ -572,6 +584,12 @@ template <int N, int R1, int R2, int L, int T, class Mid>
 NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, Mid& mid) {
   typedef RowGeom<N, R1, R2, L, T> Gm;
   constexpr int NS2 = Gm::NS2;
+  constexpr bool kHoist = (T % NS2 == 0);                  // see row_phase2
+  cpx twv[R2 > 1 ? R2 - 1 : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int r = 1; r < R2; ++r) twv[r - 1] = NIS_LDG(&twd.tw2[(r - 1) * NS2 + tid % NS2]);
+  }
   for (int w = tid; w < L * NS2; w += T) {
     const int ln = w / NS2, j = w % NS2;
     if (ln >= nlines) break;
@@ -580,7 +598,7 @@ NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, 
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
       cpx x = s[r * (NS2 + NS2 / 16)];
-      if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
+      if (r > 0) x = cmul(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, false>::run(v);

@@ -30,9 +30,15 @@
 #ifndef NIS_ROW_LR
 #define NIS_ROW_LR 2
 #endif
+// the 480-point row pass (polar grid) may use its own geometry: with T a multiple of NS2 = 96 its last-stage twiddles hoist too
+#ifndef NIS_ROW480_L
+#define NIS_ROW480_L NIS_ROW_L
+#define NIS_ROW480_T NIS_ROW_T
+#define NIS_ROW480_LR NIS_ROW_LR
+#endif
 #define NIS_ROW_PLANS(X)      \
   X(640, 8, 5, NIS_ROW_L, NIS_ROW_T, NIS_ROW_LR)     \
-  X(480, 6, 5, NIS_ROW_L, NIS_ROW_T, NIS_ROW_LR)     \
+  X(480, 6, 5, NIS_ROW480_L, NIS_ROW480_T, NIS_ROW480_LR)     \
   X(1280, 8, 10, 4, 256, 2)   \
   X(1600, 10, 10, 4, 256, 2)  \
   X(128, 8, 1, 8, 128, 8)     \
