@@ -261,6 +261,13 @@ template <int N, int R0, int R1, int R2, int T, bool INV>
 NIS_HD void col_stage1_read(int tid, const cpx* smem, const Twiddles& twd, CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1>& st) {
   typedef ColGeom<N, R0, R1, R2, T> Gm;
   const int l = tid % kColLanes, gi = tid / kColLanes;
+  // k = j % NS1 with j = gi + it*G: when the group count is a multiple of NS1 (= R0) the twiddle index is the same in every round
+  constexpr bool kHoist = (Gm::G % Gm::NS1 == 0);
+  cpx twv[R1 > 1 ? R1 - 1 : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + gi % Gm::NS1]);
+  }
 #pragma unroll
   for (int it = 0; it < Gm::ROUNDS1; ++it) {
     const int j = gi + it * Gm::G;
@@ -269,7 +276,7 @@ NIS_HD void col_stage1_read(int tid, const cpx* smem, const Twiddles& twd, Carry
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         cpx x = smem[(j + r * Gm::M1) * kColLanes + l];
-        if (r > 0) x = ctw<INV>(x, NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + k]));
+        if (r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + k]));
         st.v[it][r] = x;
       }
       Dft<R1, INV>::run(st.v[it]);
