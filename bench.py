@@ -38,7 +38,7 @@ METRIC = "pose_solves_per_sec_640x480"
 
 def ncu_traffic(kernel_family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed ncu --set full
-    capture (profiles/ncu_r01_summary.json; cold-cache replay at the default batch).  None if no capture is committed."""
+    capture (profiles/ncu_r01_summary.json; cold-cache replay, 28 images per launch).  None if no capture is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_r01_summary.json")) as f:
             cap = json.load(f)["full_capture"]
@@ -430,7 +430,8 @@ def main():
     peak, peak_src = measured_peak()
     achieved = (value / world) * BYTES_PER_SOLVE / 1e9                  # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
-                "traffic_note": "bytes per launch of the dominant kernel family (ncu --set full, cold cache, default batch); the family "
+                "traffic_note": "bytes per launch of the dominant kernel family (ncu --set full, cold cache, captured at 28 images per launch = 1.31 MB per image; "
+                                "the default batch is now 56, per-image traffic is unchanged); the family "
                                 "moves its own tile in and out once, the multi-kernel step as a whole moves ~52 MB per solve",
                 "definition": "per-GPU solves/s x %d algorithmic B/solve (SURVEY 8d) over the whole multi-kernel step" % BYTES_PER_SOLVE,
                 "peak_source": peak_src, "dominant_kernel": dom, "dominant_kernel_share": kernels[dom]["share"],

@@ -594,7 +594,7 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   ctx->maxspec = std::max(ctx->sz[0].spec, ctx->sz[1].spec);
   ctx->maxreal = std::max(ctx->sz[0].real, ctx->sz[1].real);
   const int nlanes = 8;
-  ctx->active_lanes = 4;
+  ctx->active_lanes = 3;
   const char* el = getenv("NIS_LANES");
   if (el && atoi(el) > 0) ctx->active_lanes = std::min(atoi(el), nlanes);
   ctx->lanes.resize(nlanes);
@@ -609,8 +609,8 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
     cudaDeviceProp prop;
     int sms = 148;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sms = prop.multiProcessorCount;
-    // two waves of column CTAs per launch: measured best end-to-end (uploads overlap better with fewer, larger batches)
-    ctx->default_batch = std::max(4, std::min(64, 2 * ((2 * sms) / std::max(1, W / 32))));
+    // four waves of column CTAs per launch on three lanes: measured best both HBM-resident and end to end (sweep in DESIGN.md)
+    ctx->default_batch = std::max(4, std::min(64, 4 * ((2 * sms) / std::max(1, W / 32))));
     ctx->batch = ctx->default_batch;
   }
   const char* er = getenv("NIS_ROT_CACHE_MIN");      // candidates from which a scan builds the rotated-query cache (0 = never)
@@ -662,7 +662,7 @@ int nis_set_lanes(nis_ctx* ctx, int lanes) {
   if (!ctx || lanes < 0) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   CU(cudaDeviceSynchronize());
-  ctx->active_lanes = lanes > 0 ? std::min(lanes, (int)ctx->lanes.size()) : 4;
+  ctx->active_lanes = lanes > 0 ? std::min(lanes, (int)ctx->lanes.size()) : 3;
   return NIS_OK;
 }
 int nis_set_batch(nis_ctx* ctx, int batch) {
