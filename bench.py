@@ -533,13 +533,32 @@ def main():
                 db_note = "configs[2]: 10k keyframes on one GPU"
             else:
                 db_note = "configs[%d]: %dk keyframes over %d GPU(s)" % (3 if total == 100000 else 4, total // 1000, world)
-        gcx, gcy, gang = bs.db_poses(nshard * world, seed=1)
-        for c0 in range(0, nshard, 2048):                                  # keyframes are generated and added in chunks (bounded temporaries)
-            c1 = min(nshard, c0 + 2048)
-            g0 = rank * nshard
-            db_imgs = bs.crops(canvas, gcx[g0 + c0:g0 + c1], gcy[g0 + c0:g0 + c1], gang[g0 + c0:g0 + c1], H, W)
-            lc.AddImages(None, np.arange(g0 + c0, g0 + c1, dtype=np.int32), None, ptr=db_imgs.data_ptr(), n=c1 - c0, on_device=True)
-            del db_imgs
+        def build_db(ns):
+            g0 = rank * ns
+            for c0 in range(0, ns, 2048):                                  # keyframes are generated and added in chunks (bounded temporaries)
+                c1 = min(ns, c0 + 2048)
+                db_imgs = bs.crops(canvas, gcx[g0 + c0:g0 + c1], gcy[g0 + c0:g0 + c1], gang[g0 + c0:g0 + c1], H, W)
+                lc.AddImages(None, np.arange(g0 + c0, g0 + c1, dtype=np.int32), None, ptr=db_imgs.data_ptr(), n=c1 - c0, on_device=True)
+                del db_imgs
+
+        for attempt in range(4):                                           # an allocation failure on any rank halves every shard and retries
+            gcx, gcy, gang = bs.db_poses(nshard * world, seed=1)
+            try:
+                build_db(nshard)
+                ok = 1
+            except Exception as e:                                         # NisError (out of memory) / torch OOM
+                sys.stderr.write("rank %d: keyframe store of %d failed (%s)\n" % (rank, nshard, str(e)[:120]))
+                ok = 0
+            if world > 1:
+                tok = torch.tensor([ok], dtype=torch.int64, device=dev)
+                dist.all_reduce(tok, op=dist.ReduceOp.MIN)
+                ok = int(tok.item())
+            if ok:
+                break
+            lc.clear()
+            torch.cuda.empty_cache()
+            nshard = max(64, nshard // 2)
+            db_note = "reduced to %d keyframes after an allocation failure" % (nshard * world)
         jstar = (nshard * world) // 2 + 3                                  # expected winner (global id)
         q_img = bs.crops(canvas, [gcx[jstar] + 13], [gcy[jstar] - 7], [gang[jstar] + 4.5], H, W)
         nbytes = C.sizeof(nis.LoopResultC)

@@ -129,7 +129,10 @@ static void prof_after(nis_ctx* ctx) { cudaEventRecord(ctx->prof.back().b, ctx->
 static int fail(nis_ctx* c, int status, const char* what, int cuda_err = 0) {
   if (c) {
     char buf[512];
-    if (cuda_err > 0) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString((cudaError_t)cuda_err));
+    if (cuda_err > 0) {
+      snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString((cudaError_t)cuda_err));
+      (void)cudaGetLastError();          // a failed cudaMalloc leaves a non-sticky last error: clear it so the next launch check is not blamed for it
+    }
     else snprintf(buf, sizeof buf, "%s", what);
     c->err = buf;
   }
