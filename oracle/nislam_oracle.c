@@ -4,8 +4,12 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing under ni_slam_b200/ (the product) may link, load or call this
  * file.  Users: tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl reference legs.
  *
- * PARITY UNPINNED: the reference (sair-lab/ni-slam @ 819f252) has no tests / golden vectors and cannot be
- * built in this image (Eigen, FFTW3, OpenCV C++ absent), see SURVEY.md 8(c).  This file follows
+ * PARITY PINNED TO THE REFERENCE'S SOURCE TEXT: the reference (sair-lab/ni-slam @ 819f252) has no tests / golden vectors and its
+ * own build needs Eigen, FFTW3 and OpenCV C++ (absent here), but its hot-path sources compile UNMODIFIED against the stand-in
+ * headers of oracle/ref_stubs (oracle/Makefile.ref -> oracle/_ref/libnislam_ref.so); tests/test_oracle_ref.py holds this file
+ * equal to that library (integers and theta exact, info within 1e-6; observed bit-identical) and to the committed vectors
+ * it produced (tests/golden/golden_ref.npz).  What stays unpinned is the third-party arithmetic itself (FFTW's and Eigen's
+ * rounding, see ref_stubs/mini_eigen.h for the evaluation orders assumed).  This file follows
  *   src/correlation_flow.cc:37-243, src/utils.cc:110-131,154-175, include/circ_shift.h:238-244,
  *   src/loop_closure.cc:36-73, include/loop_closure.h:15
  * and restates the published algorithms of the third-party calls on the path:
@@ -362,8 +366,8 @@ void orc_fft2(const float *x, int R, int C, float *xf) {
   }
 }
 
-/* xf: (R/2+1) x C complex -> x: R x C real, divided by R*C (correlation_flow.cc:76). */
-void orc_ifft2(const float *xf, int R, int C, float *x) {
+/* xf: (R/2+1) x C complex -> x: R x C real, divided by `den` (a true division like Eigen's x/x.size(), correlation_flow.cc:76) */
+static void ifft2_scaled(const float *xf, int R, int C, float *x, float den) {
   const int half = R / 2 + 1, hb = (C + 1) / 2;
   ws_reserve(&t_ws, (size_t)(R > C ? R : C) * (size_t)((half > hb ? half : hb) + 1));
   float *sr = t_ws.a_re, *si = t_ws.a_im;
@@ -393,18 +397,21 @@ void orc_ifft2(const float *xf, int R, int C, float *x) {
     }
   }
   fft1d_batch(R, hb, +1, zr, zi, t_ws.a_re, t_ws.a_im);
-  const float inv = 1.0f / (float)((size_t)R * C);
   for (int b0 = 0; b0 < hb; b0 += 16)
     for (int r0 = 0; r0 < R; r0 += 16)
       for (int b = b0; b < (b0 + 16 < hb ? b0 + 16 : hb); ++b) {
         float *la = x + (size_t)b * R;
         float *lb = (b + hb < C) ? x + (size_t)(b + hb) * R : NULL;
         for (int r = r0; r < (r0 + 16 < R ? r0 + 16 : R); ++r) {
-          la[r] = zr[(size_t)r * hb + b] * inv;
-          if (lb) lb[r] = zi[(size_t)r * hb + b] * inv;
+          la[r] = zr[(size_t)r * hb + b] / den;
+          if (lb) lb[r] = zi[(size_t)r * hb + b] / den;
         }
       }
 }
+/* divided by R*C (correlation_flow.cc:76) */
+void orc_ifft2(const float *xf, int R, int C, float *x) { ifft2_scaled(xf, R, C, x, (float)((size_t)R * C)); }
+/* unnormalised, like fftwf c2r (the fftw3.h stand-in of oracle/_ref; the reference's own `x/x.size()` follows) */
+void orc_ifft2_raw(const float *xf, int R, int C, float *x) { ifft2_scaled(xf, R, C, x, 1.0f); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* L1 helpers                                                                                  */
@@ -443,11 +450,12 @@ static inline void bil_w(int fx, int fy, float w[4]) {
   w[0] = y0 * x0; w[1] = y0 * x; w[2] = y * x0; w[3] = y * x;
 }
 
-/* correlation_flow.cc:228-236: cv::warpPolar(img, Size(Cp, D), (W/2,H/2), min(H/2,W/2), LINEAR|FILL_OUTLIERS)
- * src: H x W column-major, dst: D x Cp column-major (rows = angle, cols = radius).                        */
-void orc_polar(const float *src, int H, int W, int D, int Cp, float *dst) {
-  const float cx = (float)W / 2, cy = (float)H / 2;
-  const double maxRadius = (double)((H / 2) < (W / 2) ? (H / 2) : (W / 2));
+/* correlation_flow.cc:228-236: cv::warpPolar(img, Size(Cp, D), center, maxRadius, LINEAR|FILL_OUTLIERS).
+ * Stride-generic core: element (y, x) of src lives at src[y*s_ys + x*s_xs], element (phi, rho) of dst at dst[phi*d_ps + rho*d_rs];
+ * the two wrappers below instantiate it for the reference's column-major arrays and for row-major cv::Mat data. */
+static inline __attribute__((always_inline)) void warp_polar_core(const float *src, int H, int W, size_t s_ys, size_t s_xs, int D, int Cp,
+                                                                  float cx, float cy, double maxRadius, float *dst, size_t d_ps,
+                                                                  size_t d_rs) {
   const double Kangle = 2.0 * M_PI / D;
   const double Kmag = maxRadius / Cp;
   for (int phi = 0; phi < D; ++phi) {
@@ -462,21 +470,31 @@ void orc_polar(const float *src, int H, int W, int D, int Cp, float *dst) {
       bil_w(sx & 31, sy & 31, w);
       float v;
       if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
-        const float *S = src + (size_t)ix * H + iy;
-        v = S[0] * w[0] + S[H] * w[1] + S[1] * w[2] + S[H + 1] * w[3];
+        const float *S = src + (size_t)ix * s_xs + (size_t)iy * s_ys;
+        v = S[0] * w[0] + S[s_xs] * w[1] + S[s_ys] * w[2] + S[s_xs + s_ys] * w[3];
       } else if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) {
         v = 0.f;
       } else {
         const int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
-        const float v0 = ((unsigned)x0 < (unsigned)W && (unsigned)y0 < (unsigned)H) ? src[(size_t)x0 * H + y0] : 0.f;
-        const float v1 = ((unsigned)x1 < (unsigned)W && (unsigned)y0 < (unsigned)H) ? src[(size_t)x1 * H + y0] : 0.f;
-        const float v2 = ((unsigned)x0 < (unsigned)W && (unsigned)y1 < (unsigned)H) ? src[(size_t)x0 * H + y1] : 0.f;
-        const float v3 = ((unsigned)x1 < (unsigned)W && (unsigned)y1 < (unsigned)H) ? src[(size_t)x1 * H + y1] : 0.f;
+        const float v0 = ((unsigned)x0 < (unsigned)W && (unsigned)y0 < (unsigned)H) ? src[(size_t)x0 * s_xs + (size_t)y0 * s_ys] : 0.f;
+        const float v1 = ((unsigned)x1 < (unsigned)W && (unsigned)y0 < (unsigned)H) ? src[(size_t)x1 * s_xs + (size_t)y0 * s_ys] : 0.f;
+        const float v2 = ((unsigned)x0 < (unsigned)W && (unsigned)y1 < (unsigned)H) ? src[(size_t)x0 * s_xs + (size_t)y1 * s_ys] : 0.f;
+        const float v3 = ((unsigned)x1 < (unsigned)W && (unsigned)y1 < (unsigned)H) ? src[(size_t)x1 * s_xs + (size_t)y1 * s_ys] : 0.f;
         v = v0 * w[0] + v1 * w[1] + v2 * w[2] + v3 * w[3];
       }
-      dst[(size_t)rho * D + phi] = v;
+      dst[(size_t)phi * d_ps + (size_t)rho * d_rs] = v;
     }
   }
+}
+
+/* src: H x W column-major, dst: D x Cp column-major (rows = angle, cols = radius); centre and radius as CorrelationFlow::polar */
+void orc_polar(const float *src, int H, int W, int D, int Cp, float *dst) {
+  const double maxRadius = (double)((H / 2) < (W / 2) ? (H / 2) : (W / 2));
+  warp_polar_core(src, H, W, 1, (size_t)H, D, Cp, (float)W / 2, (float)H / 2, maxRadius, dst, 1, (size_t)D);
+}
+/* row-major entry point (cv::Mat data) used by oracle/ref_stubs (the cv::warpPolar stand-in of oracle/_ref) */
+void orc_warp_polar_rm(const float *src, int H, int W, int D, int Cp, float cx, float cy, double maxRadius, float *dst) {
+  warp_polar_core(src, H, W, (size_t)W, 1, D, Cp, cx, cy, maxRadius, dst, (size_t)Cp, 1);
 }
 
 static inline int wrap_idx(int p, int len) {
@@ -504,10 +522,10 @@ void orc_rotation_inverse(int H, int W, double degree, double iM[6]) {
   memcpy(iM, M, sizeof(M));
 }
 
-/* utils.cc:154-161 RotateArray: warpAffine(INTER_LINEAR, BORDER_WRAP), AB_BITS=10, INTER_BITS=5. col-major in/out. */
-void orc_rotate(const float *src, int H, int W, float degree, float *dst) {
-  double M[6];
-  orc_rotation_inverse(H, W, (double)degree, M);
+/* cv::warpAffine(INTER_LINEAR, BORDER_WRAP) given the already inverted matrix iM: AB_BITS=10, INTER_BITS=5.
+ * Stride-generic like warp_polar_core: element (y, x) at [y*s_ys + x*s_xs]. */
+static inline __attribute__((always_inline)) void warp_affine_core(const float *src, int H, int W, size_t s_ys, size_t s_xs,
+                                                                   const double M[6], float *dst) {
   for (int y = 0; y < H; ++y) {
     const int X0 = cv_round_d((M[1] * y + M[2]) * 1024.0) + 16;
     const int Y0 = cv_round_d((M[4] * y + M[5]) * 1024.0) + 16;
@@ -519,16 +537,27 @@ void orc_rotate(const float *src, int H, int W, float degree, float *dst) {
       bil_w(X & 31, Y & 31, w);
       float v;
       if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
-        const float *S = src + (size_t)ix * H + iy;
-        v = S[0] * w[0] + S[H] * w[1] + S[1] * w[2] + S[H + 1] * w[3];
+        const float *S = src + (size_t)ix * s_xs + (size_t)iy * s_ys;
+        v = S[0] * w[0] + S[s_xs] * w[1] + S[s_ys] * w[2] + S[s_xs + s_ys] * w[3];
       } else {
         const int x0 = wrap_idx(ix, W), x1 = wrap_idx(ix + 1, W), y0 = wrap_idx(iy, H), y1 = wrap_idx(iy + 1, H);
-        v = src[(size_t)x0 * H + y0] * w[0] + src[(size_t)x1 * H + y0] * w[1] + src[(size_t)x0 * H + y1] * w[2] +
-            src[(size_t)x1 * H + y1] * w[3];
+        v = src[(size_t)x0 * s_xs + (size_t)y0 * s_ys] * w[0] + src[(size_t)x1 * s_xs + (size_t)y0 * s_ys] * w[1] +
+            src[(size_t)x0 * s_xs + (size_t)y1 * s_ys] * w[2] + src[(size_t)x1 * s_xs + (size_t)y1 * s_ys] * w[3];
       }
-      dst[(size_t)x * H + y] = v;
+      dst[(size_t)x * s_xs + (size_t)y * s_ys] = v;
     }
   }
+}
+
+/* utils.cc:154-161 RotateArray: getRotationMatrix2D + warpAffine(INTER_LINEAR, BORDER_WRAP).  col-major in/out. */
+void orc_rotate(const float *src, int H, int W, float degree, float *dst) {
+  double M[6];
+  orc_rotation_inverse(H, W, (double)degree, M);
+  warp_affine_core(src, H, W, 1, (size_t)H, M, dst);
+}
+/* row-major entry point (cv::Mat data) used by oracle/ref_stubs (the cv::warpAffine stand-in of oracle/_ref) */
+void orc_warp_affine_inv_rm(const float *src, int H, int W, const double iM[6], float *dst) {
+  warp_affine_core(src, H, W, (size_t)W, 1, iM, dst);
 }
 
 /* Camera::UndistortImage (camera.cc:92-93): cv::remap(u8, map1 CV_16SC2, map2 CV_16UC1, INTER_LINEAR), BORDER_CONSTANT(0).
@@ -612,17 +641,20 @@ static int kernel_fft(const orc_cf_config *cfg, const float *xf, const float *zf
     }
   } else if (cfg->kernel == 1) {
     /* quirk kept: sums run over the stored half spectrum only (correlation_flow.cc:184-185) */
+    /* |z^2| of a complex array has no packet form in Eigen: the sum is a plain f32 running sum in storage order (pinned by oracle/_ref) */
     float xx = 0.f, zz = 0.f;
     {
-      double sx = 0, sz = 0;
+      float sx = 0.f, sz = 0.f;
       for (size_t i = 0; i < n; ++i) {
         const float ar = xf[2 * i] * xf[2 * i] - xf[2 * i + 1] * xf[2 * i + 1], ai = 2.f * xf[2 * i] * xf[2 * i + 1];
-        sx += hypotf(ar, ai);
+        const float hx = hypotf(ar, ai);
+        sx = i ? sx + hx : hx;
         const float br = z[2 * i] * z[2 * i] - z[2 * i + 1] * z[2 * i + 1], bi = 2.f * z[2 * i] * z[2 * i + 1];
-        sz += hypotf(br, bi);
+        const float hz = hypotf(br, bi);
+        sz = i ? sz + hz : hz;
       }
-      xx = (float)sx / (float)(unsigned)N;
-      zz = (float)sz / (float)(unsigned)N;
+      xx = sx / (float)(unsigned)N;
+      zz = sz / (float)(unsigned)N;
     }
     const float coef = -1.f / (cfg->sigma * cfg->sigma);
     for (size_t i = 0; i < N; ++i) {
@@ -640,17 +672,46 @@ static int kernel_fft(const orc_cf_config *cfg, const float *xf, const float *zf
   return 0;
 }
 
-/* correlation_flow.cc:238-243 */
+/* Eigen 3.3 sum() of a real f32 array as the reference builds it (-O3 -march=native, AVX): Redux.h linear vectorised traversal,
+ * 8-float packets, two packet accumulators, horizontal add ((a0+a4)+(a1+a5))+((a2+a6)+(a3+a7)), scalar tail.
+ * f(i) produces element i (GetInfo's variance reduces the expression (g-m)^2 without a temporary). */
+#define ORC_EIGEN_SUM(n, ELEM, result)                                                         \
+  do {                                                                                         \
+    const size_t n_ = (n), a2_ = (n_ / 16) * 16, a1_ = (n_ / 8) * 8;                           \
+    float p0_[8], p1_[8], res_;                                                                \
+    if (a1_ == 0) {                                                                            \
+      res_ = n_ ? ELEM(0) : 0.f;                                                               \
+      for (size_t i_ = 1; i_ < n_; ++i_) res_ = res_ + ELEM(i_);                               \
+    } else {                                                                                   \
+      for (int k_ = 0; k_ < 8; ++k_) p0_[k_] = ELEM((size_t)k_);                               \
+      if (a1_ > 8) {                                                                           \
+        for (int k_ = 0; k_ < 8; ++k_) p1_[k_] = ELEM((size_t)(8 + k_));                       \
+        for (size_t i_ = 16; i_ < a2_; i_ += 16)                                               \
+          for (int k_ = 0; k_ < 8; ++k_) {                                                     \
+            p0_[k_] = p0_[k_] + ELEM(i_ + k_);                                                 \
+            p1_[k_] = p1_[k_] + ELEM(i_ + 8 + k_);                                             \
+          }                                                                                    \
+        for (int k_ = 0; k_ < 8; ++k_) p0_[k_] = p0_[k_] + p1_[k_];                            \
+        if (a1_ > a2_)                                                                         \
+          for (int k_ = 0; k_ < 8; ++k_) p0_[k_] = p0_[k_] + ELEM(a2_ + k_);                   \
+      }                                                                                        \
+      res_ = ((p0_[0] + p0_[4]) + (p0_[1] + p0_[5])) + ((p0_[2] + p0_[6]) + (p0_[3] + p0_[7])); \
+      for (size_t i_ = a1_; i_ < n_; ++i_) res_ = res_ + ELEM(i_);                             \
+    }                                                                                          \
+    (result) = res_;                                                                           \
+  } while (0)
+
+/* correlation_flow.cc:238-243: all sums in f32, in Eigen's evaluation order (pinned by oracle/_ref) */
 static float get_info(const float *g, size_t n, float response) {
-  double s = 0;
-  for (size_t i = 0; i < n; ++i) s += g[i];
-  const float mean = ((float)s - response) / (float)(n - 1);
-  double q = 0;
-  for (size_t i = 0; i < n; ++i) {
-    const float d = g[i] - mean;
-    q += (double)(d * d);
-  }
-  const float sd = sqrtf((float)(q / (double)n));
+  float s, q;
+#define G_AT(i) (g[(i)])
+  ORC_EIGEN_SUM(n, G_AT, s);
+#undef G_AT
+  const float mean = (s - response) / (float)(n - 1);
+#define SQ_AT(i) ((g[(i)] - mean) * (g[(i)] - mean))
+  ORC_EIGEN_SUM(n, SQ_AT, q);
+#undef SQ_AT
+  const float sd = sqrtf(q / (float)n);
   return (float)((double)(response - mean) / ((double)sd + 1e-7));
 }
 

@@ -85,7 +85,10 @@ def _check_rows(rows, fn):
         assert abs(wrap_pi(pose[2] - r[4])) < 1e-6, (i, mode, pose, r)
         assert pk["trans"] == (int(r[10]), int(r[11]))
         assert pk["polar"][0] % (D // 2) == int(r[8]) % (D // 2)       # 180-degree twin peak
-        assert np.allclose(info, r[5:8], rtol=3e-4), (i, mode, info, r[5:8])
+        # cross-check of two independent f32 chains (scipy pocketfft + double sums vs the C oracle, which is held to the reference's
+        # own f32 evaluation order by tests/test_oracle_ref.py): 3e-4; below the "tracking lost" gate of 30 the peak is a noise maximum
+        tol = 3e-4 if min(r[5], r[7]) > 30 else 2e-3
+        assert np.allclose(info, r[5:8], rtol=tol), (i, mode, info, r[5:8])
 
 
 def test_pose_goldens(golden_pairs):
