@@ -217,6 +217,81 @@ def time_python_stream_mp(frames, procs, pool=None):
     return (n - 1) / dt, dt
 
 
+def ref_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import oracle_ref as orf
+        if not orf.available():
+            return False
+        orf.lib()
+        return True
+    except Exception:
+        return False
+
+
+def time_ref_stream(frames, threads):
+    """The stream through oracle/_ref = the reference's OWN correlation_flow.cc / utils.cc compiled unmodified (oracle/Makefile.ref):
+    per frame ConvertMatToNormalizedArray + ComputeIntermedium, per pair ComputePose(tracking), exactly MapBuilder's call sequence
+    (map_builder.cc:72-75, :129); one CorrelationFlow object per thread (the reference's is not re-entrant), frames / pairs spread
+    over a thread pool (the library calls release the GIL).  Returns (solves/s, seconds)."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle_c as oc
+    import oracle_ref as orf
+    cfg = oc.make_cfg(height=H, width=W)
+    local = threading.local()
+
+    def cf():
+        if not hasattr(local, "cf"):
+            local.cf = orf.CorrelationFlow(cfg)
+        return local.cf
+
+    def feat(t):
+        img = orf.normalize_u8(frames[t])
+        return (img,) + tuple(cf().compute_intermedium(img))
+
+    def pose(t):
+        return cf().compute_pose(feats[t - 1][1], feats[t][0], feats[t - 1][2], feats[t][2], True)
+    n = frames.shape[0]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        feats = list(ex.map(feat, range(n)))
+        list(ex.map(pose, range(1, n)))
+    dt = time.perf_counter() - t0
+    return (n - 1) / dt, dt
+
+
+def time_cpu_scan(db_u8, q_u8, threads, use_ref):
+    """LoopClosure::FindLoopClosure over len(db_u8) candidates on the CPU (loop_closure.cc:36-73: per candidate ComputePose(..., false)):
+    oracle/_ref when built, else the C port; candidates spread over `threads` threads.  Keyframe features are computed outside the timed
+    region (the reference reads them from its Frames).  Returns (candidates/s, seconds, winner index)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import threading
+    import oracle_c as oc
+    cfg = oc.make_cfg(height=H, width=W)
+    local = threading.local()
+    if use_ref:
+        import oracle_ref as orf
+
+        def cf():
+            if not hasattr(local, "cf"):
+                local.cf = orf.CorrelationFlow(cfg)
+            return local.cf
+        feat = lambda u: cf().compute_intermedium(oc.normalize_u8(u))
+        solve = lambda k: cf().compute_pose(feats[k][0], qi, feats[k][1], qP, False)[0]
+    else:
+        feat = lambda u: oc.compute_intermedium(cfg, oc.normalize_u8(u))
+        solve = lambda k: oc.compute_pose(cfg, feats[k][0], qi, feats[k][1], qP, False)[0]
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        feats = list(ex.map(feat, db_u8))
+        qi = oc.normalize_u8(q_u8)
+        qP = feat(q_u8)[1]
+        t0 = time.perf_counter()
+        infos = list(ex.map(solve, range(len(db_u8))))
+        dt = time.perf_counter() - t0
+    return len(db_u8) / dt, dt, int(np.argmax([i.sum() for i in infos]))
+
+
 def best_cpu_stream(frames, threads):
     """Times both CPU restatements on the same frames and returns the faster one: (solves/s, seconds, label)."""
     v_c, dt_c = time_oracle_stream(frames, threads)
@@ -231,40 +306,53 @@ def best_cpu_stream(frames, threads):
                     "python_scipy_cv2_processes": None if mp_ is None else mp_[0]},)
 
 
+def workload_config(n_frames, world):
+    """The `config` object both arms print (same workload, same keys): BASELINE.json configs[1]."""
+    return {"workload": "tracking stream %dx%d u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame " % (W, H) +
+                        "(BASELINE.json configs[1])", "frames_per_step_per_gpu": n_frames, "solves_per_step": (n_frames - 1) * world,
+            "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial",
+            "parallelism": "replicas only (tracking does not shard)" if world > 1 else "1 GPU",
+            "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of features per step vs 126 MB L2" %
+                  (n_frames * H * W / 1e6, n_frames * BYTES_PER_CANDIDATE / 1e6)}
+
+
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  oracle/_ref (the reference's
+    correlation_flow.cc / utils.cc compiled unmodified, kind "reference") when it is built, else the C port (kind "port").  The
+    workload and `config` are the GPU arm's; each step times a bounded sample of that stream (args.ref_frames frames), the value is
+    per-solve throughput, so the sample length does not enter it."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     threads = cores
     n = args.ref_frames
     frames = cpu_frames(n)
-    # pick the faster of the two CPU restatements on a warm-up pass, then time K steps of it
-    _, _, label, both = best_cpu_stream(frames[:min(n, 4 * threads + 1)], threads)
-    pool = None
-    if "worker processes" in label:
-        import multiprocessing as mp
-        pool = mp.get_context("spawn").Pool(threads, initializer=_mp_init)
-        pool.map(_mp_chunk, [frames[:2]] * threads)
-        timer = lambda fr, th: time_python_stream_mp(fr, th, pool)
+    use_ref = ref_available()
+    warm = frames[:min(n, 2 * threads + 1)]
+    others = {}
+    if use_ref:
+        time_ref_stream(warm, threads)
+        timer, kind, label = time_ref_stream, "reference", "oracle/_ref = /root/reference/src/{correlation_flow,utils}.cc compiled unmodified (oracle/Makefile.ref)"
+        try:
+            others["c_port_solves_per_sec"] = time_oracle_stream(warm, threads)[0]
+        except Exception:
+            pass
     else:
-        timer = time_python_stream if label.startswith("oracle/nislam_ref.py") else time_oracle_stream
+        _, _, label, others = best_cpu_stream(warm, threads)
+        kind = "port"
+        timer = time_python_stream if label.startswith("oracle/nislam_ref.py (scipy pocketfft f32 + cv2, thread") else time_oracle_stream
     times = []
     for _ in range(args.steps):
         _, dt = timer(frames, threads)
         times.append(dt)
-    if pool is not None:
-        pool.close()
-        pool.join()
     ms = 1e3 * float(np.mean(times))
     value = (n - 1) / (ms / 1e3)
-    sample = "%d-frame stream (%d solves) per step, %s, %d threads; warm-up solves/s of both restatements: %s" % (
-        n, n - 1, label, threads, json.dumps(both))
+    sample = "%d-frame sample of the stream (%d solves) per step, %s, %d threads; other CPU restatements on the warm-up frames: %s" % (
+        n, n - 1, label, threads, json.dumps(others))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "tracking stream %dx%d u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame" % (W, H),
-                       "frames_per_step": n, "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial"},
-            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.frames, max(1, args.gpus)),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -505,154 +593,230 @@ def main():
     except Exception as e:
         stitch = {"error": str(e)[:200]}
 
-    # ---- loop-closure scan: DB sharded by index over ranks, one NCCL all-gather of the per-rank best records
+    # ---- online latency (the reference's per-call surface, main.cpp:51-86 feeds one frame at a time): one frame in, one pose out
+    online = None
+    try:
+        fa = cf.ComputeIntermedium(frames_host[0].numpy())
+        lat = []
+        for t in range(1, 61):
+            t0 = time.perf_counter()
+            fb = cf.ComputeIntermedium(frames_host[t].numpy())             # nis_features_u8: H2D of the frame + 12 kernels + sync
+            cf.ComputePose(fa, fb, True)                                   # nis_compute_pose: 11 kernels + D2H of the record
+            lat.append((time.perf_counter() - t0) * 1e3)
+            fa.free()
+            fa = fb
+        lat = np.sort(lat[10:])
+        online = {"what": "nis_features_u8 + nis_compute_pose per frame at batch 1, pageable host frame in, pose out, wall clock",
+                  "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[min(len(lat) - 1, int(0.99 * len(lat)))]),
+                  "frames_per_sec": float(1e3 / np.mean(lat))}
+        exe = os.path.join(ROOT, "tests", "cpp", "_build", "shim_test")
+        if rank == 0 and os.path.exists(exe):                              # the same through the C++ shim's reference signatures
+            import re
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+            m = re.search(r"shim_online_ms p50 ([0-9.]+) p99 ([0-9.]+)", out)
+            if m:
+                online["shim"] = {"what": "CorrelationFlow::ComputeIntermedium + ComputePose through host/correlation_flow.hpp (Eigen-layout host "
+                                          "arrays in and out, keyframe operands cached on the device), tests/cpp/shim_test.cc",
+                                  "p50_ms": float(m.group(1)), "p99_ms": float(m.group(2))}
+    except Exception as e:
+        online = {"error": str(e)[:200]}
+
+    # ---- loop-closure scan: keyframe store sharded by index over the ranks; ONE library call per query on every rank
+    # (nis_loop_scan_sharded: ncclBroadcast of the query image, local scan, one ncclAllGather of the best records, reduction)
     loop = None
     if args.db != 0:
         lc = nis.LoopClosure(nis.LoopClosureConfig(position_response_thr=60, angle_response_thr=60), cf)
-        nshard = args.db
-        db_note = "--db"
-        if nshard < 0:
-            # BASELINE.json configs[2] (1 query vs 10k keyframes, 1 GPU) / configs[3] (100k keyframes sharded over the GPUs); a keyframe
-            # record (F, P, Ht, Hp) is 5.24 MB, so 2 GPUs cannot hold 100k: the shard is capped by free HBM and the total reported
-            total = 100000 if (W, H) == (640, 480) else 50000            # configs[3] / configs[4]
-            want = 10000 if (world == 1 and total == 100000) else -(-total // world)
-            free_b = torch.cuda.mem_get_info(dev)[0]
-            per_kf = 2 * BYTES_PER_CANDIDATE + H * W
-            cap = int(0.7 * free_b / per_kf)
-            if want * per_kf <= 0.85 * free_b:              # the configured shard fits with >= 15 % of HBM to spare: take it whole
-                cap = want
+        if world > 1:
+            ids = [nis.CorrelationFlow.NcclUniqueId() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            cf.CommInit(ids[0], rank, world)
+        free_b = torch.cuda.mem_get_info(dev)[0]
+        rec_bytes = {nis.DB_FULL: 2 * BYTES_PER_CANDIDATE, nis.DB_SPECTRA: BYTES_PER_CANDIDATE, nis.DB_IMAGE: H * W}
+        mode_name = {nis.DB_FULL: "full (F, P, Ht, Hp: %.2f MB)" % (2 * BYTES_PER_CANDIDATE / 1e6),
+                     nis.DB_SPECTRA: "spectra (F, P = the reference's Frame payload: %.2f MB; H recomputed per batch)" % (BYTES_PER_CANDIDATE / 1e6),
+                     nis.DB_IMAGE: "image (u8: %.2f MB; features recomputed per batch)" % (H * W / 1e6)}
+
+        def pick_mode(per_gpu):
+            for m in (nis.DB_FULL, nis.DB_SPECTRA, nis.DB_IMAGE):
+                if per_gpu * rec_bytes[m] <= 0.80 * free_b:
+                    return m
+            return nis.DB_IMAGE
+
+        def run_series(total, label):
+            """Builds a `total`-keyframe store over the ranks in the richest mode that fits, times args.queries sharded queries."""
+            per_gpu = -(-total // world)
+            mode = pick_mode(per_gpu)
             if world > 1:
-                tcap = torch.tensor([cap], dtype=torch.int64, device=dev)
-                dist.all_reduce(tcap, op=dist.ReduceOp.MIN)
-                cap = int(tcap.item())
-            nshard = max(64, min(want, cap))
-            if nshard < want:
-                db_note = "capped by HBM: %d of %dk keyframes fit %d GPU(s) (%.2f MB per keyframe record)" % (
-                    nshard * world, want * world // 1000, world, 2 * BYTES_PER_CANDIDATE / 1e6)
-            elif world == 1 and total == 100000:
-                db_note = "configs[2]: 10k keyframes on one GPU"
-            else:
-                db_note = "configs[%d]: %dk keyframes over %d GPU(s)" % (3 if total == 100000 else 4, total // 1000, world)
-        def build_db(ns):
-            g0 = rank * ns
-            for c0 in range(0, ns, 2048):                                  # keyframes are generated and added in chunks (bounded temporaries)
-                c1 = min(ns, c0 + 2048)
+                tm = torch.tensor([mode], dtype=torch.int64, device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                mode = int(tm.item())
+            lc.clear()
+            lc.SetMode(mode)
+            gcx, gcy, gang = bs.db_poses(per_gpu * world, seed=1)
+            g0 = rank * per_gpu
+            for c0 in range(0, per_gpu, 2048):                              # keyframes are generated and added in chunks (bounded temporaries)
+                c1 = min(per_gpu, c0 + 2048)
                 db_imgs = bs.crops(canvas, gcx[g0 + c0:g0 + c1], gcy[g0 + c0:g0 + c1], gang[g0 + c0:g0 + c1], H, W)
                 lc.AddImages(None, np.arange(g0 + c0, g0 + c1, dtype=np.int32), None, ptr=db_imgs.data_ptr(), n=c1 - c0, on_device=True)
                 del db_imgs
-
-        for attempt in range(4):                                           # an allocation failure on any rank halves every shard and retries
-            gcx, gcy, gang = bs.db_poses(nshard * world, seed=1)
-            try:
-                build_db(nshard)
-                ok = 1
-            except Exception as e:                                         # NisError (out of memory) / torch OOM
-                sys.stderr.write("rank %d: keyframe store of %d failed (%s)\n" % (rank, nshard, str(e)[:120]))
-                ok = 0
-            if world > 1:
-                tok = torch.tensor([ok], dtype=torch.int64, device=dev)
-                dist.all_reduce(tok, op=dist.ReduceOp.MIN)
-                ok = int(tok.item())
-            if ok:
-                break
-            lc.clear()
-            torch.cuda.empty_cache()
-            nshard = max(64, nshard // 2)
-            db_note = "reduced to %d keyframes after an allocation failure" % (nshard * world)
-        jstar = (nshard * world) // 2 + 3                                  # expected winner (global id)
-        q_img = bs.crops(canvas, [gcx[jstar] + 13], [gcy[jstar] - 7], [gang[jstar] + 4.5], H, W)
-        nbytes = C.sizeof(nis.LoopResultC)
-
-        def query():
-            qi = q_img.clone()
-            if world > 1:
-                dist.broadcast(qi, src=0)                                  # 307 KB u8 image; each rank recomputes its features
-            qf = cf.ComputeIntermedium(qi[0].cpu().numpy())
-            res = lc.FindLoopClosure(qf, current_frame_id=10 ** 9)
-            if world == 1:
-                return res
-            mine = torch.frombuffer(bytearray(bytes(res.raw)), dtype=torch.uint8).to(dev)
-            allb = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(allb, mine)                       # the one collective of the path
-            raw = allb.cpu().numpy().tobytes()
-            recs = [nis.LoopResultC.from_buffer_copy(raw[i * nbytes:(i + 1) * nbytes]) for i in range(world)]
-            order = [r.frame_id if r.slot >= 0 else 2 ** 62 for r in recs]
-            red, _ = lc.Reduce(recs, order)
-            return red
-
-        res = query()
-        barrier()
-        l1 = cf.kernel_launches()
-        per_query = []
-        for _ in range(args.queries):                     # each query timed on its own; the median guards against host hiccups
-            barrier()
-            t0 = time.perf_counter()
-            e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e4.record(ext)
-            res = query()
-            e5.record(ext)
+            jstar = (per_gpu * world) // 2 + 3                                  # planted keyframe (global id)
+            q_dev = bs.crops(canvas, [gcx[jstar] + 13], [gcy[jstar] - 7], [gang[jstar] + 4.5], H, W)
+            q_host = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+            q_host.copy_(q_dev[0])
             torch.cuda.synchronize()
-            per_query.append(max(e4.elapsed_time(e5), (time.perf_counter() - t0) * 1e3))
-        barrier()
-        q_ms = float(np.median(per_query))
-        tq = torch.tensor([q_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
-        q_ms = float(tq.item())
-        cand_per_s = nshard * world / (q_ms / 1e3)
-        # the store is dense (many keyframes overlap the query), so the winner need not be the planted one: check instead that the
-        # returned relative pose agrees with the winner's true pose (rotation to 0.75 deg, translation length to 2 px)
-        winner_ok = None
-        if res.loop_frame_id >= 0:
-            w = int(res.loop_frame_id)
-            qx, qy, qa = gcx[jstar] + 13, gcy[jstar] - 7, gang[jstar] + 4.5
-            dth = np.deg2rad(qa - gang[w])
-            winner_ok = bool(abs((res.relative_pose[2] - dth + np.pi) % (2 * np.pi) - np.pi) < np.deg2rad(0.75) and
-                             abs(np.hypot(res.relative_pose[0], res.relative_pose[1]) - np.hypot(qx - gcx[w], qy - gcy[w])) < 2.0)
-        loop = {"metric": "loop_closure_queries_per_sec", "db_keyframes": nshard * world, "keyframes_per_gpu": nshard, "workload": db_note,
-                "value": 1e3 / q_ms, "unit": "queries/s", "ms_per_query": q_ms, "ms_per_query_all": [round(x, 3) for x in per_query], "candidates_per_sec": cand_per_s,
-                "queries_per_sec_over_100k_extrapolated": cand_per_s / 1e5, "winner_frame_id": int(res.loop_frame_id),
-                "planted_frame_id": int(jstar), "found": bool(res.found), "relative_pose": [float(x) for x in res.relative_pose],
-                "winner_consistent_with_ground_truth": winner_ok,
-                "collective": "ncclAllGather of %d-byte records" % nbytes if world > 1 else "none (1 rank)",
-                "rotated_query_cache": "on (>= 1024 candidates)",
-                "gpu_launches_per_query": (cf.kernel_launches() - l1) // max(args.queries, 1),
-                "roofline": {"bound": "hbm", "achieved": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9 / peak,
-                             "definition": "per-GPU candidates/s x %d algorithmic B/candidate (SURVEY 8d)" % BYTES_PER_CANDIDATE}}
-        lc.clear()
 
-    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample of the same stream
+            def query():
+                return lc.FindLoopClosureSharded(q_host.numpy() if rank == 0 else None, 0, g0, current_frame_id=10 ** 9)
+            res, win, mine = query()
+            barrier()
+            l1 = cf.kernel_launches()
+            per_query = []
+            for _ in range(args.queries):                     # each query timed on its own; the median guards against host hiccups
+                barrier()
+                t0 = time.perf_counter()
+                e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e4.record(ext)
+                res, win, mine = query()
+                e5.record(ext)
+                torch.cuda.synchronize()
+                per_query.append(max(e4.elapsed_time(e5), (time.perf_counter() - t0) * 1e3))
+            barrier()
+            q_ms = float(np.median(per_query))
+            tq = torch.tensor([q_ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+            q_ms = float(tq.item())
+            cand_per_s = per_gpu * world / (q_ms / 1e3)
+            # the store is dense (many keyframes overlap the query), so the winner need not be the planted one: check that the
+            # returned relative pose agrees with the winner's true pose (rotation to 0.75 deg, translation length to 2 px)
+            winner_ok = None
+            if res.loop_frame_id >= 0:
+                w = int(res.loop_frame_id)
+                qx, qy, qa = gcx[jstar] + 13, gcy[jstar] - 7, gang[jstar] + 4.5
+                dth = np.deg2rad(qa - gang[w])
+                winner_ok = bool(abs((res.relative_pose[2] - dth + np.pi) % (2 * np.pi) - np.pi) < np.deg2rad(0.75) and
+                                 abs(np.hypot(res.relative_pose[0], res.relative_pose[1]) - np.hypot(qx - gcx[w], qy - gcy[w])) < 2.0)
+            out = {"workload": label, "db_keyframes": per_gpu * world, "keyframes_per_gpu": per_gpu, "store_mode": mode_name[mode],
+                   "value": 1e3 / q_ms, "unit": "queries/s", "ms_per_query": q_ms, "ms_per_query_all": [round(x, 3) for x in per_query],
+                   "candidates_per_sec": cand_per_s, "winner_frame_id": int(res.loop_frame_id), "winner_global_slot": int(res.loop_slot),
+                   "winner_rank": int(win), "planted_frame_id": int(jstar), "found": bool(res.found),
+                   "relative_pose": [float(x) for x in res.relative_pose], "winner_consistent_with_ground_truth": winner_ok,
+                   "gpu_launches_per_query": (cf.kernel_launches() - l1) // max(args.queries, 1),
+                   "roofline": {"bound": "hbm", "achieved": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": cand_per_s / world * BYTES_PER_CANDIDATE / 1e9 / peak,
+                                "definition": "per-GPU candidates/s x %d algorithmic B/candidate (SURVEY 8d)" % BYTES_PER_CANDIDATE}}
+            return out, (res, mine, gcx, gcy, gang, q_host, per_gpu, mode)
+
+        nfix = args.db if args.db > 0 else (10000 if (W, H) == (640, 480) else 4000)
+        total_true = 100000 if (W, H) == (640, 480) else 50000
+        series = {}
+        try:
+            series["fixed_per_gpu"], st_fixed = run_series(nfix * world, "%d keyframes PER GPU (the same problem per GPU at every N; N = 1 is BASELINE configs[2])" % nfix)
+        except Exception as e:
+            series["fixed_per_gpu"] = {"error": str(e)[:300]}
+            st_fixed = None
+        # ---- N-rank answer == single-rank answer (outside every timed region): rank 0 re-scans, alone and in the full store mode, a
+        # 256-keyframe subsample of the GLOBAL store that contains every rank's local winner, and compares records
+        check = None
+        if st_fixed is not None:
+            try:
+                res, mine, gcx, gcy, gang, q_host, per_gpu, mode = st_fixed
+                locals_ = [int(mine.loop_slot + rank * per_gpu) if mine.loop_slot >= 0 else -1]
+                resp_ = [[float(x) for x in mine.response]]
+                if world > 1:
+                    gl = [None] * world
+                    dist.all_gather_object(gl, (locals_[0], resp_[0]))
+                    locals_, resp_ = [g[0] for g in gl], [g[1] for g in gl]
+                if rank == 0:
+                    sub = sorted(set([g for g in locals_ if g >= 0]) | set(np.linspace(0, per_gpu * world - 1, 256 - world).astype(int).tolist()))
+                    lc.clear()
+                    lc.SetMode(nis.DB_FULL)
+                    imgs_sub = bs.crops(canvas, gcx[sub], gcy[sub], gang[sub], H, W)
+                    lc.AddImages(None, np.asarray(sub, np.int32), None, ptr=imgs_sub.data_ptr(), n=len(sub), on_device=True)
+                    qf = cf.ComputeIntermedium(q_host.numpy())
+                    r1, recs = lc.FindLoopClosureRecords(qf, 10 ** 9, 0.0)
+                    same_winner = int(r1.loop_frame_id) == int(res.loop_frame_id)
+                    same_pose = bool(np.array_equal(r1.relative_pose, res.relative_pose))
+                    bits = bool(np.array_equal(r1.response, res.response))
+                    close = bool(np.allclose(r1.response, res.response, rtol=1e-6))
+                    locals_ok = all(np.allclose(recs["response"][sub.index(g)], rp, rtol=1e-6) for g, rp in zip(locals_, resp_) if g >= 0)
+                    check = {"scan_equals_single_rank": bool(same_winner and same_pose and close and locals_ok), "identical_response_bits": bits,
+                             "what": "rank 0 alone re-scanned %d keyframes of the global store (every rank's local winner + an even subsample, full store "
+                                     "mode) with per-candidate records: same winner, same pose, same response as the %d-rank sharded call, and every rank's "
+                                     "local best record reproduced" % (len(sub), world)}
+                    lc.clear()
+            except Exception as e:
+                check = {"error": str(e)[:300]}
+        if world > 1:
+            barrier()
+        if args.db < 0:
+            try:
+                series["true_total"], _ = run_series(total_true, "%dk keyframes in total over %d GPU(s) (BASELINE configs[%d]), MEASURED" % (
+                    total_true // 1000, world, 3 if total_true == 100000 else 4))
+            except Exception as e:
+                series["true_total"] = {"error": str(e)[:300]}
+        lc.clear()
+        lc.SetMode(nis.DB_FULL)
+        head = series.get("true_total") if "value" in (series.get("true_total") or {}) else series.get("fixed_per_gpu")
+        loop = {"metric": "loop_closure_queries_per_sec", "series": series, "n_rank_check": check,
+                "collective": ("one ncclBroadcast (%d B u8 query image) + one ncclAllGather (104 B per rank) inside nis_loop_scan_sharded" % (H * W))
+                if world > 1 else "none (1 rank)", "rotated_query_cache": "on (>= 1024 candidates)"}
+        if head and "value" in head:
+            loop.update({k: head[k] for k in ("value", "unit", "db_keyframes", "keyframes_per_gpu", "ms_per_query", "candidates_per_sec", "store_mode", "roofline")})
+
+    # ---- CPU baselines (rank 0, N = 1 only), bounded samples of the same workloads on the host cores: oracle/_ref (the reference's own
+    # sources, kind "reference") when built, else the C port
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 1:
+        cores = os.cpu_count() or 1
+        use_ref = ref_available()
         try:
-            cores = os.cpu_count() or 1
             sample = frames_host[:args.cpu_frames].numpy()
-            v_all, dt_all, label, both = best_cpu_stream(sample, cores)
-            sub = sample[:min(9, args.cpu_frames)]
-            v_1, dt_1, label1, both1 = best_cpu_stream(sub, 1)
-            cpu = {"value": v_all, "unit": "solves/s", "cores": cores, "kind": "port",
-                   "sample": "first %d frames of the same stream (%d solves, %.1f s), faster of the two CPU restatements = %s, %d threads; "
-                             "1 thread on %d frames: %.2f solves/s (%s)" % (args.cpu_frames, args.cpu_frames - 1, dt_all, label, cores,
-                                                                            sub.shape[0], v_1, label1),
-                   "value_1_thread": v_1, "all_threads_both": both, "one_thread_both": both1}
+            if use_ref:
+                time_ref_stream(sample[:min(args.cpu_frames, cores + 1)], cores)                 # warm-up: per-thread contexts, FFT plans
+                v_all, dt_all = time_ref_stream(sample, cores)
+                v_1, dt_1 = time_ref_stream(sample[:7], 1)
+                v_c, _ = time_oracle_stream(sample, cores)
+                cpu = {"value": v_all, "unit": "solves/s", "cores": cores, "kind": "reference",
+                       "sample": "first %d frames of the same stream (%d solves, %.1f s) through oracle/_ref = the reference's correlation_flow.cc / "
+                                 "utils.cc compiled unmodified against stand-in headers (FFT = the C oracle's, warps = cv2-verified fixed point), "
+                                 "%d threads; 1 thread on 7 frames: %.2f solves/s (how the reference itself runs); the dependency-free C port on "
+                                 "the same frames, %d threads: %.1f solves/s" % (args.cpu_frames, args.cpu_frames - 1, dt_all, cores, v_1, cores, v_c),
+                       "value_1_thread": v_1, "c_port_all_threads": v_c}
+            else:
+                v_all, dt_all, label, both = best_cpu_stream(sample, cores)
+                v_1, dt_1, label1, both1 = best_cpu_stream(sample[:min(9, args.cpu_frames)], 1)
+                cpu = {"value": v_all, "unit": "solves/s", "cores": cores, "kind": "port",
+                       "sample": "first %d frames of the same stream (%d solves, %.1f s), %s, %d threads; 1 thread: %.2f solves/s" % (
+                           args.cpu_frames, args.cpu_frames - 1, dt_all, label, cores, v_1), "value_1_thread": v_1, "all_threads_both": both}
         except Exception as e:          # the checker must not take the bench down
             cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        if loop is not None:
+            try:
+                ncand = 256
+                gcx, gcy, gang = bs.db_poses(ncand, seed=1)
+                db_s = bs.crops(canvas, gcx, gcy, gang, H, W).cpu().numpy()
+                q_s = bs.crops(canvas, [gcx[ncand // 2] + 13], [gcy[ncand // 2] - 7], [gang[ncand // 2] + 4.5], H, W).cpu().numpy()[0]
+                c_all, dt_s, win_s = time_cpu_scan(db_s, q_s, cores, use_ref)
+                c_1, dt_s1, _ = time_cpu_scan(db_s[:8], q_s, 1, use_ref)
+                loop["cpu_baseline"] = {"value": c_all / 1e5, "unit": "queries/s over 100k keyframes (extrapolated linearly from the sample: constant cost per candidate)",
+                                        "candidates_per_sec": c_all, "candidates_per_sec_1_thread": c_1, "cores": cores,
+                                        "kind": "reference" if use_ref else "port",
+                                        "sample": "LoopClosure::FindLoopClosure over %d seeded keyframes (%.1f s on %d threads; 8 candidates on 1 thread: %.1f s), "
+                                                  "per candidate ComputePose(..., false) = loop_closure.cc:58-59; winner = planted keyframe: %s" % (
+                                                      ncand, dt_s, cores, dt_s1, win_s == ncand // 2)}
+            except Exception as e:
+                loop["cpu_baseline"] = {"error": str(e)[:300]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "tracking stream %dx%d u8, every frame a keyframe, ComputeIntermedium + ComputePose(tracking) per frame " % (W, H) +
-                                       "(BASELINE.json configs[1])", "frames_per_step_per_gpu": n, "solves_per_step": solves_per_step,
-                           "rotation_divisor": D, "rotation_channel": CP, "kernel": "polynomial", "batch": args.batch or "default", "lanes": args.lanes or "default",
-                           "parallelism": "replicas only (tracking does not shard)" if world > 1 else "1 GPU",
-                           "l2": "inputs larger than L2: %.0f MB of frames + %.0f MB of features per step vs 126 MB L2" %
-                                 (n * H * W / 1e6, n * BYTES_PER_CANDIDATE / 1e6)},
+                "config": workload_config(n, world), "tuning": {"batch": args.batch or "default", "lanes": args.lanes or "default"},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": n * H * W,
                         "d2h_bytes_per_step": (n - 1) * 72},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "loop_closure": loop, "undistort_front_end": front, "keyframe_policy": policy, "map_stitcher": stitch,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "loop_closure": loop, "online": online, "undistort_front_end": front, "keyframe_policy": policy, "map_stitcher": stitch,
                 "pose_ok_frac": pose_ok_frac}
         emit(line)
     cf.close()

@@ -89,8 +89,13 @@ int nis_features_u8(nis_ctx* ctx, const uint8_t* image_rowmajor, nis_frame** out
 int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out);    /* ArrayXXf H x W, reference layout */
 /* Frame::GetFFTResult (src/frame.cc:53-57): copy both spectra out in reference layout; either pointer may be NULL */
 int nis_frame_export(nis_ctx* ctx, const nis_frame* f, float* fft_result, float* fft_polar);
-/* build a frame from reference-layout arrays the caller already holds (image, fft_result, fft_polar) */
+/* build a frame from reference-layout arrays the caller already holds (image, fft_result, fft_polar); also computes the frame's
+ * keyframe factors H, so it can serve as `last` of nis_compute_pose or go into the store */
 int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, nis_frame** out);
+/* the same with any subset of the three arrays (NULL = absent) and the H factors optional: what CorrelationFlow::ComputePose actually
+ * reads is (last_fft_result, last_fft_polar [+ H]) of the last frame and (image, fft_polar) of the current one (include/correlation_flow.h:13),
+ * what FindLoopClosure reads of the query is (image, fft_polar) (src/loop_closure.cc:38-39, :58-59) */
+int nis_frame_import_ex(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, int with_h, nis_frame** out);
 int nis_frame_free(nis_ctx* ctx, nis_frame* f);
 
 /* ---- undistort front end: Camera::UndistortImage (src/camera.cc:92-93) = cv::remap(u8, _map1, _map2, INTER_LINEAR).
@@ -169,8 +174,18 @@ int nis_stitcher_frames(const nis_stitcher* st);
 int nis_stitcher_cell(nis_stitcher* st, int cell_x, int cell_y, int32_t* data, int32_t* weight, int* present);
 int nis_stitcher_dropped(nis_stitcher* st, long long* pixels_outside_window);
 
-/* ---- keyframe database = Map::AddFrame for the arrays the scan reads (include/frame.h:35-36, src/map.cc) ---- */
+/* ---- keyframe database = Map::AddFrame for the arrays the scan reads (include/frame.h:35-36, src/map.cc) ----
+ * Store mode (set while the store is empty): what a record keeps per keyframe.  A scan returns the same bits in every mode -- what is
+ * not kept is recomputed per batch of candidates by the same kernels.
+ *   NIS_DB_FULL    fft_result, fft_polar and the cached factors Ht, Hp     5.24 MB @640x480   (default; fastest scan)
+ *   NIS_DB_SPECTRA fft_result, fft_polar = Frame::_fft_result/_fft_polar   2.62 MB            (the reference's own payload)
+ *   NIS_DB_IMAGE   the u8 image                                            0.31 MB            (100 k keyframes on one GPU) */
+enum { NIS_DB_FULL = 0, NIS_DB_SPECTRA = 1, NIS_DB_IMAGE = 2 };
+int nis_db_set_mode(nis_ctx* ctx, int mode);
+int nis_db_mode(const nis_ctx* ctx);
 int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distance, int* slot);
+/* a keyframe given as the reference-layout arrays Frame::GetFFTResult hands out (src/frame.cc:53-57); not for NIS_DB_IMAGE */
+int nis_db_add_spectra(nis_ctx* ctx, const float* fft_result, const float* fft_polar, int frame_id, double acc_distance, int* slot);
 /* bulk insert: n u8 images (host or device), features computed on the GPU straight into the DB */
 int nis_db_add_images(nis_ctx* ctx, const uint8_t* images_host, int n, const int* frame_ids, const double* acc_distances);
 int nis_db_add_images_dev(nis_ctx* ctx, const uint8_t* images_dev, int n, const int* frame_ids, const double* acc_distances);
@@ -185,20 +200,48 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
                   const nis_loop_config* cfg, const int32_t* candidate_slots, int n_candidates, nis_loop_result* out,
                   double* all_responses);
 
+/* the same scan with one record per entry of the candidate list (all slots when candidate_slots == NULL): records[i].evaluated = 0 for
+ * candidates the gap / distance filters dropped (loop_closure.cc:43-53) */
+typedef struct {
+  int32_t evaluated;
+  int32_t hyp;
+  double relative_pose[3];
+  double response[3];
+  int32_t peak[4];
+} nis_scan_record;
+int nis_loop_scan_records(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance,
+                          const nis_loop_config* cfg, const int32_t* candidate_slots, int n_candidates, nis_loop_result* out,
+                          nis_scan_record* records);
+
 /* ---- candidate selection by prior pose: LoopClosure::FindLoopClosure(image, current_frame, prior_pose), src/loop_closure.cc:17-34
  *      = Map::ComputeGridLocation + the 3x3 neighbourhood + Map::GetFramesInGrids (src/map.cc:81-101).
  *      nis_db_set_position files a keyframe under its grid cell ((int)(x/grid_scale), (int)(y/grid_scale)) -- like Map::AddFrame
  *      it is the pose at insertion time that counts.  nis_loop_scan_prior scans the keyframes of the 9 cells around the prior's cell,
  *      cells in the reference's order (dx = -1..1 outer, dy = -1..1 inner), slots ascending inside a cell (the reference iterates
- *      an unordered_set there, i.e. in no defined order).  candidates_out (may be NULL, capacity max_candidates) receives that list. ---- */
+ *      an unordered_set there, i.e. in no defined order).  candidates_out (may be NULL, capacity max_candidates) receives that list.
+ *      Selection (grid cells and the gap / distance filters of nis_loop_scan alike) runs on the GPU over device-resident per-slot
+ *      frame ids, distances and cells: counts per chunk, one exclusive scan, ordered compaction -- no host loop over the store. ---- */
 int nis_db_set_position(nis_ctx* ctx, int slot, double x, double y, double grid_scale);
 int nis_loop_scan_prior(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance,
                         const nis_loop_config* cfg, double prior_x, double prior_y, double grid_scale, nis_loop_result* out,
                         int32_t* candidates_out, int max_candidates, int* n_candidates_out);
 
-/* Multi-GPU: every rank scans its own shard with nis_loop_scan, the ranks all-gather their nis_loop_result records
- * (NCCL), and each rank calls this to pick the winner with the reference's rule.  `order[i]` is the position of rank
- * i's winner in the global iteration order (ties: smallest wins); pass NULL to use the rank index. */
+/* ---- multi-GPU scan: the keyframe store is sharded by index, one context (= one process) per GPU.
+ *      nis_nccl_unique_id on one rank -> ship the 128 bytes to the others by any means -> nis_comm_init on every rank; then one
+ *      nis_loop_scan_sharded call per query on EVERY rank: the root's u8 query image (row-major H x W, raw when undistort maps are
+ *      set) is broadcast (ncclBroadcast, 307 KB), every rank computes the query's features and scans its own shard, the per-rank
+ *      best records are all-gathered (ONE ncclAllGather of 104 bytes per rank) and reduced with the reference's rule (strict '>',
+ *      earliest global slot on ties, loop_closure.cc:61).  global_slot_offset = global index of this rank's slot 0; out->slot is the
+ *      winner's GLOBAL slot, out->evaluated the total over all ranks; local_out (may be NULL) this rank's own best.
+ *      NCCL is resolved with dlopen("libnccl.so.2") (override: NIS_NCCL_LIB) on the first call; single-GPU use never needs it. ---- */
+int nis_nccl_unique_id(char id_out[128]);
+int nis_comm_init(nis_ctx* ctx, const char id[128], int rank, int n_ranks);
+int nis_comm_destroy(nis_ctx* ctx);
+int nis_loop_scan_sharded(nis_ctx* ctx, const uint8_t* query_image_rowmajor, int root, int query_frame_id, double query_acc_distance,
+                          const nis_loop_config* cfg, long long global_slot_offset, nis_loop_result* out, int* winner_rank,
+                          nis_loop_result* local_out);
+/* The reduction nis_loop_scan_sharded applies, exposed for hosts that move the records themselves: `order[i]` is the position of
+ * rank i's winner in the global iteration order (ties: smallest wins); pass NULL to use the rank index. */
 int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n_ranks, const nis_loop_config* cfg,
                     nis_loop_result* out, int* winner_rank);
 

@@ -29,8 +29,11 @@ SYMBOLS = [
     "nis_db_add_images_dev", "nis_db_size", "nis_db_clear", "nis_loop_scan", "nis_loop_reduce", "nis_db_set_position", "nis_loop_scan_prior", "nis_debug_fft2",
     "nis_debug_ifft2", "nis_debug_polar", "nis_debug_rotate", "nis_debug_estimate_trans", "nis_profile_begin",
     "nis_profile_end", "nis_stitcher_create", "nis_stitcher_destroy", "nis_stitcher_insert", "nis_stitcher_recompute",
-    "nis_stitcher_frames", "nis_stitcher_cell", "nis_stitcher_dropped",
+    "nis_stitcher_frames", "nis_stitcher_cell", "nis_stitcher_dropped", "nis_frame_import_ex", "nis_db_set_mode", "nis_db_mode",
+    "nis_db_add_spectra", "nis_loop_scan_records", "nis_nccl_unique_id", "nis_comm_init", "nis_comm_destroy", "nis_loop_scan_sharded",
 ]
+
+DB_FULL, DB_SPECTRA, DB_IMAGE = 0, 1, 2      # nis_db_set_mode
 
 
 class NisError(RuntimeError):
@@ -53,6 +56,10 @@ class LoopResultC(C.Structure):
     _fields_ = [("found", C.c_int32), ("slot", C.c_int32), ("frame_id", C.c_int32), ("hyp", C.c_int32),
                 ("relative_pose", C.c_double * 3), ("response", C.c_double * 3), ("peak", C.c_int32 * 4),
                 ("evaluated", C.c_int32)]
+
+
+SCAN_RECORD_DTYPE = np.dtype([("evaluated", np.int32), ("hyp", np.int32), ("relative_pose", np.float64, 3), ("response", np.float64, 3),
+                              ("peak", np.int32, 4)])          # nis_scan_record
 
 
 class _KfsConfigC(C.Structure):       # nis_kfs_config = KeyframeSelectionConfig (include/read_configs.h:27-32)
@@ -181,6 +188,16 @@ def load_library():
     lib.nis_db_set_position.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double]
     lib.nis_loop_scan_prior.argtypes = [vp, vp, i32, C.c_double, C.POINTER(_LoopConfigC), C.c_double, C.c_double, C.c_double,
                                         C.POINTER(LoopResultC), vp, i32, C.POINTER(i32)]
+    lib.nis_frame_import_ex.argtypes = [vp, vp, vp, vp, i32, C.POINTER(vp)]
+    lib.nis_db_set_mode.argtypes = [vp, i32]
+    lib.nis_db_mode.argtypes = [vp]
+    lib.nis_db_add_spectra.argtypes = [vp, vp, vp, i32, C.c_double, C.POINTER(i32)]
+    lib.nis_loop_scan_records.argtypes = [vp, vp, i32, C.c_double, C.POINTER(_LoopConfigC), vp, i32, C.POINTER(LoopResultC), vp]
+    lib.nis_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.nis_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
+    lib.nis_comm_destroy.argtypes = [vp]
+    lib.nis_loop_scan_sharded.argtypes = [vp, vp, i32, i32, C.c_double, C.POINTER(_LoopConfigC), C.c_longlong, C.POINTER(LoopResultC),
+                                          C.POINTER(i32), C.POINTER(LoopResultC)]
     lib.nis_debug_fft2.argtypes = [vp, i32, vp, vp]
     lib.nis_debug_ifft2.argtypes = [vp, i32, vp, vp]
     lib.nis_debug_polar.argtypes = [vp, vp, vp]
@@ -209,7 +226,9 @@ class Frame:
         return np.ascontiguousarray(F.T), np.ascontiguousarray(P.T)
 
     def free(self):
-        if self._h is not None and self._cf._ctx is not None:
+        # a context that is closed first releases the device blocks of its outstanding frames (nis_destroy); the handle is then
+        # freed without a context
+        if self._h is not None:
             self._cf._lib.nis_frame_free(self._cf._ctx, self._h)
         self._h = None
 
@@ -325,6 +344,28 @@ class CorrelationFlow:
         self._check(self._lib.nis_frame_import(self._ctx, _p(img), _p(F), _p(P), C.byref(h)))
         return Frame(self, h)
 
+    def ImportFrameEx(self, image_f32=None, fft_result=None, fft_polar=None, with_h=False) -> Frame:
+        """nis_frame_import_ex: any subset of (image, fft_result, fft_polar); what ComputePose reads is (fft_result, fft_polar, H) of the
+        last frame and (image, fft_polar) of the current one."""
+        img = np.ascontiguousarray(np.asarray(image_f32, np.float32).T) if image_f32 is not None else None
+        F = np.ascontiguousarray(np.asarray(fft_result, np.complex64).T) if fft_result is not None else None
+        P = np.ascontiguousarray(np.asarray(fft_polar, np.complex64).T) if fft_polar is not None else None
+        h = C.c_void_p()
+        self._check(self._lib.nis_frame_import_ex(self._ctx, _p(img), _p(F), _p(P), int(bool(with_h)), C.byref(h)))
+        return Frame(self, h)
+
+    # ---- multi-GPU scan plumbing (one context per rank)
+    @staticmethod
+    def NcclUniqueId() -> bytes:
+        buf = C.create_string_buffer(128)
+        st = load_library().nis_nccl_unique_id(buf)
+        if st != NIS_OK:
+            raise NisError(st, "ncclGetUniqueId failed (libnccl.so.2 not found? set NIS_NCCL_LIB)")
+        return buf.raw
+
+    def CommInit(self, unique_id: bytes, rank: int, n_ranks: int):
+        self._check(self._lib.nis_comm_init(self._ctx, C.create_string_buffer(unique_id, 128), int(rank), int(n_ranks)))
+
     def ComputePose(self, last: Frame, cur: Frame, not_large_rotation: bool, return_peaks: bool = False):
         """CorrelationFlow::ComputePose (correlation_flow.cc:97-143): returns (info[3], pose[3]) like the reference
         returns `info` and fills `pose`; the current frame carries image and fft_polar."""
@@ -437,8 +478,42 @@ class LoopClosure:
         fn = cf._lib.nis_db_add_images_dev if on_device else cf._lib.nis_db_add_images
         cf._check(fn(cf._ctx, C.c_void_p(ptr), int(n), _p(ids), _p(ds)))
 
+    def AddSpectra(self, fft_result, fft_polar, frame_id: int, acc_distance: float = 0.0) -> int:
+        """Map::AddFrame for a keyframe given as the arrays Frame::GetFFTResult hands out."""
+        F = np.ascontiguousarray(np.asarray(fft_result, np.complex64).T)
+        P = np.ascontiguousarray(np.asarray(fft_polar, np.complex64).T)
+        slot = C.c_int()
+        self._cf._check(self._cf._lib.nis_db_add_spectra(self._cf._ctx, _p(F), _p(P), int(frame_id), float(acc_distance), C.byref(slot)))
+        return slot.value
+
+    def SetMode(self, mode: int):
+        """nis_db_set_mode: DB_FULL (F, P, Ht, Hp), DB_SPECTRA (F, P), DB_IMAGE (u8 image); only while the store is empty."""
+        self._cf._check(self._cf._lib.nis_db_set_mode(self._cf._ctx, int(mode)))
+
     def size(self) -> int:
         return int(self._cf._lib.nis_db_size(self._cf._ctx))
+
+    def FindLoopClosureRecords(self, current_frame: Frame, current_frame_id: int = 0, current_distance: float = 0.0, candidate_slots=None):
+        """The scan with one nis_scan_record per entry of the candidate list (SCAN_RECORD_DTYPE): peaks, hypothesis, pose, response."""
+        cf = self._cf
+        cand = np.ascontiguousarray(candidate_slots, np.int32) if candidate_slots is not None else None
+        n = int(cand.shape[0]) if cand is not None else 0
+        recs = np.zeros(n if cand is not None else self.size(), SCAN_RECORD_DTYPE)
+        out = LoopResultC()
+        cfg = self._cfg_c()
+        cf._check(cf._lib.nis_loop_scan_records(cf._ctx, current_frame._h, int(current_frame_id), float(current_distance), C.byref(cfg),
+                                                _p(cand), n, C.byref(out), _p(recs)))
+        return _result_from_c(out), recs
+
+    def FindLoopClosureSharded(self, query_u8, root: int, global_slot_offset: int, current_frame_id: int = 0, current_distance: float = 0.0):
+        """nis_loop_scan_sharded: one call per query on every rank -> (global result, winner rank, this rank's own best)."""
+        cf = self._cf
+        q = np.ascontiguousarray(query_u8, np.uint8) if query_u8 is not None else None
+        out, loc, win = LoopResultC(), LoopResultC(), C.c_int(-1)
+        cfg = self._cfg_c()
+        cf._check(cf._lib.nis_loop_scan_sharded(cf._ctx, _p(q), int(root), int(current_frame_id), float(current_distance), C.byref(cfg),
+                                                int(global_slot_offset), C.byref(out), C.byref(win), C.byref(loc)))
+        return _result_from_c(out), win.value, _result_from_c(loc)
 
     def clear(self):
         self._cf._check(self._cf._lib.nis_db_clear(self._cf._ctx))

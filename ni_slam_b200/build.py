@@ -14,9 +14,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+# NIS_BUILD_TAG=<tag> (with NIS_NVCC_EXTRA="-D...") builds a compile-time variant beside the product library for A/B runs on the
+# GPU box (select it with NIS_LIB=ni_slam_b200/lib/libnislam_<tag>.so)
+TAG = os.environ.get("NIS_BUILD_TAG", "")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libnislam.so")
+OBJDIR = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(LIBDIR, "libnislam%s.so" % ("_" + TAG if TAG else ""))
 UNITS = ["nis_col.cu", "nis_row.cu", "nis_misc.cu", "nis_api.cu", "nis_stitch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--threads", "4"]
@@ -50,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, UNITS))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+    r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -3,6 +3,7 @@
 // only builds constant tables, sizes batches and enqueues kernels; all per-pixel arithmetic runs on the GPU and
 // there is no CPU fallback.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,13 +29,23 @@ using namespace nis;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  // Grows the buffer (contents are scratch and not preserved).  Transactional: the new block is allocated first and the old one
+  // is kept if that fails, so a caller that retries with a smaller size after NIS_ERR_OUT_OF_MEMORY still owns a valid buffer of
+  // `bytes` bytes.  Only when both blocks cannot coexist is the old one released before a second attempt; if that fails too the
+  // buffer is left empty (p == nullptr, bytes == 0) and every capacity derived from `bytes` reads 0.
   int reserve(size_t n) {
     if (n <= bytes) return 0;
-    if (p) cudaFree(p);
-    p = nullptr; bytes = 0;
-    cudaError_t e = cudaMalloc(&p, n);
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n);
+    if (e != cudaSuccess && p) {
+      (void)cudaGetLastError();
+      cudaFree(p);
+      p = nullptr; bytes = 0;
+      e = cudaMalloc(&q, n);
+    }
     if (e != cudaSuccess) return (int)e;
-    bytes = n;
+    if (p) cudaFree(p);
+    p = q; bytes = n;
     return 0;
   }
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -49,12 +60,14 @@ struct nis_frame {
   cpx* Ht = nullptr;           // T/(kernel(F)/max + lambda): the keyframe-only factor of EstimateTrans, translation stage
   cpx* Hp = nullptr;           // same for the polar stage
   void* block = nullptr;       // single allocation backing all of the above
+  // what the buffers hold: frames made by nis_features_* carry everything, imported ones what the caller handed over
+  bool has_image = true, has_spectra = true /* F */, has_polar = true /* P */, has_h = true /* Ht, Hp */;
 };
 
 struct SizeClass {             // one 2-D transform size: R rows (halved) x C cols
   int R, C;
   size_t spec, real;           // elements
-  Twiddles colf, coli, row;
+  Twiddles col, row;
 };
 
 // One lane = one CUDA stream with its own workspace.  Batches are dealt round-robin to the lanes so that several small
@@ -64,6 +77,8 @@ struct Lane {
   cudaEvent_t ev = nullptr;
   int cap = 0;                 // workspace capacity in pairs
   DevBuf t1, real, pol, maxp, maxt, maxh, stats_p, stats_t, sel, xx, zz;
+  DevBuf dbrec;                // scan scratch of the compact store modes: F, P, Ht, Hp of one batch of candidates
+  int db_cap = 0;
 };
 
 struct nis_ctx {
@@ -74,6 +89,7 @@ struct nis_ctx {
   cudaStream_t prof_stream = nullptr;
   cudaEvent_t fork_ev = nullptr;
   std::vector<void*> frame_pool;               // freed nis_frame blocks, reused by the next frame_alloc
+  std::vector<nis_frame*> live_frames;          // frames handed out and not yet freed: released by nis_destroy
   cudaStream_t copy_stream = nullptr;          // host->device uploads of a stream run back to back here, ahead of the compute lanes
   std::vector<cudaEvent_t> up_ev, feat_ev;     // per batch of a stream: upload done / features done
   nis_cf_config cfg{};
@@ -88,10 +104,13 @@ struct nis_ctx {
   int ptile_pitch = 0, ptile_rows = 0;
   // constant tables
   DevBuf tw, lut, cs, rho, mats, theta, ptab, ptiles, ptab2;
-  DevBuf recs, best, cand;
+  DevBuf recs, best, cand, stage, qgather;
+  // multi-GPU scan (nis_comm_init / nis_loop_scan_sharded): NCCL communicator of this context's rank
+  void* nccl_comm = nullptr;
+  int rank = 0, n_ranks = 1;
   int recs_cap = 0, cand_cap = 0;
   // stream slabs
-  DevBuf sF, sP, sHt, sHp, sImg, sUnd;
+  DevBuf sF, sP, sHt, sHp, sImg, sUnd, kfrec;
   // undistort front end (Camera::UndistortImage): fixed-point remap maps handed over by the caller
   DevBuf umap1, umap2;
   bool undistort = false;
@@ -103,11 +122,13 @@ struct nis_ctx {
   // keyframe DB
   std::vector<void*> chunks;
   int chunk_slots = 64;
-  std::vector<cpx*> slot_ptr;          // host copy of the device pointer table
+  std::vector<void*> slot_ptr;         // host copy of the device pointer table (record start per slot)
+  int db_mode = 0;                     // NIS_DB_FULL / NIS_DB_SPECTRA / NIS_DB_IMAGE
+  bool meta_dirty = true;              // frame ids / distances / cells changed since the last upload
+  DevBuf d_fid, d_dist, d_cell, cand_in, cand_pos, sel_scratch;
   std::vector<int> slot_frame_id;
   std::vector<double> slot_dist;
   std::vector<std::pair<int, int>> slot_cell;    // grid cell at insertion time (Map::AddFrame), INT_MIN = not filed
-  std::map<std::pair<int, int>, std::vector<int>> grid;   // cell -> slots (ascending)
   DevBuf d_slot_ptr;
   int d_slot_cap = 0;
   // pinned staging
@@ -181,7 +202,7 @@ template <class T> static Src<T> src_null() { return Src<T>{nullptr, 0, nullptr,
 // -------------------------------------------------------------------------------------------------------------
 // constant tables
 // -------------------------------------------------------------------------------------------------------------
-static void host_twiddles(const int r[3], std::vector<cpx>& out, size_t& off1, size_t& off2) {
+static void host_twiddles(const int r[3], std::vector<cpx>& out, size_t& off1, size_t& off2) {     // row passes (Stockham)
   const int R0 = r[0], R1 = r[1], R2 = r[2], N = R0 * R1 * R2;
   off1 = out.size();
   out.resize(off1 + (size_t)std::max(R1 - 1, 1) * R0, make_float2(1.f, 0.f));
@@ -196,6 +217,24 @@ static void host_twiddles(const int r[3], std::vector<cpx>& out, size_t& off1, s
     for (int k = 0; k < R0 * R1; ++k) {
       const double a = -2.0 * M_PI * (double)q * k / (double)N;
       out[off2 + (size_t)(q - 1) * R0 * R1 + k] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+// column passes (in place, see nis_fft.cuh): tw1[(b-1)*C + d2] = exp(-2 pi i b d2 / (B C)), tw2[(a-1)*BC + j] = exp(-2 pi i a j / N)
+static void host_twiddles_col(const int r[3], std::vector<cpx>& out, size_t& off1, size_t& off2) {
+  const int A = r[0], B = r[1], C = r[2], N = A * B * C;
+  off1 = out.size();
+  out.resize(off1 + (size_t)std::max(B - 1, 1) * C, make_float2(1.f, 0.f));
+  for (int q = 1; q < B; ++q)
+    for (int k = 0; k < C; ++k) {
+      const double a = -2.0 * M_PI * (double)q * k / (double)(B * C);
+      out[off1 + (size_t)(q - 1) * C + k] = make_float2((float)cos(a), (float)sin(a));
+    }
+  off2 = out.size();
+  out.resize(off2 + (size_t)std::max(A - 1, 1) * B * C, make_float2(1.f, 0.f));
+  for (int q = 1; q < A; ++q)
+    for (int k = 0; k < B * C; ++k) {
+      const double a = -2.0 * M_PI * (double)q * k / (double)N;
+      out[off2 + (size_t)(q - 1) * B * C + k] = make_float2((float)cos(a), (float)sin(a));
     }
 }
 
@@ -222,22 +261,20 @@ static int build_tables(nis_ctx* ctx) {
   const int H = ctx->H, W = ctx->W, D = ctx->D, Cp = ctx->Cp;
   // twiddles
   std::vector<cpx> tw;
-  size_t o[12];
+  size_t o[8];
   int r[3];
   for (int s = 0; s < 2; ++s) {
     SizeClass& z = ctx->sz[s];
-    plan_radices_col(z.R, false, r); host_twiddles(r, tw, o[6 * s + 0], o[6 * s + 1]);
-    plan_radices_col(z.R, true, r);  host_twiddles(r, tw, o[6 * s + 2], o[6 * s + 3]);
-    plan_radices_row(z.C, r);        host_twiddles(r, tw, o[6 * s + 4], o[6 * s + 5]);
+    plan_radices_col(z.R, r); host_twiddles_col(r, tw, o[4 * s + 0], o[4 * s + 1]);
+    plan_radices_row(z.C, r); host_twiddles(r, tw, o[4 * s + 2], o[4 * s + 3]);
   }
   RESERVE(ctx->tw, tw.size() * sizeof(cpx));
   CU(h2d(ctx, ctx->tw.p, tw.data(), tw.size() * sizeof(cpx)));
   const cpx* base = ctx->tw.as<cpx>();
   for (int s = 0; s < 2; ++s) {
     SizeClass& z = ctx->sz[s];
-    z.colf = Twiddles{base + o[6 * s + 0], base + o[6 * s + 1]};
-    z.coli = Twiddles{base + o[6 * s + 2], base + o[6 * s + 3]};
-    z.row = Twiddles{base + o[6 * s + 4], base + o[6 * s + 5]};
+    z.col = Twiddles{base + o[4 * s + 0], base + o[4 * s + 1]};
+    z.row = Twiddles{base + o[4 * s + 2], base + o[4 * s + 3]};
   }
   // u8 -> f32/255 (utils.cc:117: matrix.array()/255.0)
   float lut[256];
@@ -314,6 +351,7 @@ static int build_tables(nis_ctx* ctx) {
 static int ensure_workspace(nis_ctx* ctx, Lane& L, int pairs) {
   if (pairs <= L.cap) return NIS_OK;
   CU(cudaStreamSynchronize(L.stream));
+  L.cap = 0;                                   // stays 0 if any of the reservations below fails (no stale capacity after an OOM)
   const size_t E = 2 * (size_t)pairs;
   RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));          // the only full-size scratch: half-transformed spectra, in place
   RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float2));  // power = IFFT(|F|) feeding the polar gather (pair-duplicated: 8 B / pixel)
@@ -348,6 +386,7 @@ static int join_lanes(nis_ctx* ctx) {
 static int ensure_recs(nis_ctx* ctx, int n) {
   if (n <= ctx->recs_cap) return NIS_OK;
   CU(cudaDeviceSynchronize());
+  ctx->recs_cap = 0;
   RESERVE(ctx->recs, (size_t)n * sizeof(PoseRecord));
   RESERVE(ctx->best, sizeof(PoseRecord));
   ctx->recs_cap = n;
@@ -384,7 +423,7 @@ static int hzz_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> Z, int B, Dst<cpx> H
   if (ctx->cfg.kernel == 1) LAUNCH(launch_spec_sqsum(Z, (int)z.spec, L.zz.as<double>(), B, L.stream));
   CU(cudaMemsetAsync(L.maxh.p, 0, sizeof(unsigned) * B, L.stream));
   LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{Z, Z}, EpiSpecStore{t1}, z.R / 2 + 1, B, L.stream));
-  LAUNCH(launch_colcol(z.R, z.coli, z.colf, t1s, t1, kernel_fn(ctx, s, L.zz.as<double>(), L.zz.as<double>(), 0, L.maxh.as<unsigned>()),
+  LAUNCH(launch_colcol(z.R, z.col, t1s, t1, kernel_fn(ctx, s, L.zz.as<double>(), L.zz.as<double>(), 0, L.maxh.as<unsigned>()),
                        z.C, B, L.stream));
   LAUNCH(launch_row_fwd_h(z.C, z.row, ProSpec{t1s}, EpiHStore{Hout, L.maxh.as<unsigned>(), ctx->cfg.lambda}, z.R / 2 + 1, B, L.stream));
   return NIS_OK;
@@ -400,14 +439,14 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
   const SizeClass& zp = ctx->sz[1];
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)zt.spec};
   Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
-  if (is_u8) LAUNCH(launch_col_fwd_u8(zt.R, zt.colf, ProRealU8{u8, zt.C, ctx->lut.as<float>()}, t1, zt.C, B, L.stream));
-  else LAUNCH(launch_col_fwd_f32(zt.R, zt.colf, ProRealF32{f32, zt.C}, t1, zt.C, B, L.stream));
+  if (is_u8) LAUNCH(launch_col_fwd_u8(zt.R, zt.col, ProRealU8{u8, zt.C, ctx->lut.as<float>()}, t1, zt.C, B, L.stream));
+  else LAUNCH(launch_col_fwd_f32(zt.R, zt.col, ProRealF32{f32, zt.C}, t1, zt.C, B, L.stream));
   // fft_result = FFT(image) stored from registers; the same kernel continues with IFFT(|fft_result|) along the rows
   LAUNCH(launch_rowrow_storeabs(zt.C, zt.row, t1s, t1, MidStoreAbs{F}, zt.R / 2 + 1, B, L.stream));
   Dst<float> power{L.real.as<float>(), (long long)zt.real};
   Dst<float2> power2{L.real.as<float2>(), (long long)zt.real};
-  if (ctx->polar_fused && !ctx->polar_tiled) LAUNCH(launch_col_inv_store_pairs(zt.R, zt.coli, t1s, EpiStorePairs{power2, zt.C, (float)zt.real}, zt.C, B, L.stream));
-  else LAUNCH(launch_col_inv_store(zt.R, zt.coli, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
+  if (ctx->polar_fused && !ctx->polar_tiled) LAUNCH(launch_col_inv_store_pairs(zt.R, zt.col, t1s, EpiStorePairs{power2, zt.C, (float)zt.real}, zt.C, B, L.stream));
+  else LAUNCH(launch_col_inv_store(zt.R, zt.col, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
   // polar(fftshift(RemoveZeroComponent(power))) feeds the first FFT stage directly
   Dst<cpx> t1p{L.t1.as<cpx>(), (long long)zp.spec};
   PolarArgs pa{src_slab<float>(power.base, power.stride), src_slab<float2>(power2.base, power2.stride), ctx->H, ctx->W, ctx->Cp,
@@ -417,14 +456,14 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
     Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
     LAUNCH(launch_polar_tiled(pa.power, pol, ctx->H, ctx->W, ctx->D, ctx->Cp, ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch,
                               ctx->ptile_rows, B, L.stream));
-    LAUNCH(launch_col_fwd_f32(zp.R, zp.colf, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
+    LAUNCH(launch_col_fwd_f32(zp.R, zp.col, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
   } else if (ctx->polar_fused) {
-    LAUNCH(launch_col_fwd_polar(zp.R, zp.colf, pa, t1p, zp.C, B, L.stream));
+    LAUNCH(launch_col_fwd_polar(zp.R, zp.col, pa, t1p, zp.C, B, L.stream));
   } else {
     // the gather is latency bound: as its own full-occupancy kernel it beats riding in the register-limited FFT stage 0
     Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
     LAUNCH(launch_polar(pa.power, pol, ctx->H, ctx->W, ctx->D, ctx->Cp, pa.cs, pa.rho, pa.table, B, L.stream));
-    LAUNCH(launch_col_fwd_f32(zp.R, zp.colf, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
+    LAUNCH(launch_col_fwd_f32(zp.R, zp.col, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
   }
   LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
   if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
@@ -442,13 +481,13 @@ static int correlate_tail(nis_ctx* ctx, Lane& L, int s, Src<cpx> Hz, int E, int 
   const SizeClass& z = ctx->sz[s];
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
   Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
-  LAUNCH(launch_colcol(z.R, z.coli, z.colf, t1s, t1,
+  LAUNCH(launch_colcol(z.R, z.col, t1s, t1,
                        kernel_fn(ctx, s, xx_override ? xx_override : L.xx.as<double>(), L.zz.as<double>(), zshift, maxbuf, xx_idx), z.C, E,
                        L.stream));
   Src<cpx> Hze = Hz; Hze.shift = zshift;
   LAUNCH(launch_rowrow_filter(z.C, z.row, t1s, t1, MidFilterH{Hze, maxbuf}, z.R / 2 + 1, E, L.stream));
   EpiPeak ep{stats, z.R, (float)z.real, g_debug, (long long)z.real, z.C};
-  LAUNCH(launch_col_inv_peak(z.R, z.coli, t1s, ep, z.C, E, L.stream));
+  LAUNCH(launch_col_inv_peak(z.R, z.col, t1s, ep, z.C, E, L.stream));
   return NIS_OK;
 }
 
@@ -494,7 +533,7 @@ static int build_rot_cache(nis_ctx* ctx, Src<float> img_f32, Src<uint8_t> img_u8
     Src<float> i32 = img_f32; Src<uint8_t> i8 = img_u8;
     if (is_u8) i32 = src_null<float>(); else i8 = src_null<uint8_t>();
     RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), ctx->rotc_sel.as<int>() + i0};
-    LAUNCH(launch_col_fwd_rotate(zt.R, zt.colf, ra, t1, zt.C, nb, L.stream));
+    LAUNCH(launch_col_fwd_rotate(zt.R, zt.col, ra, t1, zt.C, nb, L.stream));
     Dst<cpx> out{ctx->rotc.as<cpx>() + (size_t)i0 * zt.spec, (long long)zt.spec};
     LAUNCH(launch_row_fwd(zt.C, zt.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, zt.R / 2 + 1, nb, L.stream));
     if (gauss) LAUNCH(launch_spec_sqsum(src_slab<cpx>(out.base, out.stride), (int)zt.spec, ctx->rotc_xx.as<double>() + i0, nb, L.stream));
@@ -536,7 +575,7 @@ static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr, ctx->rotc_xx.as<double>() - ctx->D, L.sel.as<int>()));
   } else {
     RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>()};
-    LAUNCH(launch_col_fwd_rotate(zt.R, zt.colf, ra, t1, zt.C, E, L.stream));
+    LAUNCH(launch_col_fwd_rotate(zt.R, zt.col, ra, t1, zt.C, E, L.stream));
     LAUNCH(launch_rowrow_mulconj(zt.C, zt.row, t1s, t1, MidMulConjZ{Fze, gauss ? L.xx.as<double>() : nullptr}, zt.R / 2 + 1, E, L.stream));
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr));
   }
@@ -552,6 +591,9 @@ template <class T> static void transpose_to(const T* in, int rows_in, int cols_i
   for (int r = 0; r < rows_in; ++r)
     for (int c = 0; c < cols_in; ++c) out[(size_t)c * rows_in + r] = in[(size_t)r * cols_in + c];
 }
+
+// Map::ComputeGridLocation (src/map.cc:81-85): static_cast<int>(x / grid_scale), truncation toward zero
+static std::pair<int, int> grid_cell(double x, double y, double scale) { return {(int)(x / scale), (int)(y / scale)}; }
 
 // -------------------------------------------------------------------------------------------------------------
 // C ABI
@@ -576,7 +618,7 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   if (!cfg || !out) return NIS_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   const int H = image_height, W = image_width, D = cfg->rotation_divisor, Cp = cfg->rotation_channel;
-  if (H <= 0 || W <= 0 || D <= 0 || Cp <= 0 || (H & 1) || (D & 1) || (W % 32) || (Cp % 32)) return NIS_ERR_INVALID_ARGUMENT;
+  if (H <= 0 || W <= 0 || D <= 0 || Cp <= 0 || (H & 1) || (D & 1) || (W % 16) || (Cp % 16)) return NIS_ERR_INVALID_ARGUMENT;
   if (!col_size_supported(H) || !col_size_supported(D) || !row_size_supported(W) || !row_size_supported(Cp))
     return NIS_ERR_UNSUPPORTED_SIZE;
   // the fused rotation wraps source coordinates with one conditional add/subtract (exact while the half diagonal stays
@@ -635,16 +677,20 @@ int nis_destroy(nis_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->ptiles, &ctx->ptab2, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
-                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->sUnd, &ctx->umap1, &ctx->umap2, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel};
+                    &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->sUnd, &ctx->umap1, &ctx->umap2, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel,
+                    &ctx->d_fid, &ctx->d_dist, &ctx->d_cell, &ctx->cand_in, &ctx->cand_pos, &ctx->sel_scratch, &ctx->stage, &ctx->kfrec, &ctx->qgather};
   for (DevBuf* b : bufs) b->release();
   for (Lane& L : ctx->lanes) {
-    DevBuf* lb[] = {&L.t1, &L.real, &L.pol, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz};
+    DevBuf* lb[] = {&L.t1, &L.real, &L.pol, &L.maxp, &L.maxt, &L.maxh, &L.stats_p, &L.stats_t, &L.sel, &L.xx, &L.zz, &L.dbrec};
     for (DevBuf* b : lb) b->release();
     if (L.ev) cudaEventDestroy(L.ev);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (nis_frame* f : ctx->live_frames) { if (f->block) cudaFree(f->block); f->block = nullptr; }   // the handles themselves stay valid to free
+  ctx->live_frames.clear();
+  nis_comm_destroy(ctx);
   for (void* b : ctx->frame_pool) cudaFree(b);
   for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->feat_ev) cudaEventDestroy(e);
@@ -691,13 +737,18 @@ static int frame_alloc(nis_ctx* ctx, bool u8, nis_frame** out) {
   char* p = (char*)f->block;
   f->F = (cpx*)p; f->P = (cpx*)(p + bF); f->Ht = (cpx*)(p + bF + bP); f->Hp = (cpx*)(p + 2 * bF + bP);
   if (u8) f->img_u8 = (uint8_t*)(p + 2 * (bF + bP)); else f->img_f32 = (float*)(p + 2 * (bF + bP));
+  ctx->live_frames.push_back(f);
   *out = f;
   return NIS_OK;
 }
 
 int nis_frame_free(nis_ctx* ctx, nis_frame* f) {
   if (!f) return NIS_OK;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ctx) {
+    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    auto it = std::find(ctx->live_frames.begin(), ctx->live_frames.end(), f);
+    if (it != ctx->live_frames.end()) { *it = ctx->live_frames.back(); ctx->live_frames.pop_back(); }
+  }
   if (f->block) {
     if (ctx && ctx->frame_pool.size() < 16) ctx->frame_pool.push_back(f->block);
     else cudaFree(f->block);
@@ -797,32 +848,60 @@ int nis_frame_export(nis_ctx* ctx, const nis_frame* f, float* fft_result, float*
   return NIS_OK;
 }
 
-int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, nis_frame** out) {
-  if (!ctx || !image_colmajor || !fft_result || !fft_polar || !out) return NIS_ERR_INVALID_ARGUMENT;
+// reference-layout arrays -> device frame; the column-major -> row-major conversion runs on the GPU (32 x 32 shared-memory tiles) out of
+// a staging copy, so an import costs the PCIe transfer plus a few microseconds
+static int upload_colmajor_f32(nis_ctx* ctx, const float* host, int R, int C, float* dst) {
+  RESERVE(ctx->stage, (size_t)R * C * sizeof(float));
+  CU(cudaMemcpyAsync(ctx->stage.p, host, (size_t)R * C * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->prof_stream = ctx->stream;
+  LAUNCH(launch_transpose_f32(ctx->stage.as<float>(), dst, C, R, ctx->stream));           // [C][R] lines -> [R][C]
+  CU(cudaStreamSynchronize(ctx->stream));                                                   // the staging buffer is reused by the next upload
+  return NIS_OK;
+}
+static int upload_colmajor_cpx(nis_ctx* ctx, const float* host, int half, int C, cpx* dst) {
+  RESERVE(ctx->stage, (size_t)half * C * sizeof(cpx));
+  CU(cudaMemcpyAsync(ctx->stage.p, host, (size_t)half * C * sizeof(cpx), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->prof_stream = ctx->stream;
+  LAUNCH(launch_transpose_cpx(ctx->stage.as<cpx>(), dst, C, half, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return NIS_OK;
+}
+static int h_factors(nis_ctx* ctx, cpx* F, cpx* P, cpx* Ht, cpx* Hp) {
+  // the keyframe-only factors H = T/(kernel(.)/max + lambda) of both stages (the kernel id is validated at ComputePose, like the reference)
+  if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return NIS_OK;
+  Lane& L = ctx->lanes[0];
+  TRY(ensure_workspace(ctx, L, 1));
+  TRY(hzz_batch(ctx, L, 0, src_slab<cpx>(F, 0), 1, Dst<cpx>{Ht, 0}));
+  TRY(hzz_batch(ctx, L, 1, src_slab<cpx>(P, 0), 1, Dst<cpx>{Hp, 0}));
+  return NIS_OK;
+}
+
+int nis_frame_import_ex(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, int with_h, nis_frame** out) {
+  if (!ctx || !out || (!image_colmajor && !fft_result && !fft_polar) || (with_h && (!fft_result || !fft_polar))) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   nis_frame* f = nullptr;
   TRY(frame_alloc(ctx, false, &f));
-  std::vector<float> rm(ctx->sz[0].real);
-  transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());
-  cudaError_t e = h2d(ctx, f->img_f32, rm.data(), rm.size() * sizeof(float));
-  for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
-    const SizeClass& z = ctx->sz[s];
-    std::vector<cpx> t(z.spec);
-    transpose_to((const cpx*)(s == 0 ? fft_result : fft_polar), z.C, z.R / 2 + 1, t.data());
-    e = h2d(ctx, s == 0 ? f->F : f->P, t.data(), z.spec * sizeof(cpx));
-  }
-  if (e != cudaSuccess) { nis_frame_free(ctx, f); return fail(ctx, NIS_ERR_CUDA, "frame import copy", (int)e); }
-  // the keyframe-only factors H = T/(kernel(.)/max + lambda) of both stages (the kernel id is validated at ComputePose, like the reference)
-  if (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1) {
-    Lane& L = ctx->lanes[0];
-    int st = ensure_workspace(ctx, L, 1);
-    if (st == NIS_OK) st = hzz_batch(ctx, L, 0, src_slab<cpx>(f->F, 0), 1, Dst<cpx>{f->Ht, 0});
-    if (st == NIS_OK) st = hzz_batch(ctx, L, 1, src_slab<cpx>(f->P, 0), 1, Dst<cpx>{f->Hp, 0});
+  f->has_image = image_colmajor != nullptr;
+  f->has_spectra = fft_result != nullptr;
+  f->has_polar = fft_polar != nullptr;
+  f->has_h = false;
+  int st = NIS_OK;
+  if (image_colmajor) st = upload_colmajor_f32(ctx, image_colmajor, ctx->H, ctx->W, f->img_f32);
+  if (st == NIS_OK && fft_result) st = upload_colmajor_cpx(ctx, fft_result, ctx->H / 2 + 1, ctx->W, f->F);
+  if (st == NIS_OK && fft_polar) st = upload_colmajor_cpx(ctx, fft_polar, ctx->D / 2 + 1, ctx->Cp, f->P);
+  if (st == NIS_OK && with_h) {
+    st = h_factors(ctx, f->F, f->P, f->Ht, f->Hp);
     if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "import sync", (int)cudaGetLastError());
-    if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
+    f->has_h = st == NIS_OK;
   }
+  if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
   *out = f;
   return NIS_OK;
+}
+
+int nis_frame_import(nis_ctx* ctx, const float* image_colmajor, const float* fft_result, const float* fft_polar, nis_frame** out) {
+  if (!image_colmajor || !fft_result || !fft_polar) return NIS_ERR_INVALID_ARGUMENT;
+  return nis_frame_import_ex(ctx, image_colmajor, fft_result, fft_polar, 1, out);
 }
 
 // ---- ComputePose ----------------------------------------------------------------------------------------------
@@ -834,6 +913,8 @@ static void record_out(const PoseRecord& r, double pose[3], double info[3], int3
 int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, int not_large_rotation, double pose[3],
                      double info[3], int32_t peak_rc[4]) {
   if (!ctx || !last || !cur || !pose || !info) return NIS_ERR_INVALID_ARGUMENT;
+  if (!last->has_spectra || !last->has_polar || !last->has_h) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "ComputePose: the last frame needs fft_result, fft_polar and its H factors");
+  if (!cur->has_image || !cur->has_polar) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "ComputePose: the current frame needs its image and fft_polar");
   CU(cudaSetDevice(ctx->device));
   ctx->use_rot_cache = false;
   TRY(ensure_recs(ctx, 1));
@@ -849,8 +930,21 @@ int nis_compute_pose(nis_ctx* ctx, const nis_frame* last, const nis_frame* cur, 
 }
 
 // ---- stream tracking --------------------------------------------------------------------------------------------
+static int track_stream_window(nis_ctx* ctx, const uint8_t* frames, bool on_host, int n, double* poses, double* infos);
+// Device memory is bounded: the stream is processed in windows of at most kStreamWindow pairs (5.5 MB of features per frame, so
+// <= 6 GB of slabs however long the stream is); consecutive windows share one frame, whose features are recomputed.
+static const int kStreamWindow = 1024;
 static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, int n, double* poses, double* infos) {
   if (!ctx || !frames || n < 1 || (n > 1 && (!poses || !infos))) return NIS_ERR_INVALID_ARGUMENT;
+  if (n <= kStreamWindow + 1) return track_stream_window(ctx, frames, on_host, n, poses, infos);
+  const size_t npx = ctx->sz[0].real;
+  for (int t0 = 0; t0 < n - 1; t0 += kStreamWindow) {
+    const int m = std::min(kStreamWindow + 1, n - t0);
+    TRY(track_stream_window(ctx, frames + (size_t)t0 * npx, on_host, m, poses + 3 * (size_t)t0, infos + 3 * (size_t)t0));
+  }
+  return NIS_OK;
+}
+static int track_stream_window(nis_ctx* ctx, const uint8_t* frames, bool on_host, int n, double* poses, double* infos) {
   CU(cudaSetDevice(ctx->device));
   const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec;
   RESERVE(ctx->sF, (size_t)n * spt * sizeof(cpx));
@@ -941,132 +1035,213 @@ int nis_track_stream_keyframes(nis_ctx* ctx, const uint8_t* frames_host, int n, 
   if (!ctx || !frames_host || n < 1 || !kfs || !cam || !out || cam->height < 0 || cam->fx == 0 || cam->fy == 0) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec;
-  RESERVE(ctx->sF, (size_t)n * spt * sizeof(cpx));
-  RESERVE(ctx->sP, (size_t)n * spp * sizeof(cpx));
-  RESERVE(ctx->sHt, (size_t)n * spt * sizeof(cpx));
-  RESERVE(ctx->sHp, (size_t)n * spp * sizeof(cpx));
-  RESERVE(ctx->sImg, (size_t)n * npx);
-  const uint8_t* d_raw = ctx->sImg.as<uint8_t>();
-  const uint8_t* d_frames = d_raw;
-  if (ctx->undistort) {
-    RESERVE(ctx->sUnd, (size_t)n * npx);
-    d_frames = ctx->sUnd.as<uint8_t>();
-  }
+  // Bounded device memory: frames are processed in windows of kStreamWindow; features AND keyframe factors H of a whole window are
+  // computed in full batches (any frame may become a keyframe; one frame's H on demand inside the sequential loop would cost six
+  // latency-bound launches per keyframe).  The current keyframe's record moves to a dedicated slot when its window is left.
+  const int M = std::min(n, kStreamWindow);
+  RESERVE(ctx->sF, (size_t)M * spt * sizeof(cpx));
+  RESERVE(ctx->sP, (size_t)M * spp * sizeof(cpx));
+  RESERVE(ctx->sHt, (size_t)M * spt * sizeof(cpx));
+  RESERVE(ctx->sHp, (size_t)M * spp * sizeof(cpx));
+  RESERVE(ctx->sImg, (size_t)M * npx);
+  RESERVE(ctx->kfrec, 2 * (spt + spp) * sizeof(cpx));
+  if (ctx->undistort) RESERVE(ctx->sUnd, (size_t)M * npx);
   const int B = ctx->batch, NL = ctx->active_lanes;
   TRY(ensure_recs(ctx, B));
   TRY(ensure_pinned(ctx, (size_t)B * sizeof(PoseRecord)));
   cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
   cpx* Ht = ctx->sHt.as<cpx>(); cpx* Hp = ctx->sHp.as<cpx>();
-  // features AND keyframe factors H of every frame in full batches (any frame may become a keyframe; one frame's H computed on demand
-  // inside the sequential loop below would cost six latency-bound launches per keyframe), uploads on the copy stream
-  const int nbatch = (n + B - 1) / B;
-  while ((int)ctx->up_ev.size() < nbatch) {
+  const int max_batches = (M + B - 1) / B;
+  while ((int)ctx->up_ev.size() < max_batches) {
     cudaEvent_t a = nullptr, b = nullptr;
     CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
     ctx->up_ev.push_back(a);
     CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     ctx->feat_ev.push_back(b);
   }
-  TRY(fork_lanes(ctx));
-  CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
-  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
-  for (int k = 0; k < nbatch; ++k) {
-    const int t0 = k * B, nb = std::min(B, n - t0);
-    CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames_host + (size_t)t0 * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
-                       ctx->copy_stream));
-    CU(cudaEventRecord(ctx->up_ev[k], ctx->copy_stream));
-  }
-  for (int k = 0; k < nbatch; ++k) {
-    const int t0 = k * B, nb = std::min(B, n - t0);
-    Lane& L = ctx->lanes[k % NL];
-    CU(cudaStreamWaitEvent(L.stream, ctx->up_ev[k], 0));
-    if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
-    TRY(features_batch(ctx, L, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
-                       Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
-                       Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));
-  }
-  TRY(join_lanes(ctx));
   Lane& L0 = ctx->lanes[0];
   pose::TrackerState st;
   pose::initialize(*cam, st, out[0]);
   pose::snapshot(st, out[0]);
-  int K = 0;
-  int t = 1, spec = std::min(B, 8), since_kf = 0;
-  while (t < n) {
-    const int nb = std::min(spec, n - t);
-    // frames t .. t+nb-1 against keyframe K: the keyframe operands are one slab with stride 0
-    TRY(compute_pose_batch(ctx, L0, false, src_slab<cpx>(F + (size_t)K * spt, 0), src_slab<cpx>(P + (size_t)K * spp, 0),
-                           src_slab<cpx>(Ht + (size_t)K * spt, 0), src_slab<cpx>(Hp + (size_t)K * spp, 0),
-                           src_slab<cpx>(P + (size_t)t * spp, (long long)spp), src_null<float>(),
-                           src_slab<uint8_t>(d_frames + (size_t)t * npx, (long long)npx), true, nb, t, ctx->recs.as<PoseRecord>()));
-    CU(cudaMemcpyAsync(ctx->pin, ctx->recs.p, (size_t)nb * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    const PoseRecord* r = (const PoseRecord*)ctx->pin;
-    int used = nb;
-    for (int i = 0; i < nb; ++i) {
-      nis_track_result& o = out[t + i];
-      o.keyframe = K;
-      const bool ins = pose::step(*cam, *kfs, ctx->W, ctx->H, r[i].pose, r[i].info, st, o);
-      pose::snapshot(st, o);
-      ++since_kf;
-      if (ins) {                                   // frames behind it were solved against the wrong keyframe: redo them
-        K = t + i;
-        used = i + 1;
-        spec = std::max(4, std::min(B, 2 * since_kf));
-        since_kf = 0;
-        break;
+  // keyframe operands: pointers into the window slabs, or into the dedicated slot once the window has moved on
+  const cpx *kF = nullptr, *kP = nullptr, *kHt = nullptr, *kHp = nullptr;
+  int K = 0, spec = std::min(B, 8), since_kf = 0;
+  for (int w0 = 0; w0 < n; w0 += M) {
+    const int m = std::min(M, n - w0);
+    const uint8_t* d_raw = ctx->sImg.as<uint8_t>();
+    const uint8_t* d_frames = ctx->undistort ? ctx->sUnd.as<uint8_t>() : d_raw;
+    if (w0 > 0) {                                           // park the keyframe before its slab entry is overwritten
+      cpx* kr = ctx->kfrec.as<cpx>();
+      if (kF != kr) {
+        CU(cudaMemcpyAsync(kr, kF, spt * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(kr + spt, kP, spp * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(kr + spt + spp, kHt, spt * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(kr + 2 * spt + spp, kHp, spp * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
+        kF = kr; kP = kr + spt; kHt = kr + spt + spp; kHp = kr + 2 * spt + spp;
       }
     }
-    if (used == nb && since_kf >= spec) spec = std::min(B, 2 * spec);
-    t += used;
+    const int nbatch = (m + B - 1) / B;
+    TRY(fork_lanes(ctx));
+    CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+    for (int k = 0; k < nbatch; ++k) {
+      const int t0 = k * B, nb = std::min(B, m - t0);
+      CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames_host + (size_t)(w0 + t0) * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
+                         ctx->copy_stream));
+      CU(cudaEventRecord(ctx->up_ev[k], ctx->copy_stream));
+    }
+    for (int k = 0; k < nbatch; ++k) {
+      const int t0 = k * B, nb = std::min(B, m - t0);
+      Lane& L = ctx->lanes[k % NL];
+      CU(cudaStreamWaitEvent(L.stream, ctx->up_ev[k], 0));
+      if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
+      TRY(features_batch(ctx, L, src_null<float>(), src_slab<uint8_t>(d_frames + (size_t)t0 * npx, (long long)npx), true, nb,
+                         Dst<cpx>{F + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{P + (size_t)t0 * spp, (long long)spp},
+                         Dst<cpx>{Ht + (size_t)t0 * spt, (long long)spt}, Dst<cpx>{Hp + (size_t)t0 * spp, (long long)spp}, true));
+    }
+    TRY(join_lanes(ctx));
+    if (w0 == 0) { kF = F; kP = P; kHt = Ht; kHp = Hp; }     // frame 0 is the first keyframe (map_builder.cc:35-40)
+    int t = w0 == 0 ? 1 : w0;
+    while (t < w0 + m) {
+      const int nb = std::min(spec, w0 + m - t), lt = t - w0;
+      // frames t .. t+nb-1 against keyframe K: the keyframe operands are one slab with stride 0
+      TRY(compute_pose_batch(ctx, L0, false, src_slab<cpx>(kF, 0), src_slab<cpx>(kP, 0), src_slab<cpx>(kHt, 0), src_slab<cpx>(kHp, 0),
+                             src_slab<cpx>(P + (size_t)lt * spp, (long long)spp), src_null<float>(),
+                             src_slab<uint8_t>(d_frames + (size_t)lt * npx, (long long)npx), true, nb, t, ctx->recs.as<PoseRecord>()));
+      CU(cudaMemcpyAsync(ctx->pin, ctx->recs.p, (size_t)nb * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      const PoseRecord* r = (const PoseRecord*)ctx->pin;
+      int used = nb;
+      for (int i = 0; i < nb; ++i) {
+        nis_track_result& o = out[t + i];
+        o.keyframe = K;
+        const bool ins = pose::step(*cam, *kfs, ctx->W, ctx->H, r[i].pose, r[i].info, st, o);
+        pose::snapshot(st, o);
+        ++since_kf;
+        if (ins) {                                   // frames behind it were solved against the wrong keyframe: redo them
+          K = t + i;
+          const size_t lk = (size_t)(K - w0);
+          kF = F + lk * spt; kP = P + lk * spp; kHt = Ht + lk * spt; kHp = Hp + lk * spp;
+          used = i + 1;
+          spec = std::max(4, std::min(B, 2 * since_kf));
+          since_kf = 0;
+          break;
+        }
+      }
+      if (used == nb && since_kf >= spec) spec = std::min(B, 2 * spec);
+      t += used;
+    }
   }
   return NIS_OK;
 }
 
 // ---- keyframe DB ------------------------------------------------------------------------------------------------
-// keyframe record = [F][P][Ht][Hp]
-static size_t db_record(const nis_ctx* ctx) { return 2 * (ctx->sz[0].spec + ctx->sz[1].spec); }
+// Record per keyframe, by store mode (nis_db_set_mode):
+//   NIS_DB_FULL    [F][P][Ht][Hp]  5.24 MB @640x480: a candidate costs only its own solve
+//   NIS_DB_SPECTRA [F][P]          2.62 MB: the reference's own Frame payload (include/frame.h:35-36); Ht, Hp recomputed per batch
+//   NIS_DB_IMAGE   u8 image        0.31 MB: everything recomputed per batch (100 k keyframes = 31 GB, fits one GPU)
+// The recomputation runs the same kernels on the same data, so a scan returns the same bits in every mode.
+static size_t db_record_bytes(const nis_ctx* ctx) {
+  const size_t spec = (ctx->sz[0].spec + ctx->sz[1].spec) * sizeof(cpx);
+  return ctx->db_mode == NIS_DB_FULL ? 2 * spec : (ctx->db_mode == NIS_DB_SPECTRA ? spec : ctx->sz[0].real);
+}
 
+static void db_unreserve(nis_ctx* ctx, int old) { ctx->slot_ptr.resize(old); }      // chunks stay allocated for the next insert
+
+// Reserves n_new record slots.  Transactional: on any failure the slot table and the chunk list are exactly as before the call.
 static int db_reserve_slots(nis_ctx* ctx, int n_new, int* first) {
-  const size_t rec = db_record(ctx);
+  const size_t rec = db_record_bytes(ctx);
   const int old = (int)ctx->slot_ptr.size();
+  const size_t old_chunks = ctx->chunks.size();
   *first = old;
+  auto rollback = [&]() {
+    ctx->slot_ptr.resize(old);
+    while (ctx->chunks.size() > old_chunks) { cudaFree(ctx->chunks.back()); ctx->chunks.pop_back(); }
+  };
   for (int i = 0; i < n_new; ++i) {
     const int slot = old + i;
     const int ch = slot / ctx->chunk_slots, within = slot % ctx->chunk_slots;
     if (ch >= (int)ctx->chunks.size()) {
       void* p = nullptr;
-      cudaError_t e = cudaMalloc(&p, (size_t)ctx->chunk_slots * rec * sizeof(cpx));
-      if (e != cudaSuccess) return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc DB chunk", (int)e);
+      cudaError_t e = cudaMalloc(&p, (size_t)ctx->chunk_slots * rec);
+      if (e != cudaSuccess) { rollback(); return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc DB chunk", (int)e); }
       ctx->chunks.push_back(p);
     }
-    ctx->slot_ptr.push_back((cpx*)ctx->chunks[ch] + (size_t)within * rec);
+    ctx->slot_ptr.push_back((char*)ctx->chunks[ch] + (size_t)within * rec);
   }
   const int total = old + n_new;
+  cudaError_t e = cudaSuccess;
   if (total > ctx->d_slot_cap) {
     int cap = std::max(4096, ctx->d_slot_cap);
     while (cap < total) cap *= 2;
-    CU(cudaStreamSynchronize(ctx->stream));
-    RESERVE(ctx->d_slot_ptr, (size_t)cap * sizeof(cpx*));
-    ctx->d_slot_cap = cap;
-    CU(h2d(ctx, ctx->d_slot_ptr.p, ctx->slot_ptr.data(), (size_t)total * sizeof(cpx*)));
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+      ctx->d_slot_cap = 0;
+      if (ctx->d_slot_ptr.reserve((size_t)cap * sizeof(void*))) { rollback(); return fail(ctx, NIS_ERR_OUT_OF_MEMORY, "cudaMalloc DB slot table"); }
+      ctx->d_slot_cap = cap;
+      e = h2d(ctx, ctx->d_slot_ptr.p, ctx->slot_ptr.data(), (size_t)total * sizeof(void*));
+    }
   } else {
-    CU(h2d(ctx, ctx->d_slot_ptr.as<cpx*>() + old, ctx->slot_ptr.data() + old, (size_t)n_new * sizeof(cpx*)));
+    e = h2d(ctx, ctx->d_slot_ptr.as<void*>() + old, ctx->slot_ptr.data() + old, (size_t)n_new * sizeof(void*));
   }
+  if (e != cudaSuccess) { rollback(); return fail(ctx, NIS_ERR_CUDA, "DB slot table upload", (int)e); }
   return NIS_OK;
 }
 
+static void db_push_meta(nis_ctx* ctx, int frame_id, double dist) {
+  ctx->slot_frame_id.push_back(frame_id);
+  ctx->slot_dist.push_back(dist);
+  ctx->meta_dirty = true;
+}
+
+int nis_db_set_mode(nis_ctx* ctx, int mode) {
+  if (!ctx || mode < NIS_DB_FULL || mode > NIS_DB_IMAGE) return NIS_ERR_INVALID_ARGUMENT;
+  if (nis_db_size(ctx) != 0) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "nis_db_set_mode: the keyframe store must be empty");
+  if (mode != ctx->db_mode) {                       // chunk size depends on the record size
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (void* c : ctx->chunks) cudaFree(c);
+    ctx->chunks.clear();
+  }
+  ctx->db_mode = mode;
+  return NIS_OK;
+}
+int nis_db_mode(const nis_ctx* ctx) { return ctx ? ctx->db_mode : -1; }
+
 int nis_db_add(nis_ctx* ctx, const nis_frame* f, int frame_id, double acc_distance, int* slot) {
   if (!ctx || !f) return NIS_ERR_INVALID_ARGUMENT;
+  if (ctx->db_mode == NIS_DB_IMAGE && !f->img_u8) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "NIS_DB_IMAGE stores u8 images: the frame has none");
+  if (ctx->db_mode != NIS_DB_IMAGE && !(f->has_spectra && f->has_polar)) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "the frame carries no spectra");
+  if (ctx->db_mode == NIS_DB_FULL && !f->has_h) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "the frame was imported without its H factors");
   CU(cudaSetDevice(ctx->device));
   int s0 = 0;
   TRY(db_reserve_slots(ctx, 1, &s0));
-  cpx* dst = ctx->slot_ptr[s0];
   // a frame's F, P, Ht, Hp are contiguous in the same order as a record
-  CU(cudaMemcpyAsync(dst, f->F, db_record(ctx) * sizeof(cpx), cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  ctx->slot_frame_id.push_back(frame_id);
-  ctx->slot_dist.push_back(acc_distance);
+  const void* src = ctx->db_mode == NIS_DB_IMAGE ? (const void*)f->img_u8 : (const void*)f->F;
+  cudaError_t e = cudaMemcpyAsync(ctx->slot_ptr[s0], src, db_record_bytes(ctx), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { db_unreserve(ctx, s0); return fail(ctx, NIS_ERR_CUDA, "DB record copy", (int)e); }
+  db_push_meta(ctx, frame_id, acc_distance);
+  if (slot) *slot = s0;
+  return NIS_OK;
+}
+
+// Map::AddFrame for a keyframe whose spectra the caller holds as reference-layout arrays (Frame::GetFFTResult): straight into a
+// record, H factors computed in place; no image needed (a keyframe's image is never read by the scan).  Not for NIS_DB_IMAGE.
+int nis_db_add_spectra(nis_ctx* ctx, const float* fft_result, const float* fft_polar, int frame_id, double acc_distance, int* slot) {
+  if (!ctx || !fft_result || !fft_polar) return NIS_ERR_INVALID_ARGUMENT;
+  if (ctx->db_mode == NIS_DB_IMAGE) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "NIS_DB_IMAGE stores u8 images, not spectra");
+  CU(cudaSetDevice(ctx->device));
+  int s0 = 0;
+  TRY(db_reserve_slots(ctx, 1, &s0));
+  cpx* F = (cpx*)ctx->slot_ptr[s0];
+  cpx* P = F + ctx->sz[0].spec;
+  int st = upload_colmajor_cpx(ctx, fft_result, ctx->H / 2 + 1, ctx->W, F);
+  if (st == NIS_OK) st = upload_colmajor_cpx(ctx, fft_polar, ctx->D / 2 + 1, ctx->Cp, P);
+  if (st == NIS_OK && ctx->db_mode == NIS_DB_FULL) st = h_factors(ctx, F, P, P + ctx->sz[1].spec, P + ctx->sz[1].spec + ctx->sz[0].spec);
+  if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "db_add_spectra sync", (int)cudaGetLastError());
+  if (st != NIS_OK) { db_unreserve(ctx, s0); return st; }
+  db_push_meta(ctx, frame_id, acc_distance);
   if (slot) *slot = s0;
   return NIS_OK;
 }
@@ -1075,41 +1250,49 @@ static int db_add_images_impl(nis_ctx* ctx, const uint8_t* images, bool on_host,
   if (!ctx || (!images && n > 0) || n < 0) return NIS_ERR_INVALID_ARGUMENT;
   if (n == 0) return NIS_OK;
   CU(cudaSetDevice(ctx->device));
-  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec, rec = db_record(ctx);
+  const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec, rec = db_record_bytes(ctx) / sizeof(cpx);
   int s0 = 0;
   TRY(db_reserve_slots(ctx, n, &s0));
-  const int B = ctx->batch;
-  const int NL = ctx->active_lanes;
-  const uint8_t* d_images = images;
-  if (on_host) {                      // stage the whole upload once (u8 images are 1/8.5 of the features they turn into)
-    RESERVE(ctx->sImg, (size_t)n * npx);
-    CU(cudaMemcpyAsync(ctx->sImg.p, images, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
-    d_images = ctx->sImg.as<uint8_t>();
-  }
-  const uint8_t* d_raw = d_images;
-  if (ctx->undistort) {
-    RESERVE(ctx->sUnd, (size_t)n * npx);
-    d_images = ctx->sUnd.as<uint8_t>();
-  }
-  TRY(fork_lanes(ctx));
-  for (int i0 = 0, k = 0; i0 < n; ++k) {
-    const int slot = s0 + i0;
-    const int room = ctx->chunk_slots - slot % ctx->chunk_slots;       // stay inside one chunk (contiguous records)
-    const int nb = std::min(std::min(B, n - i0), room);
-    cpx* base = ctx->slot_ptr[slot];
-    if (ctx->undistort)
-      TRY(undistort_batch(ctx, ctx->lanes[k % NL].stream, d_raw + (size_t)i0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)i0 * npx, nb));
-    TRY(features_batch(ctx, ctx->lanes[k % NL], src_null<float>(), src_slab<uint8_t>(d_images + (size_t)i0 * npx, (long long)npx), true, nb,
-                       Dst<cpx>{base, (long long)rec}, Dst<cpx>{base + spt, (long long)rec}, Dst<cpx>{base + spt + spp, (long long)rec},
-                       Dst<cpx>{base + 2 * spt + spp, (long long)rec}, true));
-    i0 += nb;
-  }
-  TRY(join_lanes(ctx));
-  CU(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < n; ++i) {
-    ctx->slot_frame_id.push_back(ids ? ids[i] : s0 + i);
-    ctx->slot_dist.push_back(dists ? dists[i] : 0.0);
-  }
+  auto body = [&]() -> int {
+    const int B = ctx->batch;
+    const int NL = ctx->active_lanes;
+    const uint8_t* d_images = images;
+    if (on_host) {                      // stage the whole upload once (u8 images are 1/8.5 of the features they turn into)
+      RESERVE(ctx->sImg, (size_t)n * npx);
+      CU(cudaMemcpyAsync(ctx->sImg.p, images, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
+      d_images = ctx->sImg.as<uint8_t>();
+    }
+    const uint8_t* d_raw = d_images;
+    if (ctx->undistort) {
+      RESERVE(ctx->sUnd, (size_t)n * npx);
+      d_images = ctx->sUnd.as<uint8_t>();
+    }
+    TRY(fork_lanes(ctx));
+    for (int i0 = 0, k = 0; i0 < n; ++k) {
+      const int slot = s0 + i0;
+      const int room = ctx->chunk_slots - slot % ctx->chunk_slots;       // stay inside one chunk (contiguous records)
+      const int nb = std::min(std::min(B, n - i0), room);
+      Lane& L = ctx->lanes[k % NL];
+      if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)i0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)i0 * npx, nb));
+      if (ctx->db_mode == NIS_DB_IMAGE) {
+        CU(cudaMemcpyAsync(ctx->slot_ptr[slot], d_images + (size_t)i0 * npx, (size_t)nb * npx, cudaMemcpyDeviceToDevice, L.stream));
+      } else {
+        cpx* base = (cpx*)ctx->slot_ptr[slot];
+        const bool full = ctx->db_mode == NIS_DB_FULL;
+        TRY(features_batch(ctx, L, src_null<float>(), src_slab<uint8_t>(d_images + (size_t)i0 * npx, (long long)npx), true, nb,
+                           Dst<cpx>{base, (long long)rec}, Dst<cpx>{base + spt, (long long)rec},
+                           Dst<cpx>{full ? base + spt + spp : nullptr, (long long)rec}, Dst<cpx>{full ? base + 2 * spt + spp : nullptr, (long long)rec},
+                           full));
+      }
+      i0 += nb;
+    }
+    TRY(join_lanes(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return NIS_OK;
+  };
+  const int st = body();
+  if (st != NIS_OK) { cudaDeviceSynchronize(); db_unreserve(ctx, s0); return st; }
+  for (int i = 0; i < n; ++i) db_push_meta(ctx, ids ? ids[i] : s0 + i, dists ? dists[i] : 0.0);
   return NIS_OK;
 }
 int nis_db_add_images(nis_ctx* ctx, const uint8_t* images_host, int n, const int* frame_ids, const double* acc_distances) {
@@ -1125,39 +1308,135 @@ int nis_db_clear(nis_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   for (void* c : ctx->chunks) cudaFree(c);
   ctx->chunks.clear(); ctx->slot_ptr.clear(); ctx->slot_frame_id.clear(); ctx->slot_dist.clear();
-  ctx->slot_cell.clear(); ctx->grid.clear();
+  ctx->slot_cell.clear(); ctx->meta_dirty = true;
+  return NIS_OK;
+}
+
+// keyframe meta data the device-side candidate selection reads (frame id, accumulated distance, grid cell), re-uploaded when dirty
+static int db_sync_meta(nis_ctx* ctx) {
+  const size_t n = ctx->slot_frame_id.size();
+  if (!ctx->meta_dirty || n == 0) return NIS_OK;
+  ctx->slot_cell.resize(n, {INT_MIN, INT_MIN});
+  CU(cudaStreamSynchronize(ctx->stream));
+  size_t cap = std::max<size_t>(4096, ctx->d_fid.bytes / sizeof(int));
+  while (cap < n) cap *= 2;
+  RESERVE(ctx->d_fid, cap * sizeof(int));
+  RESERVE(ctx->d_dist, cap * sizeof(double));
+  RESERVE(ctx->d_cell, cap * sizeof(int2));
+  std::vector<int2> cells(n);
+  for (size_t i = 0; i < n; ++i) cells[i] = make_int2(ctx->slot_cell[i].first, ctx->slot_cell[i].second);
+  CU(h2d(ctx, ctx->d_fid.p, ctx->slot_frame_id.data(), n * sizeof(int)));
+  CU(h2d(ctx, ctx->d_dist.p, ctx->slot_dist.data(), n * sizeof(double)));
+  CU(h2d(ctx, ctx->d_cell.p, cells.data(), n * sizeof(int2)));
+  ctx->meta_dirty = false;
+  return NIS_OK;
+}
+
+static void loop_result_init(nis_loop_result* out) {
+  memset(out, 0, sizeof *out);
+  out->slot = -1; out->frame_id = -1;
+  out->response[0] = out->response[1] = out->response[2] = -1.0;                                                       // loop_closure.h:15
+  for (int i = 0; i < 4; ++i) out->peak[i] = -1;
+}
+
+// materialise what the store mode does not keep for the nb candidates idx[0..nb) into the lane's record scratch
+static int db_materialize(nis_ctx* ctx, Lane& L, const int* idx, int nb, Src<cpx>& Fz, Src<cpx>& Pz, Src<cpx>& Htz, Src<cpx>& Hpz) {
+  const long long spt = (long long)ctx->sz[0].spec, spp = (long long)ctx->sz[1].spec;
+  const void* const* ptrs = ctx->d_slot_ptr.as<const void*>();
+  if (ctx->db_mode == NIS_DB_FULL) {
+    const cpx* const* p = (const cpx* const*)ptrs;
+    Fz = Src<cpx>{nullptr, 0, p, 0, idx, 0};
+    Pz = Src<cpx>{nullptr, 0, p, spt, idx, 0};
+    Htz = Src<cpx>{nullptr, 0, p, spt + spp, idx, 0};
+    Hpz = Src<cpx>{nullptr, 0, p, 2 * spt + spp, idx, 0};
+    return NIS_OK;
+  }
+  if (nb > L.db_cap) {
+    CU(cudaStreamSynchronize(L.stream));
+    L.db_cap = 0;
+    const int cap = std::max(nb, ctx->batch);
+    RESERVE(L.dbrec, (size_t)cap * 2 * (size_t)(spt + spp) * sizeof(cpx));
+    L.db_cap = cap;
+  }
+  cpx* F = L.dbrec.as<cpx>();
+  cpx* P = F + (size_t)L.db_cap * spt;
+  cpx* Ht = P + (size_t)L.db_cap * spp;
+  cpx* Hp = Ht + (size_t)L.db_cap * spt;
+  TRY(ensure_workspace(ctx, L, nb));
+  if (ctx->db_mode == NIS_DB_IMAGE) {
+    Src<uint8_t> img{nullptr, 0, (const uint8_t* const*)ptrs, 0, idx, 0};
+    TRY(features_batch(ctx, L, src_null<float>(), img, true, nb, Dst<cpx>{F, spt}, Dst<cpx>{P, spp}, Dst<cpx>{Ht, spt}, Dst<cpx>{Hp, spp}, true));
+    Fz = src_slab<cpx>(F, spt); Pz = src_slab<cpx>(P, spp);
+  } else {
+    const cpx* const* p = (const cpx* const*)ptrs;
+    Fz = Src<cpx>{nullptr, 0, p, 0, idx, 0};
+    Pz = Src<cpx>{nullptr, 0, p, spt, idx, 0};
+    TRY(hzz_batch(ctx, L, 0, Fz, nb, Dst<cpx>{Ht, spt}));
+    TRY(hzz_batch(ctx, L, 1, Pz, nb, Dst<cpx>{Hp, spp}));
+  }
+  Htz = src_slab<cpx>(Ht, spt); Hpz = src_slab<cpx>(Hp, spp);
   return NIS_OK;
 }
 
 // ---- loop-closure scan (loop_closure.cc:36-73) --------------------------------------------------------------------
-int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance, const nis_loop_config* cfg,
-                  const int32_t* candidate_slots, int n_candidates, nis_loop_result* out, double* all_responses) {
+// prior != nullptr: candidates = the keyframes filed in the 3 x 3 grid cells around prior (x, y), loop_closure.cc:17-34
+static int loop_scan_impl(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance, const nis_loop_config* cfg,
+                          const int32_t* candidate_slots, int n_candidates, const double* prior, double grid_scale, nis_loop_result* out,
+                          double* all_responses, nis_scan_record* records, int32_t* candidates_out, int max_candidates, int* n_candidates_out) {
   if (!ctx || !query || !cfg || !out || n_candidates < 0) return NIS_ERR_INVALID_ARGUMENT;
+  if (!query->has_image || !query->has_polar) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "FindLoopClosure: the query needs its image and fft_polar");
   CU(cudaSetDevice(ctx->device));
   const int ndb = nis_db_size(ctx);
   const int n_in = candidate_slots ? n_candidates : ndb;
-  std::vector<int> cand; cand.reserve(n_in);
-  std::vector<int> pos; pos.reserve(n_in);            // position in the caller's candidate list
-  for (int i = 0; i < n_in; ++i) {
-    const int slot = candidate_slots ? candidate_slots[i] : i;
-    if (slot < 0 || slot >= ndb) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "candidate slot out of range");
-    if (cfg->frame_gap_thr > 0 && abs(query_frame_id - ctx->slot_frame_id[slot]) < cfg->frame_gap_thr) continue;      // :43-46
-    if (cfg->distance_thr > 0 && fabs(query_acc_distance - ctx->slot_dist[slot]) < cfg->distance_thr) continue;        // :47-53
-    cand.push_back(slot); pos.push_back(i);
-  }
-  const int n = (int)cand.size();
-  memset(out, 0, sizeof *out);
-  out->slot = -1; out->frame_id = -1; out->evaluated = n;
-  out->response[0] = out->response[1] = out->response[2] = -1.0;                                                       // loop_closure.h:15
-  for (int i = 0; i < 4; ++i) out->peak[i] = -1;
+  loop_result_init(out);
   if (all_responses) for (int i = 0; i < 3 * n_in; ++i) all_responses[i] = -1.0;
+  if (records) for (int i = 0; i < n_in; ++i) { memset(&records[i], 0, sizeof records[i]); for (int k = 0; k < 3; ++k) records[i].response[k] = -1.0; }
+  if (n_candidates_out) *n_candidates_out = 0;
+  if (n_in == 0 || ndb == 0) return NIS_OK;
+  if (candidate_slots)
+    for (int i = 0; i < n_in; ++i)
+      if (candidate_slots[i] < 0 || candidate_slots[i] >= ndb) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "candidate slot out of range");
+  TRY(db_sync_meta(ctx));
+  // device-side candidate selection: filters (:43-53) and, with a prior pose, the grid neighbourhood (map.cc:81-101)
+  if (n_in > ctx->cand_cap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cand_cap = 0;
+    const int cap = std::max(n_in, 4096);
+    RESERVE(ctx->cand, (size_t)cap * sizeof(int));
+    RESERVE(ctx->cand_in, (size_t)cap * sizeof(int));
+    RESERVE(ctx->cand_pos, (size_t)cap * sizeof(int));
+    RESERVE(ctx->sel_scratch, (size_t)select_scratch_ints(cap) * sizeof(int));
+    ctx->cand_cap = cap;
+  }
+  if (candidate_slots) CU(cudaMemcpyAsync(ctx->cand_in.p, candidate_slots, (size_t)n_in * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  SelectArgs sa{n_in, candidate_slots ? ctx->cand_in.as<int>() : nullptr, ctx->d_fid.as<int>(), ctx->d_dist.as<double>(), ctx->d_cell.as<int2>(),
+                query_frame_id, query_acc_distance, cfg->frame_gap_thr, cfg->distance_thr, prior ? 1 : 0, 0, 0};
+  if (prior) { const auto c0 = grid_cell(prior[0], prior[1], grid_scale); sa.cx = c0.first; sa.cy = c0.second; }
+  int* d_n = ctx->sel_scratch.as<int>() + select_scratch_ints(ctx->cand_cap) - 1;
+  ctx->prof_stream = ctx->stream;
+  LAUNCH(launch_select(sa, ctx->sel_scratch.as<int>(), ctx->cand.as<int>(), ctx->cand_pos.as<int>(), d_n, ctx->stream));
+  ctx->launches += 2;
+  int n = 0;
+  CU(cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  out->evaluated = n;
+  if (n_candidates_out) *n_candidates_out = n;
+  std::vector<int> pos;
+  if (all_responses || records || candidates_out) {
+    pos.resize(n);
+    if (n) CU(cudaMemcpyAsync(pos.data(), ctx->cand_pos.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  std::vector<int> cand_h;
+  if (candidates_out && n) {
+    cand_h.resize(n);
+    CU(cudaMemcpyAsync(cand_h.data(), ctx->cand.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n && i < max_candidates; ++i) candidates_out[i] = cand_h[i];
+  }
   if (n == 0) return NIS_OK;
-  if (n > ctx->cand_cap) { RESERVE(ctx->cand, (size_t)n * sizeof(int)); ctx->cand_cap = n; }
-  CU(cudaMemcpyAsync(ctx->cand.p, cand.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   TRY(ensure_recs(ctx, n));
   const bool u8 = query->img_u8 != nullptr;
   const int B = ctx->batch;
-  const cpx* const* ptrs = ctx->d_slot_ptr.as<const cpx*>();
   const int NL = ctx->active_lanes;
   ctx->use_rot_cache = ctx->rot_cache_min > 0 && n >= ctx->rot_cache_min;
   if (ctx->use_rot_cache) TRY(build_rot_cache(ctx, src_slab<float>(query->img_f32, 0), src_slab<uint8_t>(query->img_u8, 0), u8));
@@ -1165,12 +1444,10 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   for (int b0 = 0, k = 0; b0 < n; b0 += B, ++k) {
     const int nb = std::min(B, n - b0);
     const int* idx = ctx->cand.as<int>() + b0;
-    const long long spt = (long long)ctx->sz[0].spec, spp = (long long)ctx->sz[1].spec;
-    Src<cpx> Fz{nullptr, 0, ptrs, 0, idx, 0};
-    Src<cpx> Pz{nullptr, 0, ptrs, spt, idx, 0};
-    Src<cpx> Htz{nullptr, 0, ptrs, spt + spp, idx, 0};
-    Src<cpx> Hpz{nullptr, 0, ptrs, 2 * spt + spp, idx, 0};
-    TRY(compute_pose_batch(ctx, ctx->lanes[k % NL], true, Fz, Pz, Htz, Hpz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
+    Lane& L = ctx->lanes[k % NL];
+    Src<cpx> Fz, Pz, Htz, Hpz;
+    TRY(db_materialize(ctx, L, idx, nb, Fz, Pz, Htz, Hpz));
+    TRY(compute_pose_batch(ctx, L, true, Fz, Pz, Htz, Hpz, src_slab<cpx>(query->P, 0), src_slab<float>(query->img_f32, 0),
                            src_slab<uint8_t>(query->img_u8, 0), u8, nb, b0, ctx->recs.as<PoseRecord>() + b0));
   }
   TRY(join_lanes(ctx));
@@ -1180,7 +1457,7 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   PoseRecord best;
   CU(cudaMemcpyAsync(&best, ctx->best.p, sizeof best, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<PoseRecord> all;
-  if (all_responses) {
+  if (all_responses || records) {
     all.resize(n);
     CU(cudaMemcpyAsync(all.data(), ctx->recs.p, (size_t)n * sizeof(PoseRecord), cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -1188,8 +1465,18 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   if (all_responses)
     for (int i = 0; i < n; ++i)
       for (int k = 0; k < 3; ++k) all_responses[3 * pos[i] + k] = all[i].info[k];
+  if (records)
+    for (int i = 0; i < n; ++i) {
+      nis_scan_record& r = records[pos[i]];
+      r.evaluated = 1; r.hyp = all[i].hyp;
+      for (int k = 0; k < 3; ++k) { r.relative_pose[k] = all[i].pose[k]; r.response[k] = all[i].info[k]; }
+      for (int k = 0; k < 4; ++k) r.peak[k] = all[i].peak[k];
+    }
   if (best.index >= 0) {
-    out->slot = cand[best.index];
+    int best_slot = -1;
+    CU(cudaMemcpyAsync(&best_slot, ctx->cand.as<int>() + best.index, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out->slot = best_slot;
     out->frame_id = ctx->slot_frame_id[out->slot];
     out->hyp = best.hyp;
     for (int k = 0; k < 3; ++k) { out->relative_pose[k] = best.pose[k]; out->response[k] = best.info[k]; }
@@ -1199,17 +1486,23 @@ int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, doub
   return NIS_OK;
 }
 
-// Map::ComputeGridLocation (src/map.cc:81-85): static_cast<int>(x / grid_scale), truncation toward zero
-static std::pair<int, int> grid_cell(double x, double y, double scale) { return {(int)(x / scale), (int)(y / scale)}; }
+int nis_loop_scan(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance, const nis_loop_config* cfg,
+                  const int32_t* candidate_slots, int n_candidates, nis_loop_result* out, double* all_responses) {
+  return loop_scan_impl(ctx, query, query_frame_id, query_acc_distance, cfg, candidate_slots, n_candidates, nullptr, 0.0, out, all_responses,
+                        nullptr, nullptr, 0, nullptr);
+}
+int nis_loop_scan_records(nis_ctx* ctx, const nis_frame* query, int query_frame_id, double query_acc_distance, const nis_loop_config* cfg,
+                          const int32_t* candidate_slots, int n_candidates, nis_loop_result* out, nis_scan_record* records) {
+  return loop_scan_impl(ctx, query, query_frame_id, query_acc_distance, cfg, candidate_slots, n_candidates, nullptr, 0.0, out, nullptr,
+                        records, nullptr, 0, nullptr);
+}
 
 int nis_db_set_position(nis_ctx* ctx, int slot, double x, double y, double grid_scale) {
   if (!ctx || slot < 0 || slot >= nis_db_size(ctx) || !(grid_scale > 0)) return NIS_ERR_INVALID_ARGUMENT;
   ctx->slot_cell.resize(ctx->slot_frame_id.size(), {INT_MIN, INT_MIN});
   if (ctx->slot_cell[slot].first != INT_MIN) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "slot already filed in the grid (Map::AddFrame files a frame once)");
-  const auto cell = grid_cell(x, y, grid_scale);
-  ctx->slot_cell[slot] = cell;
-  auto& v = ctx->grid[cell];
-  v.insert(std::upper_bound(v.begin(), v.end(), slot), slot);
+  ctx->slot_cell[slot] = grid_cell(x, y, grid_scale);
+  ctx->meta_dirty = true;
   return NIS_OK;
 }
 
@@ -1217,18 +1510,9 @@ int nis_loop_scan_prior(nis_ctx* ctx, const nis_frame* query, int query_frame_id
                         double prior_x, double prior_y, double grid_scale, nis_loop_result* out, int32_t* candidates_out,
                         int max_candidates, int* n_candidates_out) {
   if (!ctx || !query || !cfg || !out || !(grid_scale > 0)) return NIS_ERR_INVALID_ARGUMENT;
-  const auto c0 = grid_cell(prior_x, prior_y, grid_scale);
-  std::vector<int32_t> cand;
-  for (int i = -1; i <= 1; ++i)               // loop_closure.cc:19-28
-    for (int j = -1; j <= 1; ++j) {
-      auto it = ctx->grid.find({c0.first + i, c0.second + j});
-      if (it != ctx->grid.end()) cand.insert(cand.end(), it->second.begin(), it->second.end());
-    }
-  if (n_candidates_out) *n_candidates_out = (int)cand.size();
-  if (candidates_out)
-    for (int i = 0; i < (int)cand.size() && i < max_candidates; ++i) candidates_out[i] = cand[i];
-  static const int32_t none = 0;
-  return nis_loop_scan(ctx, query, query_frame_id, query_acc_distance, cfg, cand.empty() ? &none : cand.data(), (int)cand.size(), out, nullptr);
+  const double prior[2] = {prior_x, prior_y};
+  return loop_scan_impl(ctx, query, query_frame_id, query_acc_distance, cfg, nullptr, 0, prior, grid_scale, out, nullptr, nullptr, candidates_out,
+                        max_candidates, n_candidates_out);
 }
 
 int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n_ranks, const nis_loop_config* cfg,
@@ -1255,6 +1539,136 @@ int nis_loop_reduce(const nis_loop_result* per_rank, const int64_t* order, int n
   out->found = (out->response[0] > cfg->position_response_thr) && (out->response[2] > cfg->angle_response_thr);
   if (winner_rank) *winner_rank = best;
   return NIS_OK;
+}
+
+// ---- multi-GPU scan in the library: the keyframe store is sharded by index over the ranks (one context per GPU, one
+// process per GPU); a query is ONE call on every rank: ncclBroadcast of the 307 KB u8 query image from the root, local features +
+// local scan, ONE ncclAllGather of the per-rank best records, the reference's strict-'>' / first-wins reduction on every rank.
+// NCCL is resolved at run time (dlopen), so the library loads and runs single-GPU without it.
+struct nis_nccl_id { char internal[128]; };
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(nis_nccl_id*) = nullptr;
+  int (*CommInitRank)(void**, int, nis_nccl_id, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.h ? &api : nullptr;
+  tried = true;
+  const char* names[] = {getenv("NIS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm || !*nm) continue;
+    api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) break;
+  }
+  if (!api.h) return nullptr;
+  api.GetUniqueId = (int (*)(nis_nccl_id*))dlsym(api.h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, nis_nccl_id, int))dlsym(api.h, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(void*))dlsym(api.h, "ncclCommDestroy");
+  api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.h, "ncclBroadcast");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.h, "ncclAllGather");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllGather) { dlclose(api.h); api.h = nullptr; return nullptr; }
+  return &api;
+}
+static int nccl_fail(nis_ctx* ctx, const char* what, int rc) {
+  NcclApi* a = nccl_api();
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: %s", what, a && a->GetErrorString ? a->GetErrorString(rc) : "NCCL error");
+  return fail(ctx, NIS_ERR_CUDA, buf);
+}
+
+int nis_nccl_unique_id(char id_out[128]) {
+  NcclApi* a = nccl_api();
+  if (!a || !id_out) return NIS_ERR_CUDA;
+  nis_nccl_id id;
+  if (a->GetUniqueId(&id) != 0) return NIS_ERR_CUDA;
+  memcpy(id_out, id.internal, 128);
+  return NIS_OK;
+}
+
+int nis_comm_init(nis_ctx* ctx, const char id[128], int rank, int n_ranks) {
+  if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return NIS_ERR_INVALID_ARGUMENT;
+  NcclApi* a = nccl_api();
+  if (!a) return fail(ctx, NIS_ERR_CUDA, "libnccl.so.2 not found (set NIS_NCCL_LIB)");
+  CU(cudaSetDevice(ctx->device));
+  nis_comm_destroy(ctx);
+  nis_nccl_id uid;
+  memcpy(uid.internal, id, 128);
+  const int rc = a->CommInitRank(&ctx->nccl_comm, n_ranks, uid, rank);
+  if (rc != 0) { ctx->nccl_comm = nullptr; return nccl_fail(ctx, "ncclCommInitRank", rc); }
+  ctx->rank = rank; ctx->n_ranks = n_ranks;
+  return NIS_OK;
+}
+
+int nis_comm_destroy(nis_ctx* ctx) {
+  if (!ctx) return NIS_ERR_INVALID_ARGUMENT;
+  if (ctx->nccl_comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  ctx->rank = 0; ctx->n_ranks = 1;
+  return NIS_OK;
+}
+
+struct ShardRecord { nis_loop_result r; int64_t order; int64_t offset; };
+
+int nis_loop_scan_sharded(nis_ctx* ctx, const uint8_t* query_image_rowmajor, int root, int query_frame_id, double query_acc_distance,
+                          const nis_loop_config* cfg, long long global_slot_offset, nis_loop_result* out, int* winner_rank,
+                          nis_loop_result* local_out) {
+  if (!ctx || !cfg || !out || root < 0 || root >= ctx->n_ranks) return NIS_ERR_INVALID_ARGUMENT;
+  if (ctx->n_ranks > 1 && !ctx->nccl_comm) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "nis_loop_scan_sharded: call nis_comm_init first");
+  if (ctx->rank == root && !query_image_rowmajor) return NIS_ERR_INVALID_ARGUMENT;
+  CU(cudaSetDevice(ctx->device));
+  NcclApi* a = ctx->n_ranks > 1 ? nccl_api() : nullptr;
+  const size_t npx = ctx->sz[0].real;
+  nis_frame* q = nullptr;
+  TRY(frame_alloc(ctx, true, &q));
+  q->has_h = false;
+  auto body = [&]() -> int {
+    if (ctx->rank == root) CU(cudaMemcpyAsync(q->img_u8, query_image_rowmajor, npx, cudaMemcpyHostToDevice, ctx->stream));
+    if (a) { const int rc = a->Broadcast(q->img_u8, q->img_u8, npx, 1 /* ncclUint8 */, root, ctx->nccl_comm, ctx->stream); if (rc) return nccl_fail(ctx, "ncclBroadcast", rc); }
+    // every rank recomputes the query's features (cheaper than shipping 3.8 MB of spectra); a raw image is undistorted first when maps are set
+    if (ctx->undistort) {
+      RESERVE(ctx->sImg, npx);
+      CU(cudaMemcpyAsync(ctx->sImg.p, q->img_u8, npx, cudaMemcpyDeviceToDevice, ctx->stream));
+      TRY(undistort_batch(ctx, ctx->stream, ctx->sImg.as<uint8_t>(), q->img_u8, 1));
+    }
+    TRY(features_batch(ctx, ctx->lanes[0], src_null<float>(), src_slab<uint8_t>(q->img_u8, 0), true, 1, Dst<cpx>{q->F, 0}, Dst<cpx>{q->P, 0},
+                       Dst<cpx>{q->Ht, 0}, Dst<cpx>{q->Hp, 0}, false));
+    ShardRecord mine;
+    memset(&mine, 0, sizeof mine);
+    TRY(nis_loop_scan(ctx, q, query_frame_id, query_acc_distance, cfg, nullptr, 0, &mine.r, nullptr));
+    if (local_out) *local_out = mine.r;
+    mine.offset = global_slot_offset;
+    mine.order = mine.r.slot >= 0 ? global_slot_offset + mine.r.slot : INT64_MAX;
+    const int G = ctx->n_ranks;
+    std::vector<ShardRecord> all(G);
+    if (a) {
+      RESERVE(ctx->qgather, (size_t)(G + 1) * sizeof(ShardRecord));
+      ShardRecord* d = ctx->qgather.as<ShardRecord>();
+      CU(cudaMemcpyAsync(d + G, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+      const int rc = a->AllGather(d + G, d, sizeof(ShardRecord), 0 /* ncclChar */, ctx->nccl_comm, ctx->stream);
+      if (rc) return nccl_fail(ctx, "ncclAllGather", rc);
+      CU(cudaMemcpyAsync(all.data(), d, (size_t)G * sizeof(ShardRecord), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+      all[0] = mine;
+    }
+    std::vector<nis_loop_result> rs(G);
+    std::vector<int64_t> order(G);
+    for (int i = 0; i < G; ++i) { rs[i] = all[i].r; order[i] = all[i].order; }
+    int win = -1;
+    TRY(nis_loop_reduce(rs.data(), order.data(), G, cfg, out, &win));
+    if (win >= 0 && out->slot >= 0) out->slot = (int32_t)(all[win].offset + out->slot);       // global slot of the winner
+    if (winner_rank) *winner_rank = win;
+    return NIS_OK;
+  };
+  const int st = body();
+  nis_frame_free(ctx, q);
+  return st;
 }
 
 // ---- per-kernel-family timing (CUDA events around every launch; used by bench.py for the roofline line) ---------
@@ -1311,7 +1725,7 @@ int nis_debug_fft2(nis_ctx* ctx, int which, const float* real_in, float* spec_ou
   RESERVE(out, z.spec * sizeof(cpx));
   CU(h2d(ctx, L.real.p, real_in, z.real * sizeof(float)));
   Dst<cpx> t1{L.t1.as<cpx>(), 0};
-  LAUNCH(launch_col_fwd_f32(z.R, z.colf, ProRealF32{src_slab<float>(L.real.as<float>(), 0), z.C}, t1, z.C, 1, L.stream));
+  LAUNCH(launch_col_fwd_f32(z.R, z.col, ProRealF32{src_slab<float>(L.real.as<float>(), 0), z.C}, t1, z.C, 1, L.stream));
   LAUNCH(launch_row_fwd(z.C, z.row, ProSpec{src_slab<cpx>(t1.base, 0)}, EpiSpecStore{Dst<cpx>{out.as<cpx>(), 0}}, z.R / 2 + 1, 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpy(spec_out, out.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
@@ -1338,7 +1752,7 @@ int nis_debug_ifft2(nis_ctx* ctx, int which, const float* spec_in, float* real_o
   Dst<cpx> t1{L.t1.as<cpx>(), 0};
   LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{src_slab<cpx>(in.as<cpx>(), 0), src_slab<cpx>(one.as<cpx>(), 0)}, EpiSpecStore{t1},
                                 z.R / 2 + 1, 1, L.stream));
-  LAUNCH(launch_col_inv_store(z.R, z.coli, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{L.real.as<float>(), 0}, z.C, (float)z.real}, z.C, 1,
+  LAUNCH(launch_col_inv_store(z.R, z.col, src_slab<cpx>(t1.base, 0), EpiStore{Dst<float>{L.real.as<float>(), 0}, z.C, (float)z.real}, z.C, 1,
                               L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpy(real_out, L.real.p, z.real * sizeof(float), cudaMemcpyDeviceToHost));

@@ -1,5 +1,5 @@
 // nis_col.cu -- column-pass kernels (transform along image rows; r2c forward / c2r inverse), sm_100a.
-// One CTA = 32 adjacent real columns of one image (16 complex lines), grid = (W/32, batch).
+// One CTA = 16 adjacent real columns of one image (8 complex lines), grid = (W/16, batch).
 #include "nis_device.cuh"
 #include "nis_internal.h"
 #include "nis_sizes.h"
@@ -7,116 +7,99 @@
 
 namespace nis {
 
-template <int N, int R0, int R1, int R2, int T, class Pro>
-__global__ void __launch_bounds__(T) col_fwd_kernel(Pro pro, Twiddles twd, Dst<cpx> out, int W) {
+// resident CTAs per SM the register budget of the column kernels is sized for: 768 threads (85 registers each): the paired
+// radix-12 stages hold 24 complex values per thread; a 64-register budget spills there (measured -6 %, profiles/ab_r02.md)
+#ifndef NIS_COL_MINB
+#define NIS_COL_MINB (768 / NIS_COL_T)
+#endif
+
+template <int N, int A, int B, int C, int T, class Pro>
+__global__ void __launch_bounds__(T, NIS_COL_MINB) col_fwd_kernel(Pro pro, Twiddles twd, Dst<cpx> out, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
   const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
   const auto bp = pro.bind(b, c0);
-  col_fwd_phase0<N, R0, R1, R2, T>(tid, smem, bp);
+  col_fwd_stage_a<N, A, B, C, T>(tid, smem, twd, bp);
   __syncthreads();
-  CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1> st;
-  col_stage1_read<N, R0, R1, R2, T, false>(tid, smem, twd, st);
+  col_stage_b<N, A, B, C, T, false, false>(tid, smem, twd);
   __syncthreads();
-  col_stage1_write<N, R0, R1, R2, T, false>(tid, smem, st);
-  __syncthreads();
-  col_fwd_phase2<N, R0, R1, R2, T>(tid, smem, twd, out.at(b), W, c0);
+  col_fwd_stage_c<N, A, B, C, T>(tid, smem, out.at(b), W, c0);
 }
 
-template <int N, int R0, int R1, int R2, int T, class Epi>
-__global__ void __launch_bounds__(T) col_inv_kernel(Src<cpx> in, Twiddles twd, Epi epi, int W) {
+template <int N, int A, int B, int C, int T, class Epi>
+__global__ void __launch_bounds__(T, NIS_COL_MINB) col_inv_kernel(Src<cpx> in, Twiddles twd, Epi epi, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
   const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
-  col_inv_phase0<N, R0, R1, R2, T>(tid, smem, in.at(b), W, c0);
+  col_inv_stage_a<N, A, B, C, T>(tid, smem, twd, in.at(b), W, c0);
   __syncthreads();
-  CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1> st;
-  col_stage1_read<N, R0, R1, R2, T, true>(tid, smem, twd, st);
-  __syncthreads();
-  col_stage1_write<N, R0, R1, R2, T, true>(tid, smem, st);
+  col_stage_b<N, A, B, C, T, true, false>(tid, smem, twd);
   __syncthreads();
   auto be = epi.bind(b, c0);
-  col_inv_phase2<N, R0, R1, R2, T>(tid, smem, twd, be);
+  col_inv_stage_c<N, A, B, C, T>(tid, smem, be);
   DeviceSync sync;
   be.finish(tid, sync);
 }
 
 // fused inverse column pass -> kernel function -> forward column pass (correlation_flow.cc:212-215 / :222-225 between
-// the IFFT and the FFT): the real kernel image lives only in shared memory.
-template <int N, int I0, int I1, int I2, int F0, int F1, int F2, int T>
-__global__ void __launch_bounds__(T) colcol_kernel(Src<cpx> in, Dst<cpx> out, Twiddles twi, Twiddles twf, KernelFn kfn, int W) {
+// the IFFT and the FFT): the real kernel image exists only in registers, between the two radix-C butterflies of one thread.
+// Four barriers, four shared-memory round trips.
+template <int N, int A, int B, int C, int T>
+__global__ void __launch_bounds__(T, NIS_COL_MINB) colcol_kernel(Src<cpx> in, Dst<cpx> out, Twiddles twd, KernelFn kfn, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
   const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
-  col_inv_phase0<N, I0, I1, I2, T>(tid, smem, in.at(b), W, c0);
+  col_inv_stage_a<N, A, B, C, T>(tid, smem, twd, in.at(b), W, c0);
   __syncthreads();
-  {
-    CarryRegs<I1, ColGeom<N, I0, I1, I2, T>::ROUNDS1> st;
-    col_stage1_read<N, I0, I1, I2, T, true>(tid, smem, twi, st);
-    __syncthreads();
-    col_stage1_write<N, I0, I1, I2, T, true>(tid, smem, st);
-  }
+  col_stage_b<N, A, B, C, T, true, false>(tid, smem, twd);
   __syncthreads();
   auto fn = kfn.bind(b);
-  col_inv_phase2_inplace<N, I0, I1, I2, T>(tid, smem, twi, fn);
+  col_inv_fn_fwd_stage_c<N, A, B, C, T>(tid, smem, fn);
   __syncthreads();
-  {
-    CarryRegs<F0, ColGeom<N, F0, F1, F2, T>::ROUNDS0> st;
-    col_fwd_phase0s_read<N, F0, F1, F2, T>(tid, smem, st);
-    __syncthreads();
-    col_fwd_phase0s_write<N, F0, F1, F2, T>(tid, smem, st);
-  }
+  col_stage_b<N, A, B, C, T, false, true>(tid, smem, twd);
   __syncthreads();
-  {
-    CarryRegs<F1, ColGeom<N, F0, F1, F2, T>::ROUNDS1> st;
-    col_stage1_read<N, F0, F1, F2, T, false>(tid, smem, twf, st);
-    __syncthreads();
-    col_stage1_write<N, F0, F1, F2, T, false>(tid, smem, st);
-  }
-  __syncthreads();
-  col_fwd_phase2<N, F0, F1, F2, T>(tid, smem, twf, out.at(b), W, c0);
+  col_fwd_dit_stage_a<N, A, B, C, T>(tid, smem, twd, out.at(b), W, c0);
   DeviceSync sync;
   fn.finish(tid, sync);
 }
 
-template <int N, int I0, int I1, int I2, int F0, int F1, int F2, int T>
-static int run_colcol(Twiddles twi, Twiddles twf, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s) {
-  auto k = colcol_kernel<N, I0, I1, I2, F0, F1, F2, T>;
-  const size_t smem = ColGeom<N, F0, F1, F2, T>::kSmemBytes;
+template <int N, int A, int B, int C, int T>
+static int run_colcol(Twiddles tw, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int Bn, cudaStream_t s) {
+  auto k = colcol_kernel<N, A, B, C, T>;
+  const size_t smem = ColGeom<N, A, B, C, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / kColTile, B), T, smem, s>>>(in, out, twi, twf, fn, W);
+  k<<<dim3(W / kColTile, Bn), T, smem, s>>>(in, out, tw, fn, W);
   return (int)cudaGetLastError();
 }
 
-template <int N, int R0, int R1, int R2, int T, class Pro>
-static int run_col_fwd(Twiddles tw, Pro pro, Dst<cpx> out, int W, int B, cudaStream_t s) {
-  auto k = col_fwd_kernel<N, R0, R1, R2, T, Pro>;
-  const size_t smem = ColGeom<N, R0, R1, R2, T>::kSmemBytes;
+template <int N, int A, int B, int C, int T, class Pro>
+static int run_col_fwd(Twiddles tw, Pro pro, Dst<cpx> out, int W, int Bn, cudaStream_t s) {
+  auto k = col_fwd_kernel<N, A, B, C, T, Pro>;
+  const size_t smem = ColGeom<N, A, B, C, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / kColTile, B), T, smem, s>>>(pro, tw, out, W);
+  k<<<dim3(W / kColTile, Bn), T, smem, s>>>(pro, tw, out, W);
   return (int)cudaGetLastError();
 }
-template <int N, int R0, int R1, int R2, int T, class Epi>
-static int run_col_inv(Twiddles tw, Src<cpx> in, Epi epi, int W, int B, cudaStream_t s) {
-  auto k = col_inv_kernel<N, R0, R1, R2, T, Epi>;
-  const size_t smem = ColGeom<N, R0, R1, R2, T>::kSmemBytes;
+template <int N, int A, int B, int C, int T, class Epi>
+static int run_col_inv(Twiddles tw, Src<cpx> in, Epi epi, int W, int Bn, cudaStream_t s) {
+  auto k = col_inv_kernel<N, A, B, C, T, Epi>;
+  const size_t smem = ColGeom<N, A, B, C, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / kColTile, B), T, smem, s>>>(in, tw, epi, W);
+  k<<<dim3(W / kColTile, Bn), T, smem, s>>>(in, tw, epi, W);
   return (int)cudaGetLastError();
 }
 
 bool col_size_supported(int N) {
-#define X(n, f0, f1, f2, i0, i1, i2, t) if (N == n) return true;
+#define X(n, a, b, c, t) if (N == n) return true;
   NIS_COL_PLANS(X)
 #undef X
   return false;
 }
-void plan_radices_col(int N, bool inverse, int r[3]) {
-#define X(n, f0, f1, f2, i0, i1, i2, t) \
-  if (N == n) { if (inverse) { r[0] = i0; r[1] = i1; r[2] = i2; } else { r[0] = f0; r[1] = f1; r[2] = f2; } return; }
+void plan_radices_col(int N, int r[3]) {
+#define X(n, a, b, c, t) if (N == n) { r[0] = a; r[1] = b; r[2] = c; return; }
   NIS_COL_PLANS(X)
 #undef X
   r[0] = r[1] = r[2] = 0;
@@ -128,7 +111,7 @@ void plan_radices_col(int N, bool inverse, int r[3]) {
     NIS_COL_PLANS(FWD_CASE)                                                                        \
     default: return -1;                                                                            \
   }
-#define FWD_CASE(n, f0, f1, f2, i0, i1, i2, t) case n: return run_col_fwd<n, f0, f1, f2, t>(tw, pro, out, W, B, s);
+#define FWD_CASE(n, a, b, c, t) case n: return run_col_fwd<n, a, b, c, t>(tw, pro, out, W, B, s);
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealF32) }
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealU8) }
 int launch_col_fwd_polar(int N, Twiddles tw, PolarArgs pa, Dst<cpx> out, int W, int B, cudaStream_t s) {
@@ -152,16 +135,16 @@ int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W
     NIS_COL_PLANS(INV_CASE)                                                                        \
     default: return -1;                                                                            \
   }
-#define INV_CASE(n, f0, f1, f2, i0, i1, i2, t) case n: return run_col_inv<n, i0, i1, i2, t>(tw, in, epi, W, B, s);
+#define INV_CASE(n, a, b, c, t) case n: return run_col_inv<n, a, b, c, t>(tw, in, epi, W, B, s);
 int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 int launch_col_inv_store_pairs(int N, Twiddles tw, Src<cpx> in, EpiStorePairs epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 #undef INV_CASE
 
-int launch_colcol(int N, Twiddles twi, Twiddles twf, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s) {
+int launch_colcol(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s) {
   if (B <= 0) return 0;
   switch (N) {
-#define X(n, f0, f1, f2, i0, i1, i2, t) case n: return run_colcol<n, i0, i1, i2, f0, f1, f2, t>(twi, twf, in, out, fn, W, B, s);
+#define X(n, a, b, c, t) case n: return run_colcol<n, a, b, c, t>(tw, in, out, fn, W, B, s);
     NIS_COL_PLANS(X)
 #undef X
     default: return -1;

@@ -7,8 +7,8 @@
 //     shared-memory access is conflict-free and every global access is a 128..256 B contiguous segment.
 //   * row pass     (transform along image columns c, contiguous): lanes <-> butterfly index, first radix 16,
 //     one pad slot per 16 complex keeps the Stockham exchanges conflict-free.
-// Both families do stage 0 straight from global memory and the last stage straight to global memory; only two
-// exchanges go through shared memory.  Element-wise work of the KCC (spectrum products, |F|, the kernel function,
+// Both families do their first stage straight from global memory and the last stage straight to global memory; only two
+// exchanges go through shared memory.  The column family runs in place on a digit-addressed tile (see COLUMN PASS).  Element-wise work of the KCC (spectrum products, |F|, the kernel function,
 // the H*Kxz filter, arg-max / sum / sum-of-squares) rides in the prologue / epilogue functors of these passes.
 //
 // The bodies are written as barrier-free "phases" so the same code runs on the host under tests/cpp (thread-by-
@@ -235,7 +235,22 @@ struct Twiddles {
 #endif
 
 // =========================================================================================================
-// COLUMN PASS: lanes <-> 16 complex lines (32 real columns).  smem: cpx[N][16].  T threads, G = T/16 groups.
+// COLUMN PASS: lanes <-> kColLanes complex lines (2*kColLanes real columns), T threads, G = T/kColLanes butterfly groups.
+//
+// In-place three-stage transform of length N = A*B*C on a digit-addressed shared-memory tile: the element with digits
+// (d0 < A, d1 < B, d2 < C) of line l sits at smem[pos(d0,d1,d2) * kColLanes + l], pos = (d0*B + d1)*PADC + d2 with one pad slot
+// per block of C when C is even (so that the radix-C stage, whose groups walk whole blocks, alternates bank halves).
+//   decimation in frequency (natural index in, digit-reversed out), used by every pass that starts from global memory:
+//     n = d0*BC + d1*C + d2  ->  stage A over d0 (then * W_N^(k0 (d1 C + d2)))  ->  stage B over d1 (then * W_BC^(k1 d2))
+//     ->  stage C over d2  ->  k = k0 + A k1 + A B k2 at pos(k0,k1,k2)
+//   decimation in time (digit-reversed in, natural out), the second half of the fused inverse->forward kernel:
+//     n = d0 + A d1 + A B d2 at pos(d0,d1,d2)  ->  stage C over d2  ->  (* W_BC^(d1 e2)) stage B over d1
+//     ->  (* W_N^(d0 (e1 C + e2))) stage A over d0  ->  k = e0*BC + e1*C + e2
+// Every butterfly reads and writes the SAME R slots, so a stage needs no carry registers and no barrier between its reads and
+// its writes: one __syncthreads per stage boundary, registers = one butterfly.  Any row permutation is free at the global ends
+// (a row is an independent contiguous segment), which is what makes the digit-reversed order harmless.
+// Twiddles (forward sign, conjugated for the inverse):  tw1[(b-1)*C + d2] = exp(-2 pi i b d2 / (B C)),  b in [1,B)
+//                                                      tw2[(a-1)*BC + j] = exp(-2 pi i a j / N),         a in [1,A), j in [0,BC)
 // =========================================================================================================
 #ifndef NIS_COL_LANES
 #define NIS_COL_LANES 8
@@ -243,57 +258,46 @@ struct Twiddles {
 constexpr int kColLanes = NIS_COL_LANES;          // complex lines per CTA
 constexpr int kColTile = 2 * kColLanes;           // real image columns per CTA
 
-template <int N, int R0, int R1, int R2, int T> struct ColGeom {
-  static_assert(R0 * R1 * R2 == N, "bad factorisation");
+template <int N, int A, int B, int C, int T> struct ColGeom {
+  static_assert(A * B * C == N, "bad factorisation");
   static_assert(T % kColLanes == 0, "T must be a multiple of the lane count");
   static constexpr int G = T / kColLanes;
-  static constexpr int M0 = N / R0, M1 = N / R1, M2 = N / R2;   // butterflies per line per stage
-  static constexpr int NS1 = R0, NS2 = R0 * R1;
-  static constexpr int ROUNDS0 = (M0 + G - 1) / G;
-  static constexpr int ROUNDS1 = (M1 + G - 1) / G;
-  static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)N * kColLanes;
+  static constexpr int BC = B * C, AB = A * B, AC = A * C;
+  static constexpr int PADC = C + ((C % 2 == 0) ? 1 : 0);
+  static constexpr int SLOTS = AB * PADC;
+  static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)SLOTS * kColLanes;
+  static NIS_HD int pos(int d0, int d1, int d2) { return (d0 * B + d1) * PADC + d2; }
+  static NIS_HD int pos_j(int d0, int j) { return (d0 * B + j / C) * PADC + j % C; }      // j = d1*C + d2
 };
 
-template <int R1, int ROUNDS> struct CarryRegs { cpx v[ROUNDS][R1]; };
-
-// ---- shared middle stage (in place: read all -> barrier -> write all), both directions
-template <int N, int R0, int R1, int R2, int T, bool INV>
-NIS_HD void col_stage1_read(int tid, const cpx* smem, const Twiddles& twd, CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1>& st) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
+// ---- stage B (middle), both directions.  DIT = false: decimation in frequency (twiddle after the butterfly); true: before.
+template <int N, int A, int B, int C, int T, bool INV, bool DIT>
+NIS_HD void col_stage_b(int tid, cpx* smem, const Twiddles& twd) {
+  typedef ColGeom<N, A, B, C, T> Gm;
   const int l = tid % kColLanes, gi = tid / kColLanes;
-  // k = j % NS1 with j = gi + it*G: when the group count is a multiple of NS1 (= R0) the twiddle index is the same in every round
-  constexpr bool kHoist = (Gm::G % Gm::NS1 == 0);
-  cpx twv[R1 > 1 ? R1 - 1 : 1];
+  // butterfly index bi = d2 + C*d0: when the group count is a multiple of C the twiddle index d2 is the same in every round
+  constexpr bool kHoist = (Gm::G % C == 0);
+  cpx twv[B > 1 ? B - 1 : 1];
   if (kHoist) {
 #pragma unroll
-    for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + gi % Gm::NS1]);
+    for (int r = 1; r < B; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * C + gi % C]);
   }
+  for (int bi = gi; bi < Gm::AC; bi += Gm::G) {
+    const int d0 = bi / C, d2 = bi % C;
+    cpx* s = smem + (size_t)Gm::pos(d0, 0, d2) * kColLanes + l;
+    cpx v[B];
 #pragma unroll
-  for (int it = 0; it < Gm::ROUNDS1; ++it) {
-    const int j = gi + it * Gm::G;
-    if (j < Gm::M1) {
-      const int k = j % Gm::NS1;
-#pragma unroll
-      for (int r = 0; r < R1; ++r) {
-        cpx x = smem[(j + r * Gm::M1) * kColLanes + l];
-        if (r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * Gm::NS1 + k]));
-        st.v[it][r] = x;
-      }
-      Dft<R1, INV>::run(st.v[it]);
+    for (int r = 0; r < B; ++r) {
+      cpx x = s[r * Gm::PADC * kColLanes];
+      if (DIT && r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * C + d2]));
+      v[r] = x;
     }
-  }
-}
-template <int N, int R0, int R1, int R2, int T, bool INV>
-NIS_HD void col_stage1_write(int tid, cpx* smem, const CarryRegs<R1, ColGeom<N, R0, R1, R2, T>::ROUNDS1>& st) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  const int l = tid % kColLanes, gi = tid / kColLanes;
+    Dft<B, INV>::run(v);
 #pragma unroll
-  for (int it = 0; it < Gm::ROUNDS1; ++it) {
-    const int j = gi + it * Gm::G;
-    if (j < Gm::M1) {
-      const int k = j % Gm::NS1, j0 = (j / Gm::NS1) * Gm::NS1 * R1 + k;
-#pragma unroll
-      for (int r = 0; r < R1; ++r) smem[(j0 + r * Gm::NS1) * kColLanes + l] = st.v[it][r];
+    for (int r = 0; r < B; ++r) {
+      cpx x = v[r];
+      if (!DIT && r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * C + d2]));
+      s[r * Gm::PADC * kColLanes] = x;
     }
   }
 }
@@ -302,47 +306,22 @@ NIS_HD void col_stage1_write(int tid, cpx* smem, const CarryRegs<R1, ColGeom<N, 
 // Pro::lane(l).load_all<R>(row0, stride, v): v[r] = (real column c0+2l, real column c0+2l+1) at image row row0 + r*stride;
 // the per-lane context lets a prologue hoist everything that depends only on the column pair, and handing it all R rows at
 // once lets gather-type prologues issue every independent load before the first use
-// phase 0: stage 0 from global
-template <int N, int R0, int R1, int R2, int T, class Pro>
-NIS_HD void col_fwd_phase0(int tid, cpx* smem, const Pro& pro) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
+// stage A from global (decimation in frequency)
+template <int N, int A, int B, int C, int T, class Pro>
+NIS_HD void col_fwd_stage_a(int tid, cpx* smem, const Twiddles& twd, const Pro& pro) {
+  typedef ColGeom<N, A, B, C, T> Gm;
   const int l = tid % kColLanes, gi = tid / kColLanes;
   const auto ln = pro.lane(l);
-  for (int j = gi; j < Gm::M0; j += Gm::G) {
-    cpx v[R0];
-    ln.template load_all<R0>(j, Gm::M0, v);        // v[r] = sample at row j + r*M0
-    Dft<R0, false>::run(v);
+  for (int j = gi; j < Gm::BC; j += Gm::G) {
+    cpx v[A];
+    ln.template load_all<A>(j, Gm::BC, v);        // v[r] = sample at row j + r*BC
+    Dft<A, false>::run(v);
+    cpx* s = smem + (size_t)Gm::pos_j(0, j) * kColLanes + l;
 #pragma unroll
-    for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = v[r];
-  }
-}
-
-// phase 0 when the real pairs already sit in shared memory (fused inverse -> element-wise -> forward): in place,
-// read all -> barrier -> write all
-template <int N, int R0, int R1, int R2, int T>
-NIS_HD void col_fwd_phase0s_read(int tid, const cpx* smem, CarryRegs<R0, ColGeom<N, R0, R1, R2, T>::ROUNDS0>& st) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  const int l = tid % kColLanes, gi = tid / kColLanes;
-#pragma unroll
-  for (int it = 0; it < Gm::ROUNDS0; ++it) {
-    const int j = gi + it * Gm::G;
-    if (j < Gm::M0) {
-#pragma unroll
-      for (int r = 0; r < R0; ++r) st.v[it][r] = smem[(j + r * Gm::M0) * kColLanes + l];
-      Dft<R0, false>::run(st.v[it]);
-    }
-  }
-}
-template <int N, int R0, int R1, int R2, int T>
-NIS_HD void col_fwd_phase0s_write(int tid, cpx* smem, const CarryRegs<R0, ColGeom<N, R0, R1, R2, T>::ROUNDS0>& st) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  const int l = tid % kColLanes, gi = tid / kColLanes;
-#pragma unroll
-  for (int it = 0; it < Gm::ROUNDS0; ++it) {
-    const int j = gi + it * Gm::G;
-    if (j < Gm::M0) {
-#pragma unroll
-      for (int r = 0; r < R0; ++r) smem[(j * R0 + r) * kColLanes + l] = st.v[it][r];
+    for (int r = 0; r < A; ++r) {
+      cpx x = v[r];
+      if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * Gm::BC + j]));
+      s[r * B * Gm::PADC * kColLanes] = x;
     }
   }
 }
@@ -353,68 +332,102 @@ NIS_HD float4 r2c_split(cpx zk, cpx zn) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// phase 2: stage 2, butterflies j and NS2-j handled by one thread so Z[k] and Z[N-k] meet in registers.
+// last stage of a forward pass done by butterfly pairs (p, NS2-p): butterfly p yields Z[p + r*NS2] in v[r], butterfly NS2-p
+// yields Z[N - (p + r*NS2)] in u[R2-1-r], so Z[k] and Z[N-k] separate in registers.  Writes spectrum rows k in [0,N/2].
+template <int N, int NS2, int R2>
+NIS_HD void r2c_emit(int p, bool single, const cpx* v, const cpx* u, float4* out4, int pitch, int c0, int l) {
+#pragma unroll
+  for (int r = 0; r < R2; ++r) {
+    const int k = p + r * NS2;
+    cpx zk, zn;
+    int kk;
+    if (single) {
+      if (2 * k > N) continue;
+      kk = k;
+      zk = v[r];
+      zn = (p == 0) ? v[(R2 - r) % R2] : v[R2 - 1 - r];
+    } else if (2 * k <= N) {
+      kk = k; zk = v[r]; zn = u[R2 - 1 - r];
+    } else {
+      kk = N - k; zk = u[R2 - 1 - r]; zn = v[r];
+    }
+    out4[((size_t)kk * pitch + c0) / 2 + l] = r2c_split(zk, zn);
+  }
+}
+
+// stage C of the decimation-in-frequency forward pass: butterfly q = k0 + A*k1 yields k = q + A*B*k2
 // out: spectrum rows k in [0,N/2], row pitch `pitch` complex; this CTA's columns start at c0 (even).
-template <int N, int R0, int R1, int R2, int T>
-NIS_HD void col_fwd_phase2(int tid, const cpx* smem, const Twiddles& twd, cpx* out, int pitch, int c0) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  constexpr int NS2 = Gm::NS2;
+template <int N, int A, int B, int C, int T>
+NIS_HD void col_fwd_stage_c(int tid, const cpx* smem, cpx* out, int pitch, int c0) {
+  typedef ColGeom<N, A, B, C, T> Gm;
+  constexpr int AB = Gm::AB;
   const int l = tid % kColLanes, gi = tid / kColLanes;
   float4* out4 = reinterpret_cast<float4*>(out);   // (A.x,A.y,B.x,B.y) = two adjacent complex columns
-  for (int p = gi; 2 * p <= NS2; p += Gm::G) {
-    const bool single = (p == 0) || (2 * p == NS2);
-    cpx v[R2], u[R2];
+  for (int p = gi; 2 * p <= AB; p += Gm::G) {
+    const bool single = (p == 0) || (2 * p == AB);
+    cpx v[C], u[C];
+    const cpx* s = smem + (size_t)Gm::pos(p % A, p / A, 0) * kColLanes + l;
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      cpx x = smem[(p + r * NS2) * kColLanes + l];
-      if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + p]));
+    for (int r = 0; r < C; ++r) v[r] = s[r * kColLanes];
+    Dft<C, false>::run(v);
+    if (!single) {
+      const int q = AB - p;
+      const cpx* t = smem + (size_t)Gm::pos(q % A, q / A, 0) * kColLanes + l;
+#pragma unroll
+      for (int r = 0; r < C; ++r) u[r] = t[r * kColLanes];
+      Dft<C, false>::run(u);
+    }
+    r2c_emit<N, AB, C>(p, single, v, u, out4, pitch, c0, l);
+  }
+}
+
+// stage A of the decimation-in-time forward pass (second half of the fused kernel): butterfly j = e1*C + e2 yields k = j + BC*e0
+template <int N, int A, int B, int C, int T>
+NIS_HD void col_fwd_dit_stage_a(int tid, const cpx* smem, const Twiddles& twd, cpx* out, int pitch, int c0) {
+  typedef ColGeom<N, A, B, C, T> Gm;
+  constexpr int BC = Gm::BC;
+  const int l = tid % kColLanes, gi = tid / kColLanes;
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (int p = gi; 2 * p <= BC; p += Gm::G) {
+    const bool single = (p == 0) || (2 * p == BC);
+    cpx v[A], u[A];
+    const cpx* s = smem + (size_t)Gm::pos_j(0, p) * kColLanes + l;
+#pragma unroll
+    for (int r = 0; r < A; ++r) {
+      cpx x = s[r * B * Gm::PADC * kColLanes];
+      if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * BC + p]));
       v[r] = x;
     }
-    Dft<R2, false>::run(v);
+    Dft<A, false>::run(v);
     if (!single) {
-      const int q = NS2 - p;
+      const int q = BC - p;
+      const cpx* t = smem + (size_t)Gm::pos_j(0, q) * kColLanes + l;
 #pragma unroll
-      for (int r = 0; r < R2; ++r) {
-        cpx x = smem[(q + r * NS2) * kColLanes + l];
-        if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + q]));
+      for (int r = 0; r < A; ++r) {
+        cpx x = t[r * B * Gm::PADC * kColLanes];
+        if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * BC + q]));
         u[r] = x;
       }
-      Dft<R2, false>::run(u);
+      Dft<A, false>::run(u);
     }
-#pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      const int k = p + r * NS2;
-      cpx zk, zn;
-      int kk;
-      if (single) {
-        if (2 * k > N) continue;
-        kk = k;
-        zk = v[r];
-        zn = (p == 0) ? v[(R2 - r) % R2] : v[R2 - 1 - r];
-      } else if (2 * k <= N) {
-        kk = k; zk = v[r]; zn = u[R2 - 1 - r];
-      } else {
-        kk = N - k; zk = u[R2 - 1 - r]; zn = v[r];
-      }
-      out4[((size_t)kk * pitch + c0) / 2 + l] = r2c_split(zk, zn);
-    }
+    r2c_emit<N, BC, A>(p, single, v, u, out4, pitch, c0, l);
   }
 }
 
 // ---- inverse c2r column pass ------------------------------------------------------------------------------
 // in: half spectrum rows k in [0,N/2] (pitch complex), this CTA's columns start at c0.
-// phase 0: stage 0 (inverse) with butterflies j and M0-j paired so one (A,B) load feeds Z[k] and Z[N-k].
-template <int N, int R0, int R1, int R2, int T>
-NIS_HD void col_inv_phase0(int tid, cpx* smem, const cpx* in, int pitch, int c0) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  constexpr int M0 = Gm::M0;
+// stage A (inverse, decimation in frequency) with butterflies j and BC-j paired so one (A,B) load feeds Z[k] and Z[N-k].
+template <int N, int A, int B, int C, int T>
+NIS_HD void col_inv_stage_a(int tid, cpx* smem, const Twiddles& twd, const cpx* in, int pitch, int c0) {
+  typedef ColGeom<N, A, B, C, T> Gm;
+  constexpr int M0 = Gm::BC;
   const int l = tid % kColLanes, gi = tid / kColLanes;
   const float4* in4 = reinterpret_cast<const float4*>(in);
   for (int p = gi; 2 * p <= M0; p += Gm::G) {
     const bool single = (p == 0) || (2 * p == M0);
-    cpx v[R0], u[R0];
+    cpx v[A], u[A];
 #pragma unroll
-    for (int r = 0; r < R0; ++r) {
+    for (int r = 0; r < A; ++r) {
       const int k = p + r * M0;
       const bool lo = (2 * k <= N);
       const int kk = lo ? k : N - k;
@@ -424,58 +437,65 @@ NIS_HD void col_inv_phase0(int tid, cpx* smem, const cpx* in, int pitch, int c0)
       const cpx zlo = cadd(ca, ib);                                // A + iB        = Z[kk]
       const cpx zhi = cconj(csub(ca, ib));                         // conjA + i conjB = Z[N-kk]
       v[r] = lo ? zlo : zhi;
-      if (!single) u[R0 - 1 - r] = lo ? zhi : zlo;
+      if (!single) u[A - 1 - r] = lo ? zhi : zlo;
     }
-    Dft<R0, true>::run(v);
+    Dft<A, true>::run(v);
+    cpx* s = smem + (size_t)Gm::pos_j(0, p) * kColLanes + l;
 #pragma unroll
-    for (int r = 0; r < R0; ++r) smem[(p * R0 + r) * kColLanes + l] = v[r];
+    for (int r = 0; r < A; ++r) {
+      cpx x = v[r];
+      if (r > 0) x = cmulc(x, NIS_LDG(&twd.tw2[(r - 1) * M0 + p]));
+      s[r * B * Gm::PADC * kColLanes] = x;
+    }
     if (!single) {
       const int q = M0 - p;
-      Dft<R0, true>::run(u);
+      Dft<A, true>::run(u);
+      cpx* t = smem + (size_t)Gm::pos_j(0, q) * kColLanes + l;
 #pragma unroll
-      for (int r = 0; r < R0; ++r) smem[(q * R0 + r) * kColLanes + l] = u[r];
+      for (int r = 0; r < A; ++r) {
+        cpx x = u[r];
+        if (r > 0) x = cmulc(x, NIS_LDG(&twd.tw2[(r - 1) * M0 + q]));
+        t[r * B * Gm::PADC * kColLanes] = x;
+      }
     }
   }
 }
 
-// phase 2: stage 2 (inverse) -> epilogue.  Epi::put(row, l, re, im): re -> real column c0+2l, im -> c0+2l+1 (unnormalised).
-template <int N, int R0, int R1, int R2, int T, class Epi>
-NIS_HD void col_inv_phase2(int tid, const cpx* smem, const Twiddles& twd, Epi& epi) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  constexpr int NS2 = Gm::NS2;
+// stage C (inverse) -> epilogue.  Epi::put(row, l, re, im): re -> real column c0+2l, im -> c0+2l+1 (unnormalised).
+// Block m = d0*B + d1 (position order, so adjacent groups alternate bank halves) yields rows k = d0 + A*d1 + A*B*k2.
+template <int N, int A, int B, int C, int T, class Epi>
+NIS_HD void col_inv_stage_c(int tid, const cpx* smem, Epi& epi) {
+  typedef ColGeom<N, A, B, C, T> Gm;
   const int l = tid % kColLanes, gi = tid / kColLanes;
-  for (int j = gi; j < NS2; j += Gm::G) {
-    cpx v[R2];
+  for (int m = gi; m < Gm::AB; m += Gm::G) {
+    const cpx* s = smem + (size_t)m * Gm::PADC * kColLanes + l;
+    cpx v[C];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      cpx x = smem[(j + r * NS2) * kColLanes + l];
-      if (r > 0) x = ctw<true>(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
-      v[r] = x;
-    }
-    Dft<R2, true>::run(v);
+    for (int r = 0; r < C; ++r) v[r] = s[r * kColLanes];
+    Dft<C, true>::run(v);
+    const int row0 = m / B + A * (m % B);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) epi.put(j + r * NS2, l, v[r].x, v[r].y);
+    for (int r = 0; r < C; ++r) epi.put(row0 + r * Gm::AB, l, v[r].x, v[r].y);
   }
 }
 
-// phase 2 of the inverse pass kept in shared memory: every thread overwrites exactly the slots it read with
-// fn(re), fn(im) (the real pairs the following forward pass consumes), so no barrier is needed inside.
-template <int N, int R0, int R1, int R2, int T, class Fn>
-NIS_HD void col_inv_phase2_inplace(int tid, cpx* smem, const Twiddles& twd, Fn& fn) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  constexpr int NS2 = Gm::NS2;
+// fused middle of the inverse->forward kernel: inverse stage C, fn on both packed reals, forward (decimation-in-time) stage C,
+// all on the same block of C slots in registers -- the real kernel image never exists anywhere else.
+template <int N, int A, int B, int C, int T, class Fn>
+NIS_HD void col_inv_fn_fwd_stage_c(int tid, cpx* smem, Fn& fn) {
+  typedef ColGeom<N, A, B, C, T> Gm;
   const int l = tid % kColLanes, gi = tid / kColLanes;
-  for (int j = gi; j < NS2; j += Gm::G) {
-    cpx v[R2];
+  for (int m = gi; m < Gm::AB; m += Gm::G) {
+    cpx* s = smem + (size_t)m * Gm::PADC * kColLanes + l;
+    cpx v[C];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      cpx x = smem[(j + r * NS2) * kColLanes + l];
-      if (r > 0) x = ctw<true>(x, NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
-      v[r] = x;
-    }
-    Dft<R2, true>::run(v);
+    for (int r = 0; r < C; ++r) v[r] = s[r * kColLanes];
+    Dft<C, true>::run(v);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) smem[(j + r * NS2) * kColLanes + l] = fn.apply(v[r]);
+    for (int r = 0; r < C; ++r) v[r] = fn.apply(v[r]);
+    Dft<C, false>::run(v);
+#pragma unroll
+    for (int r = 0; r < C; ++r) s[r * kColLanes] = v[r];
   }
 }
 
@@ -483,6 +503,8 @@ NIS_HD void col_inv_phase2_inplace(int tid, cpx* smem, const Twiddles& twd, Fn& 
 // ROW PASS: contiguous complex lines of length N = 16*R1*R2, L lines per CTA, lanes <-> butterfly index.
 // smem: cpx[L][N + N/16] (one pad slot per 16).
 // =========================================================================================================
+template <int R1, int ROUNDS> struct CarryRegs { cpx v[ROUNDS][R1]; };
+
 template <int N, int R1, int R2, int L, int T> struct RowGeom {
   static_assert(16 * R1 * R2 == N, "bad factorisation");
   static constexpr int R0 = 16;

@@ -24,7 +24,7 @@ struct AngleTables {
 
 bool col_size_supported(int N);
 bool row_size_supported(int N);
-void plan_radices_col(int N, bool inverse, int r[3]);
+void plan_radices_col(int N, int r[3]);
 void plan_radices_row(int N, int r[3]);
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
@@ -39,7 +39,7 @@ int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, i
 int launch_col_inv_store_pairs(int N, Twiddles tw, Src<cpx> in, EpiStorePairs epi, int W, int B, cudaStream_t s);
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s);
 // c2r -> kernel function -> r2c in one kernel (the real kernel image never leaves shared memory); in-place allowed
-int launch_colcol(int N, Twiddles twi, Twiddles twf, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s);
+int launch_colcol(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s);
 int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
 int launch_row_fwd_h(int N, Twiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s);
 int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
@@ -73,6 +73,18 @@ int launch_polar_select(const PeakStats* polar, int D, int loop_mode, int* sel, 
 // per pair: info (GetInfo), hypothesis choice, pose
 int launch_pose_finalize(const PeakStats* polar, const PeakStats* trans, AngleTables tabs, int H, int W, int D, int Cp,
                          int loop_mode, int index0, PoseRecord* out, int B, cudaStream_t s);
+// boundary layout conversion (reference column-major <-> row-major): in[rows_in][cols_in] -> out[cols_in][rows_in]
+int launch_transpose_f32(const float* in, float* out, int rows_in, int cols_in, cudaStream_t s);
+int launch_transpose_cpx(const cpx* in, cpx* out, int rows_in, int cols_in, cudaStream_t s);
+// device-side candidate selection (filters + optional 3x3 grid neighbourhood), see nis_misc.cu
+struct SelectArgs {
+  int n_in; const int* list;                       // list == nullptr: all slots in insertion order
+  const int* frame_id; const double* dist; const int2* cell;
+  int query_id; double query_dist; int frame_gap_thr; double distance_thr;
+  int use_prior, cx, cy;
+};
+int select_scratch_ints(int n_in);
+int launch_select(SelectArgs a, int* scratch, int* cand, int* pos, int* n_out, cudaStream_t s);
 // scan: best record by response.sum(), strict '>', first in iteration order wins (loop_closure.cc:61)
 int launch_scan_reduce(const PoseRecord* recs, int n, PoseRecord* best, cudaStream_t s);
 

@@ -295,6 +295,116 @@ int launch_pose_finalize(const PeakStats* polar, const PeakStats* trans, AngleTa
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// boundary layout conversion on the device: reference column-major (C lines of R) <-> internal row-major [R][C].
+// 32 x 32 tiles through shared memory; T = float (images) or cpx (half spectra).
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int rows_in, int cols_in) {
+  __shared__ T tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < rows_in && c0 + tx < cols_in) tile[i][tx] = in[(size_t)(r0 + i) * cols_in + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols_in && r0 + tx < rows_in) out[(size_t)(c0 + i) * rows_in + r0 + tx] = tile[tx][i];
+}
+int launch_transpose_f32(const float* in, float* out, int rows_in, int cols_in, cudaStream_t s) {
+  transpose_kernel<float><<<dim3((cols_in + 31) / 32, (rows_in + 31) / 32), 256, 0, s>>>(in, out, rows_in, cols_in);
+  return (int)cudaGetLastError();
+}
+int launch_transpose_cpx(const cpx* in, cpx* out, int rows_in, int cols_in, cudaStream_t s) {
+  transpose_kernel<cpx><<<dim3((cols_in + 31) / 32, (rows_in + 31) / 32), 256, 0, s>>>(in, out, rows_in, cols_in);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// candidate selection on the device (loop_closure.cc:43-53 filters; map.cc:81-101 + loop_closure.cc:17-34 grid neighbourhood).
+// Input i in [0, n_in): slot = list ? list[i] : i.  A slot passes when the frame-gap and accumulated-distance filters keep it and,
+// with a prior cell, when its cell lies in the 3 x 3 neighbourhood; its rank is the reference's iteration order over that
+// neighbourhood (dx = -1..1 outer, dy = -1..1 inner), 0 without a prior.  Output: slots ordered by (rank, i), the input position
+// of each, and the count -- three kernels (per-chunk counts, one-CTA exclusive scan, ordered write), no host loop over the DB.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int select_rank(const SelectArgs& a, int i) {
+  const int slot = a.list ? a.list[i] : i;
+  if (a.frame_gap_thr > 0 && abs(a.query_id - a.frame_id[slot]) < a.frame_gap_thr) return -1;
+  if (a.distance_thr > 0 && fabs(a.query_dist - a.dist[slot]) < a.distance_thr) return -1;
+  if (!a.use_prior) return 0;
+  const int2 c = a.cell[slot];
+  if (c.x == INT_MIN) return -1;                                  // never filed in the grid
+  const int dx = c.x - a.cx, dy = c.y - a.cy;
+  if (dx < -1 || dx > 1 || dy < -1 || dy > 1) return -1;
+  return (dx + 1) * 3 + (dy + 1);
+}
+constexpr int kSelChunk = 2048, kSelThreads = 256, kSelPer = kSelChunk / kSelThreads;
+
+__global__ void __launch_bounds__(kSelThreads) select_count_kernel(SelectArgs a, int* __restrict__ counts, int nchunks) {
+  __shared__ int c[9];
+  if (threadIdx.x < 9) c[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSelChunk;
+  for (int k = threadIdx.x; k < kSelChunk; k += kSelThreads) {
+    const int i = base + k;
+    if (i < a.n_in) { const int r = select_rank(a, i); if (r >= 0) atomicAdd(&c[r], 1); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) counts[threadIdx.x * nchunks + blockIdx.x] = c[threadIdx.x];
+}
+// exclusive scan of counts[9 * nchunks] in (rank, chunk) order; total -> *n_out
+__global__ void __launch_bounds__(1024) select_scan_kernel(int* __restrict__ counts, int total_entries, int* __restrict__ n_out) {
+  __shared__ int part[1024];
+  const int per = (total_entries + 1023) / 1024;
+  const int lo = min(threadIdx.x * per, total_entries), hi = min(lo + per, total_entries);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int i = lo; i < hi; ++i) { const int v = counts[i]; counts[i] = run; run += v; }
+  if (threadIdx.x == 1023) *n_out = part[1023];
+}
+__global__ void __launch_bounds__(kSelThreads) select_write_kernel(SelectArgs a, const int* __restrict__ offsets, int nchunks,
+                                                                   int* __restrict__ cand, int* __restrict__ pos) {
+  __shared__ int wsum[kSelThreads / 32];
+  const int base = blockIdx.x * kSelChunk + threadIdx.x * kSelPer;       // each thread owns kSelPer consecutive inputs
+  int rk[kSelPer];
+#pragma unroll
+  for (int k = 0; k < kSelPer; ++k) rk[k] = (base + k < a.n_in) ? select_rank(a, base + k) : -1;
+  const int nranks = a.use_prior ? 9 : 1;
+  for (int r = 0; r < nranks; ++r) {
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) mine += (rk[k] == r);
+    int incl = mine;                                                      // inclusive scan over the CTA's threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += wsum[w];
+    __syncthreads();
+    int o = offsets[r * nchunks + blockIdx.x] + before + incl - mine;
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k)
+      if (rk[k] == r) { const int i = base + k; cand[o] = a.list ? a.list[i] : i; pos[o] = i; ++o; }
+  }
+}
+int select_scratch_ints(int n_in) { return 9 * ((n_in + kSelChunk - 1) / kSelChunk) + 1; }
+int launch_select(SelectArgs a, int* scratch, int* cand, int* pos, int* n_out, cudaStream_t s) {
+  const int nchunks = (a.n_in + kSelChunk - 1) / kSelChunk;
+  if (nchunks <= 0) return (int)cudaMemsetAsync(n_out, 0, sizeof(int), s);
+  select_count_kernel<<<nchunks, kSelThreads, 0, s>>>(a, scratch, nchunks);
+  select_scan_kernel<<<1, 1024, 0, s>>>(scratch, 9 * nchunks, n_out);
+  select_write_kernel<<<nchunks, kSelThreads, 0, s>>>(a, scratch, nchunks, cand, pos);
+  return (int)cudaGetLastError();
+}
+
 // best = first record with the strictly largest response.sum(); initial best = (-1,-1,-1) (loop_closure.h:15)
 __global__ void __launch_bounds__(256) scan_reduce_kernel(const PoseRecord* __restrict__ recs, int n, PoseRecord* __restrict__ best) {
   __shared__ double ssum[256];

@@ -1,27 +1,36 @@
 // nis_sizes.h -- the 1-D transform lengths the kernels are instantiated for.
-// Column pass (transform along image rows, the halved dimension: H, rotation_divisor):
-//   X(N, F0,F1,F2, I0,I1,I2, T)   forward radices (the paired, separating stage is F2), inverse radices (paired I0), threads
+// Column pass (transform along image rows, the halved dimension: H, rotation_divisor), in place on a digit-addressed tile:
+//   X(N, A, B, C, T)   N = A*B*C in stage order of the decimation-in-frequency passes (the fused kernel's forward half runs the
+//                      same digits in time order C, B, A); T threads per CTA.  B should be odd (the paired last stage of the
+//                      forward pass then alternates bank halves), C even and a divisor of T/8 (stage-B twiddles hoist).
 // Row pass (transform along image columns: W, rotation_channel), first radix fixed at 16:
 //   X(N, R1, R2, L, T, LR)        N = 16*R1*R2, L lines per CTA, threads; LR = lines per CTA of the fused fwd->mid->inv kernel
 //                                 (two line buffers, so fewer lines keep more CTAs resident)
-// Image widths must also be multiples of 32 (one column-pass CTA owns 32 real columns).
+// Image widths must also be multiples of 16 (one column-pass CTA owns 16 real columns).
 #pragma once
 #include "nis_fft.cuh"
-// T is given for 16 complex lanes per CTA and scaled with NIS_COL_LANES (nis_fft.cuh) so the butterflies per thread stay put
-#ifndef NIS_COL_TBASE
-#define NIS_COL_TBASE 256     // 128-thread column CTAs at 8 lanes: measured +3.5% over 256 (more, smaller CTAs hide barrier stalls)
+#ifndef NIS_COL_T
+#define NIS_COL_T 256
 #endif
-#define NIS_CT(t) ((t) * NIS_COL_LANES / 16)
-// (A first radix of 8 would let the middle-stage twiddles hoist for every plan -- measured 7 % slower overall, so only the
-// inverse 720 plan, whose first radix is 8 anyway, hoists.)
-#define NIS_COL_PLANS(X)                      \
-  X(480, 10, 8, 6, 6, 8, 10, NIS_CT(NIS_COL_TBASE))     \
-  X(720, 10, 9, 8, 8, 9, 10, NIS_CT(NIS_COL_TBASE))     \
-  X(960, 10, 12, 8, 8, 12, 10, NIS_CT(NIS_COL_TBASE))   \
-  X(1200, 10, 12, 10, 10, 12, 10, NIS_CT(NIS_COL_TBASE)) \
-  X(96, 4, 6, 4, 4, 6, 4, NIS_CT(128))        \
-  X(80, 5, 4, 4, 4, 4, 5, NIS_CT(128))        \
-  X(64, 4, 4, 4, 4, 4, 4, NIS_CT(128))
+// the two production lengths can be re-planned at build time for A/B runs (-DNIS_P720_A=12 -DNIS_P720_B=5 -DNIS_P720_C=12)
+#ifndef NIS_P480_A
+#define NIS_P480_A 12
+#define NIS_P480_B 5
+#define NIS_P480_C 8
+#endif
+#ifndef NIS_P720_A
+#define NIS_P720_A 12       // 720 = 12*5*12: 31 / 144 / 60 butterfly tasks per stage on 32 groups (10*9*8 leaves a 5-of-32 tail round in the
+#define NIS_P720_B 5        // paired stages; measured 64.7 k vs 59.3 k solves/s, profiles/ab_r02.md)
+#define NIS_P720_C 12
+#endif
+#define NIS_COL_PLANS(X)          \
+  X(480, NIS_P480_A, NIS_P480_B, NIS_P480_C, NIS_COL_T)     \
+  X(720, NIS_P720_A, NIS_P720_B, NIS_P720_C, NIS_COL_T)     \
+  X(960, 8, 15, 8, NIS_COL_T)     \
+  X(1200, 10, 15, 8, NIS_COL_T)   \
+  X(96, 4, 3, 8, 128)             \
+  X(80, 2, 5, 8, 128)             \
+  X(64, 8, 1, 8, 128)
 
 #ifndef NIS_ROW_L
 #define NIS_ROW_L 4             // 4 lines x 128 threads per row CTA (2 lines in the fused fwd->mid->inv kernel): measured +3.6% over 8 x 256

@@ -37,10 +37,10 @@ struct RefCtx {
   int H, W;
   CorrelationFlowPtr cf;
 };
-struct Quiet {                       // ComputePose prints two lines per call (correlation_flow.cc:139-140)
-  std::streambuf* old;
-  Quiet() : old(std::cout.rdbuf(nullptr)) {}
-  ~Quiet() { std::cout.rdbuf(old); std::cout.clear(); }
+// ComputePose prints two lines per call (correlation_flow.cc:139-140): std::cout of this shared object's process is silenced once
+// (thread-safe: callers time the library from several threads); Python's own stdout is a different stream
+struct Quiet {
+  Quiet() { static const bool once = (std::cout.rdbuf(nullptr), true); (void)once; }
 };
 Eigen::ArrayXXf real_in(const float* p, int R, int C) {
   Eigen::ArrayXXf a(R, C);

@@ -38,41 +38,54 @@ static void make_tw(int R0, int R1, int R2, std::vector<cpx>& t1, std::vector<cp
     }
 }
 
+// column-pass twiddles of the in-place engine (nis_fft.cuh): tw1[(b-1)*C + d2], tw2[(a-1)*BC + j]
+static void make_tw_col(int A, int B, int C, std::vector<cpx>& t1, std::vector<cpx>& t2) {
+  const int N = A * B * C;
+  t1.assign((size_t)(B > 1 ? (B - 1) : 1) * C, cpx{1, 0});
+  t2.assign((size_t)(A > 1 ? (A - 1) : 1) * B * C, cpx{1, 0});
+  for (int r = 1; r < B; ++r)
+    for (int k = 0; k < C; ++k) {
+      double a = -2.0 * M_PI * r * k / (double)(B * C);
+      t1[(size_t)(r - 1) * C + k] = cpx{(float)cos(a), (float)sin(a)};
+    }
+  for (int r = 1; r < A; ++r)
+    for (int k = 0; k < B * C; ++k) {
+      double a = -2.0 * M_PI * r * k / (double)N;
+      t2[(size_t)(r - 1) * B * C + k] = cpx{(float)cos(a), (float)sin(a)};
+    }
+}
+
 // ---- column forward: real [B][N][W] -> half-transformed spectrum [B][N/2+1][W]
-template <int N, int R0, int R1, int R2, int T>
-static void emu_col_fwd(const float* x, int B, int W, cpx* out) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  std::vector<cpx> t1, t2; make_tw(R0, R1, R2, t1, t2);
+template <int N, int A, int B, int C, int T>
+static void emu_col_fwd(const float* x, int Bn, int W, cpx* out) {
+  typedef ColGeom<N, A, B, C, T> Gm;
+  std::vector<cpx> t1, t2; make_tw_col(A, B, C, t1, t2);
   Twiddles twd{t1.data(), t2.data()};
-  std::vector<cpx> smem((size_t)N * kColLanes);
-  std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
+  std::vector<cpx> smem((size_t)Gm::SLOTS * kColLanes);
   ProRealF32 pro{Src<float>{x, (long long)N * W, nullptr, 0, nullptr, 0}, W};
-  for (int b = 0; b < B; ++b)
+  for (int b = 0; b < Bn; ++b)
     for (int c0 = 0; c0 < W; c0 += kColTile) {
       auto bp = pro.bind(b, c0);
-      for (int t = 0; t < T; ++t) col_fwd_phase0<N, R0, R1, R2, T>(t, smem.data(), bp);
-      for (int t = 0; t < T; ++t) col_stage1_read<N, R0, R1, R2, T, false>(t, smem.data(), twd, st[t]);
-      for (int t = 0; t < T; ++t) col_stage1_write<N, R0, R1, R2, T, false>(t, smem.data(), st[t]);
-      for (int t = 0; t < T; ++t) col_fwd_phase2<N, R0, R1, R2, T>(t, smem.data(), twd, out + (size_t)b * (N / 2 + 1) * W, W, c0);
+      for (int t = 0; t < T; ++t) col_fwd_stage_a<N, A, B, C, T>(t, smem.data(), twd, bp);
+      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, false>(t, smem.data(), twd);
+      for (int t = 0; t < T; ++t) col_fwd_stage_c<N, A, B, C, T>(t, smem.data(), out + (size_t)b * (N / 2 + 1) * W, W, c0);
     }
 }
 
 // ---- column inverse: spectrum [B][N/2+1][W] -> real [B][N][W] / n
-template <int N, int R0, int R1, int R2, int T, class Epi>
-static void emu_col_inv(const cpx* in, int B, int W, Epi& epi) {
-  typedef ColGeom<N, R0, R1, R2, T> Gm;
-  std::vector<cpx> t1, t2; make_tw(R0, R1, R2, t1, t2);
+template <int N, int A, int B, int C, int T, class Epi>
+static void emu_col_inv(const cpx* in, int Bn, int W, Epi& epi) {
+  typedef ColGeom<N, A, B, C, T> Gm;
+  std::vector<cpx> t1, t2; make_tw_col(A, B, C, t1, t2);
   Twiddles twd{t1.data(), t2.data()};
-  std::vector<cpx> smem((size_t)N * kColLanes);
-  std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
+  std::vector<cpx> smem((size_t)Gm::SLOTS * kColLanes);
   HostSync sync;
-  for (int b = 0; b < B; ++b)
+  for (int b = 0; b < Bn; ++b)
     for (int c0 = 0; c0 < W; c0 += kColTile) {
       std::vector<typename Epi::Bound> eb(T, epi.bind(b, c0));
-      for (int t = 0; t < T; ++t) col_inv_phase0<N, R0, R1, R2, T>(t, smem.data(), in + (size_t)b * (N / 2 + 1) * W, W, c0);
-      for (int t = 0; t < T; ++t) col_stage1_read<N, R0, R1, R2, T, true>(t, smem.data(), twd, st[t]);
-      for (int t = 0; t < T; ++t) col_stage1_write<N, R0, R1, R2, T, true>(t, smem.data(), st[t]);
-      for (int t = 0; t < T; ++t) col_inv_phase2<N, R0, R1, R2, T>(t, smem.data(), twd, eb[t]);
+      for (int t = 0; t < T; ++t) col_inv_stage_a<N, A, B, C, T>(t, smem.data(), twd, in + (size_t)b * (N / 2 + 1) * W, W, c0);
+      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, true, false>(t, smem.data(), twd);
+      for (int t = 0; t < T; ++t) col_inv_stage_c<N, A, B, C, T>(t, smem.data(), eb[t]);
       for (int t = 0; t < T; ++t) eb[t].finish(t, sync);
     }
 }
@@ -100,32 +113,23 @@ static void emu_row(const cpx* in, int total_lines, cpx* out) {
 }
 
 // ---- fused: inverse column pass -> kernel function -> forward column pass (colcol kernel)
-template <int N, int I0, int I1, int I2, int F0, int F1, int F2, int T>
-static void emu_colcol(const cpx* in, int B, int W, cpx* out, KernelFn kfn) {
-  typedef ColGeom<N, I0, I1, I2, T> Gi;
-  typedef ColGeom<N, F0, F1, F2, T> Gf;
-  std::vector<cpx> ti1, ti2, tf1, tf2;
-  make_tw(I0, I1, I2, ti1, ti2); make_tw(F0, F1, F2, tf1, tf2);
-  Twiddles twi{ti1.data(), ti2.data()}, twf{tf1.data(), tf2.data()};
-  std::vector<cpx> smem((size_t)N * kColLanes);
-  std::vector<CarryRegs<I1, Gi::ROUNDS1>> si(T);
-  std::vector<CarryRegs<F0, Gf::ROUNDS0>> s0(T);
-  std::vector<CarryRegs<F1, Gf::ROUNDS1>> s1(T);
+template <int N, int A, int B, int C, int T>
+static void emu_colcol(const cpx* in, int Bn, int W, cpx* out, KernelFn kfn) {
+  typedef ColGeom<N, A, B, C, T> Gm;
+  std::vector<cpx> t1, t2; make_tw_col(A, B, C, t1, t2);
+  Twiddles twd{t1.data(), t2.data()};
+  std::vector<cpx> smem((size_t)Gm::SLOTS * kColLanes);
   HostSync sync;
-  for (int b = 0; b < B; ++b)
+  for (int b = 0; b < Bn; ++b)
     for (int c0 = 0; c0 < W; c0 += kColTile) {
       const cpx* src = in + (size_t)b * (N / 2 + 1) * W;
       cpx* dst = out + (size_t)b * (N / 2 + 1) * W;
       std::vector<KernelFn::Bound> fn(T, kfn.bind(b));
-      for (int t = 0; t < T; ++t) col_inv_phase0<N, I0, I1, I2, T>(t, smem.data(), src, W, c0);
-      for (int t = 0; t < T; ++t) col_stage1_read<N, I0, I1, I2, T, true>(t, smem.data(), twi, si[t]);
-      for (int t = 0; t < T; ++t) col_stage1_write<N, I0, I1, I2, T, true>(t, smem.data(), si[t]);
-      for (int t = 0; t < T; ++t) col_inv_phase2_inplace<N, I0, I1, I2, T>(t, smem.data(), twi, fn[t]);
-      for (int t = 0; t < T; ++t) col_fwd_phase0s_read<N, F0, F1, F2, T>(t, smem.data(), s0[t]);
-      for (int t = 0; t < T; ++t) col_fwd_phase0s_write<N, F0, F1, F2, T>(t, smem.data(), s0[t]);
-      for (int t = 0; t < T; ++t) col_stage1_read<N, F0, F1, F2, T, false>(t, smem.data(), twf, s1[t]);
-      for (int t = 0; t < T; ++t) col_stage1_write<N, F0, F1, F2, T, false>(t, smem.data(), s1[t]);
-      for (int t = 0; t < T; ++t) col_fwd_phase2<N, F0, F1, F2, T>(t, smem.data(), twf, dst, W, c0);
+      for (int t = 0; t < T; ++t) col_inv_stage_a<N, A, B, C, T>(t, smem.data(), twd, src, W, c0);
+      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, true, false>(t, smem.data(), twd);
+      for (int t = 0; t < T; ++t) col_inv_fn_fwd_stage_c<N, A, B, C, T>(t, smem.data(), fn[t]);
+      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, true>(t, smem.data(), twd);
+      for (int t = 0; t < T; ++t) col_fwd_dit_stage_a<N, A, B, C, T>(t, smem.data(), twd, dst, W, c0);
       for (int t = 0; t < T; ++t) fn[t].finish(t, sync);
     }
 }
@@ -167,8 +171,8 @@ extern "C" {
 int emu_colcol_poly(const float* in, int B, int N, int W, float* out, unsigned int* maxbuf, float offset, int power) {
   memset(maxbuf, 0, sizeof(unsigned int) * B);
   KernelFn kfn{(float)((long long)N * W), 0, offset, power, 0.f, nullptr, nullptr, 0, maxbuf, nullptr};
-#define X(n, f0, f1, f2, i0, i1, i2, t) \
-  if (N == n) { emu_colcol<n, i0, i1, i2, f0, f1, f2, t>((const cpx*)in, B, W, (cpx*)out, kfn); return 0; }
+#define X(n, a, b, c, t) \
+  if (N == n) { emu_colcol<n, a, b, c, t>((const cpx*)in, B, W, (cpx*)out, kfn); return 0; }
   NIS_COL_PLANS(X)
 #undef X
   return -1;
@@ -196,8 +200,8 @@ int emu_rowrow_filter(const float* in, const float* h, const unsigned int* maxbu
 
 // returns 0 ok, -1 unsupported size
 int emu_col_fwd_f32(const float* x, int B, int N, int W, float* out) {
-#define X(n, f0, f1, f2, i0, i1, i2, t) \
-  if (N == n) { emu_col_fwd<n, f0, f1, f2, t>(x, B, W, (cpx*)out); return 0; }
+#define X(n, a, b, c, t) \
+  if (N == n) { emu_col_fwd<n, a, b, c, t>(x, B, W, (cpx*)out); return 0; }
   NIS_COL_PLANS(X)
 #undef X
   return -1;
@@ -205,8 +209,8 @@ int emu_col_fwd_f32(const float* x, int B, int N, int W, float* out) {
 
 int emu_col_inv_store(const float* in, int B, int N, int W, float* out) {
   EpiStore epi{Dst<float>{out, (long long)N * W}, W, (float)((long long)N * W)};
-#define X(n, f0, f1, f2, i0, i1, i2, t) \
-  if (N == n) { emu_col_inv<n, i0, i1, i2, t>((const cpx*)in, B, W, epi); return 0; }
+#define X(n, a, b, c, t) \
+  if (N == n) { emu_col_inv<n, a, b, c, t>((const cpx*)in, B, W, epi); return 0; }
   NIS_COL_PLANS(X)
 #undef X
   return -1;
@@ -216,8 +220,8 @@ int emu_col_inv_store(const float* in, int B, int N, int W, float* out) {
 int emu_col_inv_peak(const float* in, int B, int N, int W, void* stats, float* g_out) {
   memset(stats, 0, sizeof(PeakStats) * B);
   EpiPeak epi{(PeakStats*)stats, N, (float)((long long)N * W), g_out, (long long)N * W, W};
-#define X(n, f0, f1, f2, i0, i1, i2, t) \
-  if (N == n) { emu_col_inv<n, i0, i1, i2, t>((const cpx*)in, B, W, epi); return 0; }
+#define X(n, a, b, c, t) \
+  if (N == n) { emu_col_inv<n, a, b, c, t>((const cpx*)in, B, W, epi); return 0; }
   NIS_COL_PLANS(X)
 #undef X
   return -1;

@@ -2,10 +2,16 @@
 // classes (src/map_builder.cc:72-75, :127-138, :172-182), with a stand-in for the Eigen array types (Eigen is not in the
 // build image).  Known answers: SURVEY.md Appendix C.4/C.5/C.7 (circular rolls, identity, first-wins scan).
 // Build: g++ -std=c++17 tests/cpp/shim_test.cc -L ni_slam_b200/lib -lnislam -Wl,-rpath,... ; needs a GPU to run.
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <set>
 #include <vector>
 
 #include "../../ni_slam_b200/host/correlation_flow.hpp"
@@ -25,8 +31,107 @@ template <class T> struct ColMajor {           // minimal Eigen::Array<T,Dynamic
 struct Vec3 { double d[3]; double& operator[](int i) { return d[i]; } const double& operator[](int i) const { return d[i]; } };
 typedef ColMajor<float> ArrayXXf;
 typedef ColMajor<std::complex<float>> ArrayXXcf;
+
+// ---- stand-ins for the reference's host data model (include/frame.h, include/map.h, include/camera.h): same member functions, same
+// semantics, no Eigen / OpenCV.  The shim only ever touches them through these getters.
+namespace Eigen { typedef ::ArrayXXf ArrayXXf; typedef ::ArrayXXcf ArrayXXcf; typedef ::Vec3 Vector3d; }
+class Frame {                                                     // include/frame.h:10-42
+ public:
+  Frame(int frame_id, double timestamp, Eigen::ArrayXXf& frame, Eigen::ArrayXXcf& fft_result, Eigen::ArrayXXcf& fft_polar)
+      : _frame_id(frame_id), _timestamp(timestamp), _frame(frame), _fft_result(fft_result), _fft_polar(fft_polar) {}
+  void SetFrameId(int frame_id) { _frame_id = frame_id; }
+  int GetFrameId() { return _frame_id; }
+  void GetFFTResult(Eigen::ArrayXXcf& fft_result, Eigen::ArrayXXcf& fft_polar) { fft_result = _fft_result; fft_polar = _fft_polar; }
+  void SetPose(Eigen::Vector3d& pose) { _pose = pose; }
+  void GetPose(Eigen::Vector3d& pose) { pose = _pose; }
+ private:
+  int _frame_id; double _timestamp;
+  Eigen::ArrayXXf _frame; Eigen::ArrayXXcf _fft_result, _fft_polar; Eigen::Vector3d _pose{};
+};
+typedef std::shared_ptr<Frame> FramePtr;
+struct GridLocation { int x = 0, y = 0; };                        // include/map.h:15-32
+class Map {                                                       // include/map.h:48-76, src/map.cc
+ public:
+  explicit Map(double grid_scale) : _grid_scale(grid_scale) {}
+  void AddFrame(FramePtr& frame) {
+    if (_frames.size() < 1) frame->SetFrameId(0);
+    _frames[frame->GetFrameId()] = frame;
+    Eigen::Vector3d pose; frame->GetPose(pose);
+    GridLocation g = ComputeGridLocation(pose);
+    _grid_map[{g.x, g.y}].insert(frame);
+  }
+  void SetFrameDistance(FramePtr& frame, double distance) { _frame_distanses[frame] = distance; }
+  int GetAllFrames(std::vector<FramePtr>& frames) { for (auto kv : _frames) frames.emplace_back(kv.second); return (int)frames.size(); }
+  double GetFrameDistance(FramePtr& frame) { return _frame_distanses.count(frame) > 0 ? _frame_distanses[frame] : -1; }
+  GridLocation ComputeGridLocation(Eigen::Vector3d pose) {
+    GridLocation g; g.x = static_cast<int>(pose[0] / _grid_scale); g.y = static_cast<int>(pose[1] / _grid_scale); return g;
+  }
+  int GetFramesInGrids(std::vector<FramePtr>& frames, std::vector<GridLocation>& grid_locations) {
+    for (auto g : grid_locations) {
+      auto it = _grid_map.find({g.x, g.y});
+      if (it != _grid_map.end()) frames.insert(frames.end(), it->second.begin(), it->second.end());
+    }
+    return (int)frames.size();
+  }
+ private:
+  std::map<int, FramePtr> _frames;
+  std::map<FramePtr, double> _frame_distanses;
+  double _grid_scale;
+  std::map<std::pair<int, int>, std::set<FramePtr>> _grid_map;
+};
+typedef std::shared_ptr<Map> MapPtr;
+class Camera {                                                    // the one conversion the two call sites use (src/camera.cc:148-158)
+ public:
+  Eigen::Vector3d ConvertCenterToPrincipal(const Eigen::Vector3d& image_center_pose) { return image_center_pose; }   // principal point at the centre
+};
+typedef std::shared_ptr<Camera> CameraPtr;
+struct KeyframeSelectionConfig { double max_distance, max_angle, lower_response_thr, upper_response_thr; };
+struct Vec3Call : Vec3 { double& operator()(int i) { return d[i]; } };
+
 typedef nislam::CorrelationFlowT<ArrayXXf, ArrayXXcf, Vec3> CorrelationFlow;
-typedef nislam::LoopClosureT<ArrayXXf, ArrayXXcf, Vec3> LoopClosure;
+typedef nislam::LoopClosureT<ArrayXXf, ArrayXXcf, Vec3, FramePtr, MapPtr, GridLocation> LoopClosure;
+typedef nislam::LoopClosureResultT<Vec3, FramePtr> LoopClosureResult;
+typedef std::shared_ptr<CorrelationFlow> CorrelationFlowPtr;
+typedef std::shared_ptr<LoopClosure> LoopClosurePtr;
+
+// ---- the reference's two call sites of the hot path.  The bodies of ComputeFFTResult's second line, Tracking's ComputePose call and
+// FindLoopClosure are the text of /root/reference/src/map_builder.cc:74, :129-130 and :172-182, character for character: that this
+// translation unit compiles and passes is the drop-in claim of INTEGRATION.md.
+class MapBuilder {
+ public:
+  CameraPtr _camera;
+  CorrelationFlowPtr _correlation_flow;
+  MapPtr _map;
+  LoopClosurePtr _loop_closure;
+  Eigen::ArrayXXf _image_array;
+  Eigen::ArrayXXcf _fft_result, _fft_polar, _last_fft_result, _last_fft_polar;
+  FramePtr _current_frame;
+  Eigen::Vector3d _current_pose{};
+  std::vector<LoopClosureResult> _loop_matches;
+  void ComputeFFTResult();
+  Eigen::Vector3d TrackingCall(Eigen::Vector3d& relative_pose);
+  bool FindLoopClosure();
+};
+void MapBuilder::ComputeFFTResult(){
+  _correlation_flow->ComputeIntermedium(_image_array, _fft_result, _fft_polar); 
+}
+Eigen::Vector3d MapBuilder::TrackingCall(Eigen::Vector3d& relative_pose){
+  Eigen::Vector3d response;
+  response = _correlation_flow->ComputePose(
+      _last_fft_result, _image_array, _last_fft_polar, _fft_polar, relative_pose, true);
+  return response;
+}
+bool MapBuilder::FindLoopClosure(){
+  LoopClosureResult loop_closure_result = _loop_closure->FindLoopClosure(_image_array, _current_frame, _current_pose); 
+  if(loop_closure_result.found){
+    loop_closure_result.relative_pose = _camera->ConvertCenterToPrincipal(loop_closure_result.relative_pose);
+    _loop_matches.emplace_back(loop_closure_result);
+    std::cout << "Find a loop edge, current frame = " << loop_closure_result.current_frame->GetFrameId()
+              << ", loop frame = " << loop_closure_result.loop_frame->GetFrameId() << std::endl;
+  }
+
+  return loop_closure_result.found;
+}
 
 #define EXPECT(cond)                                                          \
   do {                                                                        \
@@ -87,29 +192,86 @@ int main() {
     try { cfb.ComputePose(Fa, a, Pa, Pa, pose, true); } catch (const std::invalid_argument& e) { threw = std::string(e.what()) == "Received invalid kernel type"; }
     EXPECT(threw);
   }
-  // scan: three copies of keyframe a -> the first inserted wins (strict '>', loop_closure.cc:61)
-  nislam::LoopClosureConfig lcfg{true, 60, 60, 0, 0};
-  LoopClosure lc(lcfg, cf);
-  ArrayXXf z; z.resize(H, W);
-  for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) z(i, j) = a((i * 7) % H, (j * 3) % W);   // unrelated texture
-  ArrayXXcf Fz, Pz;
-  cf->ComputeIntermedium(z, Fz, Pz);
-  EXPECT(lc.AddFrame(40, z, Fz, Pz, 0.0) == 0);
-  EXPECT(lc.AddFrame(41, a, Fa, Pa, 1.0) == 1);
-  EXPECT(lc.AddFrame(42, a, Fa, Pa, 2.0) == 2);
-  ArrayXXf b; b.resize(H, W);
-  for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) b((i + 5) % H, (j + 11) % W) = a(i, j);
-  ArrayXXcf Fb, Pb;
-  cf->ComputeIntermedium(b, Fb, Pb);
-  auto res = lc.FindLoopClosure(b, 99, Fb, Pb, 50.0);
-  EXPECT(res.found && res.loop_slot == 1 && res.loop_frame_id == 41);
-  EXPECT(res.relative_pose[0] == -11 && res.relative_pose[1] == -5);
-  auto res2 = lc.FindLoopClosure(b, 99, Fb, Pb, 50.0, std::vector<int32_t>{2, 1, 0});
-  EXPECT(res2.loop_slot == 2);
-  nislam::LoopClosureConfig far{true, 60, 60, 1000, 0};
-  LoopClosure lc2(far, cf);
-  auto res3 = lc2.FindLoopClosure(b, 99, Fb, Pb, 50.0);
-  EXPECT(!res3.found && res3.loop_slot == -1 && res3.response[0] == -1.0);
+  // ---- LoopClosure with the reference's own signatures, driven through the verbatim MapBuilder call sites above
+  {
+    nislam::LoopClosureConfig lcfg{true, 60, 60, 0, 0};
+    MapBuilder mb;
+    mb._camera = std::make_shared<Camera>();
+    mb._correlation_flow = cf;
+    mb._map = std::make_shared<Map>(2.0);
+    mb._loop_closure = std::shared_ptr<LoopClosure>(new LoopClosure(lcfg, mb._correlation_flow, mb._map));     // map_builder.cc:25-26
+    ArrayXXf z; z.resize(H, W);
+    for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) z(i, j) = a((i * 7) % H, (j * 3) % W);   // unrelated texture
+    ArrayXXcf Fz, Pz;
+    cf->ComputeIntermedium(z, Fz, Pz);
+    // keyframes: unrelated, a, a again (three map cells apart in x so that the prior-pose overload sees only some of them)
+    struct K { ArrayXXf* img; ArrayXXcf* F; ArrayXXcf* P; double x; };
+    K ks[3] = {{&z, &Fz, &Pz, 0.5}, {&a, &Fa, &Pa, 2.5}, {&a, &Fa, &Pa, 9.0}};
+    std::vector<FramePtr> frames;
+    for (int k = 0; k < 3; ++k) {
+      FramePtr f = std::make_shared<Frame>(40 + k, 0.0, *ks[k].img, *ks[k].F, *ks[k].P);
+      Vec3 pose{{ks[k].x, 0.5, 0.0}};
+      f->SetPose(pose);
+      mb._map->AddFrame(f);                       // the first frame is renamed to id 0 (map.cc:19-22)
+      mb._map->SetFrameDistance(f, (double)k);
+      frames.push_back(f);
+    }
+    mb._image_array.resize(H, W);
+    for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) mb._image_array((i + 5) % H, (j + 11) % W) = a(i, j);
+    mb.ComputeFFTResult();                                                                          // map_builder.cc:72-75
+    mb._current_frame = std::make_shared<Frame>(99, 1.0, mb._image_array, mb._fft_result, mb._fft_polar);
+    mb._map->SetFrameDistance(mb._current_frame, 50.0);
+    // Tracking's ComputePose call against keyframe a (map_builder.cc:129-130), twice: the second call reuses the device copy of `last`
+    mb._last_fft_result = Fa; mb._last_fft_polar = Pa;
+    Vec3 rel{}, rel2{};
+    Vec3 resp = mb.TrackingCall(rel);
+    Vec3 resp2 = mb.TrackingCall(rel2);
+    EXPECT(rel[0] == -11 && rel[1] == -5 && resp[0] > 60 && resp[2] > 60);
+    EXPECT(rel2[0] == rel[0] && rel2[1] == rel[1] && resp2[0] == resp[0] && resp2[2] == resp[2]);
+    mb._last_fft_result = Fz; mb._last_fft_polar = Pz;                  // same buffers, new keyframe content -> re-uploaded
+    Vec3 rel3{};
+    Vec3 resp3 = mb.TrackingCall(rel3);
+    EXPECT(resp3[0] < 30);
+    // prior pose in cell (1, 0): neighbourhood cells x = 0..2 -> frames 0 (z) and 1 (a); frame 2 (x = 9 -> cell 4) is out of reach
+    mb._current_pose = Vec3{{2.2, 0.4, 0.0}};
+    EXPECT(mb.FindLoopClosure());                                                                   // map_builder.cc:172-182 verbatim
+    EXPECT(mb._loop_matches.size() == 1 && mb._loop_matches[0].loop_frame == frames[1]);
+    EXPECT(mb._loop_matches[0].loop_frame->GetFrameId() == 41 && mb._loop_matches[0].current_frame->GetFrameId() == 99);
+    EXPECT(mb._loop_matches[0].relative_pose[0] == -11 && mb._loop_matches[0].relative_pose[1] == -5);
+    EXPECT(mb._loop_closure->StoredFrames() == 2);                      // only the two candidates were uploaded
+    // all-frames overload (loop_closure.cc:10-15): id order 0, 41, 42 -> the FIRST copy of a wins (strict '>', :61)
+    LoopClosureResult r_all = mb._loop_closure->FindLoopClosure(mb._image_array, mb._current_frame);
+    EXPECT(r_all.found && r_all.loop_frame == frames[1] && mb._loop_closure->StoredFrames() == 3);
+    // explicit list in another order (:36-73): iteration order decides the tie
+    std::vector<FramePtr> lst{frames[2], frames[1], frames[0]};
+    LoopClosureResult r_lst = mb._loop_closure->FindLoopClosure(mb._image_array, mb._current_frame, lst);
+    EXPECT(r_lst.found && r_lst.loop_frame == frames[2]);
+    EXPECT(r_lst.response[0] == r_all.response[0] && r_lst.response[2] == r_all.response[2]);
+    // filters (:43-53): a frame gap of 1000 removes every candidate -> initial best (-1,-1,-1), no loop frame
+    nislam::LoopClosureConfig far{true, 60, 60, 1000, 0};
+    LoopClosure lc2(far, cf, mb._map);
+    LoopClosureResult r_far = lc2.FindLoopClosure(mb._image_array, mb._current_frame);
+    EXPECT(!r_far.found && !r_far.loop_frame && r_far.response[0] == -1.0);
+    // accumulated-distance filter: |50 - d| < 49.5 drops d = 1, 2 -> only frame 0 (unrelated) is evaluated
+    nislam::LoopClosureConfig near{true, 60, 60, 0, 49.5};
+    LoopClosure lc3(near, cf, mb._map);
+    LoopClosureResult r_near = lc3.FindLoopClosure(mb._image_array, mb._current_frame);
+    EXPECT(!r_near.found && r_near.loop_frame == frames[0]);
+    // online latency through the reference's per-call surface (main.cpp:51-86 feeds one frame at a time): ComputeIntermedium +
+    // ComputePose(tracking) per frame with host arrays in and out, the keyframe's operands cached on the device
+    mb._last_fft_result = Fa; mb._last_fft_polar = Pa;
+    std::vector<double> ms;
+    for (int it = 0; it < 60; ++it) {
+      auto t0 = std::chrono::steady_clock::now();
+      mb.ComputeFFTResult();
+      Vec3 r{};
+      mb.TrackingCall(r);
+      auto t1 = std::chrono::steady_clock::now();
+      if (it >= 10) ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    std::sort(ms.begin(), ms.end());
+    printf("shim_online_ms p50 %.3f p99 %.3f\n", ms[ms.size() / 2], ms[(ms.size() * 99) / 100]);
+  }
   // MapStitcher shim (host/map_stitcher.hpp) driven like MapBuilder drives the reference (map_builder.cc:37, :62, :113): identity pose,
   // principal point at the centre -> pixel (i, j) lands on ground (i - W/2, j - H/2); first insert stores the scaled pixel itself
   {

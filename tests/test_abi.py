@@ -80,7 +80,7 @@ def test_emulated_row_pass(emu, N):
         assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-6
 
 
-@pytest.mark.parametrize("N,W", [(480, 64), (720, 32), (960, 32), (96, 64), (80, 32)])
+@pytest.mark.parametrize("N,W", [(480, 64), (720, 32), (960, 32), (1200, 16), (96, 64), (80, 32), (64, 16)])
 def test_emulated_column_pass(emu, N, W):
     rng = np.random.default_rng(N)
     B = 2
@@ -131,7 +131,7 @@ def test_cpp_shim_compiles_against_the_abi():
     assert os.path.exists(exe)
 
 
-@pytest.mark.parametrize("N,W", [(480, 32), (720, 32), (96, 64)])
+@pytest.mark.parametrize("N,W", [(480, 32), (720, 32), (960, 16), (96, 64), (80, 16), (64, 16)])
 def test_emulated_fused_colcol(emu, N, W):
     """inverse column pass -> (x/n + offset)^3 -> forward column pass, the real kernel image only in shared memory"""
     rng = np.random.default_rng(N + 1)
