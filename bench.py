@@ -657,6 +657,7 @@ def main():
             for c0 in range(0, per_gpu, 2048):                              # keyframes are generated and added in chunks (bounded temporaries)
                 c1 = min(per_gpu, c0 + 2048)
                 db_imgs = bs.crops(canvas, gcx[g0 + c0:g0 + c1], gcy[g0 + c0:g0 + c1], gang[g0 + c0:g0 + c1], H, W)
+                torch.cuda.synchronize()                                     # torch's stream and the library's (non-blocking) streams are not ordered
                 lc.AddImages(None, np.arange(g0 + c0, g0 + c1, dtype=np.int32), None, ptr=db_imgs.data_ptr(), n=c1 - c0, on_device=True)
                 del db_imgs
             jstar = (per_gpu * world) // 2 + 3                                  # planted keyframe (global id)
@@ -732,15 +733,21 @@ def main():
                     lc.clear()
                     lc.SetMode(nis.DB_FULL)
                     imgs_sub = bs.crops(canvas, gcx[sub], gcy[sub], gang[sub], H, W)
+                    torch.cuda.synchronize()
                     lc.AddImages(None, np.asarray(sub, np.int32), None, ptr=imgs_sub.data_ptr(), n=len(sub), on_device=True)
                     qf = cf.ComputeIntermedium(q_host.numpy())
                     r1, recs = lc.FindLoopClosureRecords(qf, 10 ** 9, 0.0)
                     same_winner = int(r1.loop_frame_id) == int(res.loop_frame_id)
                     same_pose = bool(np.array_equal(r1.relative_pose, res.relative_pose))
                     bits = bool(np.array_equal(r1.response, res.response))
-                    close = bool(np.allclose(r1.response, res.response, rtol=1e-6))
-                    locals_ok = all(np.allclose(recs["response"][sub.index(g)], rp, rtol=1e-6) for g, rp in zip(locals_, resp_) if g >= 0)
+                    # the sharded scan of >= 1024 candidates takes FFT(RotateArray(query)) from the per-query cache, the 256-keyframe re-scan
+                    # rotates per candidate: same peaks and poses, responses equal to f32 round-off (tests/test_gpu_parity.py, 2e-6)
+                    close = bool(np.allclose(r1.response, res.response, rtol=5e-6))
+                    locals_ok = all(np.allclose(recs["response"][sub.index(g)], rp, rtol=5e-6) for g, rp in zip(locals_, resp_) if g >= 0)
                     check = {"scan_equals_single_rank": bool(same_winner and same_pose and close and locals_ok), "identical_response_bits": bits,
+                             "same_winner": same_winner, "same_pose": same_pose, "responses_equal_to_5e-6": close, "local_bests_reproduced": locals_ok,
+                             "response_sharded": [float(x) for x in res.response], "response_single": [float(x) for x in r1.response],
+
                              "what": "rank 0 alone re-scanned %d keyframes of the global store (every rank's local winner + an even subsample, full store "
                                      "mode) with per-candidate records: same winner, same pose, same response as the %d-rank sharded call, and every rank's "
                                      "local best record reproduced" % (len(sub), world)}

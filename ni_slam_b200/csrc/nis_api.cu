@@ -816,34 +816,37 @@ int nis_features_u8(nis_ctx* ctx, const uint8_t* image, nis_frame** out) {
   return NIS_OK;
 }
 
+static int upload_colmajor_f32(nis_ctx* ctx, const float* host, int R, int C, float* dst);
+
 int nis_features_f32(nis_ctx* ctx, const float* image_colmajor, nis_frame** out) {
   if (!ctx || !image_colmajor || !out) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   nis_frame* f = nullptr;
   TRY(frame_alloc(ctx, false, &f));
-  std::vector<float> rm(ctx->sz[0].real);
-  transpose_to(image_colmajor, ctx->W, ctx->H, rm.data());      // [W][H] lines -> [H][W]
-  cudaError_t e = h2d(ctx, f->img_f32, rm.data(), rm.size() * sizeof(float));
-  int st = e == cudaSuccess ? features_batch(ctx, ctx->lanes[0], src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1,
-                                              Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0}, Dst<cpx>{f->Ht, 0}, Dst<cpx>{f->Hp, 0}, true)
-                            : fail(ctx, NIS_ERR_CUDA, "cudaMemcpy image", (int)e);
+  int st = upload_colmajor_f32(ctx, image_colmajor, ctx->H, ctx->W, f->img_f32);          // [W][H] lines -> [H][W] on the device
+  if (st == NIS_OK)
+    st = features_batch(ctx, ctx->lanes[0], src_slab<float>(f->img_f32, 0), src_null<uint8_t>(), false, 1, Dst<cpx>{f->F, 0}, Dst<cpx>{f->P, 0},
+                        Dst<cpx>{f->Ht, 0}, Dst<cpx>{f->Hp, 0}, true);
   if (st == NIS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, NIS_ERR_CUDA, "features sync", (int)cudaGetLastError());
   if (st != NIS_OK) { nis_frame_free(ctx, f); return st; }
   *out = f;
   return NIS_OK;
 }
 
+// Frame::GetFFTResult: row-major device spectra -> reference layout, transposed on the device into a staging buffer, one D2H each
 int nis_frame_export(nis_ctx* ctx, const nis_frame* f, float* fft_result, float* fft_polar) {
   if (!ctx || !f) return NIS_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaStreamSynchronize(ctx->stream));
   for (int s = 0; s < 2; ++s) {
     float* dst = s == 0 ? fft_result : fft_polar;
     if (!dst) continue;
+    if (s == 0 ? !f->has_spectra : !f->has_polar) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "frame export: the frame does not hold that array");
     const SizeClass& z = ctx->sz[s];
-    std::vector<cpx> rm(z.spec);
-    CU(cudaMemcpy(rm.data(), s == 0 ? f->F : f->P, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost));
-    transpose_to(rm.data(), z.R / 2 + 1, z.C, (cpx*)dst);       // [half][C] -> C lines of half
+    RESERVE(ctx->stage, z.spec * sizeof(cpx));
+    ctx->prof_stream = ctx->stream;
+    LAUNCH(launch_transpose_cpx(s == 0 ? f->F : f->P, ctx->stage.as<cpx>(), z.R / 2 + 1, z.C, ctx->stream));       // [half][C] -> C lines of half
+    CU(cudaMemcpyAsync(dst, ctx->stage.p, z.spec * sizeof(cpx), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
   }
   return NIS_OK;
 }
@@ -1392,10 +1395,10 @@ static int loop_scan_impl(nis_ctx* ctx, const nis_frame* query, int query_frame_
   if (all_responses) for (int i = 0; i < 3 * n_in; ++i) all_responses[i] = -1.0;
   if (records) for (int i = 0; i < n_in; ++i) { memset(&records[i], 0, sizeof records[i]); for (int k = 0; k < 3; ++k) records[i].response[k] = -1.0; }
   if (n_candidates_out) *n_candidates_out = 0;
-  if (n_in == 0 || ndb == 0) return NIS_OK;
   if (candidate_slots)
     for (int i = 0; i < n_in; ++i)
       if (candidate_slots[i] < 0 || candidate_slots[i] >= ndb) return fail(ctx, NIS_ERR_INVALID_ARGUMENT, "candidate slot out of range");
+  if (n_in == 0 || ndb == 0) return NIS_OK;
   TRY(db_sync_meta(ctx));
   // device-side candidate selection: filters (:43-53) and, with a prior pose, the grid neighbourhood (map.cc:81-101)
   if (n_in > ctx->cand_cap) {
