@@ -2,6 +2,8 @@
 // Host-side mirror of CorrelationFlow (src/correlation_flow.cc) and LoopClosure (src/loop_closure.cc): the host
 // only builds constant tables, sizes batches and enqueues kernels; all per-pixel arithmetic runs on the GPU and
 // there is no CPU fallback.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -77,6 +79,7 @@ struct Lane {
   cudaEvent_t ev = nullptr;
   int cap = 0;                 // workspace capacity in pairs
   DevBuf t1, real, pol, maxp, maxt, maxh, stats_p, stats_t, sel, xx, zz;
+  CUtensorMap hp_map;          // TMA descriptor over `real` = the lane's fftshift-ed power images [cap][H][W], box = one polar cell's footprint
   DevBuf dbrec;                // scan scratch of the compact store modes: F, P, Ht, Hp of one batch of candidates
   int db_cap = 0;
 };
@@ -99,11 +102,9 @@ struct nis_ctx {
   std::string err;
   long long launches = 0;
   int batch = 16, default_batch = 16;
-  bool polar_fused = true;
-  bool polar_tiled = true;          // tiled shared-memory polar gather (default); NIS_POLAR_TILED=0 falls back to the fused / direct gathers
   int ptile_pitch = 0, ptile_rows = 0;
   // constant tables
-  DevBuf tw, lut, cs, rho, mats, theta, ptab, ptiles, ptab2;
+  DevBuf tw, lut, cs, rho, mats, theta, ptiles, ptab2;
   DevBuf recs, best, cand, stage, qgather;
   // multi-GPU scan (nis_comm_init / nis_loop_scan_sharded): NCCL communicator of this context's rank
   void* nccl_comm = nullptr;
@@ -292,13 +293,9 @@ static int build_tables(nis_ctx* ctx) {
   RESERVE(ctx->rho, rho.size() * sizeof(float));
   CU(h2d(ctx, ctx->cs.p, cs.data(), cs.size() * sizeof(double)));
   CU(h2d(ctx, ctx->rho.p, rho.data(), rho.size() * sizeof(float)));
-  RESERVE(ctx->ptab, (size_t)D * Cp * sizeof(uint32_t));
   {
-    int e_ = launch_polar_table(ctx->ptab.as<uint32_t>(), H, W, D, Cp, ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->stream);
-    if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_table", e_);
-    CU(cudaStreamSynchronize(ctx->stream));
-  }
-  if (ctx->polar_tiled) {
+    // polar cells (kPolarTA angles x kPolarTR radii): bounding box of every cell's source footprint; all cells load a tile of the common
+    // size pitch x rows through TMA (out-of-range parts arrive as zeros), the per-pixel table holds offsets inside the cell's tile
     const int tr = (Cp + kPolarTR - 1) / kPolarTR, ta = (D + kPolarTA - 1) / kPolarTA;
     RESERVE(ctx->ptiles, (size_t)tr * ta * sizeof(int4));
     RESERVE(ctx->ptab2, (size_t)D * Cp * sizeof(uint32_t));
@@ -309,16 +306,16 @@ static int build_tables(nis_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     int bh = 1, bw = 1;
     for (const int4& t : tiles) { bh = std::max(bh, t.z); bw = std::max(bw, t.w); }
-    ctx->ptile_pitch = bw | 1;
-    ctx->ptile_rows = bh + 1;                                      // the tap at (dy+1, dx+1) of the last row stays inside the allocation
-    if ((size_t)ctx->ptile_rows * ctx->ptile_pitch > 65535 || (size_t)ctx->ptile_rows * ctx->ptile_pitch * sizeof(float) > 48 * 1024) {
-      ctx->polar_tiled = false;                                    // cell footprint too large for this geometry: direct gathers
-    } else {
-      e_ = launch_polar_tile_table(ctx->ptab2.as<uint32_t>(), ctx->ptiles.as<int4>(), ctx->ptile_pitch, H, W, D, Cp, ctx->cs.as<double>(),
-                                   ctx->rho.as<float>(), ctx->stream);
-      if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_tile_table", e_);
-      CU(cudaStreamSynchronize(ctx->stream));
-    }
+    int pitch = (bw + 3) & ~3;                                       // TMA: the inner box extent must be a multiple of 16 bytes
+    if (pitch % 8 == 0) pitch += 4;                                  // pitch = 4 (mod 8): rows of a tile repeat their banks only every 8th row
+    ctx->ptile_pitch = pitch;
+    ctx->ptile_rows = bh;
+    if (pitch > 256 || bh > 256 || (size_t)bh * pitch > 65535 || (size_t)bh * pitch * sizeof(float) > 160 * 1024)
+      return fail(ctx, NIS_ERR_UNSUPPORTED_SIZE, "polar cell footprint too large for a TMA tile");
+    e_ = launch_polar_tile_table(ctx->ptab2.as<uint32_t>(), ctx->ptiles.as<int4>(), ctx->ptile_pitch, H, W, D, Cp, ctx->cs.as<double>(),
+                                 ctx->rho.as<float>(), ctx->stream);
+    if (e_ != 0) return fail(ctx, NIS_ERR_CUDA, "launch_polar_tile_table", e_);
+    CU(cudaStreamSynchronize(ctx->stream));
   }
   // per polar-peak-row angle tables (correlation_flow.cc:105-136): every float/double step of the reference, once
   std::vector<double> mats(3 * (size_t)D * 6), theta(3 * (size_t)D);
@@ -348,14 +345,36 @@ static int build_tables(nis_ctx* ctx) {
   return NIS_OK;
 }
 
+// TMA descriptor (cuTensorMapEncodeTiled, resolved through the runtime's driver entry point: no link against libcuda) over the lane's
+// shifted power images: rank 3 {W, H, images} f32, box {pitch, rows, 1}, no swizzle, out-of-range elements read as zero
+static int encode_hp_map(nis_ctx* ctx, Lane& L, int pairs) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(ctx, NIS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->H, (cuuint64_t)pairs};
+  const cuuint64_t strides[2] = {(cuuint64_t)ctx->W * sizeof(float), (cuuint64_t)ctx->W * ctx->H * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)ctx->ptile_pitch, (cuuint32_t)ctx->ptile_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(&L.hp_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, L.real.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NIS_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return NIS_OK;
+}
+
 static int ensure_workspace(nis_ctx* ctx, Lane& L, int pairs) {
   if (pairs <= L.cap) return NIS_OK;
   CU(cudaStreamSynchronize(L.stream));
   L.cap = 0;                                   // stays 0 if any of the reservations below fails (no stale capacity after an OOM)
   const size_t E = 2 * (size_t)pairs;
   RESERVE(L.t1, E * ctx->maxspec * sizeof(cpx));          // the only full-size scratch: half-transformed spectra, in place
-  RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float2));  // power = IFFT(|F|) feeding the polar gather (pair-duplicated: 8 B / pixel)
-  RESERVE(L.pol, (size_t)pairs * ctx->sz[1].real * sizeof(float)); // polar image (when the gather is not fused into the FFT)
+  RESERVE(L.real, (size_t)pairs * ctx->maxreal * sizeof(float));   // power = IFFT(|F|), stored fftshift-ed: what the polar gather's TMA tiles read
+  RESERVE(L.pol, (size_t)pairs * ctx->sz[1].real * sizeof(float)); // polar image
+  TRY(encode_hp_map(ctx, L, pairs));
   RESERVE(L.maxp, (size_t)pairs * sizeof(unsigned));
   RESERVE(L.maxt, E * sizeof(unsigned));
   RESERVE(L.maxh, (size_t)pairs * sizeof(unsigned));
@@ -443,28 +462,16 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
   else LAUNCH(launch_col_fwd_f32(zt.R, zt.col, ProRealF32{f32, zt.C}, t1, zt.C, B, L.stream));
   // fft_result = FFT(image) stored from registers; the same kernel continues with IFFT(|fft_result|) along the rows
   LAUNCH(launch_rowrow_storeabs(zt.C, zt.row, t1s, t1, MidStoreAbs{F}, zt.R / 2 + 1, B, L.stream));
+  // power = IFFT(|fft_result|) lands fftshift-ed; RemoveZeroComponent in place; polar cells gather from TMA-staged tiles; the polar
+  // image (it stays in L2) then takes a plain r2c column pass   (correlation_flow.cc:92-94)
   Dst<float> power{L.real.as<float>(), (long long)zt.real};
-  Dst<float2> power2{L.real.as<float2>(), (long long)zt.real};
-  if (ctx->polar_fused && !ctx->polar_tiled) LAUNCH(launch_col_inv_store_pairs(zt.R, zt.col, t1s, EpiStorePairs{power2, zt.C, (float)zt.real}, zt.C, B, L.stream));
-  else LAUNCH(launch_col_inv_store(zt.R, zt.col, t1s, EpiStore{power, zt.C, (float)zt.real}, zt.C, B, L.stream));
-  // polar(fftshift(RemoveZeroComponent(power))) feeds the first FFT stage directly
+  LAUNCH(launch_col_inv_store_shift(zt.R, zt.col, t1s, EpiStoreShift{power, zt.R, zt.C, (float)zt.real}, zt.C, B, L.stream));
+  LAUNCH(launch_rzc_fix(power, ctx->H, ctx->W, B, L.stream));
   Dst<cpx> t1p{L.t1.as<cpx>(), (long long)zp.spec};
-  PolarArgs pa{src_slab<float>(power.base, power.stride), src_slab<float2>(power2.base, power2.stride), ctx->H, ctx->W, ctx->Cp,
-               ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->ptab.as<uint32_t>()};
-  if (ctx->polar_tiled) {
-    // cell-tiled gather from shared memory, then a plain r2c column pass over the polar image (it stays in L2)
-    Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
-    LAUNCH(launch_polar_tiled(pa.power, pol, ctx->H, ctx->W, ctx->D, ctx->Cp, ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch,
-                              ctx->ptile_rows, B, L.stream));
-    LAUNCH(launch_col_fwd_f32(zp.R, zp.col, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
-  } else if (ctx->polar_fused) {
-    LAUNCH(launch_col_fwd_polar(zp.R, zp.col, pa, t1p, zp.C, B, L.stream));
-  } else {
-    // the gather is latency bound: as its own full-occupancy kernel it beats riding in the register-limited FFT stage 0
-    Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
-    LAUNCH(launch_polar(pa.power, pol, ctx->H, ctx->W, ctx->D, ctx->Cp, pa.cs, pa.rho, pa.table, B, L.stream));
-    LAUNCH(launch_col_fwd_f32(zp.R, zp.col, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
-  }
+  Dst<float> pol{L.pol.as<float>(), (long long)zp.real};
+  LAUNCH(launch_polar_tma(&L.hp_map, pol, ctx->D, ctx->Cp, ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch, ctx->ptile_rows, B,
+                          L.stream));
+  LAUNCH(launch_col_fwd_f32(zp.R, zp.col, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
   LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
   if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
     TRY(hzz_batch(ctx, L, 0, src_slab<cpx>(F.base, F.stride), B, Ht));
@@ -618,7 +625,7 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   if (!cfg || !out) return NIS_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   const int H = image_height, W = image_width, D = cfg->rotation_divisor, Cp = cfg->rotation_channel;
-  if (H <= 0 || W <= 0 || D <= 0 || Cp <= 0 || (H & 1) || (D & 1) || (W % 16) || (Cp % 16)) return NIS_ERR_INVALID_ARGUMENT;
+  if (H <= 0 || W <= 0 || D <= 0 || Cp <= 0 || (H & 1) || (D & 1) || (W % 32) || (Cp % 16)) return NIS_ERR_INVALID_ARGUMENT;
   if (!col_size_supported(H) || !col_size_supported(D) || !row_size_supported(W) || !row_size_supported(Cp))
     return NIS_ERR_UNSUPPORTED_SIZE;
   // the fused rotation wraps source coordinates with one conditional add/subtract (exact while the half diagonal stays
@@ -660,10 +667,6 @@ int nis_create(const nis_cf_config* cfg, int image_height, int image_width, int 
   }
   const char* er = getenv("NIS_ROT_CACHE_MIN");      // candidates from which a scan builds the rotated-query cache (0 = never)
   if (er) ctx->rot_cache_min = atoi(er);
-  const char* ef = getenv("NIS_POLAR_FUSED");
-  if (ef) ctx->polar_fused = atoi(ef) != 0;
-  ef = getenv("NIS_POLAR_TILED");
-  if (ef) ctx->polar_tiled = atoi(ef) != 0;
   const char* eb = getenv("NIS_BATCH");
   if (eb && atoi(eb) > 0) ctx->batch = atoi(eb);
   int st = build_tables(ctx);
@@ -676,7 +679,7 @@ int nis_destroy(nis_ctx* ctx) {
   if (!ctx) return NIS_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptab, &ctx->ptiles, &ctx->ptab2, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
+  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptiles, &ctx->ptab2, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
                     &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->sUnd, &ctx->umap1, &ctx->umap2, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel,
                     &ctx->d_fid, &ctx->d_dist, &ctx->d_cell, &ctx->cand_in, &ctx->cand_pos, &ctx->sel_scratch, &ctx->stage, &ctx->kfrec, &ctx->qgather};
   for (DevBuf* b : bufs) b->release();
@@ -1771,13 +1774,17 @@ int nis_debug_polar(nis_ctx* ctx, const float* power_in, float* polar_out) {
   ctx->prof_stream = L.stream;
   DevBuf out;
   RESERVE(out, ctx->sz[1].real * sizeof(float));
-  CU(h2d(ctx, L.real.p, power_in, ctx->sz[0].real * sizeof(float)));
-  if (ctx->polar_tiled)           // the production gather
-    LAUNCH(launch_polar_tiled(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
-                              ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch, ctx->ptile_rows, 1, L.stream));
-  else
-    LAUNCH(launch_polar(src_slab<float>(L.real.as<float>(), 0), Dst<float>{out.as<float>(), 0}, ctx->H, ctx->W, ctx->D, ctx->Cp,
-                        ctx->cs.as<double>(), ctx->rho.as<float>(), ctx->ptab.as<uint32_t>(), 1, L.stream));
+  {
+    // the production path receives power already fftshift-ed from the inverse column pass (EpiStoreShift): shift here on the host
+    const int H = ctx->H, W = ctx->W;
+    std::vector<float> sh((size_t)H * W);
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) sh[(size_t)y * W + x] = power_in[(size_t)((y - H / 2 + H) % H) * W + (x - W / 2 + W) % W];
+    CU(h2d(ctx, L.real.p, sh.data(), sh.size() * sizeof(float)));
+  }
+  LAUNCH(launch_rzc_fix(Dst<float>{L.real.as<float>(), 0}, ctx->H, ctx->W, 1, L.stream));
+  LAUNCH(launch_polar_tma(&L.hp_map, Dst<float>{out.as<float>(), 0}, ctx->D, ctx->Cp, ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch,
+                          ctx->ptile_rows, 1, L.stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpy(polar_out, out.p, ctx->sz[1].real * sizeof(float), cudaMemcpyDeviceToHost));
   out.release();

@@ -114,10 +114,6 @@ void plan_radices_col(int N, int r[3]) {
 #define FWD_CASE(n, a, b, c, t) case n: return run_col_fwd<n, a, b, c, t>(tw, pro, out, W, B, s);
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealF32) }
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealU8) }
-int launch_col_fwd_polar(int N, Twiddles tw, PolarArgs pa, Dst<cpx> out, int W, int B, cudaStream_t s) {
-  ProPolar pro{pa.power2, pa.H, pa.W, pa.Cp, pa.cs, pa.rho, pa.table};
-  FWD_DISPATCH(ProPolar)
-}
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int B, cudaStream_t s) {
   if (ra.is_u8) {
     ProRotate<true> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel};
@@ -137,7 +133,7 @@ int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W
   }
 #define INV_CASE(n, a, b, c, t) case n: return run_col_inv<n, a, b, c, t>(tw, in, epi, W, B, s);
 int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
-int launch_col_inv_store_pairs(int N, Twiddles tw, Src<cpx> in, EpiStorePairs epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
+int launch_col_inv_store_shift(int N, Twiddles tw, Src<cpx> in, EpiStoreShift epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s) { INV_DISPATCH }
 #undef INV_CASE
 

@@ -29,14 +29,10 @@ void plan_radices_row(int N, int r[3]);
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
 struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; };
-struct PolarArgs { Src<float> power; Src<float2> power2;   // plain f32 (stand-alone kernel) / pair-duplicated (fused prologue)
-                   int H, W, Cp; const double* cs; const float* rho; const uint32_t* table; };
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int E, cudaStream_t s);   // RotateArray fused into stage 0
-int launch_col_fwd_polar(int N, Twiddles tw, PolarArgs pa, Dst<cpx> out, int W, int B, cudaStream_t s);     // warpPolar fused into stage 0
 int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, int B, cudaStream_t s);
-int launch_col_inv_store_pairs(int N, Twiddles tw, Src<cpx> in, EpiStorePairs epi, int W, int B, cudaStream_t s);
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s);
 // c2r -> kernel function -> r2c in one kernel (the real kernel image never leaves shared memory); in-place allowed
 int launch_colcol(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s);
@@ -49,18 +45,17 @@ int launch_rowrow_filter(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidFilte
 int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s);
 
 // ---- warps and bookkeeping kernels -----------------------------------------------------------------------
-// polar: power [B][H][W] (IFFT(|F|), unshifted) -> polar image [B][D][Cp]; RemoveZeroComponent + fftshift fused in the taps
-int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
-                 const uint32_t* table, int B, cudaStream_t s);
-// tiled polar gather (nis_misc.cu): one CTA per cell of kPolarTA angles x kPolarTR radii, source box staged in shared memory
+// tiled polar gather (nis_misc.cu): one CTA per cell of kPolarTA angles x kPolarTR radii, source box staged in shared memory by TMA
 constexpr int kPolarTA = 16, kPolarTR = 64;
 int launch_polar_tile_bbox(int4* tiles, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s);
 int launch_polar_tile_table(uint32_t* table, const int4* tiles, int pitch, int H, int W, int D, int Cp, const double* cs_table,
                             const float* rho_table, cudaStream_t s);
-int launch_polar_tiled(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const int4* tiles, const uint32_t* table, int pitch,
-                       int box_rows, int B, cudaStream_t s);
-// one-time polar gather table [D][Cp] (see nis_warp.cuh)
-int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s);
+// hp_map: CUtensorMap (cuTensorMapEncodeTiled) over the lane's shifted power images [B][H][W] f32 with box {pitch, box_rows, 1}
+int launch_polar_tma(const void* hp_map, Dst<float> out, int D, int Cp, const int4* tiles, const uint32_t* table, int pitch, int box_rows, int B,
+                     cudaStream_t s);
+// RemoveZeroComponent on the fftshift-ed power image, in place
+int launch_rzc_fix(Dst<float> hp, int H, int W, int B, cudaStream_t s);
+int launch_col_inv_store_shift(int N, Twiddles tw, Src<cpx> in, EpiStoreShift epi, int W, int B, cudaStream_t s);
 // rotate: out[e] = warpAffine(image[e], rot_mats[sel[e]]) with BORDER_WRAP.  Exactly one of img_f32 / img_u8 is used.
 int launch_rotate(Src<float> img_f32, Src<uint8_t> img_u8, const float* lut, Dst<float> out, int H, int W, const double* mats,
                   const int* sel, int E, cudaStream_t s);

@@ -1,10 +1,11 @@
 // nis_misc.cu -- the two OpenCV-exact resampling kernels and the per-pair bookkeeping kernels (sm_100a).
-//   polar_kernel   : RemoveZeroComponent + fftshift + cv::warpPolar   (correlation_flow.cc:79-87, :94, :228-236)
+//   polar_tma_kernel + rzc_fix_kernel : RemoveZeroComponent + fftshift + cv::warpPolar   (correlation_flow.cc:79-87, :94, :228-236)
 //   rotate_kernel  : RotateArray = getRotationMatrix2D + warpAffine   (utils.cc:154-161)
 //   polar_select / pose_finalize / scan_reduce : ComputePose control flow and the FindLoopClosure arg-max
 //   (correlation_flow.cc:97-138, loop_closure.cc:61-71) kept on the device so a batch never syncs with the host.
 // All interpolation arithmetic is written with explicit round-to-nearest intrinsics (no FMA contraction) so the
 // fixed-point coordinates and the 4-tap sums equal OpenCV's scalar code bit for bit.
+#include <cuda.h>
 #include <limits.h>
 
 #include "nis_device.cuh"
@@ -13,53 +14,17 @@
 
 namespace nis {
 
-// one thread per pair of adjacent output pixels; `table` (may be null) is the per-context gather table of nis_warp.cuh
-__global__ void __launch_bounds__(256) polar_kernel(Src<float> power, Dst<float> out, int H, int W, int D, int Cp,
-                                                    const double* __restrict__ cs, const float* __restrict__ rho_tab,
-                                                    const uint32_t* __restrict__ table) {
-  const int b = blockIdx.z, phi = blockIdx.y;
-  const int rho = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (rho >= Cp) return;
-  const float* p = power.at(b);
-  float2 v;
-  if (table) {
-    const uint2 e = __ldg(reinterpret_cast<const uint2*>(table + (size_t)phi * Cp + rho));
-    double cp = 0.0, sp = 0.0;
-    if ((e.x | e.y) & kPolarSlow) { cp = cs[2 * phi]; sp = cs[2 * phi + 1]; }
-    v = make_float2(polar_pixel_tab(p, H, W, e.x, cp, sp, rho_tab[rho]), polar_pixel_tab(p, H, W, e.y, cp, sp, rho_tab[rho + 1]));
-  } else {
-    v = make_float2(polar_pixel(p, H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho]),
-                    polar_pixel(p, H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho + 1]));
-  }
-  reinterpret_cast<float2*>(out.at(b) + (size_t)phi * Cp)[rho / 2] = v;
-}
-
-int launch_polar(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table,
-                 const uint32_t* table, int B, cudaStream_t s) {
-  if (B <= 0) return 0;
-  const int T = Cp >= 512 ? 256 : 128;
-  polar_kernel<<<dim3((Cp / 2 + T - 1) / T, D, B), T, 0, s>>>(power, out, H, W, D, Cp, cs_table, rho_table, table);
-  return (int)cudaGetLastError();
-}
-
-__global__ void polar_table_kernel(uint32_t* __restrict__ table, int H, int W, int D, int Cp, const double* __restrict__ cs,
-                                   const float* __restrict__ rho_tab) {
-  const int phi = blockIdx.y, rho = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rho >= Cp) return;
-  table[(size_t)phi * Cp + rho] = polar_table_entry(H, W, cs[2 * phi], cs[2 * phi + 1], rho_tab[rho]);
-}
-int launch_polar_table(uint32_t* table, int H, int W, int D, int Cp, const double* cs_table, const float* rho_table, cudaStream_t s) {
-  polar_table_kernel<<<dim3((Cp + 127) / 128, D), 128, 0, s>>>(table, H, W, D, Cp, cs_table, rho_table);
-  return (int)cudaGetLastError();
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// tiled polar gather.  The direct gathers above touch ~8 different 128-byte lines per warp request (a ray crosses image rows),
-// which makes the L1 tag stage the limiter.  Here one CTA owns a polar cell of kPolarTA angles x kPolarTR radii, stages the
-// bounding box of its source footprint -- already fftshift-ed, RemoveZeroComponent-ed and zero-filled outside the image, so the
-// gather has no special cases -- in shared memory with row-contiguous loads, and gathers the four taps from there.
+// tiled polar gather over a TMA-staged tile.
+// A ray of the polar grid crosses image rows, so a direct gather touches ~8 different 128-byte lines per warp request and the L1
+// tag stage is the limiter.  Here the inverse column pass before it (EpiStoreShift) writes power = IFFT(|F|) ALREADY fftshift-ed
+// into `hp`, rzc_fix_kernel applies RemoveZeroComponent to it in place, and one CTA per polar cell of kPolarTA angles x kPolarTR
+// radii loads the bounding box of its source footprint as ONE 2-D tile: cp.async.bulk.tensor (TMA) straight into shared memory,
+// completion on an mbarrier, out-of-range taps zero-filled by the TMA unit -- which is exactly cv::warpPolar's
+// WARP_FILL_OUTLIERS / BORDER_CONSTANT(0).  While the tile is in flight the threads fetch their table entries; the four taps then
+// come from shared memory with the 1/32-px weights of the per-context table.  Same fixed-point arithmetic as polar_pixel, bit for bit.
 // Per-context tables (built once): tiles[t] = {y0, x0, bh, bw} of the cell's box in shifted coordinates, and per output pixel
-// (dy * pitch + dx) | fx << 16 | fy << 21 relative to that box.  Same fixed-point arithmetic as polar_pixel, bit for bit.
+// (dy * pitch + dx) | fx << 16 | fy << 21 relative to that box (pitch = the common tile width).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void polar_fixed_point(int H, int W, double cp, double sp, float rf, int& ix, int& iy, int& fx, int& fy) {
   const float cx = (float)W / 2, cy = (float)H / 2;
@@ -84,7 +49,13 @@ __global__ void __launch_bounds__(256) polar_tile_bbox_kernel(int4* __restrict__
   }
   atomicMin(&red[0], ymin); atomicMin(&red[1], xmin); atomicMax(&red[2], ymax); atomicMax(&red[3], xmax);
   __syncthreads();
-  if (threadIdx.x == 0) tiles[blockIdx.y * gridDim.x + blockIdx.x] = make_int4(red[0], red[1], red[2] - red[0] + 1, red[3] - red[1] + 1);
+  if (threadIdx.x == 0) {
+    // TMA: the innermost start coordinate must be 16-byte aligned (4 floats); x & ~3 floors negative values too
+    // (probed on the B200 with tools/ubench/tma_tile.cu: an unaligned start raises "illegal instruction", an aligned one -- negative or
+    // partly outside the image -- zero-fills)
+    const int x0 = red[1] & ~3;
+    tiles[blockIdx.y * gridDim.x + blockIdx.x] = make_int4(red[0], x0, red[2] - red[0] + 1, red[3] - x0 + 1);
+  }
 }
 
 __global__ void polar_tile_table_kernel(uint32_t* __restrict__ table, const int4* __restrict__ tiles, int tiles_r, int pitch, int H, int W,
@@ -97,35 +68,76 @@ __global__ void polar_tile_table_kernel(uint32_t* __restrict__ table, const int4
   table[(size_t)phi * Cp + rho] = (uint32_t)((iy - t.x) * pitch + (ix - t.y)) | ((uint32_t)fx << 16) | ((uint32_t)fy << 21);
 }
 
-__global__ void __launch_bounds__(256) polar_tile_kernel(Src<float> power, Dst<float> out, int H, int W, int D, int Cp,
-                                                         const int4* __restrict__ tiles, const uint32_t* __restrict__ table, int pitch) {
-  extern __shared__ float box[];
+// RemoveZeroComponent (correlation_flow.cc:79-87) on the fftshift-ed image, in place: unshifted row 0 / column 0 are shifted row H/2 /
+// column W/2.  y.row(0) = (x.row(1) + x.row(R-1)) / 2, y.col(0) = (x.col(1) + x.col(C-1)) / 2, both from the ORIGINAL x, and y(0,0)
+// comes from the column rule: all reads first, then the row, then the column.  One CTA per image.
+__global__ void __launch_bounds__(1024) rzc_fix_kernel(Dst<float> hp, int H, int W) {
+  float* p = hp.at(blockIdx.x);
+  const int hs = H / 2, ws = W / 2;
+  auto sh = [&](int r, int c) -> float* {                 // unshifted (r, c) -> its place in the shifted image
+    const int y = r + hs - (r + hs >= H ? H : 0), x = c + ws - (c + ws >= W ? W : 0);
+    return p + (size_t)y * W + x;
+  };
+  float rowv[2], colv[2];
+  int nr = 0, nc = 0;
+  for (int c = threadIdx.x; c < W && nr < 2; c += blockDim.x) rowv[nr++] = __fadd_rn(*sh(1, c), *sh(H - 1, c)) * 0.5f;
+  for (int r = threadIdx.x; r < H && nc < 2; r += blockDim.x) colv[nc++] = __fadd_rn(*sh(r, 1), *sh(r, W - 1)) * 0.5f;
+  __syncthreads();
+  nr = 0;
+  for (int c = threadIdx.x; c < W && nr < 2; c += blockDim.x) *sh(0, c) = rowv[nr++];
+  __syncthreads();
+  nc = 0;
+  for (int r = threadIdx.x; r < H && nc < 2; r += blockDim.x) *sh(r, 0) = colv[nc++];
+}
+int launch_rzc_fix(Dst<float> hp, int H, int W, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  if (W > 2048 || H > 2048) return -1;
+  rzc_fix_kernel<<<B, 1024, 0, s>>>(hp, H, W);
+  return (int)cudaGetLastError();
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) polar_tma_kernel(const __grid_constant__ CUtensorMap hp_map, Dst<float> out, int D, int Cp,
+                                                        const int4* __restrict__ tiles, const uint32_t* __restrict__ table, int pitch,
+                                                        int tile_bytes) {
+  extern __shared__ __align__(128) float box[];
+  __shared__ __align__(8) unsigned long long mbar;
   const int b = blockIdx.z, tid = threadIdx.x;
-  const float* p = power.at(b);
-  const int4 t = __ldg(&tiles[blockIdx.y * gridDim.x + blockIdx.x]);        // y0, x0, bh, bw
-  // staging, flat over the box (full lanes): the row index comes from a multiply-high with the per-tile reciprocal instead of an
-  // integer division; interior elements cost two wraps and a load, the RemoveZeroComponent row / column (r == 0, c == 0) and
-  // everything outside the image go through the exact general tap
-  const unsigned rcp = 0xffffffffu / (unsigned)t.w + 1u;        // floor(i / w) == umulhi(i, rcp) for i * w < 2^32
-  for (int i = tid; i < t.z * t.w; i += 256) {
-    const int ly = (int)__umulhi((unsigned)i, rcp), lx = i - ly * t.w;
-    const int y = t.x + ly, x = t.y + lx;
-    int r = y - H / 2; r += (r < 0) ? H : 0;
-    int c = x - W / 2; c += (c < 0) ? W : 0;
-    const bool plain = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W && r != 0 && c != 0;
-    box[ly * pitch + lx] = plain ? __ldg(p + (size_t)r * W + c) : shifted_tap(p, y, x, H, W);
+  const uint32_t bar = smem_u32(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (tid == 0) {
+    const int4 t = __ldg(&tiles[blockIdx.y * gridDim.x + blockIdx.x]);        // y0, x0, bh, bw
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(box)), "l"(&hp_map), "r"(t.y), "r"(t.x), "r"(b), "r"(bar) : "memory");
+  }
+  // table entries of this thread's four output pixels while the tile is in flight
   const int rho = blockIdx.x * kPolarTR + (tid % kPolarTR);
+  uint32_t e[kPolarTA * kPolarTR / 256];
+#pragma unroll
+  for (int k = 0; k < kPolarTA * kPolarTR / 256; ++k) {
+    const int phi = blockIdx.y * kPolarTA + tid / kPolarTR + k * (256 / kPolarTR);
+    e[k] = (rho < Cp && phi < D) ? __ldg(table + (size_t)phi * Cp + rho) : 0u;
+  }
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+  }
   if (rho >= Cp) return;
   float* o = out.at(b);
 #pragma unroll
   for (int k = 0; k < kPolarTA * kPolarTR / 256; ++k) {
     const int phi = blockIdx.y * kPolarTA + tid / kPolarTR + k * (256 / kPolarTR);
     if (phi >= D) break;
-    const uint32_t e = __ldg(table + (size_t)phi * Cp + rho);
-    const float* q = box + (e & 0xffffu);
-    o[(size_t)phi * Cp + rho] = bilinear4(q[0], q[1], q[pitch], q[pitch + 1], (e >> 16) & 31, (e >> 21) & 31);
+    const float* q = box + (e[k] & 0xffffu);
+    o[(size_t)phi * Cp + rho] = bilinear4(q[0], q[1], q[pitch], q[pitch + 1], (e[k] >> 16) & 31, (e[k] >> 21) & 31);
   }
 }
 
@@ -138,11 +150,12 @@ int launch_polar_tile_table(uint32_t* table, const int4* tiles, int pitch, int H
   polar_tile_table_kernel<<<dim3((Cp + 127) / 128, D), 128, 0, s>>>(table, tiles, (Cp + kPolarTR - 1) / kPolarTR, pitch, H, W, D, Cp, cs_table, rho_table);
   return (int)cudaGetLastError();
 }
-int launch_polar_tiled(Src<float> power, Dst<float> out, int H, int W, int D, int Cp, const int4* tiles, const uint32_t* table, int pitch,
-                       int box_rows, int B, cudaStream_t s) {
+int launch_polar_tma(const void* hp_map, Dst<float> out, int D, int Cp, const int4* tiles, const uint32_t* table, int pitch, int box_rows, int B,
+                     cudaStream_t s) {
   if (B <= 0) return 0;
-  const size_t smem = (size_t)box_rows * pitch * sizeof(float);
-  polar_tile_kernel<<<dim3((Cp + kPolarTR - 1) / kPolarTR, (D + kPolarTA - 1) / kPolarTA, B), 256, smem, s>>>(power, out, H, W, D, Cp, tiles, table, pitch);
+  const int tile_bytes = box_rows * pitch * (int)sizeof(float);
+  polar_tma_kernel<<<dim3((Cp + kPolarTR - 1) / kPolarTR, (D + kPolarTA - 1) / kPolarTA, B), 256, tile_bytes, s>>>(
+      *reinterpret_cast<const CUtensorMap*>(hp_map), out, D, Cp, tiles, table, pitch, tile_bytes);
   return (int)cudaGetLastError();
 }
 

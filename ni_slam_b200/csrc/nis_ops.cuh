@@ -149,24 +149,19 @@ struct EpiStore {
   NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, 1.0f / n}; }
 };
 
-// power = IFFT(|F|) in the pair-duplicated layout the fused polar gather reads: entry[r][c] = (p[r][c], p[r][c+1]), so one
-// 8-byte load fetches both horizontal taps of a bilinear footprint (half the gather wavefronts on the L1 data pipe).  Each
-// thread owns columns c = c0+2l and c+1: it writes entry[c] whole, the .x half of entry[c+1] and the .y half of entry[c-1].
-struct EpiStorePairs {
-  Dst<float2> dst; int W; float n;
+// power = IFFT(|F|) stored fftshift-ed (circ_shift.h:238-244: out(r, c) = in((r - R/2) mod R, (c - C/2) mod C)), the layout the TMA-staged
+// polar gather reads; the column pair (c0+2l, c0+2l+1) stays adjacent because c0 and C/2 are multiples of 16
+struct EpiStoreShift {
+  Dst<float> dst; int H, W; float n;
   struct Bound {
-    float2* img; int W, c0; float rn;
+    float* img; int H, W, cs; float rn;
     NIS_HD void put(int row, int l, float re, float im) {
-      const int c = c0 + 2 * l;
-      float2* rowp = img + (size_t)row * W + c;
-      const cpx v = cscale(make_float2(re, im), rn);
-      rowp[0] = v;
-      rowp[1].x = v.y;
-      if (c > 0) rowp[-1].y = v.x;
+      const int y = row + H / 2 - (row + H / 2 >= H ? H : 0);
+      reinterpret_cast<float2*>(img + (size_t)y * W + cs)[l] = cscale(make_float2(re, im), rn);
     }
     template <class Sync> NIS_HD void finish(int, Sync&) {}
   };
-  NIS_HD Bound bind(int b, int c0) const { return Bound{dst.at(b), W, c0, 1.0f / n}; }
+  NIS_HD Bound bind(int b, int c0) const { const int x = c0 + W / 2 - (c0 + W / 2 >= W ? W : 0); return Bound{dst.at(b), H, W, x, 1.0f / n}; }
 };
 
 // rare kernel-function paths (general integer power, gaussian): kept out of line so the 20 inlined call sites of the fused
