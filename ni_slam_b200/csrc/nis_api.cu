@@ -104,7 +104,7 @@ struct nis_ctx {
   int batch = 16, default_batch = 16;
   int ptile_pitch = 0, ptile_rows = 0;
   // constant tables
-  DevBuf tw, lut, cs, rho, mats, theta, ptiles, ptab2;
+  DevBuf tw, lut, cs, rho, mats, theta, ptiles, ptab2, rowtab;
   DevBuf recs, best, cand, stage, qgather;
   // multi-GPU scan (nis_comm_init / nis_loop_scan_sharded): NCCL communicator of this context's rank
   void* nccl_comm = nullptr;
@@ -258,6 +258,13 @@ static void rotation_inverse(int H, int W, double degree, double* M) {
   M[2] = b1; M[5] = b2;
 }
 
+static void rotate_row_table(const double* M, int H, int2* out) {
+  for (int y = 0; y < H; ++y) {
+    out[y].x = (int)lrint((M[1] * (double)y + M[2]) * 1024.0) + 16;
+    out[y].y = (int)lrint((M[4] * (double)y + M[5]) * 1024.0) + 16;
+  }
+}
+
 static int build_tables(nis_ctx* ctx) {
   const int H = ctx->H, W = ctx->W, D = ctx->D, Cp = ctx->Cp;
   // twiddles
@@ -338,6 +345,12 @@ static int build_tables(nis_ctx* ctx) {
   }
   // one extra matrix slot (index 3*D) for nis_debug_rotate
   mats.resize(mats.size() + 6, 0.0);
+  // per (matrix slot, output row): X0, Y0 of warpAffine's fixed-point walk (AB_BITS = 10, round_delta = 16), the same two roundings
+  // as OpenCV's per-row set-up; the fused rotation prologue reads them instead of redoing the double arithmetic per column pair
+  std::vector<int2> rowtab((size_t)(3 * D + 1) * H);
+  for (size_t slot = 0; slot < (size_t)3 * D; ++slot) rotate_row_table(&mats[slot * 6], H, &rowtab[slot * H]);
+  RESERVE(ctx->rowtab, rowtab.size() * sizeof(int2));
+  CU(h2d(ctx, ctx->rowtab.p, rowtab.data(), rowtab.size() * sizeof(int2)));
   RESERVE(ctx->mats, mats.size() * sizeof(double));
   RESERVE(ctx->theta, theta.size() * sizeof(double));
   CU(h2d(ctx, ctx->mats.p, mats.data(), mats.size() * sizeof(double)));
@@ -539,7 +552,7 @@ static int build_rot_cache(nis_ctx* ctx, Src<float> img_f32, Src<uint8_t> img_u8
     Dst<cpx> t1{L.t1.as<cpx>(), (long long)zt.spec};
     Src<float> i32 = img_f32; Src<uint8_t> i8 = img_u8;
     if (is_u8) i32 = src_null<float>(); else i8 = src_null<uint8_t>();
-    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), ctx->rotc_sel.as<int>() + i0};
+    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), ctx->rotc_sel.as<int>() + i0, ctx->rowtab.as<int2>()};
     LAUNCH(launch_col_fwd_rotate(zt.R, zt.col, ra, t1, zt.C, nb, L.stream));
     Dst<cpx> out{ctx->rotc.as<cpx>() + (size_t)i0 * zt.spec, (long long)zt.spec};
     LAUNCH(launch_row_fwd(zt.C, zt.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, zt.R / 2 + 1, nb, L.stream));
@@ -581,7 +594,7 @@ static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz
     LAUNCH(launch_row_inv_mulconj(zt.C, zt.row, ProMulConj{Xc, Fze}, EpiSpecStore{t1}, zt.R / 2 + 1, E, L.stream));
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr, ctx->rotc_xx.as<double>() - ctx->D, L.sel.as<int>()));
   } else {
-    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>()};
+    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), ctx->rowtab.as<int2>()};
     LAUNCH(launch_col_fwd_rotate(zt.R, zt.col, ra, t1, zt.C, E, L.stream));
     LAUNCH(launch_rowrow_mulconj(zt.C, zt.row, t1s, t1, MidMulConjZ{Fze, gauss ? L.xx.as<double>() : nullptr}, zt.R / 2 + 1, E, L.stream));
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr));
@@ -679,7 +692,7 @@ int nis_destroy(nis_ctx* ctx) {
   if (!ctx) return NIS_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptiles, &ctx->ptab2, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
+  DevBuf* bufs[] = {&ctx->tw, &ctx->lut, &ctx->cs, &ctx->rho, &ctx->mats, &ctx->theta, &ctx->ptiles, &ctx->ptab2, &ctx->rowtab, &ctx->recs, &ctx->best, &ctx->cand, &ctx->sF,
                     &ctx->sP, &ctx->sHt, &ctx->sHp, &ctx->sImg, &ctx->sUnd, &ctx->umap1, &ctx->umap2, &ctx->d_slot_ptr, &ctx->rotc, &ctx->rotc_xx, &ctx->rotc_sel,
                     &ctx->d_fid, &ctx->d_dist, &ctx->d_cell, &ctx->cand_in, &ctx->cand_pos, &ctx->sel_scratch, &ctx->stage, &ctx->kfrec, &ctx->qgather};
   for (DevBuf* b : bufs) b->release();

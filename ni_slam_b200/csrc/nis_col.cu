@@ -9,6 +9,13 @@ namespace nis {
 
 // resident CTAs per SM the register budget of the column kernels is sized for: 768 threads (85 registers each): the paired
 // radix-12 stages hold 24 complex values per thread; a 64-register budget spills there (measured -6 %, profiles/ab_r02.md)
+template <class Pro, class = void> struct ProTraits { static constexpr bool kSmemLut = false; };
+template <class Pro> struct ProTraits<Pro, decltype((void)Pro::kSmemLut)> { static constexpr bool kSmemLut = Pro::kSmemLut; };
+template <class Pro> __device__ __forceinline__ auto bind_pro(const Pro& pro, int b, int c0, const float* lut_s) {
+  if constexpr (ProTraits<Pro>::kSmemLut) return pro.bind(b, c0, lut_s);
+  else return pro.bind(b, c0);
+}
+
 #ifndef NIS_COL_MINB
 #define NIS_COL_MINB (768 / NIS_COL_T)
 #endif
@@ -18,7 +25,14 @@ __global__ void __launch_bounds__(T, NIS_COL_MINB) col_fwd_kernel(Pro pro, Twidd
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
   const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
-  const auto bp = pro.bind(b, c0);
+  const float* lut_s = nullptr;
+  if constexpr (ProTraits<Pro>::kSmemLut) {          // gather prologues on u8 images: the u8 -> f32/255 table comes from shared memory
+    __shared__ float lut_sh[256];
+    for (int i = tid; i < 256; i += T) lut_sh[i] = __ldg(pro.lut + i);
+    __syncthreads();
+    lut_s = lut_sh;
+  }
+  const auto bp = bind_pro(pro, b, c0, lut_s);
   col_fwd_stage_a<N, A, B, C, T>(tid, smem, twd, bp);
   __syncthreads();
   col_stage_b<N, A, B, C, T, false, false>(tid, smem, twd);
@@ -116,10 +130,10 @@ int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, 
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealU8) }
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int B, cudaStream_t s) {
   if (ra.is_u8) {
-    ProRotate<true> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel};
+    ProRotate<true> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab};
     FWD_DISPATCH(ProRotate<true>)
   } else {
-    ProRotate<false> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel};
+    ProRotate<false> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab};
     FWD_DISPATCH(ProRotate<false>)
   }
 }

@@ -28,7 +28,8 @@ void plan_radices_col(int N, int r[3]);
 void plan_radices_row(int N, int r[3]);
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
-struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; };
+// rowtab[slot][y] = (X0, Y0) of cv::warpAffine's fixed-point walk for output row y under rotation-matrix slot `slot` (host-built beside mats)
+struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; const int2* rowtab; };
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int E, cudaStream_t s);   // RotateArray fused into stage 0

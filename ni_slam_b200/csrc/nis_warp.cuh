@@ -63,30 +63,35 @@ __device__ __forceinline__ float rotate_pixel(const float* __restrict__ f32, con
 
 // ---- column-pass prologue: the rotation feeds the first FFT stage directly, the rotated image is never stored ------
 template <bool U8> struct ProRotate {
-  Src<float> f32; Src<uint8_t> u8; const float* lut; int H, W; const double* mats; const int* sel;
+  static constexpr bool kSmemLut = U8;        // the kernel stages the 256-entry u8 -> f32/255 table in shared memory and hands it to bind()
+  Src<float> f32; Src<uint8_t> u8; const float* lut; int H, W; const double* mats; const int* sel; const int2* rowtab;
   struct Lane {
-    const float* f; const uint8_t* u; const float* lut; int H, W; const double* M; int a0, b0, a1, b1;   // adelta / bdelta of both columns
+    const float* f; const uint8_t* u; const float* lut; int H, W; const int2* rt; int a0, b0, a1, b1;   // adelta / bdelta of both columns
     __device__ __forceinline__ float pixel(int X0, int Y0, int ad, int bd) const {
       const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
-      const int ix = sat_short(X >> 5), iy = sat_short(Y >> 5);
+      // cv::warpAffine saturates X >> 5, Y >> 5 to int16; for the sizes nis_create accepts (<= 2048 px, rotation about the centre) the
+      // coordinates stay within a few image sizes, far inside that range, so the saturation is the identity and is not emitted
+      const int ix = X >> 5, iy = Y >> 5;
       // BORDER_WRAP, branch-free: a rotation about the centre keeps every source coordinate inside (-len, 2 len) for the aspect
       // ratios nis_create accepts (max(W,H) <= 2.8 min(W,H)), so one conditional add / subtract is the exact modulo
-      int x0 = wrap1(ix, W), x1 = wrap1(ix + 1, W), y0 = wrap1(iy, H), y1 = wrap1(iy + 1, H);
-      const int r0 = y0 * W, r1 = y1 * W;          // 32-bit indexing: an image has < 2^31 pixels
+      const int x0 = wrap1(ix, W), y0 = wrap1(iy, H);
+      const int x1 = (x0 + 1 == W) ? 0 : x0 + 1, y1 = (y0 + 1 == H) ? 0 : y0 + 1;
+      const unsigned r0 = (unsigned)(y0 * W), r1 = (unsigned)(y1 * W);          // 32-bit indexing: an image has < 2^31 pixels
       float v0, v1, v2, v3;
       if (U8) {
-        v0 = u8_to_unit(__ldg(u + r0 + x0)); v1 = u8_to_unit(__ldg(u + r0 + x1));
-        v2 = u8_to_unit(__ldg(u + r1 + x0)); v3 = u8_to_unit(__ldg(u + r1 + x1));
+        // exact (float)(u / 255.0) (utils.cc:117) from the staged table: one shared-memory load per tap instead of a conversion and a
+        // three-instruction correctly rounded division
+        v0 = lut[u[r0 + (unsigned)x0]]; v1 = lut[u[r0 + (unsigned)x1]];
+        v2 = lut[u[r1 + (unsigned)x0]]; v3 = lut[u[r1 + (unsigned)x1]];
       } else {
-        v0 = __ldg(f + r0 + x0); v1 = __ldg(f + r0 + x1);
-        v2 = __ldg(f + r1 + x0); v3 = __ldg(f + r1 + x1);
+        v0 = __ldg(f + r0 + (unsigned)x0); v1 = __ldg(f + r0 + (unsigned)x1);
+        v2 = __ldg(f + r1 + (unsigned)x0); v3 = __ldg(f + r1 + (unsigned)x1);
       }
       return bilinear4(v0, v1, v2, v3, X & 31, Y & 31);
     }
     __device__ __forceinline__ cpx load(int y) const {
-      int X0, Y0;
-      rotate_row_setup(M, y, X0, Y0);
-      return make_float2(pixel(X0, Y0, a0, b0), pixel(X0, Y0, a1, b1));
+      const int2 xy = __ldg(rt + y);              // (X0, Y0) of warpAffine's fixed-point walk for this output row, per rotation matrix
+      return make_float2(pixel(xy.x, xy.y, a0, b0), pixel(xy.x, xy.y, a1, b1));
     }
     template <int R> __device__ __forceinline__ void load_all(int row0, int stride, cpx* v) const {
 #pragma unroll
@@ -94,16 +99,17 @@ template <bool U8> struct ProRotate {
     }
   };
   struct Bound {
-    const float* f; const uint8_t* u; const float* lut; int H, W, c0; const double* M;
+    const float* f; const uint8_t* u; const float* lut; int H, W, c0; const double* M; const int2* rt;
     __device__ __forceinline__ Lane lane(int l) const {
       const int x = c0 + 2 * l;
-      return Lane{f, u, lut, H, W, M,
+      return Lane{f, u, lut, H, W, rt,
                   __double2int_rn(__dmul_rn(M[0], (double)x) * 1024.0), __double2int_rn(__dmul_rn(M[3], (double)x) * 1024.0),
                   __double2int_rn(__dmul_rn(M[0], (double)(x + 1)) * 1024.0), __double2int_rn(__dmul_rn(M[3], (double)(x + 1)) * 1024.0)};
     }
   };
-  __device__ __forceinline__ Bound bind(int e, int c0) const {
-    return Bound{U8 ? nullptr : f32.at(e), U8 ? u8.at(e) : nullptr, lut, H, W, c0, mats + 6 * (size_t)sel[e]};
+  __device__ __forceinline__ Bound bind(int e, int c0, const float* lut_s = nullptr) const {
+    const int slot = sel[e];
+    return Bound{U8 ? nullptr : f32.at(e), U8 ? u8.at(e) : nullptr, lut_s ? lut_s : lut, H, W, c0, mats + 6 * (size_t)slot, rowtab + (size_t)slot * H};
   }
 };
 
