@@ -154,6 +154,12 @@ int launch_polar_tma(const void* hp_map, Dst<float> out, int D, int Cp, const in
                      cudaStream_t s) {
   if (B <= 0) return 0;
   const int tile_bytes = box_rows * pitch * (int)sizeof(float);
+  static int attr_bytes = 0;
+  if (tile_bytes > 48 * 1024 && tile_bytes > attr_bytes) {
+    const cudaError_t e = cudaFuncSetAttribute(polar_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_bytes = tile_bytes;
+  }
   polar_tma_kernel<<<dim3((Cp + kPolarTR - 1) / kPolarTR, (D + kPolarTA - 1) / kPolarTA, B), 256, tile_bytes, s>>>(
       *reinterpret_cast<const CUtensorMap*>(hp_map), out, D, Cp, tiles, table, pitch, tile_bytes);
   return (int)cudaGetLastError();

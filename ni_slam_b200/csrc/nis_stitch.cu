@@ -192,6 +192,9 @@ int nis_stitcher_destroy(nis_stitcher* st) {
 
 int nis_stitcher_insert(nis_stitcher* st, const uint8_t* image_u8, const double robot_pose[3], const nis_camera_model* cam, int* frame_slot) {
   if (!st || !image_u8 || !robot_pose || !cam || cam->height <= 0 || cam->fx == 0 || cam->fy == 0) return NIS_ERR_INVALID_ARGUMENT;
+  // a NaN / infinite / absurdly distant pose would make the integer ground positions undefined behaviour and the scatter box enormous
+  for (int i = 0; i < 3; ++i)
+    if (!isfinite(robot_pose[i]) || fabs(robot_pose[i]) > 1e8) return NIS_ERR_INVALID_ARGUMENT;
   SCU(cudaSetDevice(st->device));
   const size_t npx = (size_t)st->H * st->W;
   const int slot = st->frames;
@@ -202,11 +205,12 @@ int nis_stitcher_insert(nis_stitcher* st, const uint8_t* image_u8, const double 
   }
   SCU(cudaMemcpyAsync(st->staging, image_u8, npx, cudaMemcpyHostToDevice, st->stream));
   stitch_normalize_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st->stream>>>(st->staging, const_cast<uint8_t*>(frame_ptr(st, slot)), (int)npx);
-  st->frames = slot + 1;
+  // the frame only counts once it has been merged: a failure below (e.g. no memory for the scatter box) leaves the stitcher as it was
   const int rc = add_image(st, slot, robot_pose, cam);
   if (rc != NIS_OK) return rc;
   SCU(commit(st));
   SCU(cudaStreamSynchronize(st->stream));          // the caller's image buffer is free again, like the reference's synchronous call
+  st->frames = slot + 1;
   if (frame_slot) *frame_slot = slot;
   return NIS_OK;
 }

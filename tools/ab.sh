@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for spec in "$@"; do
   name=${spec%%=*}; envs=${spec#*=}; [ "$envs" = "-" ] && envs=""
-  env $(echo $envs | tr ',' ' ') python bench.py --db 0 --cpu-frames 0 --steps 6 --warmup 3 > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  env $(echo $envs | tr ',' ' ') python bench.py --db 0 --cpu-frames 0 --no-cfg4 --no-extras --steps 6 --warmup 3 > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
   python - "$name" <<PY
 import json,sys
 n=sys.argv[1]

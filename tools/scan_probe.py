@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import ni_slam_b200 as nis, bench_synth as bs
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+nq = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 dev = torch.device("cuda:0")
 cf = nis.CorrelationFlow(nis.CFConfig(), 480, 640, device=0)
 lc = nis.LoopClosure(nis.LoopClosureConfig(position_response_thr=60, angle_response_thr=60), cf)
@@ -16,7 +17,7 @@ for c0 in range(0, n, 2048):
     del imgs
 j = n // 2 + 3
 q = bs.crops(canvas, [gcx[j] + 13], [gcy[j] - 7], [gang[j] + 4.5])[0].cpu().numpy()
-for i in range(12):
+for i in range(nq):
     t0 = time.perf_counter()
     qf = cf.ComputeIntermedium(q)
     t1 = time.perf_counter()
