@@ -36,14 +36,23 @@ BYTES_PER_CANDIDATE = (H // 2 + 1) * W * 8 + (D // 2 + 1) * CP * 8              
 METRIC = "pose_solves_per_sec_640x480"
 
 
+NCU_FAMILY = {"colcol": ("colcol_kernel",), "rowrow_filter": ("rowrow_kernel", "MidFilterH"), "rowrow_storeabs": ("rowrow_kernel", "MidStoreAbs"),
+              "rowrow_mulconj": ("rowrow_kernel", "MidMulConjZ"), "row_inv_mulconj": ("row_kernel", "ProMulConj"), "row_fwd_h": ("row_kernel", "EpiHStore"),
+              "row_fwd": ("row_kernel", "ProSpec, EpiSpecStore"), "col_fwd_rotate": ("col_fwd_kernel", "ProRotate"), "col_fwd_u8": ("col_fwd_kernel", "ProRealU8"),
+              "col_fwd_f32": ("col_fwd_kernel", "ProRealF32"), "col_inv_peak": ("col_inv_kernel", "EpiPeak"),
+              "col_inv_store_shift": ("col_inv_kernel", "EpiStoreShift"), "polar_tma": ("polar_tma_kernel",), "rzc_fix": ("rzc_fix_kernel",)}
+NCU_SUMMARY = "ncu_r02_summary.json"
+
+
 def ncu_traffic(kernel_family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed ncu --set full
-    capture (profiles/ncu_r01_summary.json; cold-cache replay, 28 images per launch).  None if no capture is committed."""
+    capture of the same command (profiles/ncu_r02_summary.json: cold-cache replay, 56 images per launch = the default batch; mean over
+    the family's instantiations, e.g. the 480- and the 720-point colcol).  None if no capture is committed."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_r01_summary.json")) as f:
-            cap = json.load(f)["full_capture"]
-        vals = [v["dram_bytes_per_launch"] for k, v in cap.items() if kernel_family.split("_")[0] in k and
-                (kernel_family in k.replace("_kernel", "") or kernel_family.startswith(k.split("_kernel")[0]))]
+        with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as f:
+            cap = json.load(f)["tracking"]["full_capture"]
+        pat = NCU_FAMILY[kernel_family]
+        vals = [(v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for k, v in cap.items() if all(p in k for p in pat)]
         return float(np.mean(vals)) if vals else None
     except Exception:
         return None
@@ -522,12 +531,19 @@ def main():
         peak, peak_src = measured_peak()
         achieved = (value / world) * BYTES_PER_SOLVE / 1e9                  # per GPU
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
-                    "traffic_note": "bytes per launch of the dominant kernel family (ncu --set full, cold cache, captured at 28 images per launch = 1.31 MB per image; "
-                                    "the default batch is now 56, per-image traffic is unchanged); the family "
-                                    "moves its own tile in and out once, the multi-kernel step as a whole moves ~52 MB per solve",
+                    "traffic_note": "DRAM bytes per launch of the dominant kernel family (ncu --set full of this command, cold cache, 56 images per "
+                                    "launch = the default batch, profiles/%s); the same capture sums to 38.6 MB of DRAM traffic and 8.6 M warp "
+                                    "instructions per solve over the whole multi-kernel step" % NCU_SUMMARY,
                     "definition": "per-GPU solves/s x %d algorithmic B/solve (SURVEY 8d) over the whole multi-kernel step" % BYTES_PER_SOLVE,
                     "peak_source": peak_src, "dominant_kernel": dom, "dominant_kernel_share": kernels[dom]["share"],
                     "dominant_kernel_avg_launch_ms": kernels[dom]["ms"] / max(kernels[dom]["launches"], 1), "kernels": kernels}
+        if dom == "colcol":     # the fused column kernel reads and writes one half spectrum per image: its own compulsory bytes per launch
+            c_t, c_p = (H // 2 + 1) * W * 8, (D // 2 + 1) * CP * 8
+            per_step = n * 4 * (c_t + c_p)                                   # per frame 2 launches per size (Kzz and Kxz), each in + out
+            gbs = per_step / (kernels[dom]["ms"] * 1e-3) / 1e9
+            roofline["dominant_kernel_hbm"] = {"what": "colcol: one half spectrum in + out per image and launch (%d B translation size, %d B polar size), "
+                                                       "all launches of one step over their summed "
+                                                       "live device time" % (2 * c_t, 2 * c_p), "achieved": gbs, "unit": "GB/s", "frac": gbs / peak}
 
         # ---- next-row measurement: the same stream entering as RAW camera frames through the undistort front end
         front = None

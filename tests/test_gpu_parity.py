@@ -716,14 +716,14 @@ def test_scan_matches_compiled_reference_goldens(cf, gref, imgs):
 
 
 # ------------------------------------------------------------------ the scan at DB scale: every candidate against the oracle
-def _db_fixture(n):
+def _db_fixture(n, h=H, w=W, size=2048):
     import torch
     import bench_synth as bs
-    canvas = bs.make_canvas(2048, seed=11, device="cuda")
-    cx, cy, ang = bs.db_poses(n, seed=12, size=2048, H=H, W=W)
-    db = bs.crops(canvas, cx, cy, ang, H, W).cpu().numpy()
+    canvas = bs.make_canvas(size, seed=11, device="cuda")
+    cx, cy, ang = bs.db_poses(n, seed=12, size=size, H=h, W=w)
+    db = bs.crops(canvas, cx, cy, ang, h, w).cpu().numpy()
     j = n // 3
-    q = bs.crops(canvas, [cx[j] + 13], [cy[j] - 7], [ang[j] + 4.5], H, W).cpu().numpy()[0]
+    q = bs.crops(canvas, [cx[j] + 13], [cy[j] - 7], [ang[j] + 4.5], h, w).cpu().numpy()[0]
     torch.cuda.synchronize()
     return db, q, j
 
@@ -819,6 +819,31 @@ def test_scan_256_keyframes_every_candidate_vs_oracle(cfg, monkeypatch):
             lcg = nis.LoopClosure(nis.LoopClosureConfig(30, 60, frame_gap_thr=250, distance_thr=0.0), c)
             r4 = lcg.FindLoopClosure(q, 1000, 1e6)                               # |1000 - id| < 250 dropped: ids 1250..1255 remain
             assert r4.evaluated == 6 and 250 <= r4.loop_slot <= 255
+        c.close()
+
+
+def test_scan_1280x960_vs_oracle():
+    """BASELINE configs[4] image size through the loop-mode scan (960-/1200-point column plans, 1280-point row plan): 8 keyframes x 2
+    hypotheses, every candidate against the C oracle, full and image-only store modes (same bits)."""
+    import ni_slam_b200 as nis
+    h, w = 960, 1280
+    db, q_u8, j = _db_fixture(8, h, w, size=4096)
+    cfg4 = oc.make_cfg(height=h, width=w)
+    orc = _oracle_records(cfg4, db, q_u8, workers=8)
+    assert int(np.argmax([i.sum() for i, _, _ in orc])) == j
+    prev = None
+    for mode in (nis.DB_FULL, nis.DB_IMAGE):
+        c = nis.CorrelationFlow(nis.CFConfig(), h, w)
+        c.set_batch(3)                                               # three batches, ragged tail
+        lc = nis.LoopClosure(nis.LoopClosureConfig(30, 60), c)
+        lc.SetMode(mode)
+        lc.AddImages(db, list(range(8)))
+        res, recs = lc.FindLoopClosureRecords(c.ComputeIntermedium(q_u8), 99, 1e6)
+        assert res.evaluated == 8 and res.loop_slot == j and res.found
+        _compare_records(recs, orc)
+        if prev is not None:
+            assert np.array_equal(recs["response"], prev["response"]) and np.array_equal(recs["relative_pose"], prev["relative_pose"])
+        prev = recs.copy()
         c.close()
 
 
