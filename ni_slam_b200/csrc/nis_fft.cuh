@@ -500,87 +500,92 @@ NIS_HD void col_inv_fn_fwd_stage_c(int tid, cpx* smem, Fn& fn) {
 }
 
 // =========================================================================================================
-// ROW PASS: contiguous complex lines of length N = 16*R1*R2, L lines per CTA, lanes <-> butterfly index.
-// smem: cpx[L][N + N/16] (one pad slot per 16).
+// ROW PASS: contiguous complex lines of length N = R0*R1*R2 (Stockham, decimation in time), L lines per CTA, lanes <-> butterfly index.
+// smem: cpx[L][N + N/R0] (one pad slot per R0, so that the R0 contiguous outputs of neighbouring stage-0 butterflies start R0+1
+// slots apart; R0+1 must be odd or the plan pays bank conflicts).
+// Global-memory alignment: stage 0 reads runs of M0 = N/R0 consecutive elements and the last stage writes runs of N/R2; a warp's
+// request covers whole 128-byte lines exactly when both are multiples of 16 elements.  The production plans (R0 = 16: runs of
+// 40 / 30) do not, on purpose -- see nis_sizes.h for the measurement.
 // =========================================================================================================
 template <int R1, int ROUNDS> struct CarryRegs { cpx v[ROUNDS][R1]; };
 
-template <int N, int R1, int R2, int L, int T> struct RowGeom {
-  static_assert(16 * R1 * R2 == N, "bad factorisation");
-  static constexpr int R0 = 16;
-  static constexpr int M0 = N / 16, M1 = N / R1, M2 = N / R2;
-  static constexpr int NS1 = 16, NS2 = 16 * R1;
-  static constexpr int PITCH = N + N / 16;
+template <int N, int R0, int R1, int R2, int L, int T> struct RowGeom {
+  static_assert(R0 * R1 * R2 == N, "bad factorisation");
+  static constexpr int M0 = N / R0, M1 = N / R1, M2 = N / R2;
+  static constexpr int NS1 = R0, NS2 = R0 * R1;
+  static constexpr int PITCH = N + N / R0;
   static constexpr int ROUNDS1 = (L * M1 + T - 1) / T;
   static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)L * PITCH;
-  static_assert(M1 % 16 == 0 && NS2 % 16 == 0, "stage strides must be multiples of the pad period");
-  static NIS_HD int pad(int i) { return i + (i >> 4); }
+  static_assert(M1 % R0 == 0 && NS2 % R0 == 0, "stage strides must be multiples of the pad period");
+  static NIS_HD int pad(int i) { return i + i / R0; }
 };
 
 // Pro::line(ln).load(c) -> cpx for local line index ln in [0,L) (caller guards valid lines); c in [0,N)
-template <int N, int R1, int R2, int L, int T, bool INV, class Pro>
+template <int N, int R0, int R1, int R2, int L, int T, bool INV, class Pro>
 NIS_HD void row_phase0(int tid, cpx* smem, const Pro& pro, int nlines) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
   for (int w = tid; w < L * Gm::M0; w += T) {
     const int ln = w / Gm::M0, j = w % Gm::M0;
     if (ln >= nlines) break;
-    cpx v[16];
+    cpx v[R0];
     const auto lc = pro.line(ln);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = lc.load(j + r * Gm::M0);
-    Dft<16, INV>::run(v);
-    cpx* s = smem + ln * Gm::PITCH + j * 17;     // pad(16 j + r) = 17 j + r
+    for (int r = 0; r < R0; ++r) v[r] = lc.load(j + r * Gm::M0);
+    Dft<R0, INV>::run(v);
+    cpx* s = smem + ln * Gm::PITCH + j * (R0 + 1);     // pad(R0 j + r) = (R0 + 1) j + r
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[r] = v[r];
+    for (int r = 0; r < R0; ++r) s[r] = v[r];
   }
 }
 
-template <int N, int R1, int R2, int L, int T, bool INV>
-NIS_HD void row_stage1_read(int tid, const cpx* smem, const Twiddles& twd, int nlines, CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1>& st) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
-  static_assert(T % 16 == 0, "the stage-1 twiddle index j & 15 must not depend on the round");
-  // k = j & 15 with j = (tid + it*T) % M1; T and M1 are multiples of 16, so k = tid & 15 in every round: the R1-1 twiddles are
-  // loaded once per thread instead of once per round (they were two thirds of this kernel's global loads)
+template <int N, int R0, int R1, int R2, int L, int T, bool INV>
+NIS_HD void row_stage1_read(int tid, const cpx* smem, const Twiddles& twd, int nlines, CarryRegs<R1, RowGeom<N, R0, R1, R2, L, T>::ROUNDS1>& st) {
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
+  // k = j % R0 with j = (tid + it*T) % M1; M1 is a multiple of R0, so when T is one too k = tid % R0 in every round: the R1-1
+  // twiddles are loaded once per thread instead of once per round (they were two thirds of this kernel's global loads)
+  constexpr bool kHoist = (T % R0 == 0);
   cpx twv[R1 > 1 ? R1 - 1 : 1];
+  if (kHoist) {
 #pragma unroll
-  for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * 16 + (tid & 15)]);
+    for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * R0 + tid % R0]);
+  }
 #pragma unroll
   for (int it = 0; it < Gm::ROUNDS1; ++it) {
     const int w = tid + it * T;
     const int ln = w / Gm::M1, j = w % Gm::M1;
     if (w < L * Gm::M1 && ln < nlines) {
-      // M1 is a multiple of 16, so pad(j + r*M1) = pad(j) + r*(M1 + M1/16): one padded base, constant offsets
+      // M1 is a multiple of R0, so pad(j + r*M1) = pad(j) + r*(M1 + M1/R0): one padded base, constant offsets
       const cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
-        cpx x = s[r * (Gm::M1 + Gm::M1 / 16)];
-        if (r > 0) x = ctw<INV>(x, twv[r - 1]);
+        cpx x = s[r * (Gm::M1 + Gm::M1 / R0)];
+        if (r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * R0 + j % R0]));
         st.v[it][r] = x;
       }
       Dft<R1, INV>::run(st.v[it]);
     }
   }
 }
-template <int N, int R1, int R2, int L, int T, bool INV>
-NIS_HD void row_stage1_write(int tid, cpx* smem, int nlines, const CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1>& st) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
+template <int N, int R0, int R1, int R2, int L, int T, bool INV>
+NIS_HD void row_stage1_write(int tid, cpx* smem, int nlines, const CarryRegs<R1, RowGeom<N, R0, R1, R2, L, T>::ROUNDS1>& st) {
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
 #pragma unroll
   for (int it = 0; it < Gm::ROUNDS1; ++it) {
     const int w = tid + it * T;
     const int ln = w / Gm::M1, j = w % Gm::M1;
     if (w < L * Gm::M1 && ln < nlines) {
-      const int k = j & 15, j0 = (j >> 4) * 16 * R1 + k;
-      cpx* s = smem + ln * Gm::PITCH + Gm::pad(j0);      // pad(j0 + 16 r) = pad(j0) + 17 r
+      const int k = j % R0, j0 = (j / R0) * R0 * R1 + k;
+      cpx* s = smem + ln * Gm::PITCH + Gm::pad(j0);      // pad(j0 + R0 r) = pad(j0) + (R0 + 1) r
 #pragma unroll
-      for (int r = 0; r < R1; ++r) s[r * 17] = st.v[it][r];
+      for (int r = 0; r < R1; ++r) s[r * (R0 + 1)] = st.v[it][r];
     }
   }
 }
 
 // Epi::line(ln).put(c, value)
-template <int N, int R1, int R2, int L, int T, bool INV, class Epi>
+template <int N, int R0, int R1, int R2, int L, int T, bool INV, class Epi>
 NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines, Epi& epi) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
   constexpr int NS2 = Gm::NS2;
   // when T is a multiple of NS2 the butterfly index j = w % NS2 is the same in every round: hoist the R2-1 twiddles
   constexpr bool kHoist = (T % NS2 == 0);
@@ -592,11 +597,11 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
   for (int w = tid; w < L * NS2; w += T) {
     const int ln = w / NS2, j = w % NS2;
     if (ln >= nlines) break;
-    const cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);    // NS2 is a multiple of 16: pad(j + r*NS2) = pad(j) + r*(NS2 + NS2/16)
+    const cpx* s = smem + ln * Gm::PITCH + Gm::pad(j);    // NS2 is a multiple of R0: pad(j + r*NS2) = pad(j) + r*(NS2 + NS2/R0)
     cpx v[R2];
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
-      cpx x = s[r * (NS2 + NS2 / 16)];
+      cpx x = s[r * (NS2 + NS2 / R0)];
       if (r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
@@ -609,9 +614,9 @@ NIS_HD void row_phase2(int tid, const cpx* smem, const Twiddles& twd, int nlines
 
 // forward phase 2 kept in shared memory with an element-wise step (fused forward -> element-wise -> inverse):
 // Mid::line(ln).apply(c, value) -> value; every thread overwrites exactly the padded slots it read.
-template <int N, int R1, int R2, int L, int T, class Mid>
+template <int N, int R0, int R1, int R2, int L, int T, class Mid>
 NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, Mid& mid) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
   constexpr int NS2 = Gm::NS2;
   constexpr bool kHoist = (T % NS2 == 0);                  // see row_phase2
   cpx twv[R2 > 1 ? R2 - 1 : 1];
@@ -626,22 +631,22 @@ NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, 
     cpx v[R2];
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
-      cpx x = s[r * (NS2 + NS2 / 16)];
+      cpx x = s[r * (NS2 + NS2 / R0)];
       if (r > 0) x = cmul(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw2[(r - 1) * NS2 + j]));
       v[r] = x;
     }
     Dft<R2, false>::run(v);
     auto lc = mid.line(ln);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) s[r * (NS2 + NS2 / 16)] = lc.apply(j + r * NS2, v[r]);
+    for (int r = 0; r < R2; ++r) s[r * (NS2 + NS2 / R0)] = lc.apply(j + r * NS2, v[r]);
     lc.flush();
   }
 }
 
 // prologue reading a natural-order padded line out of shared memory (input of the fused inverse pass)
-template <int PITCH> struct SmemLinePro {
+template <int PITCH, int R0> struct SmemLinePro {
   const cpx* base;
-  struct Line { const cpx* p; NIS_HD cpx load(int c) const { return p[c + (c >> 4)]; } };
+  struct Line { const cpx* p; NIS_HD cpx load(int c) const { return p[c + c / R0]; } };
   NIS_HD Line line(int ln) const { return Line{base + ln * PITCH}; }
 };
 

@@ -10,7 +10,7 @@
 
 namespace nis {
 
-template <int N, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
+template <int N, int R0, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
 __global__ void __launch_bounds__(T, (T <= 256 ? NIS_ROW_THREADS_PER_SM / T : 1)) row_kernel(Pro pro, Epi epi, Twiddles twd, int nrows, int total_lines) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
@@ -19,21 +19,21 @@ __global__ void __launch_bounds__(T, (T <= 256 ? NIS_ROW_THREADS_PER_SM / T : 1)
   const LineMap m{line0, nrows, N};
   const auto bp = pro.bind(m);
   auto be = epi.bind(m);
-  row_phase0<N, R1, R2, L, T, INV>(tid, smem, bp, nl);
+  row_phase0<N, R0, R1, R2, L, T, INV>(tid, smem, bp, nl);
   __syncthreads();
-  CarryRegs<R1, RowGeom<N, R1, R2, L, T>::ROUNDS1> st;
-  row_stage1_read<N, R1, R2, L, T, INV>(tid, smem, twd, nl, st);
+  CarryRegs<R1, RowGeom<N, R0, R1, R2, L, T>::ROUNDS1> st;
+  row_stage1_read<N, R0, R1, R2, L, T, INV>(tid, smem, twd, nl, st);
   __syncthreads();
-  row_stage1_write<N, R1, R2, L, T, INV>(tid, smem, nl, st);
+  row_stage1_write<N, R0, R1, R2, L, T, INV>(tid, smem, nl, st);
   __syncthreads();
-  row_phase2<N, R1, R2, L, T, INV>(tid, smem, twd, nl, be);
+  row_phase2<N, R0, R1, R2, L, T, INV>(tid, smem, twd, nl, be);
 }
 
 // fused forward row pass -> element-wise -> inverse row pass: K^xz, X = FFT(rotated image) and the filtered spectrum G
 // exist only in registers / shared memory.  Two padded line buffers (the inverse stage 0 cannot run in place).
-template <int N, int R1, int R2, int L, int T, class Mid>
+template <int N, int R0, int R1, int R2, int L, int T, class Mid>
 __global__ void __launch_bounds__(T, (T <= 256 ? NIS_ROW_THREADS_PER_SM / T : 1)) rowrow_kernel(Src<cpx> in, Dst<cpx> out, Mid mid, Twiddles twd, int nrows, int total_lines) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* bufA = reinterpret_cast<cpx*>(smem_raw);
   cpx* bufB = bufA + L * Gm::PITCH;
@@ -44,40 +44,40 @@ __global__ void __launch_bounds__(T, (T <= 256 ? NIS_ROW_THREADS_PER_SM / T : 1)
   if (tid < L) line_acc[tid] = 0.f;
   {
     const auto bp = ProSpec{in}.bind(m);
-    row_phase0<N, R1, R2, L, T, false>(tid, bufA, bp, nl);
+    row_phase0<N, R0, R1, R2, L, T, false>(tid, bufA, bp, nl);
   }
   __syncthreads();
   {
     CarryRegs<R1, Gm::ROUNDS1> st;
-    row_stage1_read<N, R1, R2, L, T, false>(tid, bufA, twd, nl, st);
+    row_stage1_read<N, R0, R1, R2, L, T, false>(tid, bufA, twd, nl, st);
     __syncthreads();
-    row_stage1_write<N, R1, R2, L, T, false>(tid, bufA, nl, st);
+    row_stage1_write<N, R0, R1, R2, L, T, false>(tid, bufA, nl, st);
   }
   __syncthreads();
   auto bm = mid.bind(m, line_acc);
-  row_phase2_mid<N, R1, R2, L, T>(tid, bufA, twd, nl, bm);
+  row_phase2_mid<N, R0, R1, R2, L, T>(tid, bufA, twd, nl, bm);
   __syncthreads();
   {
-    const SmemLinePro<Gm::PITCH> sp{bufA};
-    row_phase0<N, R1, R2, L, T, true>(tid, bufB, sp, nl);
+    const SmemLinePro<Gm::PITCH, R0> sp{bufA};
+    row_phase0<N, R0, R1, R2, L, T, true>(tid, bufB, sp, nl);
   }
   __syncthreads();
   {
     CarryRegs<R1, Gm::ROUNDS1> st;
-    row_stage1_read<N, R1, R2, L, T, true>(tid, bufB, twd, nl, st);
+    row_stage1_read<N, R0, R1, R2, L, T, true>(tid, bufB, twd, nl, st);
     __syncthreads();
-    row_stage1_write<N, R1, R2, L, T, true>(tid, bufB, nl, st);
+    row_stage1_write<N, R0, R1, R2, L, T, true>(tid, bufB, nl, st);
   }
   __syncthreads();
   auto be = EpiSpecStore{out}.bind(m);
-  row_phase2<N, R1, R2, L, T, true>(tid, bufB, twd, nl, be);
+  row_phase2<N, R0, R1, R2, L, T, true>(tid, bufB, twd, nl, be);
   if (tid < nl) bm.finish_line(tid);
 }
 
-template <int N, int R1, int R2, int L, int T, class Mid>
+template <int N, int R0, int R1, int R2, int L, int T, class Mid>
 static int run_rowrow(Twiddles tw, Src<cpx> in, Dst<cpx> out, Mid mid, int nrows, int B, cudaStream_t s) {
-  auto k = rowrow_kernel<N, R1, R2, L, T, Mid>;
-  const size_t smem = 2 * RowGeom<N, R1, R2, L, T>::kSmemBytes;
+  auto k = rowrow_kernel<N, R0, R1, R2, L, T, Mid>;
+  const size_t smem = 2 * RowGeom<N, R0, R1, R2, L, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
   const int total = nrows * B;
@@ -89,10 +89,10 @@ static int run_rowrow(Twiddles tw, Src<cpx> in, Dst<cpx> out, Mid mid, int nrows
 // was built and measured in round 2: 60.5k solves/s against 68.6k with the kernels above (profiles/ab_r02.md) -- 8 resident CTAs per
 // SM already hide the load latency and the staging buffers cost two of them.  It lives in the history (commit 53c9120), not here.
 
-template <int N, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
+template <int N, int R0, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
 static int run_row(Twiddles tw, Pro pro, Epi epi, int nrows, int B, cudaStream_t s) {
-  auto k = row_kernel<N, R1, R2, L, T, INV, Pro, Epi>;
-  const size_t smem = RowGeom<N, R1, R2, L, T>::kSmemBytes;
+  auto k = row_kernel<N, R0, R1, R2, L, T, INV, Pro, Epi>;
+  const size_t smem = RowGeom<N, R0, R1, R2, L, T>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
   const int total = nrows * B;
@@ -101,13 +101,13 @@ static int run_row(Twiddles tw, Pro pro, Epi epi, int nrows, int B, cudaStream_t
 }
 
 bool row_size_supported(int N) {
-#define X(n, r1, r2, l, t, lr) if (N == n) return true;
+#define X(n, r0, r1, r2, l, t, lr) if (N == n) return true;
   NIS_ROW_PLANS(X)
 #undef X
   return false;
 }
 void plan_radices_row(int N, int r[3]) {
-#define X(n, r1, r2, l, t, lr) if (N == n) { r[0] = 16; r[1] = r1; r[2] = r2; return; }
+#define X(n, r0, r1, r2, l, t, lr) if (N == n) { r[0] = r0; r[1] = r1; r[2] = r2; return; }
   NIS_ROW_PLANS(X)
 #undef X
   r[0] = r[1] = r[2] = 0;
@@ -119,8 +119,8 @@ void plan_radices_row(int N, int r[3]) {
     NIS_ROW_PLANS(ROW_CASE_##INV)        \
     default: return -1;                  \
   }
-#define ROW_CASE_false(n, r1, r2, l, t, lr) case n: return run_row<n, r1, r2, l, t, false>(tw, pro, epi, nrows, B, s);
-#define ROW_CASE_true(n, r1, r2, l, t, lr) case n: return run_row<n, r1, r2, l, t, true>(tw, pro, epi, nrows, B, s);
+#define ROW_CASE_false(n, r0, r1, r2, l, t, lr) case n: return run_row<n, r0, r1, r2, l, t, false>(tw, pro, epi, nrows, B, s);
+#define ROW_CASE_true(n, r0, r1, r2, l, t, lr) case n: return run_row<n, r0, r1, r2, l, t, true>(tw, pro, epi, nrows, B, s);
 int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
 int launch_row_fwd_h(int N, Twiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false) }
 int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(true) }
@@ -131,7 +131,7 @@ int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi,
     NIS_ROW_PLANS(RR_CASE)                \
     default: return -1;                   \
   }
-#define RR_CASE(n, r1, r2, l, t, lr) case n: return run_rowrow<n, r1, r2, lr, t>(tw, in, out, mid, nrows, B, s);
+#define RR_CASE(n, r0, r1, r2, l, t, lr) case n: return run_rowrow<n, r0, r1, r2, lr, t>(tw, in, out, mid, nrows, B, s);
 int launch_rowrow_mulconj(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 int launch_rowrow_filter(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }

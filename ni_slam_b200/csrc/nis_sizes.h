@@ -3,9 +3,10 @@
 //   X(N, A, B, C, T)   N = A*B*C in stage order of the decimation-in-frequency passes (the fused kernel's forward half runs the
 //                      same digits in time order C, B, A); T threads per CTA.  B should be odd (the paired last stage of the
 //                      forward pass then alternates bank halves), C even and a divisor of T/8 (stage-B twiddles hoist).
-// Row pass (transform along image columns: W, rotation_channel), first radix fixed at 16:
-//   X(N, R1, R2, L, T, LR)        N = 16*R1*R2, L lines per CTA, threads; LR = lines per CTA of the fused fwd->mid->inv kernel
-//                                 (two line buffers, so fewer lines keep more CTAs resident)
+// Row pass (transform along image columns: W, rotation_channel):
+//   X(N, R0, R1, R2, L, T, LR)    N = R0*R1*R2 in stage order, L lines per CTA, threads; LR = lines per CTA of the fused
+//                                 fwd->mid->inv kernel (two line buffers, so fewer lines keep more CTAs resident).  N/R0 and N/R2
+//                                 should be multiples of 16 (128-byte aligned global runs), R0 + 1 odd (bank conflicts)
 // Image widths must also be multiples of 16 (one column-pass CTA owns 16 real columns).
 #pragma once
 #include "nis_fft.cuh"
@@ -47,11 +48,25 @@
 #define NIS_ROW480_T NIS_ROW_T
 #define NIS_ROW480_LR NIS_ROW_LR
 #endif
+// radices of the two production row lengths (re-plannable at build time for A/B runs: -DNIS_R640_0=8 -DNIS_R640_1=10 -DNIS_R640_2=8).
+// Radix 16 FIRST is deliberate: its runs of 40 / 30 elements touch 2.0x / 3.4x the 128-byte lines the data occupies, but the plans
+// with line-aligned runs (640 = 8*10*8 or 8*8*10, 480 = 10*8*6 or 6*8*10) measured 59.3 k - 67.0 k solves/s against 68.6 k
+// (profiles/ab_r02.md): sixteen independent loads per thread in flight matter more than L1 wavefronts -- the pass is latency bound.
+#ifndef NIS_R640_0
+#define NIS_R640_0 16
+#define NIS_R640_1 8
+#define NIS_R640_2 5
+#endif
+#ifndef NIS_R480_0
+#define NIS_R480_0 16
+#define NIS_R480_1 6
+#define NIS_R480_2 5
+#endif
 #define NIS_ROW_PLANS(X)      \
-  X(640, 8, 5, NIS_ROW_L, NIS_ROW_T, NIS_ROW_LR)     \
-  X(480, 6, 5, NIS_ROW480_L, NIS_ROW480_T, NIS_ROW480_LR)     \
-  X(1280, 8, 10, 4, 256, 2)   \
-  X(1600, 10, 10, 4, 256, 2)  \
-  X(128, 8, 1, 8, 128, 8)     \
-  X(96, 6, 1, 8, 128, 8)      \
-  X(64, 4, 1, 8, 128, 8)
+  X(640, NIS_R640_0, NIS_R640_1, NIS_R640_2, NIS_ROW_L, NIS_ROW_T, NIS_ROW_LR)     \
+  X(480, NIS_R480_0, NIS_R480_1, NIS_R480_2, NIS_ROW480_L, NIS_ROW480_T, NIS_ROW480_LR)     \
+  X(1280, 16, 8, 10, 4, 256, 2)   \
+  X(1600, 16, 10, 10, 4, 256, 2)  \
+  X(128, 16, 8, 1, 8, 128, 8)     \
+  X(96, 16, 6, 1, 8, 128, 8)      \
+  X(64, 16, 4, 1, 8, 128, 8)

@@ -91,10 +91,10 @@ static void emu_col_inv(const cpx* in, int Bn, int W, Epi& epi) {
 }
 
 // ---- row pass: [nlines][N] complex, forward or inverse, plain load/store
-template <int N, int R1, int R2, int L, int T, bool INV>
+template <int N, int R0, int R1, int R2, int L, int T, bool INV>
 static void emu_row(const cpx* in, int total_lines, cpx* out) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
-  std::vector<cpx> t1, t2; make_tw(16, R1, R2, t1, t2);
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
+  std::vector<cpx> t1, t2; make_tw(R0, R1, R2, t1, t2);
   Twiddles twd{t1.data(), t2.data()};
   std::vector<cpx> smem((size_t)L * Gm::PITCH);
   std::vector<CarryRegs<R1, Gm::ROUNDS1>> st(T);
@@ -105,10 +105,10 @@ static void emu_row(const cpx* in, int total_lines, cpx* out) {
     LineMap m{line0, total_lines, N};
     auto bp = pro.bind(m);
     auto be = epi.bind(m);
-    for (int t = 0; t < T; ++t) row_phase0<N, R1, R2, L, T, INV>(t, smem.data(), bp, nl);
-    for (int t = 0; t < T; ++t) row_stage1_read<N, R1, R2, L, T, INV>(t, smem.data(), twd, nl, st[t]);
-    for (int t = 0; t < T; ++t) row_stage1_write<N, R1, R2, L, T, INV>(t, smem.data(), nl, st[t]);
-    for (int t = 0; t < T; ++t) row_phase2<N, R1, R2, L, T, INV>(t, smem.data(), twd, nl, be);
+    for (int t = 0; t < T; ++t) row_phase0<N, R0, R1, R2, L, T, INV>(t, smem.data(), bp, nl);
+    for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, INV>(t, smem.data(), twd, nl, st[t]);
+    for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, INV>(t, smem.data(), nl, st[t]);
+    for (int t = 0; t < T; ++t) row_phase2<N, R0, R1, R2, L, T, INV>(t, smem.data(), twd, nl, be);
   }
 }
 
@@ -135,10 +135,10 @@ static void emu_colcol(const cpx* in, int Bn, int W, cpx* out, KernelFn kfn) {
 }
 
 // ---- fused: forward row pass -> element-wise -> inverse row pass (rowrow kernel)
-template <int N, int R1, int R2, int L, int T, class Mid>
+template <int N, int R0, int R1, int R2, int L, int T, class Mid>
 static void emu_rowrow(const cpx* in, int nrows, int B, cpx* out, Mid mid) {
-  typedef RowGeom<N, R1, R2, L, T> Gm;
-  std::vector<cpx> t1, t2; make_tw(16, R1, R2, t1, t2);
+  typedef RowGeom<N, R0, R1, R2, L, T> Gm;
+  std::vector<cpx> t1, t2; make_tw(R0, R1, R2, t1, t2);
   Twiddles twd{t1.data(), t2.data()};
   const int total = nrows * B;
   std::vector<cpx> A((size_t)L * Gm::PITCH), Bb((size_t)L * Gm::PITCH);
@@ -152,15 +152,15 @@ static void emu_rowrow(const cpx* in, int nrows, int B, cpx* out, Mid mid) {
     auto bp = pro.bind(m);
     auto be = epi.bind(m);
     auto bm = mid.bind(m, acc);
-    for (int t = 0; t < T; ++t) row_phase0<N, R1, R2, L, T, false>(t, A.data(), bp, nl);
-    for (int t = 0; t < T; ++t) row_stage1_read<N, R1, R2, L, T, false>(t, A.data(), twd, nl, st[t]);
-    for (int t = 0; t < T; ++t) row_stage1_write<N, R1, R2, L, T, false>(t, A.data(), nl, st[t]);
-    for (int t = 0; t < T; ++t) row_phase2_mid<N, R1, R2, L, T>(t, A.data(), twd, nl, bm);
-    SmemLinePro<Gm::PITCH> sp{A.data()};
-    for (int t = 0; t < T; ++t) row_phase0<N, R1, R2, L, T, true>(t, Bb.data(), sp, nl);
-    for (int t = 0; t < T; ++t) row_stage1_read<N, R1, R2, L, T, true>(t, Bb.data(), twd, nl, st[t]);
-    for (int t = 0; t < T; ++t) row_stage1_write<N, R1, R2, L, T, true>(t, Bb.data(), nl, st[t]);
-    for (int t = 0; t < T; ++t) row_phase2<N, R1, R2, L, T, true>(t, Bb.data(), twd, nl, be);
+    for (int t = 0; t < T; ++t) row_phase0<N, R0, R1, R2, L, T, false>(t, A.data(), bp, nl);
+    for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, false>(t, A.data(), twd, nl, st[t]);
+    for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, false>(t, A.data(), nl, st[t]);
+    for (int t = 0; t < T; ++t) row_phase2_mid<N, R0, R1, R2, L, T>(t, A.data(), twd, nl, bm);
+    SmemLinePro<Gm::PITCH, R0> sp{A.data()};
+    for (int t = 0; t < T; ++t) row_phase0<N, R0, R1, R2, L, T, true>(t, Bb.data(), sp, nl);
+    for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, true>(t, Bb.data(), twd, nl, st[t]);
+    for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, true>(t, Bb.data(), nl, st[t]);
+    for (int t = 0; t < T; ++t) row_phase2<N, R0, R1, R2, L, T, true>(t, Bb.data(), twd, nl, be);
     for (int t = 0; t < nl; ++t) bm.finish_line(t);
   }
 }
@@ -181,8 +181,8 @@ int emu_colcol_poly(const float* in, int B, int N, int W, float* out, unsigned i
 // in/out: [B][nrows][N]; z: [B][nrows][N]; out = IFFT_rows(FFT_rows(in) * conj(z)) (unnormalised); xx_sum[B] += sum |FFT_rows(in)|^2
 int emu_rowrow_mulconj(const float* in, const float* z, int B, int nrows, int N, float* out, double* xx_sum) {
   MidMulConjZ mid{Src<cpx>{(const cpx*)z, (long long)nrows * N, nullptr, 0, nullptr, 0}, xx_sum};
-#define X(n, r1, r2, l, t, lr) \
-  if (N == n) { emu_rowrow<n, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+#define X(n, r0, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r0, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
   NIS_ROW_PLANS(X)
 #undef X
   return -1;
@@ -191,8 +191,8 @@ int emu_rowrow_mulconj(const float* in, const float* z, int B, int nrows, int N,
 // out = IFFT_rows(H * FFT_rows(in) / max[b])
 int emu_rowrow_filter(const float* in, const float* h, const unsigned int* maxbuf, int B, int nrows, int N, float* out) {
   MidFilterH mid{Src<cpx>{(const cpx*)h, (long long)nrows * N, nullptr, 0, nullptr, 0}, maxbuf};
-#define X(n, r1, r2, l, t, lr) \
-  if (N == n) { emu_rowrow<n, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+#define X(n, r0, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r0, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
   NIS_ROW_PLANS(X)
 #undef X
   return -1;
@@ -228,10 +228,10 @@ int emu_col_inv_peak(const float* in, int B, int N, int W, void* stats, float* g
 }
 
 int emu_row(const float* in, int total_lines, int N, int inverse, float* out) {
-#define X(n, r1, r2, l, t, lr)                                                          \
+#define X(n, r0, r1, r2, l, t, lr)                                                      \
   if (N == n) {                                                                         \
-    if (inverse) emu_row<n, r1, r2, l, t, true>((const cpx*)in, total_lines, (cpx*)out); \
-    else emu_row<n, r1, r2, l, t, false>((const cpx*)in, total_lines, (cpx*)out);        \
+    if (inverse) emu_row<n, r0, r1, r2, l, t, true>((const cpx*)in, total_lines, (cpx*)out); \
+    else emu_row<n, r0, r1, r2, l, t, false>((const cpx*)in, total_lines, (cpx*)out);        \
     return 0;                                                                           \
   }
   NIS_ROW_PLANS(X)
