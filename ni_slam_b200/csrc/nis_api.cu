@@ -69,7 +69,8 @@ struct nis_frame {
 struct SizeClass {             // one 2-D transform size: R rows (halved) x C cols
   int R, C;
   size_t spec, real;           // elements
-  Twiddles col, row;
+  Twiddles col;
+  RowTwiddles row;             // plan A and plan B tables (b = a when the length has no plan B)
 };
 
 // One lane = one CUDA stream with its own workspace.  Batches are dealt round-robin to the lanes so that several small
@@ -269,12 +270,15 @@ static int build_tables(nis_ctx* ctx) {
   const int H = ctx->H, W = ctx->W, D = ctx->D, Cp = ctx->Cp;
   // twiddles
   std::vector<cpx> tw;
-  size_t o[8];
+  size_t o[8], ob[4];
+  bool has_b[2];
   int r[3];
   for (int s = 0; s < 2; ++s) {
     SizeClass& z = ctx->sz[s];
     plan_radices_col(z.R, r); host_twiddles_col(r, tw, o[4 * s + 0], o[4 * s + 1]);
     plan_radices_row(z.C, r); host_twiddles(r, tw, o[4 * s + 2], o[4 * s + 3]);
+    has_b[s] = plan_radices_row_b(z.C, r);
+    if (has_b[s]) host_twiddles(r, tw, ob[2 * s], ob[2 * s + 1]);
   }
   RESERVE(ctx->tw, tw.size() * sizeof(cpx));
   CU(h2d(ctx, ctx->tw.p, tw.data(), tw.size() * sizeof(cpx)));
@@ -282,7 +286,8 @@ static int build_tables(nis_ctx* ctx) {
   for (int s = 0; s < 2; ++s) {
     SizeClass& z = ctx->sz[s];
     z.col = Twiddles{base + o[4 * s + 0], base + o[4 * s + 1]};
-    z.row = Twiddles{base + o[4 * s + 2], base + o[4 * s + 3]};
+    z.row.a = Twiddles{base + o[4 * s + 2], base + o[4 * s + 3]};
+    z.row.b = has_b[s] ? Twiddles{base + ob[2 * s], base + ob[2 * s + 1]} : z.row.a;
   }
   // u8 -> f32/255 (utils.cc:117: matrix.array()/255.0)
   float lut[256];
@@ -555,7 +560,7 @@ static int build_rot_cache(nis_ctx* ctx, Src<float> img_f32, Src<uint8_t> img_u8
     RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), ctx->rotc_sel.as<int>() + i0, ctx->rowtab.as<int2>()};
     LAUNCH(launch_col_fwd_rotate(zt.R, zt.col, ra, t1, zt.C, nb, L.stream));
     Dst<cpx> out{ctx->rotc.as<cpx>() + (size_t)i0 * zt.spec, (long long)zt.spec};
-    LAUNCH(launch_row_fwd(zt.C, zt.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, zt.R / 2 + 1, nb, L.stream));
+    LAUNCH(launch_row_fwd(zt.C, zt.row, ProSpec{src_slab<cpx>(t1.base, t1.stride)}, EpiSpecStore{out}, zt.R / 2 + 1, nb, L.stream, /*match_fused=*/true));
     if (gauss) LAUNCH(launch_spec_sqsum(src_slab<cpx>(out.base, out.stride), (int)zt.spec, ctx->rotc_xx.as<double>() + i0, nb, L.stream));
   }
   TRY(join_lanes(ctx));
@@ -591,7 +596,7 @@ static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz
   if (loop_mode && ctx->use_rot_cache) {
     // FFT(RotateArray(query, angle)) comes from the per-query cache: one inverse row pass instead of warp + 3 passes
     Src<cpx> Xc{ctx->rotc.as<cpx>() - (size_t)ctx->D * zt.spec, (long long)zt.spec, nullptr, 0, L.sel.as<int>(), 0};
-    LAUNCH(launch_row_inv_mulconj(zt.C, zt.row, ProMulConj{Xc, Fze}, EpiSpecStore{t1}, zt.R / 2 + 1, E, L.stream));
+    LAUNCH(launch_row_inv_mulconj(zt.C, zt.row, ProMulConj{Xc, Fze}, EpiSpecStore{t1}, zt.R / 2 + 1, E, L.stream, /*match_fused=*/true));
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr, ctx->rotc_xx.as<double>() - ctx->D, L.sel.as<int>()));
   } else {
     RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), ctx->rowtab.as<int2>()};

@@ -159,6 +159,31 @@ template <bool INV> struct Dft<16, INV> {
   }
 };
 
+// radix 32 = 2 x 16 with W32 twiddles (first stage of the two-stage row plans: 32 independent loads per thread in flight)
+template <bool INV> struct Dft<32, INV> {
+  static NIS_HD void run(cpx* v) {
+    const float h = 0.70710678118654752440f;
+    const float c1 = 0.98078528040323044913f, s1 = 0.19509032201612826785f;   // cos/sin(pi/16)
+    const float c2 = 0.92387953251128675613f, s2 = 0.38268343236508977173f;   // cos/sin(pi/8)
+    const float c3 = 0.83146961230254523708f, s3 = 0.55557023301960222474f;   // cos/sin(3pi/16)
+    cpx e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Dft<16, INV>::run(e); Dft<16, INV>::run(o);
+    // forward twiddles w32^k = (cos, -sin)(2 pi k / 32), k = 0..15
+    const float wr[16] = {1.f, c1, c2, c3, h, s3, s2, s1, 0.f, -s1, -s2, -s3, -h, -c3, -c2, -c1};
+    const float wi[16] = {0.f, -s1, -s2, -s3, -h, -c3, -c2, -c1, -1.f, -c1, -c2, -c3, -h, -s3, -s2, -s1};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      cpx t;
+      if (k == 0) t = o[0];
+      else if (k == 8) t = mul_mi<INV>(o[8]);
+      else t = ctw<INV>(o[k], make_float2(wr[k], wi[k]));
+      v[k] = cadd(e[k], t); v[k + 16] = csub(e[k], t);
+    }
+  }
+};
+
 // radix 9 = 3 x 3 with W9 twiddles
 template <bool INV> struct Dft<9, INV> {
   static NIS_HD void run(cpx* v) {
@@ -217,6 +242,7 @@ template <bool INV> struct Dft<6, INV> { static NIS_HD void run(cpx* v) { DftPfa
 template <bool INV> struct Dft<10, INV> { static NIS_HD void run(cpx* v) { DftPfa<2, 5, INV>::run(v); } };
 template <bool INV> struct Dft<12, INV> { static NIS_HD void run(cpx* v) { DftPfa<4, 3, INV>::run(v); } };
 template <bool INV> struct Dft<15, INV> { static NIS_HD void run(cpx* v) { DftPfa<3, 5, INV>::run(v); } };
+template <bool INV> struct Dft<20, INV> { static NIS_HD void run(cpx* v) { DftPfa<4, 5, INV>::run(v); } };
 
 // ---------------------------------------------------------------------------------------------------------
 // twiddle tables (built on the host in double, stored f32): for a 3-stage plan (R0,R1,R2), N = R0*R1*R2
@@ -639,6 +665,63 @@ NIS_HD void row_phase2_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, 
     auto lc = mid.line(ln);
 #pragma unroll
     for (int r = 0; r < R2; ++r) s[r * (NS2 + NS2 / R0)] = lc.apply(j + r * NS2, v[r]);
+    lc.flush();
+  }
+}
+
+// ---- two-stage plans (R2 == 1, N = R0*R1): ONE shared-memory exchange and ONE barrier per pass.  Stage-1 butterfly j in [0,R0) of
+// a line reads the padded slots pad(j) + r (R0+1) (= stage-0 outputs k0 = j of the sub-sequences r) and yields the natural indices
+// j + R0 r, which go straight to the epilogue (or, in the fused kernel, back into the slots they were read from).
+template <int N, int R0, int R1, int L, int T, bool INV, class Epi>
+NIS_HD void row_stage1_out(int tid, const cpx* smem, const Twiddles& twd, int nlines, Epi& epi) {
+  typedef RowGeom<N, R0, R1, 1, L, T> Gm;
+  constexpr bool kHoist = (T % R0 == 0);
+  cpx twv[R1 > 1 ? R1 - 1 : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * R0 + tid % R0]);
+  }
+  for (int w = tid; w < L * R0; w += T) {
+    const int ln = w / R0, j = w % R0;
+    if (ln >= nlines) break;
+    const cpx* s = smem + ln * Gm::PITCH + j;              // pad(j) = j for j < R0
+    cpx v[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      cpx x = s[r * (R0 + 1)];
+      if (r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * R0 + j]));
+      v[r] = x;
+    }
+    Dft<R1, INV>::run(v);
+    const auto lc = epi.line(ln);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) lc.put(j + R0 * r, v[r]);
+  }
+}
+template <int N, int R0, int R1, int L, int T, class Mid>
+NIS_HD void row_stage1_mid(int tid, cpx* smem, const Twiddles& twd, int nlines, Mid& mid) {
+  typedef RowGeom<N, R0, R1, 1, L, T> Gm;
+  constexpr bool kHoist = (T % R0 == 0);
+  cpx twv[R1 > 1 ? R1 - 1 : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int r = 1; r < R1; ++r) twv[r - 1] = NIS_LDG(&twd.tw1[(r - 1) * R0 + tid % R0]);
+  }
+  for (int w = tid; w < L * R0; w += T) {
+    const int ln = w / R0, j = w % R0;
+    if (ln >= nlines) break;
+    cpx* s = smem + ln * Gm::PITCH + j;
+    cpx v[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      cpx x = s[r * (R0 + 1)];
+      if (r > 0) x = cmul(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * R0 + j]));
+      v[r] = x;
+    }
+    Dft<R1, false>::run(v);
+    auto lc = mid.line(ln);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) s[r * (R0 + 1)] = lc.apply(j + R0 * r, v[r]);      // natural index j + R0 r sits at pad(j + R0 r) = j + (R0+1) r
     lc.flush();
   }
 }

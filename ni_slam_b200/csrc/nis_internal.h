@@ -26,6 +26,9 @@ bool col_size_supported(int N);
 bool row_size_supported(int N);
 void plan_radices_col(int N, int r[3]);
 void plan_radices_row(int N, int r[3]);
+bool plan_radices_row_b(int N, int r[3]);     // the size's two-stage plan B, if it has one (nis_sizes.h)
+// twiddle tables of both row plans of one size; every row launcher picks the plan its kernel family measured faster with
+struct RowTwiddles { Twiddles a, b; };
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
 // rowtab[slot][y] = (X0, Y0) of cv::warpAffine's fixed-point walk for output row y under rotation-matrix slot `slot` (host-built beside mats)
@@ -37,13 +40,13 @@ int launch_col_inv_store(int N, Twiddles tw, Src<cpx> in, EpiStore epi, int W, i
 int launch_col_inv_peak(int N, Twiddles tw, Src<cpx> in, EpiPeak epi, int W, int B, cudaStream_t s);
 // c2r -> kernel function -> r2c in one kernel (the real kernel image never leaves shared memory); in-place allowed
 int launch_colcol(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W, int B, cudaStream_t s);
-int launch_row_fwd(int N, Twiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
-int launch_row_fwd_h(int N, Twiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s);
-int launch_row_inv_mulconj(int N, Twiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s);
+int launch_row_fwd(int N, RowTwiddles tw, ProSpec pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s, bool match_fused = false);
+int launch_row_fwd_h(int N, RowTwiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s);
+int launch_row_inv_mulconj(int N, RowTwiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s, bool match_fused = false);
 // forward -> element-wise -> inverse in one kernel; in-place allowed (a CTA reads and writes only its own lines)
-int launch_rowrow_mulconj(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s);
-int launch_rowrow_filter(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s);
-int launch_rowrow_storeabs(int N, Twiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s);
+int launch_rowrow_mulconj(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s);
+int launch_rowrow_filter(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s);
+int launch_rowrow_storeabs(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s);
 
 // ---- warps and bookkeeping kernels -----------------------------------------------------------------------
 // tiled polar gather (nis_misc.cu): one CTA per cell of kPolarTA angles x kPolarTR radii, source box staged in shared memory by TMA

@@ -48,10 +48,11 @@
 #define NIS_ROW480_T NIS_ROW_T
 #define NIS_ROW480_LR NIS_ROW_LR
 #endif
-// radices of the two production row lengths (re-plannable at build time for A/B runs: -DNIS_R640_0=8 -DNIS_R640_1=10 -DNIS_R640_2=8).
-// Radix 16 FIRST is deliberate: its runs of 40 / 30 elements touch 2.0x / 3.4x the 128-byte lines the data occupies, but the plans
-// with line-aligned runs (640 = 8*10*8 or 8*8*10, 480 = 10*8*6 or 6*8*10) measured 59.3 k - 67.0 k solves/s against 68.6 k
-// (profiles/ab_r02.md): sixteen independent loads per thread in flight matter more than L1 wavefronts -- the pass is latency bound.
+// Plan A of the two production row lengths: three stages, radix 16 first (re-plannable at build time for A/B runs:
+// -DNIS_R640_0=8 -DNIS_R640_1=10 -DNIS_R640_2=8).  Radix 16 FIRST is deliberate: its runs of 40 / 30 elements touch 2.0x / 3.4x
+// the 128-byte lines the data occupies, but the plans with line-aligned runs (640 = 8*10*8 or 8*8*10, 480 = 10*8*6 or 6*8*10)
+// measured 59.3 k - 67.0 k solves/s against 68.6 k (profiles/ab_r02.md): sixteen independent loads per thread in flight matter
+// more than L1 wavefronts -- the pass is latency bound.
 #ifndef NIS_R640_0
 #define NIS_R640_0 16
 #define NIS_R640_1 8
@@ -70,3 +71,29 @@
   X(128, 16, 8, 1, 8, 128, 8)     \
   X(96, 16, 6, 1, 8, 128, 8)      \
   X(64, 16, 4, 1, 8, 128, 8)
+
+// Plan B: TWO stages (radix 32, then 20 / 15): one shared-memory exchange and one barrier per pass, 32 loads per thread in flight,
+// 80-96 registers.  Measured per kernel family against plan A (ms per 1000 frames, profiles/ab_r02.md): fused fwd->mid->inv kernels
+// 2.17 -> 1.72 (filter), 1.07 -> 0.80 (store-abs), 0.92 -> 0.84 (mul-conj); row_fwd_h 1.21 -> 1.10; row_fwd 0.60 -> 0.59; but the
+// inverse pass with the two-operand product prologue 2.02 -> 2.34 (64 loads per thread, 96 registers).  So each launcher picks its
+// plan (NIS_ROWB_* below); sizes without a plan B entry use plan A everywhere.
+#ifndef NIS_ROWB_L
+#define NIS_ROWB_L 3            // 3 lines x 96 threads: stage 1 (32 butterflies per line) fills the CTA exactly
+#define NIS_ROWB_T 96
+#define NIS_ROWB_LR 3
+#endif
+#define NIS_ROW_PLANS_B(X)    \
+  X(640, 32, 20, 1, NIS_ROWB_L, NIS_ROWB_T, NIS_ROWB_LR)   \
+  X(480, 32, 15, 1, NIS_ROWB_L, NIS_ROWB_T, NIS_ROWB_LR)
+#ifndef NIS_ROWB_FWD
+#define NIS_ROWB_FWD 1          // row_fwd (P)
+#endif
+#ifndef NIS_ROWB_FWDH
+#define NIS_ROWB_FWDH 1         // row_fwd_h (keyframe factor H)
+#endif
+#ifndef NIS_ROWB_INVMC
+#define NIS_ROWB_INVMC 0        // row_inv_mulconj
+#endif
+#ifndef NIS_ROWB_RR
+#define NIS_ROWB_RR 1           // the three fused fwd->mid->inv kernels
+#endif

@@ -106,6 +106,10 @@ static void emu_row(const cpx* in, int total_lines, cpx* out) {
     auto bp = pro.bind(m);
     auto be = epi.bind(m);
     for (int t = 0; t < T; ++t) row_phase0<N, R0, R1, R2, L, T, INV>(t, smem.data(), bp, nl);
+    if constexpr (R2 == 1) {
+      for (int t = 0; t < T; ++t) row_stage1_out<N, R0, R1, L, T, INV>(t, smem.data(), twd, nl, be);
+      continue;
+    }
     for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, INV>(t, smem.data(), twd, nl, st[t]);
     for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, INV>(t, smem.data(), nl, st[t]);
     for (int t = 0; t < T; ++t) row_phase2<N, R0, R1, R2, L, T, INV>(t, smem.data(), twd, nl, be);
@@ -153,14 +157,22 @@ static void emu_rowrow(const cpx* in, int nrows, int B, cpx* out, Mid mid) {
     auto be = epi.bind(m);
     auto bm = mid.bind(m, acc);
     for (int t = 0; t < T; ++t) row_phase0<N, R0, R1, R2, L, T, false>(t, A.data(), bp, nl);
-    for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, false>(t, A.data(), twd, nl, st[t]);
-    for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, false>(t, A.data(), nl, st[t]);
-    for (int t = 0; t < T; ++t) row_phase2_mid<N, R0, R1, R2, L, T>(t, A.data(), twd, nl, bm);
+    if constexpr (R2 == 1) {
+      for (int t = 0; t < T; ++t) row_stage1_mid<N, R0, R1, L, T>(t, A.data(), twd, nl, bm);
+    } else {
+      for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, false>(t, A.data(), twd, nl, st[t]);
+      for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, false>(t, A.data(), nl, st[t]);
+      for (int t = 0; t < T; ++t) row_phase2_mid<N, R0, R1, R2, L, T>(t, A.data(), twd, nl, bm);
+    }
     SmemLinePro<Gm::PITCH, R0> sp{A.data()};
     for (int t = 0; t < T; ++t) row_phase0<N, R0, R1, R2, L, T, true>(t, Bb.data(), sp, nl);
-    for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, true>(t, Bb.data(), twd, nl, st[t]);
-    for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, true>(t, Bb.data(), nl, st[t]);
-    for (int t = 0; t < T; ++t) row_phase2<N, R0, R1, R2, L, T, true>(t, Bb.data(), twd, nl, be);
+    if constexpr (R2 == 1) {
+      for (int t = 0; t < T; ++t) row_stage1_out<N, R0, R1, L, T, true>(t, Bb.data(), twd, nl, be);
+    } else {
+      for (int t = 0; t < T; ++t) row_stage1_read<N, R0, R1, R2, L, T, true>(t, Bb.data(), twd, nl, st[t]);
+      for (int t = 0; t < T; ++t) row_stage1_write<N, R0, R1, R2, L, T, true>(t, Bb.data(), nl, st[t]);
+      for (int t = 0; t < T; ++t) row_phase2<N, R0, R1, R2, L, T, true>(t, Bb.data(), twd, nl, be);
+    }
     for (int t = 0; t < nl; ++t) bm.finish_line(t);
   }
 }
@@ -239,10 +251,39 @@ int emu_row(const float* in, int total_lines, int N, int inverse, float* out) {
   return -1;
 }
 
+// the two-stage plan B of the production row lengths (nis_sizes.h NIS_ROW_PLANS_B)
+int emu_row_b(const float* in, int total_lines, int N, int inverse, float* out) {
+#define X(n, r0, r1, r2, l, t, lr)                                                      \
+  if (N == n) {                                                                         \
+    if (inverse) emu_row<n, r0, r1, r2, l, t, true>((const cpx*)in, total_lines, (cpx*)out); \
+    else emu_row<n, r0, r1, r2, l, t, false>((const cpx*)in, total_lines, (cpx*)out);        \
+    return 0;                                                                           \
+  }
+  NIS_ROW_PLANS_B(X)
+#undef X
+  return -1;
+}
+int emu_rowrow_mulconj_b(const float* in, const float* z, int B, int nrows, int N, float* out, double* xx_sum) {
+  MidMulConjZ mid{Src<cpx>{(const cpx*)z, (long long)nrows * N, nullptr, 0, nullptr, 0}, xx_sum};
+#define X(n, r0, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r0, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+  NIS_ROW_PLANS_B(X)
+#undef X
+  return -1;
+}
+int emu_rowrow_filter_b(const float* in, const float* h, const unsigned int* maxbuf, int B, int nrows, int N, float* out) {
+  MidFilterH mid{Src<cpx>{(const cpx*)h, (long long)nrows * N, nullptr, 0, nullptr, 0}, maxbuf};
+#define X(n, r0, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r0, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+  NIS_ROW_PLANS_B(X)
+#undef X
+  return -1;
+}
+
 // in-register DFT check: v (R complex) -> DFT
 int emu_dft(float* v, int R, int inverse) {
 #define D(r) if (R == r) { if (inverse) Dft<r, true>::run((cpx*)v); else Dft<r, false>::run((cpx*)v); return 0; }
-  D(1) D(2) D(3) D(4) D(5) D(6) D(8) D(9) D(10) D(12) D(15) D(16)
+  D(1) D(2) D(3) D(4) D(5) D(6) D(8) D(9) D(10) D(12) D(15) D(16) D(20) D(32)
 #undef D
   return -1;
 }

@@ -59,7 +59,7 @@ def P(a):
 
 def test_emulated_register_dfts(emu):
     rng = np.random.default_rng(0)
-    for R in (1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16):
+    for R in (1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 20, 32):
         for inv in (0, 1):
             v = (rng.standard_normal(R) + 1j * rng.standard_normal(R)).astype(np.complex64)
             w = v.copy()
@@ -68,14 +68,16 @@ def test_emulated_register_dfts(emu):
             assert np.abs(w - ref).max() / np.abs(ref).max() < 1e-6, (R, inv)
 
 
-@pytest.mark.parametrize("N", [640, 480, 1280, 128, 64])
-def test_emulated_row_pass(emu, N):
+@pytest.mark.parametrize("N,plan", [(640, "a"), (480, "a"), (1280, "a"), (128, "a"), (64, "a"), (640, "b"), (480, "b")])
+def test_emulated_row_pass(emu, N, plan):
+    """plan a = three stages (radix 16 first; 128 / 64 are two-stage with R2 = 1), plan b = the two-stage 32 x 20 / 32 x 15 plans"""
     rng = np.random.default_rng(N)
     nl = 11          # not a multiple of the CTA's line count: exercises the ragged last CTA
     x = (rng.standard_normal((nl, N)) + 1j * rng.standard_normal((nl, N))).astype(np.complex64)
+    fn = emu.emu_row if plan == "a" else emu.emu_row_b
     for inv in (0, 1):
         out = np.zeros_like(x)
-        assert emu.emu_row(P(x), nl, N, inv, P(out)) == 0
+        assert fn(P(x), nl, N, inv, P(out)) == 0
         ref = np.fft.ifft(x.astype(np.complex128), axis=1) * N if inv else np.fft.fft(x.astype(np.complex128), axis=1)
         assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-6
 
@@ -148,23 +150,25 @@ def test_emulated_fused_colcol(emu, N, W):
     assert np.allclose(mx.view(np.float32), np.abs(k).reshape(B, -1).max(axis=1), rtol=1e-5)
 
 
-@pytest.mark.parametrize("N", [640, 480, 128])
-def test_emulated_fused_rowrow(emu, N):
+@pytest.mark.parametrize("N,plan", [(640, "a"), (480, "a"), (128, "a"), (640, "b"), (480, "b")])
+def test_emulated_fused_rowrow(emu, N, plan):
     """forward row pass -> element-wise (x conj z | H x / max) -> inverse row pass"""
+    mulconj = emu.emu_rowrow_mulconj if plan == "a" else emu.emu_rowrow_mulconj_b
+    filt = emu.emu_rowrow_filter if plan == "a" else emu.emu_rowrow_filter_b
     rng = np.random.default_rng(N + 2)
     B, nrows = 2, 7
     x = (rng.standard_normal((B, nrows, N)) + 1j * rng.standard_normal((B, nrows, N))).astype(np.complex64)
     z = (rng.standard_normal((B, nrows, N)) + 1j * rng.standard_normal((B, nrows, N))).astype(np.complex64)
     out = np.zeros_like(x)
     xx = np.zeros(B, np.float64)
-    assert emu.emu_rowrow_mulconj(P(x), P(z), B, nrows, N, P(out), P(xx)) == 0
+    assert mulconj(P(x), P(z), B, nrows, N, P(out), P(xx)) == 0
     X = np.fft.fft(x.astype(np.complex128), axis=2)
     want = np.fft.ifft(X * np.conj(z), axis=2) * N
     assert np.abs(out - want).max() / np.abs(want).max() < 3e-6
     assert np.allclose(xx, (np.abs(X) ** 2).sum(axis=(1, 2)), rtol=1e-5)
     mx = np.array([2.0, 0.5], np.float32).view(np.uint32)
     out2 = np.zeros_like(x)
-    assert emu.emu_rowrow_filter(P(x), P(z), P(mx), B, nrows, N, P(out2)) == 0
+    assert filt(P(x), P(z), P(mx), B, nrows, N, P(out2)) == 0
     want2 = np.fft.ifft(X * z / np.array([2.0, 0.5]).reshape(B, 1, 1), axis=2) * N
     assert np.abs(out2 - want2).max() / np.abs(want2).max() < 3e-6
 
