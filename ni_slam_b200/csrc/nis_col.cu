@@ -16,8 +16,10 @@ template <class Pro> __device__ __forceinline__ auto bind_pro(const Pro& pro, in
   else return pro.bind(b, c0);
 }
 
+// Two-stage plans (B == 1: one paired radix-A stage and one radix-C stage, e.g. 480 = 15 x 32) hold up to 32 complex values per
+// thread and are sized for 480 resident threads (136 registers).
 #ifndef NIS_COL_MINB
-#define NIS_COL_MINB (768 / NIS_COL_T)
+#define NIS_COL_MINB (B == 1 ? (480 / T > 0 ? 480 / T : 1) : 768 / T)
 #endif
 
 template <int N, int A, int B, int C, int T, class Pro>
@@ -35,8 +37,10 @@ __global__ void __launch_bounds__(T, NIS_COL_MINB) col_fwd_kernel(Pro pro, Twidd
   const auto bp = bind_pro(pro, b, c0, lut_s);
   col_fwd_stage_a<N, A, B, C, T>(tid, smem, twd, bp);
   __syncthreads();
-  col_stage_b<N, A, B, C, T, false, false>(tid, smem, twd);
-  __syncthreads();
+  if constexpr (B > 1) {
+    col_stage_b<N, A, B, C, T, false, false>(tid, smem, twd);
+    __syncthreads();
+  }
   col_fwd_stage_c<N, A, B, C, T>(tid, smem, out.at(b), W, c0);
 }
 
@@ -47,8 +51,10 @@ __global__ void __launch_bounds__(T, NIS_COL_MINB) col_inv_kernel(Src<cpx> in, T
   const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
   col_inv_stage_a<N, A, B, C, T>(tid, smem, twd, in.at(b), W, c0);
   __syncthreads();
-  col_stage_b<N, A, B, C, T, true, false>(tid, smem, twd);
-  __syncthreads();
+  if constexpr (B > 1) {
+    col_stage_b<N, A, B, C, T, true, false>(tid, smem, twd);
+    __syncthreads();
+  }
   auto be = epi.bind(b, c0);
   col_inv_stage_c<N, A, B, C, T>(tid, smem, be);
   DeviceSync sync;
@@ -65,13 +71,17 @@ __global__ void __launch_bounds__(T, NIS_COL_MINB) colcol_kernel(Src<cpx> in, Ds
   const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
   col_inv_stage_a<N, A, B, C, T>(tid, smem, twd, in.at(b), W, c0);
   __syncthreads();
-  col_stage_b<N, A, B, C, T, true, false>(tid, smem, twd);
-  __syncthreads();
+  if constexpr (B > 1) {
+    col_stage_b<N, A, B, C, T, true, false>(tid, smem, twd);
+    __syncthreads();
+  }
   auto fn = kfn.bind(b);
   col_inv_fn_fwd_stage_c<N, A, B, C, T>(tid, smem, fn);
   __syncthreads();
-  col_stage_b<N, A, B, C, T, false, true>(tid, smem, twd);
-  __syncthreads();
+  if constexpr (B > 1) {
+    col_stage_b<N, A, B, C, T, false, true>(tid, smem, twd);
+    __syncthreads();
+  }
   col_fwd_dit_stage_a<N, A, B, C, T>(tid, smem, twd, out.at(b), W, c0);
   DeviceSync sync;
   fn.finish(tid, sync);

@@ -159,7 +159,8 @@ int launch_row_fwd(int N, RowTwiddles tw, ProSpec pro, EpiSpecStore epi, int nro
 }
 int launch_row_fwd_h(int N, RowTwiddles tw, ProSpec pro, EpiHStore epi, int nrows, int B, cudaStream_t s) { ROW_DISPATCH(false, NIS_ROWB_FWDH) }
 int launch_row_inv_mulconj(int N, RowTwiddles tw, ProMulConj pro, EpiSpecStore epi, int nrows, int B, cudaStream_t s, bool match_fused) {
-  ROW_DISPATCH(true, match_fused ? NIS_ROWB_RR : NIS_ROWB_INVMC)
+  const bool auto_form = pro.x.base == pro.z.base && pro.x.ptrs == pro.z.ptrs && pro.x.idx == pro.z.idx && pro.x.offset == pro.z.offset;
+  ROW_DISPATCH(true, match_fused ? NIS_ROWB_RR : (auto_form ? NIS_ROWB_INVMC_AUTO : NIS_ROWB_INVMC))
 }
 
 #define RR_DISPATCH                                        \

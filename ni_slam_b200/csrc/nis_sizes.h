@@ -19,13 +19,16 @@
 #define NIS_P480_B 5
 #define NIS_P480_C 8
 #endif
+#ifndef NIS_P480_T
+#define NIS_P480_T NIS_COL_T
+#endif
 #ifndef NIS_P720_A
 #define NIS_P720_A 12       // 720 = 12*5*12: 31 / 144 / 60 butterfly tasks per stage on 32 groups (10*9*8 leaves a 5-of-32 tail round in the
 #define NIS_P720_B 5        // paired stages; measured 64.7 k vs 59.3 k solves/s, profiles/ab_r02.md)
 #define NIS_P720_C 12
 #endif
 #define NIS_COL_PLANS(X)          \
-  X(480, NIS_P480_A, NIS_P480_B, NIS_P480_C, NIS_COL_T)     \
+  X(480, NIS_P480_A, NIS_P480_B, NIS_P480_C, NIS_P480_T)     \
   X(720, NIS_P720_A, NIS_P720_B, NIS_P720_C, NIS_COL_T)     \
   X(960, 8, 15, 8, NIS_COL_T)     \
   X(1200, 10, 15, 8, NIS_COL_T)   \
@@ -93,6 +96,9 @@
 #endif
 #ifndef NIS_ROWB_INVMC
 #define NIS_ROWB_INVMC 0        // row_inv_mulconj
+#endif
+#ifndef NIS_ROWB_INVMC_AUTO
+#define NIS_ROWB_INVMC_AUTO 0    // row_inv_mulconj in its auto form |Z|^2 (one operand)
 #endif
 #ifndef NIS_ROWB_RR
 #define NIS_ROWB_RR 1           // the three fused fwd->mid->inv kernels

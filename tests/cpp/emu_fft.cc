@@ -67,7 +67,7 @@ static void emu_col_fwd(const float* x, int Bn, int W, cpx* out) {
     for (int c0 = 0; c0 < W; c0 += kColTile) {
       auto bp = pro.bind(b, c0);
       for (int t = 0; t < T; ++t) col_fwd_stage_a<N, A, B, C, T>(t, smem.data(), twd, bp);
-      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, false>(t, smem.data(), twd);
+      if constexpr (B > 1) for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, false>(t, smem.data(), twd);
       for (int t = 0; t < T; ++t) col_fwd_stage_c<N, A, B, C, T>(t, smem.data(), out + (size_t)b * (N / 2 + 1) * W, W, c0);
     }
 }
@@ -84,7 +84,7 @@ static void emu_col_inv(const cpx* in, int Bn, int W, Epi& epi) {
     for (int c0 = 0; c0 < W; c0 += kColTile) {
       std::vector<typename Epi::Bound> eb(T, epi.bind(b, c0));
       for (int t = 0; t < T; ++t) col_inv_stage_a<N, A, B, C, T>(t, smem.data(), twd, in + (size_t)b * (N / 2 + 1) * W, W, c0);
-      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, true, false>(t, smem.data(), twd);
+      if constexpr (B > 1) for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, true, false>(t, smem.data(), twd);
       for (int t = 0; t < T; ++t) col_inv_stage_c<N, A, B, C, T>(t, smem.data(), eb[t]);
       for (int t = 0; t < T; ++t) eb[t].finish(t, sync);
     }
@@ -130,9 +130,9 @@ static void emu_colcol(const cpx* in, int Bn, int W, cpx* out, KernelFn kfn) {
       cpx* dst = out + (size_t)b * (N / 2 + 1) * W;
       std::vector<KernelFn::Bound> fn(T, kfn.bind(b));
       for (int t = 0; t < T; ++t) col_inv_stage_a<N, A, B, C, T>(t, smem.data(), twd, src, W, c0);
-      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, true, false>(t, smem.data(), twd);
+      if constexpr (B > 1) for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, true, false>(t, smem.data(), twd);
       for (int t = 0; t < T; ++t) col_inv_fn_fwd_stage_c<N, A, B, C, T>(t, smem.data(), fn[t]);
-      for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, true>(t, smem.data(), twd);
+      if constexpr (B > 1) for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, true>(t, smem.data(), twd);
       for (int t = 0; t < T; ++t) col_fwd_dit_stage_a<N, A, B, C, T>(t, smem.data(), twd, dst, W, c0);
       for (int t = 0; t < T; ++t) fn[t].finish(t, sync);
     }
