@@ -12,12 +12,12 @@ namespace nis {
 
 // resident CTAs per SM the register budget is sized for: 64 registers per thread for the three-stage plans; the two-stage plans
 // (R2 == 1) hold a radix-32 butterfly per thread and get 102
-template <int R0, int R2, int T> constexpr int row_min_blocks() {
-  return T > 256 ? 1 : ((R2 == 1 && R0 >= 32) ? 640 / T : NIS_ROW_THREADS_PER_SM / T);
+template <int R0, int R1, int R2, int T> constexpr int row_min_blocks() {
+  return T > 256 ? 1 : ((R2 == 1 && (R0 >= 32 || R1 >= 32)) ? 640 / T : NIS_ROW_THREADS_PER_SM / T);
 }
 
 template <int N, int R0, int R1, int R2, int L, int T, bool INV, class Pro, class Epi>
-__global__ void __launch_bounds__(T, (row_min_blocks<R0, R2, T>())) row_kernel(Pro pro, Epi epi, Twiddles twd, int nrows, int total_lines) {
+__global__ void __launch_bounds__(T, (row_min_blocks<R0, R1, R2, T>())) row_kernel(Pro pro, Epi epi, Twiddles twd, int nrows, int total_lines) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
   const int tid = threadIdx.x, line0 = blockIdx.x * L;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(T, (row_min_blocks<R0, R2, T>())) row_kernel(P
 // fused forward row pass -> element-wise -> inverse row pass: K^xz, X = FFT(rotated image) and the filtered spectrum G
 // exist only in registers / shared memory.  Two padded line buffers (the inverse stage 0 cannot run in place).
 template <int N, int R0, int R1, int R2, int L, int T, class Mid>
-__global__ void __launch_bounds__(T, (row_min_blocks<R0, R2, T>())) rowrow_kernel(Src<cpx> in, Dst<cpx> out, Mid mid, Twiddles twd, int nrows, int total_lines) {
+__global__ void __launch_bounds__(T, (row_min_blocks<R0, R1, R2, T>())) rowrow_kernel(Src<cpx> in, Dst<cpx> out, Mid mid, Twiddles twd, int nrows, int total_lines) {
   typedef RowGeom<N, R0, R1, R2, L, T> Gm;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* bufA = reinterpret_cast<cpx*>(smem_raw);

@@ -85,9 +85,17 @@
 #define NIS_ROWB_T 96
 #define NIS_ROWB_LR 3
 #endif
+#ifndef NIS_RB640_0
+#define NIS_RB640_0 32
+#define NIS_RB640_1 20
+#endif
+#ifndef NIS_RB480_0
+#define NIS_RB480_0 32
+#define NIS_RB480_1 15
+#endif
 #define NIS_ROW_PLANS_B(X)    \
-  X(640, 32, 20, 1, NIS_ROWB_L, NIS_ROWB_T, NIS_ROWB_LR)   \
-  X(480, 32, 15, 1, NIS_ROWB_L, NIS_ROWB_T, NIS_ROWB_LR)
+  X(640, NIS_RB640_0, NIS_RB640_1, 1, NIS_ROWB_L, NIS_ROWB_T, NIS_ROWB_LR)   \
+  X(480, NIS_RB480_0, NIS_RB480_1, 1, NIS_ROWB_L, NIS_ROWB_T, NIS_ROWB_LR)
 #ifndef NIS_ROWB_FWD
 #define NIS_ROWB_FWD 1          // row_fwd (P)
 #endif
