@@ -37,7 +37,7 @@ METRIC = "pose_solves_per_sec_640x480"
 
 
 NCU_FAMILY = {"colcol": ("colcol_kernel",), "rowrow_filter": ("rowrow_kernel", "MidFilterH"), "rowrow_storeabs": ("rowrow_kernel", "MidStoreAbs"),
-              "rowrow_mulconj": ("rowrow_kernel", "MidMulConjZ"), "row_inv_mulconj": ("row_kernel", "ProMulConj"), "row_fwd_h": ("row_kernel", "EpiHStore"),
+              "rowrow_mulconj": ("rowrow_kernel", "MidMulConjZ"), "rowrow_storesq": ("rowrow_kernel", "MidStoreSq"), "row_inv_mulconj": ("row_kernel", "ProMulConj"), "row_fwd_h": ("row_kernel", "EpiHStore"),
               "row_fwd": ("row_kernel", "ProSpec, EpiSpecStore"), "col_fwd_rotate": ("col_fwd_kernel", "ProRotate"), "col_fwd_u8": ("col_fwd_kernel", "ProRealU8"),
               "col_fwd_f32": ("col_fwd_kernel", "ProRealF32"), "col_inv_peak": ("col_inv_kernel", "EpiPeak"),
               "col_inv_store_shift": ("col_inv_kernel", "EpiStoreShift"), "polar_tma": ("polar_tma_kernel",), "rzc_fix": ("rzc_fix_kernel",)}

@@ -451,21 +451,32 @@ static KernelFn kernel_fn(const nis_ctx* ctx, int s, const double* xx, const dou
 
 // H = T / (kernel(Z)/max + lambda) for B keyframe spectra of size class s (the keyframe-only factor of EstimateTrans,
 // correlation_flow.cc:157-171: Kzz = kernel(z); H = output_fft/(Kzz + lambda)).  3 kernels, nothing real-valued is stored.
-static int hzz_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> Z, int B, Dst<cpx> Hout) {
-  ctx->prof_stream = L.stream;
+// hzz_tail: the last two of them, for a caller whose own kernel has already left the row half of IFFT(Z conj Z) in the lane scratch.
+static int hzz_tail(nis_ctx* ctx, Lane& L, int s, int B, Dst<cpx> Hout) {
   const SizeClass& z = ctx->sz[s];
-  if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return fail(ctx, NIS_ERR_INVALID_KERNEL, "Received invalid kernel type");
   Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
   Src<cpx> t1s = src_slab<cpx>(t1.base, t1.stride);
-  if (ctx->cfg.kernel == 1) LAUNCH(launch_spec_sqsum(Z, (int)z.spec, L.zz.as<double>(), B, L.stream));
-  CU(cudaMemsetAsync(L.maxh.p, 0, sizeof(unsigned) * B, L.stream));
-  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{Z, Z}, EpiSpecStore{t1}, z.R / 2 + 1, B, L.stream));
   LAUNCH(launch_colcol(z.R, z.col, t1s, t1, kernel_fn(ctx, s, L.zz.as<double>(), L.zz.as<double>(), 0, L.maxh.as<unsigned>()),
                        z.C, B, L.stream));
   LAUNCH(launch_row_fwd_h(z.C, z.row, ProSpec{t1s}, EpiHStore{Hout, L.maxh.as<unsigned>(), ctx->cfg.lambda}, z.R / 2 + 1, B, L.stream));
   return NIS_OK;
 }
+static int hzz_batch(nis_ctx* ctx, Lane& L, int s, Src<cpx> Z, int B, Dst<cpx> Hout) {
+  ctx->prof_stream = L.stream;
+  const SizeClass& z = ctx->sz[s];
+  if (ctx->cfg.kernel != 0 && ctx->cfg.kernel != 1) return fail(ctx, NIS_ERR_INVALID_KERNEL, "Received invalid kernel type");
+  Dst<cpx> t1{L.t1.as<cpx>(), (long long)z.spec};
+  if (ctx->cfg.kernel == 1) LAUNCH(launch_spec_sqsum(Z, (int)z.spec, L.zz.as<double>(), B, L.stream));
+  CU(cudaMemsetAsync(L.maxh.p, 0, sizeof(unsigned) * B, L.stream));
+  // polar size: features_batch computes this factor through the fused store-and-square row kernel; stored spectra (compact store
+  // modes, imported frames) take the same plan here so that both routes give the same bits
+  LAUNCH(launch_row_inv_mulconj(z.C, z.row, ProMulConj{Z, Z}, EpiSpecStore{t1}, z.R / 2 + 1, B, L.stream, /*match_fused=*/s == 1));
+  return hzz_tail(ctx, L, s, B, Hout);
+}
 
+#ifndef NIS_FUSE_PSQ
+#define NIS_FUSE_PSQ 1      // A/B switch: 0 = fft_polar by a plain row pass, its keyframe factor by the three-kernel chain
+#endif
 // ComputeIntermedium (correlation_flow.cc:89-95) for B images, plus the cached H factors of both stages.
 // with_h = false skips the H factors (frames that are only ever "current").
 static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8, bool is_u8, int B, Dst<cpx> F, Dst<cpx> P,
@@ -490,10 +501,20 @@ static int features_batch(nis_ctx* ctx, Lane& L, Src<float> f32, Src<uint8_t> u8
   LAUNCH(launch_polar_tma(&L.hp_map, pol, ctx->D, ctx->Cp, ctx->ptiles.as<int4>(), ctx->ptab2.as<uint32_t>(), ctx->ptile_pitch, ctx->ptile_rows, B,
                           L.stream));
   LAUNCH(launch_col_fwd_f32(zp.R, zp.col, ProRealF32{src_slab<float>(pol.base, pol.stride), zp.C}, t1p, zp.C, B, L.stream));
-  LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
-  if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
+  if (NIS_FUSE_PSQ && with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {   // an invalid kernel id only throws in ComputePose (:168)
+    // fft_polar is stored from registers and the same kernel continues with the row half of IFFT(P conj P): the polar-stage keyframe
+    // factor starts without re-reading P
+    LAUNCH(launch_rowrow_storesq(zp.C, zp.row, src_slab<cpx>(t1p.base, t1p.stride), t1p, MidStoreSq{P}, zp.R / 2 + 1, B, L.stream));
+    if (ctx->cfg.kernel == 1) LAUNCH(launch_spec_sqsum(src_slab<cpx>(P.base, P.stride), (int)zp.spec, L.zz.as<double>(), B, L.stream));
+    CU(cudaMemsetAsync(L.maxh.p, 0, sizeof(unsigned) * B, L.stream));
+    TRY(hzz_tail(ctx, L, 1, B, Hp));
     TRY(hzz_batch(ctx, L, 0, src_slab<cpx>(F.base, F.stride), B, Ht));
-    TRY(hzz_batch(ctx, L, 1, src_slab<cpx>(P.base, P.stride), B, Hp));
+  } else {
+    LAUNCH(launch_row_fwd(zp.C, zp.row, ProSpec{src_slab<cpx>(t1p.base, t1p.stride)}, EpiSpecStore{P}, zp.R / 2 + 1, B, L.stream));
+    if (with_h && (ctx->cfg.kernel == 0 || ctx->cfg.kernel == 1)) {
+      TRY(hzz_batch(ctx, L, 0, src_slab<cpx>(F.base, F.stride), B, Ht));
+      TRY(hzz_batch(ctx, L, 1, src_slab<cpx>(P.base, P.stride), B, Hp));
+    }
   }
   return NIS_OK;
 }

@@ -47,6 +47,7 @@ int launch_row_inv_mulconj(int N, RowTwiddles tw, ProMulConj pro, EpiSpecStore e
 int launch_rowrow_mulconj(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s);
 int launch_rowrow_filter(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s);
 int launch_rowrow_storeabs(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s);
+int launch_rowrow_storesq(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreSq mid, int nrows, int B, cudaStream_t s);
 
 // ---- warps and bookkeeping kernels -----------------------------------------------------------------------
 // tiled polar gather (nis_misc.cu): one CTA per cell of kPolarTA angles x kPolarTR radii, source box staged in shared memory by TMA

@@ -260,13 +260,17 @@ struct ProSpec {      // plain spectrum load
   NIS_HD Bound bind(const LineMap& m) const { return Bound{x, m}; }
 };
 
+// |z|^2 with one fixed rounding sequence: the auto form of the product prologue and the fused store-and-square step of the row
+// kernel must agree bit for bit (a keyframe's H factor may be computed through either)
+NIS_HD float sqmag(cpx z) { return fmaf(z.x, z.x, z.y * z.y); }
+
 struct ProMulConj {   // x * conj(z)  (:210-211); auto form when x aliases z (:220-221)
   Src<cpx> x, z;
   struct Line {
     const cpx* px; const cpx* pz;
     NIS_HD cpx load(int c) const {
       const cpx x = NIS_LDG(px + c);
-      if (px == pz) return make_float2(x.x * x.x + x.y * x.y, 0.f);     // auto form z * conj(z): one load, imaginary part exactly 0
+      if (px == pz) return make_float2(sqmag(x), 0.f);     // auto form z * conj(z): one load, imaginary part exactly 0
       return cmulc(x, NIS_LDG(pz + c));
     }
   };
@@ -317,6 +321,23 @@ struct MidFilterH {
     NIS_HD void finish_line(int) const {}
   };
   NIS_HD Bound bind(const LineMap& m, float*) const { return Bound{h, max_xz, m}; }
+};
+
+// store P = x, continue with x * conj(x) = |x|^2: fft_polar leaves the forward row pass and the same kernel runs the row half of
+// IFFT(P conj P), the first step of the keyframe factor Kzz of the polar stage (correlation_flow.cc:94 followed by :220-221)
+struct MidStoreSq {
+  Dst<cpx> f;
+  struct Line {
+    cpx* pf;
+    NIS_HD cpx apply(int c, cpx x) const { pf[c] = x; return make_float2(sqmag(x), 0.f); }
+    NIS_HD void flush() const {}
+  };
+  struct Bound {
+    Dst<cpx> f; LineMap m;
+    NIS_HD Line line(int ln) const { int b, k1; size_t off; m.map(ln, b, off, k1); return Line{f.at(b) + off}; }
+    NIS_HD void finish_line(int) const {}
+  };
+  NIS_HD Bound bind(const LineMap& m, float*) const { return Bound{f, m}; }
 };
 
 // store F = x, continue with |x| (ComputeIntermedium: fft_result = FFT(image); IFFT(fft_result.abs()), :91-92)

@@ -178,5 +178,6 @@ int launch_row_inv_mulconj(int N, RowTwiddles tw, ProMulConj pro, EpiSpecStore e
 int launch_rowrow_mulconj(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidMulConjZ mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 int launch_rowrow_filter(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidFilterH mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 int launch_rowrow_storeabs(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreAbs mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
+int launch_rowrow_storesq(int N, RowTwiddles tw, Src<cpx> in, Dst<cpx> out, MidStoreSq mid, int nrows, int B, cudaStream_t s) { RR_DISPATCH }
 
 }  // namespace nis

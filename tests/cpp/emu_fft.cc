@@ -251,6 +251,17 @@ int emu_row(const float* in, int total_lines, int N, int inverse, float* out) {
   return -1;
 }
 
+// f = FFT_rows(in) stored, out = IFFT_rows(|f|^2) (unnormalised); plan_b selects the two-stage plans
+int emu_rowrow_storesq(const float* in, int B, int nrows, int N, float* f, float* out, int plan_b) {
+  MidStoreSq mid{Dst<cpx>{(cpx*)f, (long long)nrows * N}};
+#define X(n, r0, r1, r2, l, t, lr) \
+  if (N == n) { emu_rowrow<n, r0, r1, r2, lr, t>((const cpx*)in, nrows, B, (cpx*)out, mid); return 0; }
+  if (plan_b) { NIS_ROW_PLANS_B(X) }
+  NIS_ROW_PLANS(X)
+#undef X
+  return -1;
+}
+
 // the two-stage plan B of the production row lengths (nis_sizes.h NIS_ROW_PLANS_B)
 int emu_row_b(const float* in, int total_lines, int N, int inverse, float* out) {
 #define X(n, r0, r1, r2, l, t, lr)                                                      \

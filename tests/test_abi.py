@@ -173,6 +173,21 @@ def test_emulated_fused_rowrow(emu, N, plan):
     assert np.abs(out2 - want2).max() / np.abs(want2).max() < 3e-6
 
 
+@pytest.mark.parametrize("N,plan_b", [(480, 0), (480, 1), (640, 1)])
+def test_emulated_fused_store_and_square(emu, N, plan_b):
+    """forward row pass -> store the spectrum, continue with |.|^2 -> inverse row pass (fft_polar and the first step of its Kzz)"""
+    rng = np.random.default_rng(N + 3)
+    B, nrows = 2, 5
+    x = (rng.standard_normal((B, nrows, N)) + 1j * rng.standard_normal((B, nrows, N))).astype(np.complex64)
+    f = np.zeros_like(x)
+    out = np.zeros_like(x)
+    assert emu.emu_rowrow_storesq(P(x), B, nrows, N, P(f), P(out), plan_b) == 0
+    X = np.fft.fft(x.astype(np.complex128), axis=2)
+    assert np.abs(f - X).max() / np.abs(X).max() < 2e-6
+    want = np.fft.ifft(np.abs(X) ** 2, axis=2) * N
+    assert np.abs(out - want).max() / np.abs(want).max() < 3e-6
+
+
 def test_host_pose_math_matches_tracker_restatement():
     """ni_slam_b200/host/pose_math.hpp (gate, pose composition, keyframe test of nis_track_stream_keyframes) against the Python
     restatement of map_builder.cc:30-70 on 300 scripted ComputePose outputs: decisions identical, poses to 1e-12."""
