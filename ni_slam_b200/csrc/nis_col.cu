@@ -22,11 +22,11 @@ template <class Pro> __device__ __forceinline__ auto bind_pro(const Pro& pro, in
 #define NIS_COL_MINB (B == 1 ? (480 / T > 0 ? 480 / T : 1) : 768 / T)
 #endif
 
-template <int N, int A, int B, int C, int T, class Pro>
+template <int N, int A, int B, int C, int T, class Pro, int LN>
 __global__ void __launch_bounds__(T, NIS_COL_MINB) col_fwd_kernel(Pro pro, Twiddles twd, Dst<cpx> out, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx* smem = reinterpret_cast<cpx*>(smem_raw);
-  const int b = blockIdx.y, c0 = blockIdx.x * kColTile, tid = threadIdx.x;
+  const int b = blockIdx.y, c0 = blockIdx.x * (2 * LN), tid = threadIdx.x;
   const float* lut_s = nullptr;
   if constexpr (ProTraits<Pro>::kSmemLut) {          // gather prologues on u8 images: the u8 -> f32/255 table comes from shared memory
     __shared__ float lut_sh[256];
@@ -35,13 +35,13 @@ __global__ void __launch_bounds__(T, NIS_COL_MINB) col_fwd_kernel(Pro pro, Twidd
     lut_s = lut_sh;
   }
   const auto bp = bind_pro(pro, b, c0, lut_s);
-  col_fwd_stage_a<N, A, B, C, T>(tid, smem, twd, bp);
+  col_fwd_stage_a<N, A, B, C, T, decltype(bp), LN>(tid, smem, twd, bp);
   __syncthreads();
   if constexpr (B > 1) {
-    col_stage_b<N, A, B, C, T, false, false>(tid, smem, twd);
+    col_stage_b<N, A, B, C, T, false, false, LN>(tid, smem, twd);
     __syncthreads();
   }
-  col_fwd_stage_c<N, A, B, C, T>(tid, smem, out.at(b), W, c0);
+  col_fwd_stage_c<N, A, B, C, T, LN>(tid, smem, out.at(b), W, c0);
 }
 
 template <int N, int A, int B, int C, int T, class Epi>
@@ -97,13 +97,14 @@ static int run_colcol(Twiddles tw, Src<cpx> in, Dst<cpx> out, KernelFn fn, int W
   return (int)cudaGetLastError();
 }
 
-template <int N, int A, int B, int C, int T, class Pro>
+template <int N, int A, int B, int C, int T, int LN = kColLanes, class Pro>
 static int run_col_fwd(Twiddles tw, Pro pro, Dst<cpx> out, int W, int Bn, cudaStream_t s) {
-  auto k = col_fwd_kernel<N, A, B, C, T, Pro>;
-  const size_t smem = ColGeom<N, A, B, C, T>::kSmemBytes;
+  auto k = col_fwd_kernel<N, A, B, C, T, Pro, LN>;
+  const size_t smem = ColGeom<N, A, B, C, T, LN>::kSmemBytes;
   static int attr = set_smem(k, smem);
   if (attr) return attr;
-  k<<<dim3(W / kColTile, Bn), T, smem, s>>>(pro, tw, out, W);
+  if (W % (2 * LN)) return -1;
+  k<<<dim3(W / (2 * LN), Bn), T, smem, s>>>(pro, tw, out, W);
   return (int)cudaGetLastError();
 }
 template <int N, int A, int B, int C, int T, class Epi>
@@ -138,6 +139,16 @@ void plan_radices_col(int N, int r[3]) {
 #define FWD_CASE(n, a, b, c, t) case n: return run_col_fwd<n, a, b, c, t>(tw, pro, out, W, B, s);
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealF32) }
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s) { FWD_DISPATCH(ProRealU8) }
+#undef FWD_CASE
+// Lane count of the forward pass with the rotation prologue.  16 lanes (32 adjacent columns per CTA) make the gather itself faster
+// (col_fwd_rotate 1.71 -> 1.38 ms per 1000 frames) but the whole step SLOWER (73.8 k -> 66.2 k solves/s, profiles/ab_r02.md): three
+// 69 KB tiles per SM push the SM's shared-memory carveout to its maximum, and every kernel of the other lanes that shares the SM then
+// runs with the smallest L1 (the library-wide carveout experiment shows what that costs: +10-20 % per kernel).  Kept at 8.
+#ifndef NIS_ROT_LANES
+#define NIS_ROT_LANES 8
+#endif
+constexpr int rot_lanes(int n) { return n <= 512 ? NIS_ROT_LANES : kColLanes; }
+#define FWD_CASE(n, a, b, c, t) case n: return run_col_fwd<n, a, b, c, t, rot_lanes(n)>(tw, pro, out, W, B, s);
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int B, cudaStream_t s) {
   if (ra.is_u8) {
     ProRotate<true> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab};

@@ -2,7 +2,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "nis_ops.cuh"
+
+#ifndef NIS_SMEM_CARVEOUT_DEFAULT
+#define NIS_SMEM_CARVEOUT_DEFAULT -1
+#endif
 
 namespace nis {
 
@@ -56,8 +62,28 @@ struct DeviceSync {
   }
 };
 
+// Shared-memory carveout override for A/B runs: NIS_SMEM_CARVEOUT = percent of the maximum for EVERY kernel of the library (-1, the
+// default, leaves the driver's per-kernel choice).  Measured (profiles/ab_r02.md): 100 % costs every FFT kernel 10-20 % (the twiddle
+// and table loads want the L1), 75 % equals the default, 50 % loses occupancy -- the driver's choice stays.
+inline int smem_carveout() {
+  static const int pct = [] {
+    const char* e = getenv("NIS_SMEM_CARVEOUT");
+    return e ? atoi(e) : NIS_SMEM_CARVEOUT_DEFAULT;
+  }();
+  return pct;
+}
+// kernels without a dynamic shared-memory request: the carveout alone (call once per kernel: `static int a = set_carveout(k);`)
+template <class K> inline int set_carveout(K kernel) {
+  const int pct = smem_carveout();
+  return pct >= 0 ? (int)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) : 0;
+}
 template <class K> inline int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (bytes > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int pct = smem_carveout();
+  if (pct >= 0) return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   return 0;
 }
 

@@ -284,23 +284,25 @@ struct Twiddles {
 constexpr int kColLanes = NIS_COL_LANES;          // complex lines per CTA
 constexpr int kColTile = 2 * kColLanes;           // real image columns per CTA
 
-template <int N, int A, int B, int C, int T> struct ColGeom {
+// LN = complex lines per CTA (2 LN real columns); the forward pass is templated on it for the lane-count experiments recorded in
+// nis_col.cu (NIS_ROT_LANES); production uses kColLanes everywhere
+template <int N, int A, int B, int C, int T, int LN = kColLanes> struct ColGeom {
   static_assert(A * B * C == N, "bad factorisation");
-  static_assert(T % kColLanes == 0, "T must be a multiple of the lane count");
-  static constexpr int G = T / kColLanes;
+  static_assert(T % LN == 0, "T must be a multiple of the lane count");
+  static constexpr int G = T / LN;
   static constexpr int BC = B * C, AB = A * B, AC = A * C;
   static constexpr int PADC = C + ((C % 2 == 0) ? 1 : 0);
   static constexpr int SLOTS = AB * PADC;
-  static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)SLOTS * kColLanes;
+  static constexpr size_t kSmemBytes = sizeof(cpx) * (size_t)SLOTS * LN;
   static NIS_HD int pos(int d0, int d1, int d2) { return (d0 * B + d1) * PADC + d2; }
   static NIS_HD int pos_j(int d0, int j) { return (d0 * B + j / C) * PADC + j % C; }      // j = d1*C + d2
 };
 
 // ---- stage B (middle), both directions.  DIT = false: decimation in frequency (twiddle after the butterfly); true: before.
-template <int N, int A, int B, int C, int T, bool INV, bool DIT>
+template <int N, int A, int B, int C, int T, bool INV, bool DIT, int LN = kColLanes>
 NIS_HD void col_stage_b(int tid, cpx* smem, const Twiddles& twd) {
-  typedef ColGeom<N, A, B, C, T> Gm;
-  const int l = tid % kColLanes, gi = tid / kColLanes;
+  typedef ColGeom<N, A, B, C, T, LN> Gm;
+  const int l = tid % LN, gi = tid / LN;
   // butterfly index bi = d2 + C*d0: when the group count is a multiple of C the twiddle index d2 is the same in every round
   constexpr bool kHoist = (Gm::G % C == 0);
   cpx twv[B > 1 ? B - 1 : 1];
@@ -310,11 +312,11 @@ NIS_HD void col_stage_b(int tid, cpx* smem, const Twiddles& twd) {
   }
   for (int bi = gi; bi < Gm::AC; bi += Gm::G) {
     const int d0 = bi / C, d2 = bi % C;
-    cpx* s = smem + (size_t)Gm::pos(d0, 0, d2) * kColLanes + l;
+    cpx* s = smem + (size_t)Gm::pos(d0, 0, d2) * LN + l;
     cpx v[B];
 #pragma unroll
     for (int r = 0; r < B; ++r) {
-      cpx x = s[r * Gm::PADC * kColLanes];
+      cpx x = s[r * Gm::PADC * LN];
       if (DIT && r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * C + d2]));
       v[r] = x;
     }
@@ -323,7 +325,7 @@ NIS_HD void col_stage_b(int tid, cpx* smem, const Twiddles& twd) {
     for (int r = 0; r < B; ++r) {
       cpx x = v[r];
       if (!DIT && r > 0) x = ctw<INV>(x, kHoist ? twv[r - 1] : NIS_LDG(&twd.tw1[(r - 1) * C + d2]));
-      s[r * Gm::PADC * kColLanes] = x;
+      s[r * Gm::PADC * LN] = x;
     }
   }
 }
@@ -333,21 +335,21 @@ NIS_HD void col_stage_b(int tid, cpx* smem, const Twiddles& twd) {
 // the per-lane context lets a prologue hoist everything that depends only on the column pair, and handing it all R rows at
 // once lets gather-type prologues issue every independent load before the first use
 // stage A from global (decimation in frequency)
-template <int N, int A, int B, int C, int T, class Pro>
+template <int N, int A, int B, int C, int T, class Pro, int LN = kColLanes>
 NIS_HD void col_fwd_stage_a(int tid, cpx* smem, const Twiddles& twd, const Pro& pro) {
-  typedef ColGeom<N, A, B, C, T> Gm;
-  const int l = tid % kColLanes, gi = tid / kColLanes;
+  typedef ColGeom<N, A, B, C, T, LN> Gm;
+  const int l = tid % LN, gi = tid / LN;
   const auto ln = pro.lane(l);
   for (int j = gi; j < Gm::BC; j += Gm::G) {
     cpx v[A];
     ln.template load_all<A>(j, Gm::BC, v);        // v[r] = sample at row j + r*BC
     Dft<A, false>::run(v);
-    cpx* s = smem + (size_t)Gm::pos_j(0, j) * kColLanes + l;
+    cpx* s = smem + (size_t)Gm::pos_j(0, j) * LN + l;
 #pragma unroll
     for (int r = 0; r < A; ++r) {
       cpx x = v[r];
       if (r > 0) x = cmul(x, NIS_LDG(&twd.tw2[(r - 1) * Gm::BC + j]));
-      s[r * B * Gm::PADC * kColLanes] = x;
+      s[r * B * Gm::PADC * LN] = x;
     }
   }
 }
@@ -383,24 +385,24 @@ NIS_HD void r2c_emit(int p, bool single, const cpx* v, const cpx* u, float4* out
 
 // stage C of the decimation-in-frequency forward pass: butterfly q = k0 + A*k1 yields k = q + A*B*k2
 // out: spectrum rows k in [0,N/2], row pitch `pitch` complex; this CTA's columns start at c0 (even).
-template <int N, int A, int B, int C, int T>
+template <int N, int A, int B, int C, int T, int LN = kColLanes>
 NIS_HD void col_fwd_stage_c(int tid, const cpx* smem, cpx* out, int pitch, int c0) {
-  typedef ColGeom<N, A, B, C, T> Gm;
+  typedef ColGeom<N, A, B, C, T, LN> Gm;
   constexpr int AB = Gm::AB;
-  const int l = tid % kColLanes, gi = tid / kColLanes;
+  const int l = tid % LN, gi = tid / LN;
   float4* out4 = reinterpret_cast<float4*>(out);   // (A.x,A.y,B.x,B.y) = two adjacent complex columns
   for (int p = gi; 2 * p <= AB; p += Gm::G) {
     const bool single = (p == 0) || (2 * p == AB);
     cpx v[C], u[C];
-    const cpx* s = smem + (size_t)Gm::pos(p % A, p / A, 0) * kColLanes + l;
+    const cpx* s = smem + (size_t)Gm::pos(p % A, p / A, 0) * LN + l;
 #pragma unroll
-    for (int r = 0; r < C; ++r) v[r] = s[r * kColLanes];
+    for (int r = 0; r < C; ++r) v[r] = s[r * LN];
     Dft<C, false>::run(v);
     if (!single) {
       const int q = AB - p;
-      const cpx* t = smem + (size_t)Gm::pos(q % A, q / A, 0) * kColLanes + l;
+      const cpx* t = smem + (size_t)Gm::pos(q % A, q / A, 0) * LN + l;
 #pragma unroll
-      for (int r = 0; r < C; ++r) u[r] = t[r * kColLanes];
+      for (int r = 0; r < C; ++r) u[r] = t[r * LN];
       Dft<C, false>::run(u);
     }
     r2c_emit<N, AB, C>(p, single, v, u, out4, pitch, c0, l);

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(1024) rzc_fix_kernel(Dst<float> hp, int H, int
 int launch_rzc_fix(Dst<float> hp, int H, int W, int B, cudaStream_t s) {
   if (B <= 0) return 0;
   if (W > 2048 || H > 2048) return -1;
+  static int attr = set_carveout(rzc_fix_kernel);
+  if (attr) return attr;
   rzc_fix_kernel<<<B, 1024, 0, s>>>(hp, H, W);
   return (int)cudaGetLastError();
 }
@@ -154,6 +156,8 @@ int launch_polar_tma(const void* hp_map, Dst<float> out, int D, int Cp, const in
                      cudaStream_t s) {
   if (B <= 0) return 0;
   const int tile_bytes = box_rows * pitch * (int)sizeof(float);
+  static int attr = set_carveout(polar_tma_kernel);
+  if (attr) return attr;
   static int attr_bytes = 0;
   if (tile_bytes > 48 * 1024 && tile_bytes > attr_bytes) {
     const cudaError_t e = cudaFuncSetAttribute(polar_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_bytes);
@@ -241,6 +245,8 @@ __global__ void __launch_bounds__(256) spec_sqsum_kernel(Src<cpx> x, int count, 
 }
 int launch_spec_sqsum(Src<cpx> x, int count, double* out, int B, cudaStream_t s) {
   if (B <= 0) return 0;
+  static int attr = set_carveout(spec_sqsum_kernel);
+  if (attr) return attr;
   spec_sqsum_kernel<<<B, 256, 0, s>>>(x, count, out);
   return (int)cudaGetLastError();
 }
@@ -275,6 +281,8 @@ __global__ void polar_select_kernel(const PeakStats* __restrict__ polar, int D, 
 }
 int launch_polar_select(const PeakStats* polar, int D, int loop_mode, int* sel, int B, cudaStream_t s) {
   if (B <= 0) return 0;
+  static int attr = set_carveout(polar_select_kernel);
+  if (attr) return attr;
   polar_select_kernel<<<(B + 127) / 128, 128, 0, s>>>(polar, D, loop_mode, sel, B);
   return (int)cudaGetLastError();
 }
@@ -310,6 +318,8 @@ __global__ void pose_finalize_kernel(const PeakStats* __restrict__ polar, const 
 int launch_pose_finalize(const PeakStats* polar, const PeakStats* trans, AngleTables tabs, int H, int W, int D, int Cp,
                          int loop_mode, int index0, PoseRecord* out, int B, cudaStream_t s) {
   if (B <= 0) return 0;
+  static int attr = set_carveout(pose_finalize_kernel);
+  if (attr) return attr;
   pose_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(polar, trans, tabs, H, W, D, Cp, loop_mode, index0, out, B);
   return (int)cudaGetLastError();
 }

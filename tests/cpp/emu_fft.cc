@@ -56,19 +56,19 @@ static void make_tw_col(int A, int B, int C, std::vector<cpx>& t1, std::vector<c
 }
 
 // ---- column forward: real [B][N][W] -> half-transformed spectrum [B][N/2+1][W]
-template <int N, int A, int B, int C, int T>
+template <int N, int A, int B, int C, int T, int LN = kColLanes>
 static void emu_col_fwd(const float* x, int Bn, int W, cpx* out) {
-  typedef ColGeom<N, A, B, C, T> Gm;
+  typedef ColGeom<N, A, B, C, T, LN> Gm;
   std::vector<cpx> t1, t2; make_tw_col(A, B, C, t1, t2);
   Twiddles twd{t1.data(), t2.data()};
-  std::vector<cpx> smem((size_t)Gm::SLOTS * kColLanes);
+  std::vector<cpx> smem((size_t)Gm::SLOTS * LN);
   ProRealF32 pro{Src<float>{x, (long long)N * W, nullptr, 0, nullptr, 0}, W};
   for (int b = 0; b < Bn; ++b)
-    for (int c0 = 0; c0 < W; c0 += kColTile) {
+    for (int c0 = 0; c0 < W; c0 += 2 * LN) {
       auto bp = pro.bind(b, c0);
-      for (int t = 0; t < T; ++t) col_fwd_stage_a<N, A, B, C, T>(t, smem.data(), twd, bp);
-      if constexpr (B > 1) for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, false>(t, smem.data(), twd);
-      for (int t = 0; t < T; ++t) col_fwd_stage_c<N, A, B, C, T>(t, smem.data(), out + (size_t)b * (N / 2 + 1) * W, W, c0);
+      for (int t = 0; t < T; ++t) col_fwd_stage_a<N, A, B, C, T, decltype(bp), LN>(t, smem.data(), twd, bp);
+      if constexpr (B > 1) for (int t = 0; t < T; ++t) col_stage_b<N, A, B, C, T, false, false, LN>(t, smem.data(), twd);
+      for (int t = 0; t < T; ++t) col_fwd_stage_c<N, A, B, C, T, LN>(t, smem.data(), out + (size_t)b * (N / 2 + 1) * W, W, c0);
     }
 }
 
@@ -214,6 +214,15 @@ int emu_rowrow_filter(const float* in, const float* h, const unsigned int* maxbu
 int emu_col_fwd_f32(const float* x, int B, int N, int W, float* out) {
 #define X(n, a, b, c, t) \
   if (N == n) { emu_col_fwd<n, a, b, c, t>(x, B, W, (cpx*)out); return 0; }
+  NIS_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
+// the 16-lane forward pass (32 real columns per CTA) the rotation prologue runs with
+int emu_col_fwd_f32_l16(const float* x, int B, int N, int W, float* out) {
+#define X(n, a, b, c, t) \
+  if (N == n) { emu_col_fwd<n, a, b, c, t, 16>(x, B, W, (cpx*)out); return 0; }
   NIS_COL_PLANS(X)
 #undef X
   return -1;
