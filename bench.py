@@ -58,6 +58,29 @@ def ncu_traffic(kernel_family):
         return None
 
 
+def bind_to_gpu_cpus(torch, local_rank):
+    """Multi-rank runs: pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the e2e leg
+    are first-touched on that GPU's NUMA node (eight ranks otherwise stream 2.5 GB of frames per step through one socket's memory
+    controllers).  Returns the number of CPUs bound, or None when the topology is not available.  Not applied at N = 1, where the
+    CPU baseline of the same invocation must see every core."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -436,6 +459,7 @@ def main():
     nis_build.build()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_cpus(torch, local_rank) if world > 1 else None      # before any pinned allocation (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -860,7 +884,7 @@ def main():
             line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                     "data": "synthetic",
-                    "config": workload_config(n, world), "tuning": {"batch": args.batch or "default", "lanes": args.lanes or "default"},
+                    "config": workload_config(n, world), "tuning": {"batch": args.batch or "default", "lanes": args.lanes or "default", "cpus_bound_per_rank": numa},
                     "clocks": clk,
                     "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": n * H * W,
                             "d2h_bytes_per_step": (n - 1) * 72},
