@@ -19,8 +19,10 @@
 #define NIS_P480_B 5
 #define NIS_P480_C 8
 #endif
+// 480 = 12*5*8 has 21 / 96 / 60 butterfly tasks per stage: 24 thread groups (192 threads, 4 CTAs per SM) fit them better than 32
+// (measured 73.9 k -> 76.0 k solves/s, col_fwd_rotate 1.71 -> 1.52 ms per 1000 frames, profiles/ab_r02.md)
 #ifndef NIS_P480_T
-#define NIS_P480_T NIS_COL_T
+#define NIS_P480_T 192
 #endif
 #ifndef NIS_P720_A
 #define NIS_P720_A 12       // 720 = 12*5*12: 31 / 144 / 60 butterfly tasks per stage on 32 groups (10*9*8 leaves a 5-of-32 tail round in the
