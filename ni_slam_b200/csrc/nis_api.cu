@@ -597,7 +597,6 @@ static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz
   PeakStats* st = L.stats_t.as<PeakStats>();
   // rotation: EstimateTrans(last_fft_polar, fft_polar, ...)   (:103)
   TRY(estimate_trans_stored(ctx, L, 1, Pz, Hpz, Px, B, L.maxp.as<unsigned>(), sp, nullptr));
-  LAUNCH(launch_polar_select(sp, ctx->D, loop_mode ? 1 : 0, L.sel.as<int>(), B, L.stream));
   // translation: FFT(RotateArray(image, -deg [+180])) never leaves the chip; one or two hypotheses per pair   (:107-132)
   const SizeClass& zt = ctx->sz[0];
   const int shift = loop_mode ? 1 : 0, E = B << shift;
@@ -615,12 +614,15 @@ static int compute_pose_batch(nis_ctx* ctx, Lane& L, bool loop_mode, Src<cpx> Fz
   CU(cudaMemsetAsync(st, 0, sizeof(PeakStats) * E, L.stream));
   Src<cpx> Fze = Fz; Fze.shift = shift;
   if (loop_mode && ctx->use_rot_cache) {
-    // FFT(RotateArray(query, angle)) comes from the per-query cache: one inverse row pass instead of warp + 3 passes
+    // FFT(RotateArray(query, angle)) comes from the per-query cache: one inverse row pass instead of warp + 3 passes; the cache is
+    // indexed through sel[] (two hypotheses per candidate), written by the select kernel
+    LAUNCH(launch_polar_select(sp, ctx->D, 1, L.sel.as<int>(), B, L.stream));
     Src<cpx> Xc{ctx->rotc.as<cpx>() - (size_t)ctx->D * zt.spec, (long long)zt.spec, nullptr, 0, L.sel.as<int>(), 0};
     LAUNCH(launch_row_inv_mulconj(zt.C, zt.row, ProMulConj{Xc, Fze}, EpiSpecStore{t1}, zt.R / 2 + 1, E, L.stream, /*match_fused=*/true));
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr, ctx->rotc_xx.as<double>() - ctx->D, L.sel.as<int>()));
   } else {
-    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), L.sel.as<int>(), ctx->rowtab.as<int2>()};
+    // the rotation prologue reads the polar-stage peak itself: no select launch between the two stages
+    RotateArgs ra{i32, i8, is_u8, ctx->lut.as<float>(), ctx->H, ctx->W, ctx->mats.as<double>(), nullptr, ctx->rowtab.as<int2>(), sp, ctx->D, shift};
     LAUNCH(launch_col_fwd_rotate(zt.R, zt.col, ra, t1, zt.C, E, L.stream));
     LAUNCH(launch_rowrow_mulconj(zt.C, zt.row, t1s, t1, MidMulConjZ{Fze, gauss ? L.xx.as<double>() : nullptr}, zt.R / 2 + 1, E, L.stream));
     TRY(correlate_tail(ctx, L, 0, Htz, E, shift, L.maxt.as<unsigned>(), st, nullptr));

@@ -151,10 +151,10 @@ constexpr int rot_lanes(int n) { return n <= 512 ? NIS_ROT_LANES : kColLanes; }
 #define FWD_CASE(n, a, b, c, t) case n: return run_col_fwd<n, a, b, c, t, rot_lanes(n)>(tw, pro, out, W, B, s);
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int B, cudaStream_t s) {
   if (ra.is_u8) {
-    ProRotate<true> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab};
+    ProRotate<true> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab, ra.polar, ra.D, ra.loop};
     FWD_DISPATCH(ProRotate<true>)
   } else {
-    ProRotate<false> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab};
+    ProRotate<false> pro{ra.f32, ra.u8, ra.lut, ra.H, ra.W, ra.mats, ra.sel, ra.rowtab, ra.polar, ra.D, ra.loop};
     FWD_DISPATCH(ProRotate<false>)
   }
 }

@@ -32,7 +32,10 @@ struct RowTwiddles { Twiddles a, b; };
 
 // ---- FFT passes (return cudaError_t as int; -1 = unsupported size) --------------------------------------
 // rowtab[slot][y] = (X0, Y0) of cv::warpAffine's fixed-point walk for output row y under rotation-matrix slot `slot` (host-built beside mats)
-struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; const int2* rowtab; };
+// sel[e] = rotation-matrix slot of entry e; or, when `polar` is given, derived in the kernel from the polar-stage peak of pair e >> loop
+// (slot = polar row for tracking, D + row / 2 D + row for the two loop hypotheses: correlation_flow.cc:105-121) -- no select launch
+struct RotateArgs { Src<float> f32; Src<uint8_t> u8; bool is_u8; const float* lut; int H, W; const double* mats; const int* sel; const int2* rowtab;
+                    const PeakStats* polar = nullptr; int D = 0; int loop = 0; };
 int launch_col_fwd_f32(int N, Twiddles tw, ProRealF32 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_u8(int N, Twiddles tw, ProRealU8 pro, Dst<cpx> out, int W, int B, cudaStream_t s);
 int launch_col_fwd_rotate(int N, Twiddles tw, RotateArgs ra, Dst<cpx> out, int W, int E, cudaStream_t s);   // RotateArray fused into stage 0

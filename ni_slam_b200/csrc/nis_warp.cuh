@@ -65,6 +65,7 @@ __device__ __forceinline__ float rotate_pixel(const float* __restrict__ f32, con
 template <bool U8> struct ProRotate {
   static constexpr bool kSmemLut = U8;        // the kernel stages the 256-entry u8 -> f32/255 table in shared memory and hands it to bind()
   Src<float> f32; Src<uint8_t> u8; const float* lut; int H, W; const double* mats; const int* sel; const int2* rowtab;
+  const PeakStats* polar; int D, loop;          // polar != nullptr: the slot comes from the polar-stage peak (see RotateArgs)
   struct Lane {
     const float* f; const uint8_t* u; const float* lut; int H, W; const int2* rt; int a0, b0, a1, b1;   // adelta / bdelta of both columns
     __device__ __forceinline__ float pixel(int X0, int Y0, int ad, int bd) const {
@@ -108,7 +109,14 @@ template <bool U8> struct ProRotate {
     }
   };
   __device__ __forceinline__ Bound bind(int e, int c0, const float* lut_s = nullptr) const {
-    const int slot = sel[e];
+    int slot;
+    if (polar) {
+      const uint32_t idx = 0xffffffffu - (uint32_t)(polar[e >> loop].key & 0xffffffffull);      // peak_key: column-major index col * D + row
+      const int row = (int)(idx % (uint32_t)D);
+      slot = loop ? ((e & 1) ? 2 * D + row : D + row) : row;
+    } else {
+      slot = sel[e];
+    }
     return Bound{U8 ? nullptr : f32.at(e), U8 ? u8.at(e) : nullptr, lut_s ? lut_s : lut, H, W, c0, mats + 6 * (size_t)slot, rowtab + (size_t)slot * H};
   }
 };
