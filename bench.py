@@ -757,7 +757,21 @@ def main():
                     dth = np.deg2rad(qa - gang[w])
                     winner_ok = bool(abs((res.relative_pose[2] - dth + np.pi) % (2 * np.pi) - np.pi) < np.deg2rad(0.75) and
                                      abs(np.hypot(res.relative_pose[0], res.relative_pose[1]) - np.hypot(qx - gcx[w], qy - gcy[w])) < 2.0)
+                # where one query's device time goes (one extra query with events around every launch, one lane): the query's own
+                # features, the rotated-query cache (col_fwd_rotate + row_fwd over all 2 D angles, a fixed cost per query) and the scan
+                fam = None
+                try:
+                    cf.set_lanes(1)
+                    cf.profile_begin()
+                    query()
+                    prof = cf.profile_end()
+                    cf.set_lanes(args.lanes)
+                    fam = {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+                    fam["rotated_query_cache_ms"] = round(prof.get("col_fwd_rotate", {"ms": 0.0})["ms"] + prof.get("row_fwd", {"ms": 0.0})["ms"], 3)
+                except Exception as e:
+                    fam = {"error": str(e)[:200]}
                 out = {"workload": label, "db_keyframes": per_gpu * world, "keyframes_per_gpu": per_gpu, "store_mode": mode_name[mode],
+                       "kernel_ms_per_query_one_lane": fam,
                        "value": 1e3 / q_ms, "unit": "queries/s", "ms_per_query": q_ms, "ms_per_query_all": [round(x, 3) for x in per_query],
                        "candidates_per_sec": cand_per_s, "winner_frame_id": int(res.loop_frame_id), "winner_global_slot": int(res.loop_slot),
                        "winner_rank": int(win), "planted_frame_id": int(jstar), "found": bool(res.found),
