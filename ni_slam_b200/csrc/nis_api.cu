@@ -991,6 +991,9 @@ static int track_stream_impl(nis_ctx* ctx, const uint8_t* frames, bool on_host, 
   }
   return NIS_OK;
 }
+#ifndef NIS_STREAM_RAMP
+#define NIS_STREAM_RAMP 1
+#endif
 static int track_stream_window(nis_ctx* ctx, const uint8_t* frames, bool on_host, int n, double* poses, double* infos) {
   CU(cudaSetDevice(ctx->device));
   const size_t npx = ctx->sz[0].real, spt = ctx->sz[0].spec, spp = ctx->sz[1].spec;
@@ -1013,7 +1016,12 @@ static int track_stream_window(nis_ctx* ctx, const uint8_t* frames, bool on_host
   const int NL = ctx->active_lanes;
   cpx* F = ctx->sF.as<cpx>(); cpx* P = ctx->sP.as<cpx>();
   cpx* Ht = ctx->sHt.as<cpx>(); cpx* Hp = ctx->sHp.as<cpx>();
-  const int nbatch = (n + B - 1) / B;
+  // batch k covers frames [starts[k], starts[k+1]).  Frames coming from the host start with a quarter batch: nothing can be computed
+  // before the first upload has landed, so the pipeline is primed with a small one (NIS_STREAM_RAMP=0 builds without)
+  std::vector<int> starts{0};
+  if (NIS_STREAM_RAMP && on_host && n > B && B >= 8) starts.push_back(B / 4);
+  while (starts.back() < n) starts.push_back(std::min(n, starts.back() + B));
+  const int nbatch = (int)starts.size() - 1;
   while ((int)ctx->up_ev.size() < nbatch) {
     cudaEvent_t a = nullptr, b = nullptr;
     CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -1029,14 +1037,14 @@ static int track_stream_window(nis_ctx* ctx, const uint8_t* frames, bool on_host
     CU(cudaEventRecord(ctx->fork_ev, ctx->stream));               // the copy stream, too, starts after everything already queued
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
     for (int k = 0; k < nbatch; ++k) {
-      const int t0 = k * B, nb = std::min(B, n - t0);
+      const int t0 = starts[k], nb = starts[k + 1] - t0;
       CU(cudaMemcpyAsync(ctx->sImg.as<uint8_t>() + (size_t)t0 * npx, frames + (size_t)t0 * npx, (size_t)nb * npx, cudaMemcpyHostToDevice,
                          ctx->copy_stream));
       CU(cudaEventRecord(ctx->up_ev[k], ctx->copy_stream));
     }
   }
   auto pose_of_batch = [&](int j, Lane& L) -> int {                 // pairs (t, t+1) with t in batch j
-    const int p0 = j * B, nb = std::min(B, n - 1 - p0);
+    const int p0 = starts[j], nb = std::min(starts[j + 1] - p0, n - 1 - p0);
     if (nb <= 0) return NIS_OK;
     return compute_pose_batch(ctx, L, false, src_slab<cpx>(F + (size_t)p0 * spt, (long long)spt),
                               src_slab<cpx>(P + (size_t)p0 * spp, (long long)spp), src_slab<cpx>(Ht + (size_t)p0 * spt, (long long)spt),
@@ -1045,7 +1053,7 @@ static int track_stream_window(nis_ctx* ctx, const uint8_t* frames, bool on_host
                               ctx->recs.as<PoseRecord>() + p0);
   };
   for (int k = 0; k < nbatch; ++k) {
-    const int t0 = k * B, nb = std::min(B, n - t0);
+    const int t0 = starts[k], nb = starts[k + 1] - t0;
     Lane& L = ctx->lanes[k % NL];
     if (on_host) CU(cudaStreamWaitEvent(L.stream, ctx->up_ev[k], 0));
     if (ctx->undistort) TRY(undistort_batch(ctx, L.stream, d_raw + (size_t)t0 * npx, ctx->sUnd.as<uint8_t>() + (size_t)t0 * npx, nb));
