@@ -1610,26 +1610,27 @@ struct NcclApi {
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
-static NcclApi* nccl_api() {
-  static NcclApi api;
-  static bool tried = false;
-  if (tried) return api.h ? &api : nullptr;
-  tried = true;
+static NcclApi load_nccl() {
+  NcclApi api;
   const char* names[] = {getenv("NIS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) {
     if (!nm || !*nm) continue;
     api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (api.h) break;
   }
-  if (!api.h) return nullptr;
+  if (!api.h) return api;
   api.GetUniqueId = (int (*)(nis_nccl_id*))dlsym(api.h, "ncclGetUniqueId");
   api.CommInitRank = (int (*)(void**, int, nis_nccl_id, int))dlsym(api.h, "ncclCommInitRank");
   api.CommDestroy = (int (*)(void*))dlsym(api.h, "ncclCommDestroy");
   api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.h, "ncclBroadcast");
   api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.h, "ncclAllGather");
   api.GetErrorString = (const char* (*)(int))dlsym(api.h, "ncclGetErrorString");
-  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllGather) { dlclose(api.h); api.h = nullptr; return nullptr; }
-  return &api;
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllGather) { dlclose(api.h); api.h = nullptr; }
+  return api;
+}
+static NcclApi* nccl_api() {
+  static NcclApi api = load_nccl();          // resolved once, thread-safe (C++11 static initialisation)
+  return api.h ? &api : nullptr;
 }
 static int nccl_fail(nis_ctx* ctx, const char* what, int rc) {
   NcclApi* a = nccl_api();
@@ -1691,14 +1692,20 @@ int nis_loop_scan_sharded(nis_ctx* ctx, const uint8_t* query_image_rowmajor, int
       CU(cudaMemcpyAsync(ctx->sImg.p, q->img_u8, npx, cudaMemcpyDeviceToDevice, ctx->stream));
       TRY(undistort_batch(ctx, ctx->stream, ctx->sImg.as<uint8_t>(), q->img_u8, 1));
     }
-    TRY(features_batch(ctx, ctx->lanes[0], src_null<float>(), src_slab<uint8_t>(q->img_u8, 0), true, 1, Dst<cpx>{q->F, 0}, Dst<cpx>{q->P, 0},
-                       Dst<cpx>{q->Ht, 0}, Dst<cpx>{q->Hp, 0}, false));
+    // From here on a rank that fails must still reach the all-gather, or the others wait in it forever: the local part runs in its own
+    // scope, its status travels in the record (order = INT64_MIN), and every rank returns an error if any rank reported one.
     ShardRecord mine;
     memset(&mine, 0, sizeof mine);
-    TRY(nis_loop_scan(ctx, q, query_frame_id, query_acc_distance, cfg, nullptr, 0, &mine.r, nullptr));
-    if (local_out) *local_out = mine.r;
+    auto local_part = [&]() -> int {
+      TRY(features_batch(ctx, ctx->lanes[0], src_null<float>(), src_slab<uint8_t>(q->img_u8, 0), true, 1, Dst<cpx>{q->F, 0}, Dst<cpx>{q->P, 0},
+                         Dst<cpx>{q->Ht, 0}, Dst<cpx>{q->Hp, 0}, false));
+      TRY(nis_loop_scan(ctx, q, query_frame_id, query_acc_distance, cfg, nullptr, 0, &mine.r, nullptr));
+      return NIS_OK;
+    };
+    const int local_status = local_part();
+    if (local_status == NIS_OK && local_out) *local_out = mine.r;
     mine.offset = global_slot_offset;
-    mine.order = mine.r.slot >= 0 ? global_slot_offset + mine.r.slot : INT64_MAX;
+    mine.order = local_status != NIS_OK ? INT64_MIN : (mine.r.slot >= 0 ? global_slot_offset + mine.r.slot : INT64_MAX);
     const int G = ctx->n_ranks;
     std::vector<ShardRecord> all(G);
     if (a) {
@@ -1712,6 +1719,13 @@ int nis_loop_scan_sharded(nis_ctx* ctx, const uint8_t* query_image_rowmajor, int
     } else {
       all[0] = mine;
     }
+    if (local_status != NIS_OK) return local_status;                 // this rank's own error (message already recorded)
+    for (int i = 0; i < G; ++i)
+      if (all[i].order == INT64_MIN) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "nis_loop_scan_sharded: rank %d failed its local scan", i);
+        return fail(ctx, NIS_ERR_CUDA, buf);
+      }
     std::vector<nis_loop_result> rs(G);
     std::vector<int64_t> order(G);
     for (int i = 0; i < G; ++i) { rs[i] = all[i].r; order[i] = all[i].order; }

@@ -315,6 +315,24 @@ def test_scan_rotated_query_cache_is_result_preserving(cf, imgs, monkeypatch):
     cf2.close()
 
 
+def test_sharded_entry_point_single_rank(cf, imgs):
+    """nis_loop_scan_sharded on a one-rank communicator (no NCCL call): query image in, features on the device, local scan, the
+    reduction -- same winner, pose and response bits as ComputeIntermedium + FindLoopClosure; the slot comes back as a GLOBAL slot."""
+    import ni_slam_b200 as nis
+    order = [3, 0, 5, 6, 2, 4, 7]
+    lc = nis.LoopClosure(nis.LoopClosureConfig(60, 60), cf)
+    lc.clear()
+    lc.AddImages(imgs[order])
+    ref = lc.FindLoopClosure(cf.ComputeIntermedium(imgs[1]), 99, 50.0)
+    res, win, mine = lc.FindLoopClosureSharded(imgs[1], 0, 1000, current_frame_id=99, current_distance=50.0)
+    assert win == 0 and res.found == ref.found and res.loop_slot == 1000 + ref.loop_slot and mine.loop_slot == ref.loop_slot
+    assert res.evaluated == ref.evaluated == len(order)
+    assert np.array_equal(res.relative_pose, ref.relative_pose) and np.array_equal(res.response, ref.response)
+    lc.clear()
+    empty, win0, _ = lc.FindLoopClosureSharded(imgs[1], 0, 0)            # empty shard: no winner, nothing found
+    assert win0 == -1 and not empty.found and empty.loop_slot == -1 and empty.evaluated == 0
+
+
 def test_prior_pose_candidate_selection(cf, imgs):
     """FindLoopClosure(image, frame, prior_pose): Map::ComputeGridLocation + 3x3 cells + GetFramesInGrids (loop_closure.cc:17-34)."""
     import ni_slam_b200 as nis
