@@ -272,6 +272,43 @@ int main() {
     std::sort(ms.begin(), ms.end());
     printf("shim_online_ms p50 %.3f p99 %.3f\n", ms[ms.size() / 2], ms[(ms.size() * 99) / 100]);
   }
+  // Multi-GPU scan entry points from a C++ host, on a one-rank communicator: NCCL id -> nis_comm_init -> ONE call per query
+  // (image in; broadcast, features, local scan, all-gather and reduction inside the library) == nis_features_u8 + nis_loop_scan
+  {
+    nis_cf_config c{0.1f, 0, 0.2f, 0.1f, 3, 720, 480};
+    nis_ctx* ctx = nullptr;
+    EXPECT(nis_create(&c, H, W, 0, &ctx) == 0);
+    std::vector<uint8_t> imgs((size_t)3 * H * W), query((size_t)H * W);
+    // keyframes: the texture mirrored top-bottom, the texture itself, the texture mirrored left-right (mirror images do not correlate
+    // under translation); the query is the middle one moved by (sy, sx) = (3, -9)
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < W; ++j) {
+        imgs[((size_t)0 * H + i) * W + j] = (uint8_t)std::lrint(a(H - 1 - i, j) * 255.f);
+        imgs[((size_t)1 * H + i) * W + j] = (uint8_t)std::lrint(a(i, j) * 255.f);
+        imgs[((size_t)2 * H + i) * W + j] = (uint8_t)std::lrint(a(i, W - 1 - j) * 255.f);
+      }
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < W; ++j) query[(size_t)i * W + j] = (uint8_t)std::lrint(a((i - 3 + H) % H, (j + 9 + W) % W) * 255.f);
+    const int ids[3] = {10, 11, 12};
+    EXPECT(nis_db_add_images(ctx, imgs.data(), 3, ids, nullptr) == 0 && nis_db_size(ctx) == 3);
+    char id[128];
+    EXPECT(nis_nccl_unique_id(id) == 0);
+    EXPECT(nis_comm_init(ctx, id, 0, 1) == 0);
+    nis_loop_config lcfg{60.0, 60.0, 0, 0.0};
+    nis_loop_result sharded, local, direct;
+    int winner_rank = -7;
+    EXPECT(nis_loop_scan_sharded(ctx, query.data(), 0, 99, 0.0, &lcfg, 5000, &sharded, &winner_rank, &local) == 0);
+    nis_frame* qf = nullptr;
+    EXPECT(nis_features_u8(ctx, query.data(), &qf) == 0);
+    EXPECT(nis_loop_scan(ctx, qf, 99, 0.0, &lcfg, nullptr, 0, &direct, nullptr) == 0);
+    EXPECT(winner_rank == 0 && direct.found && direct.slot == 1 && direct.frame_id == 11 && direct.evaluated == 3);
+    EXPECT(local.slot == direct.slot && sharded.slot == 5000 + direct.slot && sharded.frame_id == direct.frame_id && sharded.found == direct.found);
+    EXPECT(direct.relative_pose[0] == 9.0 && direct.relative_pose[1] == -3.0);          // content rolled by (sy, sx) = (3, -9) -> pose (-sx, -sy, 0)
+    for (int i = 0; i < 3; ++i) EXPECT(sharded.relative_pose[i] == direct.relative_pose[i] && sharded.response[i] == direct.response[i]);
+    nis_frame_free(ctx, qf);
+    EXPECT(nis_comm_destroy(ctx) == 0);
+    nis_destroy(ctx);
+  }
   // MapStitcher shim (host/map_stitcher.hpp) driven like MapBuilder drives the reference (map_builder.cc:37, :62, :113): identity pose,
   // principal point at the centre -> pixel (i, j) lands on ground (i - W/2, j - H/2); first insert stores the scaled pixel itself
   {
