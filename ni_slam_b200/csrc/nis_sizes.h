@@ -5,9 +5,9 @@
 //                      forward pass then alternates bank halves), C even and a divisor of T/8 (stage-B twiddles hoist).
 // Row pass (transform along image columns: W, rotation_channel):
 //   X(N, R0, R1, R2, L, T, LR)    N = R0*R1*R2 in stage order, L lines per CTA, threads; LR = lines per CTA of the fused
-//                                 fwd->mid->inv kernel (two line buffers, so fewer lines keep more CTAs resident).  N/R0 and N/R2
-//                                 should be multiples of 16 (128-byte aligned global runs), R0 + 1 odd (bank conflicts)
-// Image widths must also be multiples of 16 (one column-pass CTA owns 16 real columns).
+//                                 fwd->mid->inv kernel (two line buffers, so fewer lines keep more CTAs resident); R0 + 1 odd (bank
+//                                 conflicts); R2 = 1 selects the two-stage code path
+// Image widths must be multiples of 32 and rotation_channel of 16 (one column-pass CTA owns 16 real columns; nis_create checks).
 #pragma once
 #include "nis_fft.cuh"
 #ifndef NIS_COL_T
@@ -81,7 +81,8 @@
 // 80-96 registers.  Measured per kernel family against plan A (ms per 1000 frames, profiles/ab_r02.md): fused fwd->mid->inv kernels
 // 2.17 -> 1.72 (filter), 1.07 -> 0.80 (store-abs), 0.92 -> 0.84 (mul-conj); row_fwd_h 1.21 -> 1.10; row_fwd 0.60 -> 0.59; but the
 // inverse pass with the two-operand product prologue 2.02 -> 2.34 (64 loads per thread, 96 registers).  So each launcher picks its
-// plan (NIS_ROWB_* below); sizes without a plan B entry use plan A everywhere.
+// plan (NIS_ROWB_* below); sizes without a plan B entry use plan A everywhere.  With the big radix second (20 x 32, 15 x 32) every
+// family is slower than with three stages: it is the 32 independent loads of the first stage that pay.
 #ifndef NIS_ROWB_L
 #define NIS_ROWB_L 3            // 3 lines x 96 threads: stage 1 (32 butterflies per line) fills the CTA exactly
 #define NIS_ROWB_T 96
@@ -111,5 +112,5 @@
 #define NIS_ROWB_INVMC_AUTO 0    // row_inv_mulconj in its auto form |Z|^2 (one operand)
 #endif
 #ifndef NIS_ROWB_RR
-#define NIS_ROWB_RR 1           // the three fused fwd->mid->inv kernels
+#define NIS_ROWB_RR 1           // the fused fwd->mid->inv kernels (store-abs, store-square, mul-conj, filter)
 #endif
