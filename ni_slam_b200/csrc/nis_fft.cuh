@@ -533,7 +533,9 @@ NIS_HD void col_inv_fn_fwd_stage_c(int tid, cpx* smem, Fn& fn) {
 // slots apart; R0+1 must be odd or the plan pays bank conflicts).
 // Global-memory alignment: stage 0 reads runs of M0 = N/R0 consecutive elements and the last stage writes runs of N/R2; a warp's
 // request covers whole 128-byte lines exactly when both are multiples of 16 elements.  The production plans (R0 = 16: runs of
-// 40 / 30) do not, on purpose -- see nis_sizes.h for the measurement.
+// 40 / 30; R0 = 32: runs of 20 / 15) do not, on purpose -- the passes are latency bound and what pays is the number of independent
+// loads a thread has in flight in stage 0 (see nis_sizes.h for the measurements).  Plans with R2 == 1 take the two-stage path
+// (row_stage1_out / row_stage1_mid): one exchange, one barrier.
 // =========================================================================================================
 template <int R1, int ROUNDS> struct CarryRegs { cpx v[ROUNDS][R1]; };
 
